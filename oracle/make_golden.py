@@ -1,0 +1,97 @@
+"""Generate tests/golden/*.pt by running the REAL reference (imported from /root/reference) on CPU.
+
+Run in the build container only (``python oracle/make_golden.py``); the GPU box has no /root/reference.
+Recipe: put the reference on sys.path, patch ``is_main_process`` so torchvision
+does not try to download ResNet weights, patch ``BertModel.from_pretrained`` to build a random-init BERT
+from a config (no network), build with the reference's own argparse parser, load by-name synthetic
+weights, run forward + criterion-equivalent loss + backward, and store inputs' recipe + outputs.
+
+The fixtures hold only outputs (a few KB each): weights and inputs are regenerated from seeds by
+``reftr_b200.synthetic`` on the consumer side.
+"""
+import argparse
+import os
+import sys
+
+import torch
+
+REF = os.environ.get("REFTR_REF", "/root/reference")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, REF)
+
+from reftr_b200.synthetic import synthetic_samples, synthetic_targets, synthetic_weights  # noqa: E402
+from oracle.cases import CASES, bert_config  # noqa: E402
+
+
+def load_reference():
+    import numpy as np  # noqa: F401  (main_vg's parser uses np.pi)
+    import models.modeling.backbone as rb
+    rb.is_main_process = lambda: False
+    import models.reftr_transformer as rt
+    import models.reftr_segmentation as rs
+    from transformers import BertModel
+
+    class _FakeBert:
+        cfg = None
+
+        @staticmethod
+        def from_pretrained(name):
+            torch.manual_seed(1234)
+            return BertModel(_FakeBert.cfg)
+
+    rt.BertModel = rs.BertModel = _FakeBert
+    rt.RobertaModel = rs.RobertaModel = _FakeBert
+    src = open(os.path.join(REF, "main_vg.py")).read()
+    a, b = src.index("def get_args_parser"), src.index("def main(args)")
+    ns = {"argparse": argparse, "np": np}
+    exec(src[a:b], ns)
+    import models
+    from util.misc import NestedTensor
+    return models, ns["get_args_parser"], NestedTensor, _FakeBert
+
+
+def run_case(name, case, models, get_args_parser, NestedTensor, fake_bert):
+    from oracle.reftr_oracle import total_box_loss
+    parser = argparse.ArgumentParser(parents=[get_args_parser()])
+    args = parser.parse_args(case["flags"] + ["--device", "cpu"])
+    fake_bert.cfg = bert_config(case)
+    torch.manual_seed(0)
+    model, criterion, post = models.build_reftr(args)
+    synthetic_weights(model, seed=case["wseed"])
+    model.eval()  # dropout inactive: parity is only defined without it
+    s = synthetic_samples(**case["inputs"])
+    samples = dict(s)
+    samples["img"] = NestedTensor(s["img"].tensors, s["img"].mask)
+    out = model(samples)
+    n_ph = max(case["inputs"].get("n_ph", 0), 1)
+    tgt = synthetic_targets(case["inputs"]["B"], n_ph)
+    loss = total_box_loss(out, tgt)
+    if "pred_masks" in out:
+        loss = loss + out["pred_masks"].sigmoid().mean()
+    loss.backward()
+    gold = {"pred_boxes": out["pred_boxes"].detach(), "phrase_mask": out["phrase_mask"], "loss": loss.detach()}
+    if out.get("aux_outputs"):
+        gold["aux_boxes"] = torch.stack([a["pred_boxes"].detach() for a in out["aux_outputs"]])
+    if "pred_masks" in out:
+        gold["pred_masks"] = out["pred_masks"].detach()
+        gold["mask_att"] = out["mask_att"].detach()
+    grads = {}
+    for pname, p in model.named_parameters():
+        if p.grad is not None and case["grad_filter"](pname):
+            grads[pname] = (p.grad.norm().item(), p.grad.flatten()[:8].clone())
+    gold["grads"] = grads
+    gold["n_params_with_grad"] = sum(1 for _, p in model.named_parameters() if p.grad is not None)
+    gold["state_dict_keys"] = [(k, tuple(v.shape)) for k, v in model.state_dict().items()]
+    path = os.path.join(ROOT, "tests", "golden", f"{name}.pt")
+    torch.save(gold, path)
+    print(name, "loss", float(loss), "boxes", gold["pred_boxes"].flatten()[:4].tolist(), "->", path,
+          os.path.getsize(path), "bytes")
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(os.cpu_count())
+    ref = load_reference()
+    only = sys.argv[1:] or list(CASES)
+    for name in only:
+        run_case(name, CASES[name], *ref)

@@ -1,0 +1,561 @@
+"""CPU/fp32 ORACLE for the RefTR forward/backward hot path -- TEST INFRASTRUCTURE ONLY.
+
+This file is a plain-PyTorch fp32 restatement of the reference algorithm (ubc-vision/RefTR).
+It is the checker the CUDA path is compared against.  Only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference`` legs may
+import it; nothing under ``reftr_b200/`` does.
+
+Parity status: PINNED AGAINST THE REFERENCE ITSELF.  The reference ships no tests and no golden
+vectors, so ``oracle/make_golden.py`` imports the real reference from
+``/root/reference`` in the build container, loads the same by-name synthetic weights
+(``reftr_b200.synthetic.synthetic_weights``) and writes input/output fixtures to
+``tests/golden/``; ``tests/test_oracle_golden.py`` checks this restatement against those
+fixtures on CPU.
+
+Every function cites the reference file:line it follows (paths relative to /root/reference).
+The state_dict layout is the reference's, so weights move between the
+reference, this oracle and the CUDA module with ``load_state_dict``.
+
+Third-party arithmetic that is NOT under /root/reference and is restated here:
+  * torchvision 0.26 ``resnet50/101`` Bottleneck v1.5 (stride on the 3x3) -- call site
+    models/modeling/backbone.py:119-121.
+  * torch 2.11 ``nn.MultiheadAttention`` need_weights branch -- call sites
+    models/modeling/transformer.py:174, :239, :243.
+  * HF transformers 5.5 ``BertModel`` is used as is (third party in the reference too,
+    models/reftr_transformer.py:8, :200).
+"""
+import math
+from typing import List, Optional
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+
+# --------------------------------------------------------------------------------------
+# Backbone: FrozenBatchNorm2d + torchvision Bottleneck ResNet (backbone.py:43-121)
+# --------------------------------------------------------------------------------------
+class FrozenBN(nn.Module):
+    """backbone.py:43-80 -- y = x*scale + bias, scale = w*rsqrt(rv+eps), bias = b - rm*scale."""
+
+    def __init__(self, n, eps=1e-5):
+        super().__init__()
+        self.register_buffer("weight", torch.ones(n))
+        self.register_buffer("bias", torch.zeros(n))
+        self.register_buffer("running_mean", torch.zeros(n))
+        self.register_buffer("running_var", torch.ones(n))
+        self.eps = eps
+
+    def _load_from_state_dict(self, state_dict, prefix, *args):
+        state_dict.pop(prefix + "num_batches_tracked", None)  # backbone.py:62-64
+        super()._load_from_state_dict(state_dict, prefix, *args)
+
+    def forward(self, x):
+        scale = self.weight.reshape(1, -1, 1, 1) * (self.running_var.reshape(1, -1, 1, 1) + self.eps).rsqrt()
+        bias = self.bias.reshape(1, -1, 1, 1) - self.running_mean.reshape(1, -1, 1, 1) * scale
+        return x * scale + bias
+
+
+class Bottleneck(nn.Module):
+    """torchvision Bottleneck v1.5: 1x1 -> 3x3(stride) -> 1x1(x4), ReLU after the residual add."""
+    expansion = 4
+
+    def __init__(self, inplanes, planes, stride=1, downsample=False, dilation=1):
+        super().__init__()
+        self.conv1 = nn.Conv2d(inplanes, planes, 1, bias=False)
+        self.bn1 = FrozenBN(planes)
+        self.conv2 = nn.Conv2d(planes, planes, 3, stride=stride, padding=dilation, dilation=dilation, bias=False)
+        self.bn2 = FrozenBN(planes)
+        self.conv3 = nn.Conv2d(planes, planes * 4, 1, bias=False)
+        self.bn3 = FrozenBN(planes * 4)
+        self.downsample = None
+        if downsample:
+            self.downsample = nn.Sequential(nn.Conv2d(inplanes, planes * 4, 1, stride=stride, bias=False),
+                                            FrozenBN(planes * 4))
+
+    def forward(self, x):
+        out = F.relu(self.bn1(self.conv1(x)))
+        out = F.relu(self.bn2(self.conv2(out)))
+        out = self.bn3(self.conv3(out))
+        identity = x if self.downsample is None else self.downsample(x)
+        return F.relu(out + identity)
+
+
+RESNET_BLOCKS = {"resnet50": [3, 4, 6, 3], "resnet101": [3, 4, 23, 3]}
+
+
+class ResNetBody(nn.Module):
+    """Parameter names follow torchvision's ResNet so that ``img_backbone.0.body.*`` matches."""
+
+    def __init__(self, name="resnet50", dilation=False):
+        super().__init__()
+        blocks = RESNET_BLOCKS[name]
+        self.conv1 = nn.Conv2d(3, 64, 7, stride=2, padding=3, bias=False)
+        self.bn1 = FrozenBN(64)
+        inplanes, dil = 64, 1
+        for li, (planes, nb) in enumerate(zip([64, 128, 256, 512], blocks)):
+            stride = 1 if li == 0 else 2
+            prev_dil = dil
+            if li == 3 and dilation:  # replace_stride_with_dilation=[F,F,dilation], backbone.py:119-120
+                dil *= stride
+                stride = 1
+            layers = [Bottleneck(inplanes, planes, stride, downsample=(stride != 1 or inplanes != planes * 4),
+                                 dilation=prev_dil)]
+            inplanes = planes * 4
+            for _ in range(1, nb):
+                layers.append(Bottleneck(inplanes, planes, dilation=dil))
+            setattr(self, f"layer{li + 1}", nn.Sequential(*layers))
+
+    def forward(self, x, return_interm):
+        x = F.relu(self.bn1(self.conv1(x)))
+        x = F.max_pool2d(x, 3, 2, 1)
+        outs = []
+        for li in range(1, 5):
+            x = getattr(self, f"layer{li}")(x)
+            outs.append(x)
+        return outs if return_interm else outs[-1:]
+
+
+class BackboneBase(nn.Module):
+    """backbone.py:83-109: freezes conv1/layer1, returns layer4 (or layer1-4) + nearest-resized masks."""
+
+    def __init__(self, name, train_backbone, return_interm_layers, dilation):
+        super().__init__()
+        self.body = ResNetBody(name, dilation)
+        for pname, p in self.body.named_parameters():
+            if not train_backbone or ("layer2" not in pname and "layer3" not in pname and "layer4" not in pname):
+                p.requires_grad_(False)  # backbone.py:87-89
+        self.return_interm = return_interm_layers
+        self.num_channels = [256, 512, 1024, 2048] if return_interm_layers else [2048]
+
+    def forward(self, img, mask):
+        feats = self.body(img, self.return_interm)
+        masks = [F.interpolate(mask[None].float(), size=f.shape[-2:]).to(torch.bool)[0] for f in feats]  # :107
+        return feats, masks
+
+
+def sine_position_embedding(mask, num_pos_feats=128, temperature=10000.0):
+    """position_encoding.py:36-56 with normalize=True, scale=2*pi."""
+    not_mask = ~mask
+    y_embed = not_mask.cumsum(1, dtype=torch.float32)
+    x_embed = not_mask.cumsum(2, dtype=torch.float32)
+    eps, scale = 1e-6, 2 * math.pi
+    y_embed = (y_embed - 0.5) / (y_embed[:, -1:, :] + eps) * scale
+    x_embed = (x_embed - 0.5) / (x_embed[:, :, -1:] + eps) * scale
+    dim_t = torch.arange(num_pos_feats, dtype=torch.float32, device=mask.device)
+    dim_t = temperature ** (2 * (dim_t // 2) / num_pos_feats)
+    pos_x = x_embed[:, :, :, None] / dim_t
+    pos_y = y_embed[:, :, :, None] / dim_t
+    pos_x = torch.stack((pos_x[:, :, :, 0::2].sin(), pos_x[:, :, :, 1::2].cos()), dim=4).flatten(3)
+    pos_y = torch.stack((pos_y[:, :, :, 0::2].sin(), pos_y[:, :, :, 1::2].cos()), dim=4).flatten(3)
+    return torch.cat((pos_y, pos_x), dim=3).permute(0, 3, 1, 2)
+
+
+class PosSine(nn.Module):
+    """Parameter-free placeholder so that ``img_backbone`` stays a 2-element Sequential (Joiner, backbone.py:128)."""
+
+    def __init__(self, n):
+        super().__init__()
+        self.n = n
+
+    def forward(self, mask):
+        return sine_position_embedding(mask, self.n)
+
+
+class Joiner(nn.Sequential):
+    """backbone.py:128-145."""
+
+    def __init__(self, backbone, pos):
+        super().__init__(backbone, pos)
+        self.num_channels = backbone.num_channels
+
+    def forward(self, img, mask):
+        feats, masks = self[0](img, mask)
+        pos = [self[1](m).to(f.dtype) for f, m in zip(feats, masks)]
+        return feats, masks, pos
+
+
+# --------------------------------------------------------------------------------------
+# torch.nn.MultiheadAttention restated (need_weights=True branch of
+# F.multi_head_attention_forward; called from transformer.py:174/:239/:243)
+# --------------------------------------------------------------------------------------
+class MHA(nn.Module):
+    def __init__(self, d, h, dropout=0.0):
+        super().__init__()
+        self.d, self.h, self.p = d, h, dropout
+        self.in_proj_weight = nn.Parameter(torch.empty(3 * d, d))
+        self.in_proj_bias = nn.Parameter(torch.zeros(3 * d))
+        self.out_proj = nn.Linear(d, d)
+        nn.init.xavier_uniform_(self.in_proj_weight)
+        nn.init.zeros_(self.out_proj.bias)
+
+    def forward(self, query, key, value, key_padding_mask=None):
+        T, B, d = query.shape
+        S = key.shape[0]
+        h, dh = self.h, d // self.h
+        wq, wk, wv = self.in_proj_weight.chunk(3)
+        bq, bk, bv = self.in_proj_bias.chunk(3)
+        q = F.linear(query, wq, bq).view(T, B * h, dh).transpose(0, 1)
+        k = F.linear(key, wk, bk).view(S, B * h, dh).transpose(0, 1)
+        v = F.linear(value, wv, bv).view(S, B * h, dh).transpose(0, 1)
+        q = q * (dh ** -0.5)  # scale BEFORE QK^T
+        attn = torch.bmm(q, k.transpose(1, 2))
+        if key_padding_mask is not None:
+            m = key_padding_mask.view(B, 1, 1, S).expand(-1, h, -1, -1).reshape(B * h, 1, S)
+            attn = attn.masked_fill(m, float("-inf"))
+        attn = F.softmax(attn, dim=-1)
+        attn = F.dropout(attn, self.p, self.training)
+        out = torch.bmm(attn, v).transpose(0, 1).reshape(T, B, d)
+        return self.out_proj(out)
+
+
+class EncoderLayer(nn.Module):
+    """transformer.py:146-181 (forward_post)."""
+
+    def __init__(self, d, h, dff, dropout):
+        super().__init__()
+        self.self_attn = MHA(d, h, dropout)
+        self.linear1 = nn.Linear(d, dff)
+        self.linear2 = nn.Linear(dff, d)
+        self.norm1 = nn.LayerNorm(d)
+        self.norm2 = nn.LayerNorm(d)
+        self.p = dropout
+
+    def forward(self, src, mask, pos):
+        q = k = src + pos
+        src2 = self.self_attn(q, k, src, key_padding_mask=mask)
+        src = self.norm1(src + F.dropout(src2, self.p, self.training))
+        src2 = self.linear2(F.dropout(F.relu(self.linear1(src)), self.p, self.training))
+        return self.norm2(src + F.dropout(src2, self.p, self.training))
+
+
+class DecoderLayer(nn.Module):
+    """transformer.py:206-252 (forward_post)."""
+
+    def __init__(self, d, h, dff, dropout):
+        super().__init__()
+        self.self_attn = MHA(d, h, dropout)
+        self.multihead_attn = MHA(d, h, dropout)
+        self.linear1 = nn.Linear(d, dff)
+        self.linear2 = nn.Linear(dff, d)
+        self.norm1 = nn.LayerNorm(d)
+        self.norm2 = nn.LayerNorm(d)
+        self.norm3 = nn.LayerNorm(d)
+        self.p = dropout
+
+    def forward(self, tgt, memory, tgt_mask, memory_mask, pos, query_pos):
+        q = k = tgt + query_pos
+        tgt2 = self.self_attn(q, k, tgt, key_padding_mask=tgt_mask)
+        tgt = self.norm1(tgt + F.dropout(tgt2, self.p, self.training))
+        tgt2 = self.multihead_attn(tgt + query_pos, memory + pos, memory, key_padding_mask=memory_mask)
+        tgt = self.norm2(tgt + F.dropout(tgt2, self.p, self.training))
+        tgt2 = self.linear2(F.dropout(F.relu(self.linear1(tgt)), self.p, self.training))
+        return self.norm3(tgt + F.dropout(tgt2, self.p, self.training))
+
+
+class Encoder(nn.Module):
+    def __init__(self, d, h, dff, dropout, n):
+        super().__init__()
+        self.layers = nn.ModuleList([EncoderLayer(d, h, dff, dropout) for _ in range(n)])
+
+    def forward(self, src, mask, pos):  # transformer.py:89-102 (norm is None for post-LN)
+        for layer in self.layers:
+            src = layer(src, mask, pos)
+        return src
+
+
+class Decoder(nn.Module):
+    def __init__(self, d, h, dff, dropout, n):
+        super().__init__()
+        self.layers = nn.ModuleList([DecoderLayer(d, h, dff, dropout) for _ in range(n)])
+        self.norm = nn.LayerNorm(d)
+
+    def forward(self, tgt, memory, tgt_mask, memory_mask, pos, query_pos):
+        # transformer.py:114-143 with return_intermediate=True: shared LN on every layer's output.
+        inter = []
+        for layer in self.layers:
+            tgt = layer(tgt, memory, tgt_mask, memory_mask, pos, query_pos)
+            inter.append(self.norm(tgt))
+        return torch.stack(inter)
+
+
+class VLTransformer(nn.Module):
+    """reftr.py:10-137."""
+
+    def __init__(self, d=256, h=8, enc=6, dec=6, dff=2048, dropout=0.1, num_feature_levels=1, max_lang_seq=128):
+        super().__init__()
+        self.d_model, self.nhead, self.max_lang_seq = d, h, max_lang_seq
+        self.lang_pos_embeddings = nn.Embedding(max_lang_seq, d)
+        self.token_type_embeddings = nn.Embedding(2, d)
+        self.level_embed = nn.Parameter(torch.zeros(num_feature_levels, d))
+        self.encoder = Encoder(d, h, dff, dropout, enc)
+        self.use_decoder = dec > 0
+        if self.use_decoder:
+            self.decoder = Decoder(d, h, dff, dropout, dec)
+        for p in self.parameters():
+            if p.dim() > 1:
+                nn.init.xavier_uniform_(p)
+        nn.init.normal_(self.level_embed)
+
+    def encode(self, img_srcs, img_masks, img_pos, lang_srcs, lang_masks):
+        # reftr.py:51-77 (visual), :79-97 (language), :115-119 (language FIRST, then visual)
+        srcs, masks, poss = [], [], []
+        for lvl, (src, mask, pos) in enumerate(zip(img_srcs, img_masks, img_pos)):
+            srcs.append(src.flatten(2).transpose(1, 2))
+            masks.append(mask.flatten(1))
+            poss.append(pos.flatten(2).transpose(1, 2) + self.level_embed[lvl].view(1, 1, -1))
+        img_src = torch.cat(srcs, 1)
+        img_mask = torch.cat(masks, 1)
+        img_pos_f = torch.cat(poss, 1) + self.token_type_embeddings.weight[1].view(1, 1, -1)
+        B, L, _ = lang_srcs.shape
+        assert L <= self.max_lang_seq
+        lang_pos = (self.lang_pos_embeddings.weight[:L] + self.token_type_embeddings.weight[0]).unsqueeze(0).expand(B, -1, -1)
+        lang_mask = lang_masks.logical_not()
+        masks = torch.cat([lang_mask, img_mask], dim=1)
+        src = torch.cat([lang_srcs.transpose(0, 1), img_src.transpose(0, 1)], dim=0)
+        pos = torch.cat([lang_pos.transpose(0, 1), img_pos_f.transpose(0, 1)], dim=0)
+        return self.encoder(src, masks, pos), masks, pos
+
+
+# --------------------------------------------------------------------------------------
+# RefTR top module (reftr_transformer.py:14-304)
+# --------------------------------------------------------------------------------------
+def mlp_mapping(i, o):  # reftr_transformer.py:14-23
+    return nn.Sequential(nn.Linear(i, o), nn.LayerNorm(o), nn.ReLU(), nn.Dropout(0.1),
+                         nn.Linear(o, o), nn.LayerNorm(o), nn.ReLU())
+
+
+class MLP(nn.Module):  # backbone.py:26-38
+    def __init__(self, i, hdim, o, n):
+        super().__init__()
+        dims = [i] + [hdim] * (n - 1) + [o]
+        self.layers = nn.ModuleList(nn.Linear(a, b) for a, b in zip(dims[:-1], dims[1:]))
+
+    def forward(self, x):
+        for k, layer in enumerate(self.layers):
+            x = layer(x)
+            if k < len(self.layers) - 1:
+                x = F.relu(x)
+        return x
+
+
+class QueryEncoder(nn.Module):
+    """reftr_transformer.py:26-66. Note: no 1/sqrt(d) scale; query is the post-encoder CLS token."""
+
+    def __init__(self, n_q, d):
+        super().__init__()
+        self.hidden_dim = d
+        self.query_embed = nn.Embedding(n_q, d * 2)
+        self.linear1 = nn.Linear(d, d)
+        self.linear2 = nn.Linear(d, d)
+        self.linear3 = nn.Linear(d, d)
+        self.fuse_encoder_query = mlp_mapping(d * 2, d)
+        self.context_out = nn.Sequential(nn.Linear(d, d), nn.LayerNorm(d))
+
+    def forward(self, ctx, phrase, mask_ctx):
+        B, n_ph, _ = phrase.shape
+        n_q = self.query_embed.weight.size(0)
+        k = self.linear1(ctx[:, 0:1, :])
+        q = self.linear2(ctx).transpose(1, 2)
+        v = self.linear3(ctx).unsqueeze(1)
+        att = torch.bmm(k, q).expand(-1, n_ph, -1).masked_fill(mask_ctx, float("-inf"))
+        att = F.softmax(att, dim=-1).unsqueeze(-1)
+        c = self.context_out((v * att).sum(dim=-2))
+        c = ctx[:, None, 0, :] + c
+        f = self.fuse_encoder_query(torch.cat([c, phrase], dim=-1))
+        pq = f.view(B, n_ph, 1, -1).repeat(1, 1, 1, 2) + self.query_embed.weight.view(1, 1, n_q, -1)
+        pq = pq.view(B, n_ph * n_q, -1).transpose(0, 1)
+        return torch.split(pq, self.hidden_dim, dim=-1)
+
+
+class RefTROracle(nn.Module):
+    def __init__(self, lang_backbone, backbone="resnet50", enc=6, dec=6, d=256, h=8, dff=2048, dropout=0.1,
+                 n_q=1, aux_loss=True, masks=False, dilation=False, max_lang_seq=128, train_backbone=True):
+        super().__init__()
+        self.img_backbone = Joiner(BackboneBase(backbone, train_backbone, masks, dilation), PosSine(d // 2))
+        self.lang_backbone = lang_backbone
+        self.vl_transformer = VLTransformer(d, h, enc, dec, dff, dropout, 1, max_lang_seq)
+        self.num_queries_per_phrase = n_q
+        self.hidden_dim = d
+        self.bbox_embed = MLP(d, d, 4, 3)
+        self.map_sentence = mlp_mapping(lang_backbone.config.hidden_size, d)
+        self.map_phrase = mlp_mapping(lang_backbone.config.hidden_size, d)
+        self.query_encoder = QueryEncoder(n_q, d)
+        self.input_proj = nn.ModuleList([nn.Sequential(nn.Conv2d(2048, d, 1), nn.GroupNorm(32, d))])
+        self.aux_loss = aux_loss
+        nn.init.constant_(self.bbox_embed.layers[-1].weight, 0)  # reftr_transformer.py:131-132
+        nn.init.constant_(self.bbox_embed.layers[-1].bias, 0)
+
+    # -- pieces shared by the box and segmentation forward --------------------------------
+    def trunk(self, samples):
+        img = samples["img"]
+        img, mask = img.decompose() if hasattr(img, "decompose") else img  # NestedTensor or (tensors, mask)
+        feats, masks, pos = self.img_backbone(img, mask)
+        src = self.input_proj[0](feats[-1])  # reftr_transformer.py:172-175
+        sentence, sentence_mask = samples["sentence"], samples["sentence_mask"]
+        lang_out = self.lang_backbone(sentence, token_type_ids=None, attention_mask=sentence_mask)
+        sent_feat, sent_pooled = lang_out[0], lang_out[1]
+        sent_feat = self.map_sentence(sent_feat)
+        B, n_q = sentence.size(0), self.num_queries_per_phrase
+        if "phrase" in samples:  # reftr_transformer.py:206-238
+            phrases, phrase_masks = samples["phrase"], samples["phrase_mask"]
+            n_ph = phrases.size(1)
+            pooled = self.lang_backbone(phrases.view(B * n_ph, -1), token_type_ids=None,
+                                        attention_mask=phrase_masks.view(B * n_ph, -1))[1]
+            L = sentence_mask.size(1)
+            ar = torch.arange(L, device=sentence.device).view(1, 1, L)
+            inside = (ar >= samples["phrase_pos_l"].unsqueeze(-1)) & (ar < samples["phrase_pos_r"].unsqueeze(-1))
+            mask_context = ~inside  # ones, zero on [l, r)  (:223-229)
+            query_mask = phrase_masks.view(B, n_ph, -1)[:, :, 2:3].logical_not().expand(-1, -1, n_q).reshape(B, n_ph * n_q)
+        else:  # :239-248
+            n_ph = 1
+            pooled = sent_pooled
+            slen = sentence_mask.to(torch.int32).sum(-1)
+            mask_context = sentence_mask.view(B, 1, -1).logical_not().to(torch.bool).clone()
+            mask_context[:, :, 0] = True
+            mask_context[torch.arange(B), :, (slen - 1).long()] = True
+            query_mask = torch.zeros((B, 1), dtype=torch.bool, device=sentence.device)
+        pooled = self.map_phrase(pooled).view(B, n_ph, -1)
+        memory, memory_mask, memory_pos = self.vl_transformer.encode([src], [masks[-1]], [pos[-1]], sent_feat, sentence_mask)
+        L = sent_feat.size(1)
+        query, query_pos = self.query_encoder(memory[:L].transpose(0, 1), pooled, mask_context)
+        hs = self.vl_transformer.decoder(query, memory, query_mask, memory_mask, memory_pos, query_pos).transpose(1, 2)
+        hs = hs.view(hs.size(0), B, n_ph, n_q, -1)
+        return dict(hs=hs, query_mask=query_mask, memory=memory, L=L, src=src, feats=feats, masks=masks)
+
+    def forward(self, samples):
+        t = self.trunk(samples)
+        coord = self.bbox_embed(t["hs"]).sigmoid()  # reftr_transformer.py:287
+        pm = t["query_mask"].logical_not()
+        out = {"pred_boxes": coord[-1], "phrase_mask": pm}
+        if self.aux_loss:
+            out["aux_outputs"] = [{"pred_boxes": b, "phrase_mask": pm} for b in coord[:-1]]
+        out["_memory"] = t["memory"]  # extra, for block-level parity checks
+        return out
+
+
+# --------------------------------------------------------------------------------------
+# Segmentation (reftr_segmentation.py:44-280)
+# --------------------------------------------------------------------------------------
+class MHAttentionMap(nn.Module):
+    """reftr_segmentation.py:178-207: softmax jointly over heads*H*W."""
+
+    def __init__(self, d, h):
+        super().__init__()
+        self.num_heads, self.hidden_dim = h, d
+        self.q_linear = nn.Linear(d, d)
+        self.k_linear = nn.Linear(d, d)
+        self.normalize_fact = float(d / h) ** -0.5
+
+    def forward(self, q, k, mask):
+        q = self.q_linear(q)
+        k = F.conv2d(k, self.k_linear.weight.unsqueeze(-1).unsqueeze(-1), self.k_linear.bias)
+        qh = q.view(q.shape[0], q.shape[1], self.num_heads, self.hidden_dim // self.num_heads)
+        kh = k.view(k.shape[0], self.num_heads, self.hidden_dim // self.num_heads, k.shape[-2], k.shape[-1])
+        w = torch.einsum("bqnc,bnchw->bqnhw", qh * self.normalize_fact, kh)
+        w = w.masked_fill(mask.unsqueeze(1).unsqueeze(1), float("-inf"))
+        return F.softmax(w.flatten(2), dim=-1).view_as(w)
+
+
+class MaskHeadSmallConv(nn.Module):
+    """reftr_segmentation.py:210-280."""
+
+    def __init__(self, dim, fpn_dims, ctx):
+        super().__init__()
+        inter = [dim, ctx // 2, ctx // 4, ctx // 8, ctx // 16]
+        self.lay1 = nn.Conv2d(dim, dim, 3, padding=1)
+        self.gn1 = nn.GroupNorm(8, dim)
+        self.lay2 = nn.Conv2d(dim, inter[1], 3, padding=1)
+        self.gn2 = nn.GroupNorm(8, inter[1])
+        self.lay3 = nn.Conv2d(inter[1], inter[2], 3, padding=1)
+        self.gn3 = nn.GroupNorm(8, inter[2])
+        self.lay4 = nn.Conv2d(inter[2], inter[3], 3, padding=1)
+        self.gn4 = nn.GroupNorm(8, inter[3])
+        self.lay5 = nn.Conv2d(inter[3], inter[4], 3, padding=1)
+        self.gn5 = nn.GroupNorm(8, inter[4])
+        self.out_lay = nn.Conv2d(inter[4], 1, 3, padding=1)
+        self.adapter1 = nn.Conv2d(fpn_dims[0], inter[1], 1)
+        self.adapter2 = nn.Conv2d(fpn_dims[1], inter[2], 1)
+        self.adapter3 = nn.Conv2d(fpn_dims[2], inter[3], 1)
+
+    def forward(self, x, bbox_mask, fpns):
+        x = torch.cat([x, bbox_mask.flatten(0, 1)], 1)  # one query per image (n_ph = n_q = 1)
+        x = F.relu(self.gn1(self.lay1(x)))
+        x = F.relu(self.gn2(self.lay2(x)))
+        for adapter, lay, gn, fpn in ((self.adapter1, self.lay3, self.gn3, fpns[0]),
+                                      (self.adapter2, self.lay4, self.gn4, fpns[1]),
+                                      (self.adapter3, self.lay5, self.gn5, fpns[2])):
+            cur = adapter(fpn)
+            x = cur + F.interpolate(x, size=cur.shape[-2:], mode="nearest")
+            x = F.relu(gn(lay(x)))
+        return self.out_lay(x), x
+
+
+class RefTRSegOracle(RefTROracle):
+    def __init__(self, lang_backbone, **kw):
+        kw = dict(kw)
+        kw["masks"] = True
+        kw["aux_loss"] = False  # reftr_segmentation.py:51
+        super().__init__(lang_backbone, **kw)
+        d, h = self.hidden_dim, self.vl_transformer.nhead
+        self.bbox_attention = MHAttentionMap(d, h)
+        self.mask_head = MaskHeadSmallConv(d * 2 + h, [1024, 512, 256], d)
+
+    def forward(self, samples):
+        assert "phrase" not in samples  # reftr_segmentation.py:97
+        t = self.trunk(samples)
+        last = t["hs"][-1]
+        out = {"pred_boxes": self.bbox_embed(last).sigmoid(), "phrase_mask": t["query_mask"].logical_not()}
+        feats, src = t["feats"], t["src"]
+        B, _, hh, ww = feats[-1].shape
+        mem_vis = t["memory"][t["L"]:].transpose(0, 1).transpose(1, 2).reshape(B, -1, hh, ww)  # :166
+        bbox_mask = self.bbox_attention(last.flatten(1, 2), mem_vis, t["masks"][-1])
+        seg, _ = self.mask_head(torch.cat([src, mem_vis], 1), bbox_mask, [feats[2], feats[1], feats[0]])
+        out["pred_masks"] = seg
+        out["mask_att"] = bbox_mask[:, 0]
+        out["_memory"] = t["memory"]
+        return out
+
+
+# --------------------------------------------------------------------------------------
+# Losses restated (criterion.py:113-153, box_ops.py; segmentation.py:178-221) -- used by the
+# bench's reference arm so that the timed region is fwd + criterion + bwd like engine_vg.py:40-61.
+# --------------------------------------------------------------------------------------
+def box_cxcywh_to_xyxy(x):
+    cx, cy, w, h = x.unbind(-1)
+    return torch.stack([cx - 0.5 * w, cy - 0.5 * h, cx + 0.5 * w, cy + 0.5 * h], dim=-1)
+
+
+def giou_diag(a, b):
+    """Diagonal of box_ops.generalized_box_iou (box_ops.py:52-77) for paired boxes."""
+    area_a = (a[:, 2] - a[:, 0]) * (a[:, 3] - a[:, 1])
+    area_b = (b[:, 2] - b[:, 0]) * (b[:, 3] - b[:, 1])
+    lt, rb = torch.max(a[:, :2], b[:, :2]), torch.min(a[:, 2:], b[:, 2:])
+    wh = (rb - lt).clamp(min=0)
+    inter = wh[:, 0] * wh[:, 1]
+    union = area_a + area_b - inter
+    iou = inter / union
+    lt2, rb2 = torch.min(a[:, :2], b[:, :2]), torch.max(a[:, 2:], b[:, 2:])
+    wh2 = (rb2 - lt2).clamp(min=0)
+    area = wh2[:, 0] * wh2[:, 1]
+    return iou - (area - union) / area
+
+
+def box_losses(pred_boxes, phrase_mask, target_boxes, num_boxes):
+    """criterion.py:113-153 for targets given as a dense [B, n_ph, 4] tensor + the phrase mask."""
+    B, n_ph, k, _ = pred_boxes.shape
+    m = phrase_mask.view(B, n_ph, k)
+    p = pred_boxes[m]
+    t = target_boxes.unsqueeze(2).expand(-1, -1, k, -1)[m]
+    l1 = F.l1_loss(p, t, reduction="none").sum() / (num_boxes * k)
+    giou = (1 - giou_diag(box_cxcywh_to_xyxy(p), box_cxcywh_to_xyxy(t))).sum() / (num_boxes * k)
+    return {"loss_bbox": l1, "loss_giou": giou}
+
+
+def total_box_loss(out, target_boxes):
+    """Sum of L1 + GIoU over the last and the auxiliary decoder layers (criterion.py:166-201, weights 1)."""
+    num_boxes = max(float(out["phrase_mask"].sum().item()), 1.0)
+    loss = sum(box_losses(out["pred_boxes"], out["phrase_mask"], target_boxes, num_boxes).values())
+    for aux in out.get("aux_outputs", []):
+        loss = loss + sum(box_losses(aux["pred_boxes"], aux["phrase_mask"], target_boxes, num_boxes).values())
+    return loss
