@@ -1,0 +1,60 @@
+"""ctypes binding of libreftr_b200.so (the C ABI declared in include/reftr_b200.h).
+
+The library is built in-tree by ``reftr_b200/csrc/build.sh`` (``__graft_entry__.build()``).  There is no CPU or
+PyTorch fallback: if the library is missing, every op raises.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libreftr_b200.so")
+
+
+class Geom(C.Structure):
+    _fields_ = [("mode", C.c_int), ("Wp", C.c_int), ("HpWp", C.c_int), ("H", C.c_int), ("W", C.c_int), ("Rs", C.c_int)]
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [
+        ("mode", C.c_int),
+        ("A", C.c_void_p), ("a_rows", C.c_longlong), ("a_cols", C.c_int), ("lda", C.c_longlong),
+        ("B", C.c_void_p), ("b_rows", C.c_longlong), ("b_cols", C.c_int), ("ldb", C.c_longlong),
+        ("M", C.c_int), ("N", C.c_int), ("K", C.c_int),
+        ("taps", C.c_int),
+        ("a_rowoff", C.c_int * 16),
+        ("b_koff", C.c_int * 16),
+        ("splits", C.c_int),
+        ("block_n", C.c_int),
+        ("out_row_off", C.c_longlong),
+        ("bias", C.c_void_p),
+        ("res", C.c_void_p), ("ldres", C.c_longlong),
+        ("res32", C.c_void_p), ("ldres32", C.c_longlong),
+        ("mask_src", C.c_void_p), ("ldmask", C.c_longlong),
+        ("out", C.c_void_p), ("ldo", C.c_longlong),
+        ("out32", C.c_void_p), ("ldo32", C.c_longlong),
+        ("out32_z_stride", C.c_longlong),
+        ("relu", C.c_int),
+        ("atomic", C.c_int),
+        ("geom", Geom),
+    ]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(reftr_b200 has no CPU/PyTorch fallback)")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.rb_last_error.restype = C.c_char_p
+        _lib.rb_version.restype = C.c_int
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        raise RuntimeError(f"{what}: {lib().rb_last_error().decode()}")

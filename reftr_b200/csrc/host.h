@@ -1,0 +1,21 @@
+// Host-side helpers shared by the C-ABI translation units: error reporting and TMA descriptor encoding.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/reftr_b200.h"
+
+namespace rb {
+int rb_fail(const char* fmt, ...);
+// 2D bf16 row-major tensor [rows, inner] with `pitch_bytes` per row; box = [box_rows, box_inner]; 128B swizzle
+// (box_inner*2 must be <= 128); out-of-bounds elements (including negative coordinates) read as zero.
+int make_tmap_2d(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t rows, uint64_t pitch_bytes, uint32_t box_inner,
+                 uint32_t box_rows);
+}  // namespace rb
+
+#define RB_CUDA(expr)                                                                         \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) return ::rb::rb_fail("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)

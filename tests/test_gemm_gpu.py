@@ -1,0 +1,101 @@
+"""GPU parity of the tcgen05 GEMM / implicit-conv kernel (rb_gemm, through the C ABI) against a torch fp32 reference
+of the same op computed from the same bf16-rounded operands.  Tolerance: fp32 accumulation order only -> 2e-3 of the
+output scale (bf16 output rounding adds 2^-8 relative)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    return ((a.float() - b.float()).abs().max() / (b.float().abs().max() + 1e-6)).item()
+
+
+@pytest.mark.parametrize("M,N,K,bn", [(300, 96, 160, 0), (128, 32, 64, 32), (1000, 64, 576, 64), (777, 256, 2048, 128),
+                                      (512, 512, 256, 256), (16, 256, 256, 0), (4100, 2048, 256, 0)])
+def test_gemm_nt_linear(M, N, K, bn):
+    from reftr_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    B = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    res = torch.randn(M, N, device="cuda", generator=g).bfloat16()
+    out = torch.full((M, N), 7.0, device="cuda", dtype=torch.bfloat16)
+    out32 = torch.full((M, N), 7.0, device="cuda")
+    ops.gemm(A, B, M, N, K, bias=bias, res=res, relu=True, out=out, out32=out32, block_n=bn)
+    ref = torch.relu(A.float() @ B.float().t() + bias + res.float())
+    assert _rel(out32, ref) < 2e-3
+    assert _rel(out, ref) < 8e-3
+
+
+def test_gemm_nt_ragged_n_and_res32():
+    from reftr_b200 import ops
+    M, N, K = 50, 4, 256
+    A = torch.randn(M, K, device="cuda").bfloat16()
+    B = torch.zeros(8, K, device="cuda", dtype=torch.bfloat16)
+    B[:N] = (torch.randn(N, K, device="cuda") / 16).bfloat16()
+    bias = torch.randn(N, device="cuda")
+    res32 = torch.randn(M, N, device="cuda")
+    out32 = torch.zeros(M, N, device="cuda")
+    ops.gemm(A, B, M, N, K, bias=bias, out32=out32)
+    ref = A.float() @ B[:N].float().t() + bias
+    assert _rel(out32, ref) < 2e-3
+
+
+def _pad_nhwc(x):  # NCHW fp32 -> padded NHWC bf16 [N, H+2, W+2, C]
+    return F.pad(x.permute(0, 2, 3, 1), (0, 0, 1, 1, 1, 1)).bfloat16().contiguous()
+
+
+@pytest.mark.parametrize("Nb,H,W,Cin,Cout", [(2, 20, 20, 64, 64), (3, 14, 10, 128, 256), (1, 40, 40, 256, 128)])
+def test_conv3x3_as_shifted_gemm(Nb, H, W, Cin, Cout):
+    from reftr_b200 import ops
+    x = torch.randn(Nb, Cin, H, W, device="cuda")
+    w = torch.randn(Cout, Cin, 3, 3, device="cuda") / (Cin * 9) ** 0.5
+    bias = torch.randn(Cout, device="cuda")
+    xp = _pad_nhwc(x)
+    Wp, Hp = W + 2, H + 2
+    R = Nb * Hp * Wp
+    wk = w.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).bfloat16().contiguous()  # [Cout, (r,s), Cin]
+    taps = [((r - 1) * Wp + (s - 1), (r * 3 + s) * Cin) for r in range(3) for s in range(3)]
+    out = torch.full((R, Cout), 5.0, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(xp.view(R, Cin), wk, R, Cout, Cin, taps=taps, bias=bias, relu=True, out=out,
+             geom=ops.make_geom(1, Wp, Hp * Wp, H, W))
+    ref = F.relu(F.conv2d(xp[:, 1:-1, 1:-1].permute(0, 3, 1, 2).float(), wk.view(Cout, 3, 3, Cin).permute(0, 3, 1, 2).float(),
+                          bias, padding=1))
+    got = out.view(Nb, Hp, Wp, Cout)
+    assert _rel(got[:, 1:-1, 1:-1].permute(0, 3, 1, 2), ref) < 1e-2
+    border = got.clone()
+    border[:, 1:-1, 1:-1] = 0
+    assert border.abs().max().item() == 0.0  # padding rows must be written as exact zeros
+
+
+@pytest.mark.parametrize("R,Mo,No,splits,bn", [(1000, 128, 192, 3, 64), (6400, 256, 128, 8, 128), (200, 64, 64, 1, 64),
+                                             (333, 512, 256, 2, 256)])
+def test_gemm_tn_wgrad(R, Mo, No, splits, bn):
+    from reftr_b200 import ops
+    dY = torch.randn(R, Mo, device="cuda").bfloat16()
+    X = torch.randn(R, No, device="cuda").bfloat16()
+    out32 = torch.zeros(Mo, No, device="cuda")
+    ops.gemm(dY, X, Mo, No, R, mode=1, out32=out32, atomic=True, splits=splits, block_n=bn)
+    ref = dY.float().t() @ X.float()
+    assert _rel(out32, ref) < 2e-3
+
+
+def test_conv3x3_wgrad_taps():
+    from reftr_b200 import ops
+    Nb, H, W, Cin, Cout = 2, 12, 9, 128, 128
+    Wp, Hp = W + 2, H + 2
+    R = Nb * Hp * Wp
+    x = torch.randn(Nb, Cin, H, W, device="cuda")
+    dy = torch.randn(Nb, Cout, H, W, device="cuda")
+    xp, dyp = _pad_nhwc(x), _pad_nhwc(dy)
+    taps = [(0, (r - 1) * Wp + (s - 1)) for r in range(3) for s in range(3)]
+    out32 = torch.zeros(Cout, 9, Cin, device="cuda")
+    ops.gemm(dyp.view(R, Cout), xp.view(R, Cin), Cout, Cin, R, mode=1, taps=taps, out32=out32, atomic=True, splits=2,
+             out32_z_stride=Cin)
+    xr = xp[:, 1:-1, 1:-1].permute(0, 3, 1, 2).float().requires_grad_()
+    wz = torch.zeros(Cout, Cin, 3, 3, device="cuda", requires_grad=True)
+    F.conv2d(xr, wz, padding=1).backward(dyp[:, 1:-1, 1:-1].permute(0, 3, 1, 2).float())
+    ref = wz.grad.permute(0, 2, 3, 1).reshape(Cout, 9, Cin)
+    assert _rel(out32, ref) < 2e-3
