@@ -92,8 +92,8 @@ def test_conv3x3_wgrad_taps():
     xp, dyp = _pad_nhwc(x), _pad_nhwc(dy)
     taps = [(0, (r - 1) * Wp + (s - 1)) for r in range(3) for s in range(3)]
     out32 = torch.zeros(Cout, 9, Cin, device="cuda")
-    ops.gemm(dyp.view(R, Cout), xp.view(R, Cin), Cout, Cin, R, mode=1, taps=taps, out32=out32, atomic=True, splits=2,
-             out32_z_stride=Cin)
+    ops.gemm(dyp.view(R, Cout), xp.view(R, Cin), Cout, Cin, R, mode=1, taps=taps, out32=out32.view(Cout, 9 * Cin),
+             atomic=True, splits=2, out32_z_stride=Cin)
     xr = xp[:, 1:-1, 1:-1].permute(0, 3, 1, 2).float().requires_grad_()
     wz = torch.zeros(Cout, Cin, 3, 3, device="cuda", requires_grad=True)
     F.conv2d(xr, wz, padding=1).backward(dyp[:, 1:-1, 1:-1].permute(0, 3, 1, 2).float())
