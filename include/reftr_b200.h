@@ -29,7 +29,7 @@ typedef struct {
   int mode; /* 0 none; 1 padded NHWC grid; 2 parity planes */
   int Wp;   /* pixels per padded row (W+2, or Wo+2 for planes) */
   int HpWp; /* pixels per padded image */
-  int H, W; /* interior size (Ho, Wo for planes) */
+  int H, W; /* interior size of the grid (mode 2: of the FULL-resolution grid the planes were split from) */
   int Rs;   /* rows per plane (mode 2) */
 } rb_geom;
 
@@ -70,6 +70,69 @@ typedef struct {
 } rb_gemm_args;
 
 int rb_gemm(const rb_gemm_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Backbone support kernels (HBM-bound).  Replace torchvision ResNet stem / pooling / stride handling reached from
+ * models/modeling/backbone.py:99-102, and FrozenBatchNorm2d (backbone.py:70-80) which is folded into the weights.
+ * ------------------------------------------------------------------------------------------------------------- */
+/* img fp32 NCHW [B,3,H,W] -> out bf16 [B*H1*W1, 160]: im2col of the 7x7/2 pad-3 stem, column (r*7+s)*3+c, 147.. zero */
+int rb_stem_im2col(const float* img, void* out, int B, int H, int W, int H1, int W1, void* stream);
+/* in bf16 NHWC [B,H1,W1,C] -> out padded NHWC [B,H2+2,W2+2,C]; 3x3 stride 2 pad 1 max-pool */
+int rb_maxpool_3x3s2(const void* in, void* out, int B, int H1, int W1, int C, int H2, int W2, void* stream);
+/* padded NHWC [B,H+2,W+2,C] <-> 4 parity planes [4,B,Ho+2,Wo+2,C] (see header comment); merge = backward of split,
+ * with optional addend `add` (padded layout) and ReLU mask `mask_src` (padded layout, keep where > 0) */
+int rb_parity_split(const void* x, void* xs, int B, int H, int W, int C, int Ho, int Wo, void* stream);
+int rb_parity_merge(const void* dxs, const void* add, const void* mask_src, void* dx, int B, int H, int W, int C, int Ho, int Wo, void* stream);
+/* conv weight fp32 OIHW (+ FrozenBN buffers or conv bias) -> bf16 [Cout, ldk] ((r,s,ci) columns, BN scale folded),
+ * flipped/transposed dgrad copy bf16 [Cin, kh*kw*Cout] (nullable), per-channel scale and bias (fp32, nullable) */
+int rb_pack_conv(const float* w, int Cout, int Cin, int kh, int kw, const float* bn_w, const float* bn_b, const float* bn_rm, const float* bn_rv,
+                 float eps, const float* conv_bias, void* fwd, int ldk, void* dgr, float* scale_out, float* bias_out, void* stream);
+/* linear weight fp32 [N,K] (dense) -> bf16 [N,K] (wb, pitch ldwb, nullable) and bf16 [K,N] (wt, pitch ldwt, nullable) */
+int rb_pack_linear(const float* w, int N, int K, void* wb, long long ldwb, void* wt, long long ldwt, void* stream);
+/* folded-layout weight gradient fp32 [Cout,taps,Cin] -> parameter layout fp32 [Cout,Cin,kh,kw], times scale[co] (nullable) */
+int rb_unpack_conv_grad(const float* dwf, const float* scale, float* grad, int Cout, int Cin, int taps, void* stream);
+int rb_cast_bf16(const float* in, void* out, long long n, void* stream);
+/* out[n] += sum_rows x[row, n] (x bf16 or fp32 with pitch ld) -- bias gradients */
+int rb_colsum(const void* x, int is_bf16, long long ld, long long rows, int N, float* out, void* stream);
+/* y = a + b (b nullable); optional bf16 copy yb */
+int rb_add(const float* a, const float* b, float* y, void* yb, long long n, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Normalisation, positions, masks.  Row maps: row r of the compact tensor lives at (r / group) * stride + r % group
+ * + offset of the mapped tensor (group = 0: identity); used to write language rows into the [B*S,256] token matrix.
+ * ------------------------------------------------------------------------------------------------------------- */
+/* nn.LayerNorm(256) (+ optional ReLU, reftr_transformer.py:14-23): fp32 in, fp32 / bf16 / bf16(+pos) out, saves mean, rstd */
+int rb_layernorm_fwd(const float* x, const float* gamma, const float* beta, long long rows, int D, float eps, float* y32, void* yb, const float* pos32,
+                     void* ypb, int relu, float* mean, float* rstd, int map_group, int map_stride, int map_offset, void* stream);
+int rb_layernorm_bwd(const float* dy, const float* dy2, const float* y_relu, const float* x, const float* gamma, const float* mean, const float* rstd,
+                     long long rows, int D, float* dx32, void* dxb, float* dgamma, float* dbeta, int map_group, int map_stride, int map_offset, void* stream);
+/* input_proj GroupNorm(32,256) (reftr_transformer.py:121-125) fused with flatten/transpose/concat (reftr.py:57,115-117):
+ * x fp32 padded NHWC [B,h+2,w+2,256] -> token rows b*S+L+p of y32 / yb / ypb */
+int rb_groupnorm_tokens_fwd(const float* x, const float* gamma, const float* beta, int B, int h, int w, int S, int L, float eps, float* y32, void* yb,
+                            const float* pos32, void* ypb, float* mean, float* rstd, void* stream);
+int rb_groupnorm_tokens_bwd(const float* dy, const float* dy2, const float* x, const float* gamma, const float* mean, const float* rstd, int B, int h, int w,
+                            int S, int L, void* dx, float* dgamma, float* dbeta, void* stream);
+/* PositionEmbeddingSine (position_encoding.py:36-56) + level/type/language-position embeddings (reftr.py:57-97) and the
+ * key-padding mask [B,S] (u8, 1 = ignore) from the image padding mask (backbone.py:107) and sentence_mask (int64) */
+int rb_build_pos_mask(const void* img_mask, int B, int H, int W, int h, int w, const long long* sent_mask, int L, const float* lang_pos,
+                      const float* token_type, const float* level_embed, float* pos32, void* kpm, void* stream);
+/* gradients of lang_pos_embeddings [L rows], token_type_embeddings [2,256], level_embed [1,256] from d(pos) [B*S,256] */
+int rb_embed_grad(const float* dpos, int B, int S, int L, float* d_lang_pos, float* d_token_type, float* d_level, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Attention core, head_dim 32 (bmm / softmax / bmm of F.multi_head_attention_forward; transformer.py:174, :239, :243).
+ * Q [B*Tq, ldq], K/V [B*Sk, ld], head h at columns [32h, 32h+32); kpm [B,Sk] u8 (1 = ignore, nullable);
+ * LSE, Dbuf fp32 [B,H,Tq].  scale multiplies q before QK^T as torch does.
+ * ------------------------------------------------------------------------------------------------------------- */
+int rb_attn_fwd(const void* Q, const void* K, const void* V, const void* kpm, void* O, float* LSE, int B, int H, int dh, int Tq, int Sk, long long ldq,
+                long long ldk, long long ldv, long long ldo, float scale, void* stream);
+int rb_attn_bwd(const void* Q, const void* K, const void* V, const void* kpm, const void* O, const void* dO, const float* LSE, void* dQ, void* dK, void* dV,
+                float* Dbuf, int B, int H, int dh, int Tq, int Sk, long long ldq, long long ldk, long long ldv, long long ldo, long long lddo, long long lddq,
+                long long lddk, long long lddv, float scale, void* stream);
+/* QueryEncoder attended pooling (reftr_transformer.py:47-55): k [B,256], q,v [B*L,256] fp32, mask [B,n_ph,L] u8 */
+int rb_qenc_pool_fwd(const float* k, const float* q, const float* v, const void* mask, int B, int L, int n_ph, float* att, float* c, void* stream);
+int rb_qenc_pool_bwd(const float* dc, const float* k, const float* q, const float* v, const float* att, int B, int L, int n_ph, float* dk, float* dq,
+                     float* dv, void* stream);
 
 #ifdef __cplusplus
 }

@@ -40,6 +40,34 @@ class GemmArgs(C.Structure):
 
 
 _lib = None
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "reftr_b200.h")
+
+
+def header_prototypes(path=HEADER_PATH):
+    """Parses `int rb_xxx(...)` prototypes of the C header -> {name: [ctypes argtypes]} (the header is the single
+    source of truth for the ABI; tests check that every declared symbol is exported)."""
+    import re
+    src = open(path).read()
+    src = re.sub(r"/\*.*?\*/", " ", src, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\bint\s+(rb_\w+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S):
+        name, args = m.group(1), m.group(2).strip()
+        types = []
+        if args and args != "void":
+            for a in args.split(","):
+                a = " ".join(a.split())
+                if "*" in a:
+                    types.append(C.c_void_p)
+                elif a.startswith("long long"):
+                    types.append(C.c_longlong)
+                elif a.startswith("float"):
+                    types.append(C.c_float)
+                elif a.startswith("int"):
+                    types.append(C.c_int)
+                else:
+                    raise ValueError(f"unhandled C type in header: {a!r}")
+        protos[name] = types
+    return protos
 
 
 def lib():
@@ -51,8 +79,18 @@ def lib():
                 "(reftr_b200 has no CPU/PyTorch fallback)")
         _lib = C.CDLL(LIB_PATH)
         _lib.rb_last_error.restype = C.c_char_p
-        _lib.rb_version.restype = C.c_int
+        for name, argtypes in header_prototypes().items():
+            fn = getattr(_lib, name)
+            fn.argtypes = argtypes
+            fn.restype = C.c_int
     return _lib
+
+
+def call(name, *args):
+    """Calls a C-ABI function; tensors are passed as data_ptr() ints or None; raises on a non-zero return."""
+    rc = getattr(lib(), name)(*args)
+    if rc != 0:
+        raise RuntimeError(f"{name}: {lib().rb_last_error().decode()}")
 
 
 def check(rc, what):

@@ -1,0 +1,311 @@
+// Memory-bound support kernels of the backbone path: stem im2col, max-pool, parity split/merge for stride-2 blocks,
+// weight packing (FrozenBN fold, OIHW -> [O,(r,s),I] bf16, transposes), gradient unpacking, casts and reductions.
+// All are HBM-bound: 128-bit accesses, one 16-byte chunk (8 bf16) per thread, grids sized from the element count.
+#include "common.cuh"
+#include "host.h"
+
+namespace rb {
+
+static inline unsigned blocks_for(long long n, int threads) { return static_cast<unsigned>((n + threads - 1) / threads); }
+
+// ------------------------------------------------------------------------------------------------ stem im2col
+// img fp32 NCHW [B,3,H,W] -> out bf16 [B*H1*W1, 160]; column k = (r*7+s)*3+c for the 7x7/stride-2/pad-3 stem
+// (torchvision ResNet conv1, reached from backbone.py:99-102); columns 147..159 are zero.
+__global__ void stem_im2col_kernel(const float* __restrict__ img, uint4* __restrict__ out, int B, int H, int W, int H1, int W1) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(B) * H1 * W1 * 20;
+  if (idx >= total) return;
+  const int chunk = static_cast<int>(idx % 20);
+  const long long pix = idx / 20;
+  const int wo = static_cast<int>(pix % W1);
+  const int ho = static_cast<int>((pix / W1) % H1);
+  const int b = static_cast<int>(pix / (static_cast<long long>(W1) * H1));
+  float v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int k = chunk * 8 + e;
+    float x = 0.f;
+    if (k < 147) {
+      const int c = k % 3, rs = k / 3, s = rs % 7, r = rs / 7;
+      const int y = 2 * ho - 3 + r, xx = 2 * wo - 3 + s;
+      if (y >= 0 && y < H && xx >= 0 && xx < W) x = __ldg(img + ((static_cast<long long>(b) * 3 + c) * H + y) * W + xx);
+    }
+    v[e] = x;
+  }
+  uint4 o;
+  o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]); o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+  out[idx] = o;
+}
+
+// ------------------------------------------------------------------------------------------------ max-pool 3x3/2 pad 1
+// in: bf16 NHWC [B,H1,W1,C] (un-padded, post-ReLU so >= 0) -> out: padded NHWC [B,H2+2,W2+2,C] with zero border.
+__global__ void maxpool_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B, int H1, int W1, int C8, int H2, int W2) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int Hp = H2 + 2, Wp = W2 + 2;
+  const long long total = static_cast<long long>(B) * Hp * Wp * C8;
+  if (idx >= total) return;
+  const int c = static_cast<int>(idx % C8);
+  const long long pix = idx / C8;
+  const int v = static_cast<int>(pix % Wp), u = static_cast<int>((pix / Wp) % Hp);
+  const int b = static_cast<int>(pix / (static_cast<long long>(Wp) * Hp));
+  uint4 o = make_uint4(0, 0, 0, 0);
+  if (u >= 1 && u <= H2 && v >= 1 && v <= W2) {
+    float m[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) m[e] = -3.0e38f;
+    const int y0 = 2 * (u - 1) - 1, x0 = 2 * (v - 1) - 1;
+    for (int dy = 0; dy < 3; ++dy) {
+      const int y = y0 + dy;
+      if (y < 0 || y >= H1) continue;
+      for (int dx = 0; dx < 3; ++dx) {
+        const int x = x0 + dx;
+        if (x < 0 || x >= W1) continue;
+        const uint4 t = __ldg(in + ((static_cast<long long>(b) * H1 + y) * W1 + x) * C8 + c);
+        m[0] = fmaxf(m[0], bf16_lo(t.x)); m[1] = fmaxf(m[1], bf16_hi(t.x)); m[2] = fmaxf(m[2], bf16_lo(t.y)); m[3] = fmaxf(m[3], bf16_hi(t.y));
+        m[4] = fmaxf(m[4], bf16_lo(t.z)); m[5] = fmaxf(m[5], bf16_hi(t.z)); m[6] = fmaxf(m[6], bf16_lo(t.w)); m[7] = fmaxf(m[7], bf16_hi(t.w));
+      }
+    }
+    o.x = pack_bf16x2(m[0], m[1]); o.y = pack_bf16x2(m[2], m[3]); o.z = pack_bf16x2(m[4], m[5]); o.w = pack_bf16x2(m[6], m[7]);
+  }
+  out[idx] = o;
+}
+
+// ------------------------------------------------------------------------------------------------ parity split / merge
+// x padded [B,H+2,W+2,C] -> xs [4,B,Hs,Ws,C] (Hs=Ho+2, Ws=Wo+2); plane (p,q) cell (u,v) = x[2u+p, 2v+q] or 0.
+__global__ void parity_split_kernel(const uint4* __restrict__ x, uint4* __restrict__ xs, int B, int H, int W, int C8, int Hs, int Ws) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long per_plane = static_cast<long long>(B) * Hs * Ws * C8;
+  if (idx >= 4 * per_plane) return;
+  const int plane = static_cast<int>(idx / per_plane);
+  long long r = idx - plane * per_plane;
+  const int c = static_cast<int>(r % C8); r /= C8;
+  const int v = static_cast<int>(r % Ws); r /= Ws;
+  const int u = static_cast<int>(r % Hs);
+  const int b = static_cast<int>(r / Hs);
+  const int y = 2 * u + (plane >> 1), xx = 2 * v + (plane & 1);
+  uint4 o = make_uint4(0, 0, 0, 0);
+  if (y <= H + 1 && xx <= W + 1) o = __ldg(x + ((static_cast<long long>(b) * (H + 2) + y) * (W + 2) + xx) * C8 + c);
+  xs[idx] = o;
+}
+
+// dx[b,y,x,:] = relu_mask(dxs[plane(y&1,x&1), b, y>>1, x>>1, :] (+ add[b,y,x,:])) on interior pixels, 0 on the border.
+__global__ void parity_merge_kernel(const uint4* __restrict__ dxs, const uint4* __restrict__ add, const uint4* __restrict__ mask_src,
+                                    uint4* __restrict__ dx, int B, int H, int W, int C8, int Hs, int Ws) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int Hp = H + 2, Wp = W + 2;
+  const long long total = static_cast<long long>(B) * Hp * Wp * C8;
+  if (idx >= total) return;
+  const int c = static_cast<int>(idx % C8);
+  const long long pix = idx / C8;
+  const int xx = static_cast<int>(pix % Wp), y = static_cast<int>((pix / Wp) % Hp);
+  const int b = static_cast<int>(pix / (static_cast<long long>(Wp) * Hp));
+  uint4 o = make_uint4(0, 0, 0, 0);
+  if (y >= 1 && y <= H && xx >= 1 && xx <= W) {
+    const int plane = ((y & 1) << 1) | (xx & 1);
+    const uint4 t = __ldg(dxs + (((static_cast<long long>(plane) * B + b) * Hs + (y >> 1)) * Ws + (xx >> 1)) * C8 + c);
+    float f[8] = {bf16_lo(t.x), bf16_hi(t.x), bf16_lo(t.y), bf16_hi(t.y), bf16_lo(t.z), bf16_hi(t.z), bf16_lo(t.w), bf16_hi(t.w)};
+    if (add) {
+      const uint4 a = __ldg(add + idx);
+      f[0] += bf16_lo(a.x); f[1] += bf16_hi(a.x); f[2] += bf16_lo(a.y); f[3] += bf16_hi(a.y);
+      f[4] += bf16_lo(a.z); f[5] += bf16_hi(a.z); f[6] += bf16_lo(a.w); f[7] += bf16_hi(a.w);
+    }
+    if (mask_src) {
+      const uint4 m = __ldg(mask_src + idx);
+      const float g[8] = {bf16_lo(m.x), bf16_hi(m.x), bf16_lo(m.y), bf16_hi(m.y), bf16_lo(m.z), bf16_hi(m.z), bf16_lo(m.w), bf16_hi(m.w)};
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        if (!(g[e] > 0.f)) f[e] = 0.f;
+    }
+    o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]); o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
+  }
+  dx[idx] = o;
+}
+
+// ------------------------------------------------------------------------------------------------ weight packing
+// Conv weight fp32 [Cout,Cin,kh,kw] (+ FrozenBN buffers, backbone.py:70-80) ->
+//   fwd  bf16 [Cout, ldk]            column (r*kw+s)*Cin + ci            (zero padded to ldk)
+//   dgr  bf16 [Cin, kh*kw*Cout]      column ((kh-1-r)*kw+(kw-1-s))*Cout + co   (taps flipped: dgrad == conv with same shifts)
+//   scale[co] = w*rsqrt(rv+eps), bias[co] = b - rm*scale  (scale = 1, bias = conv bias when there is no BN)
+__global__ void pack_conv_kernel(const float* __restrict__ w, int Cout, int Cin, int kh, int kw, const float* bn_w, const float* bn_b,
+                                 const float* bn_rm, const float* bn_rv, float eps, const float* conv_bias, __nv_bfloat16* fwd, int ldk,
+                                 __nv_bfloat16* dgr, float* scale_out, float* bias_out) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(Cout) * ldk;
+  if (idx >= total) return;
+  const int co = static_cast<int>(idx / ldk), k = static_cast<int>(idx % ldk);
+  float sc = 1.f, bi = conv_bias ? conv_bias[co] : 0.f;
+  if (bn_w) {
+    sc = bn_w[co] * rsqrtf(bn_rv[co] + eps);
+    bi = bn_b[co] - bn_rm[co] * sc;
+  }
+  if (k == 0) {
+    if (scale_out) scale_out[co] = sc;
+    if (bias_out) bias_out[co] = bi;
+  }
+  float v = 0.f;
+  const int taps = kh * kw;
+  if (k < taps * Cin) {
+    const int ci = k % Cin, t = k / Cin, s = t % kw, r = t / kw;
+    v = w[((static_cast<long long>(co) * Cin + ci) * kh + r) * kw + s] * sc;
+    if (dgr) dgr[static_cast<long long>(ci) * taps * Cout + (static_cast<long long>((kh - 1 - r) * kw + (kw - 1 - s))) * Cout + co] = __float2bfloat16(v);
+  }
+  fwd[idx] = __float2bfloat16(v);
+}
+
+// Linear weight fp32 [N,K] -> wb bf16 [N,K] and (optionally) wt bf16 [K,N].
+__global__ void pack_linear_kernel(const float* __restrict__ w, int N, int K, __nv_bfloat16* wb, long long ldwb, __nv_bfloat16* wt, long long ldwt) {
+  __shared__ float tile[32][33];
+  const int k0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int n = n0 + i, k = k0 + threadIdx.x;
+    float v = 0.f;
+    if (n < N && k < K) {
+      v = w[static_cast<long long>(n) * K + k];
+      if (wb) wb[static_cast<long long>(n) * ldwb + k] = __float2bfloat16(v);
+    }
+    tile[i][threadIdx.x] = v;
+  }
+  __syncthreads();
+  if (wt) {
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+      const int k = k0 + i, n = n0 + threadIdx.x;
+      if (n < N && k < K) wt[static_cast<long long>(k) * ldwt + n] = __float2bfloat16(tile[threadIdx.x][i]);
+    }
+  }
+}
+
+// dWfold fp32 [Cout, taps, Cin] -> grad fp32 [Cout, Cin, kh, kw] * scale[co]
+__global__ void unpack_conv_grad_kernel(const float* __restrict__ dwf, const float* __restrict__ scale, float* __restrict__ grad, int Cout,
+                                        int Cin, int taps) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(Cout) * Cin * taps;
+  if (idx >= total) return;
+  const int t = static_cast<int>(idx % taps);
+  const int ci = static_cast<int>((idx / taps) % Cin);
+  const int co = static_cast<int>(idx / (static_cast<long long>(taps) * Cin));
+  grad[idx] = dwf[(static_cast<long long>(co) * taps + t) * Cin + ci] * (scale ? scale[co] : 1.f);
+}
+
+// ------------------------------------------------------------------------------------------------ casts / reductions
+__global__ void cast_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n) {
+  const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    const float4 v = *reinterpret_cast<const float4*>(in + i);
+    uint2 o;
+    o.x = pack_bf16x2(v.x, v.y); o.y = pack_bf16x2(v.z, v.w);
+    *reinterpret_cast<uint2*>(out + i) = o;
+  } else {
+    for (long long j = i; j < n; ++j) out[j] = __float2bfloat16(in[j]);
+  }
+}
+
+// out[n] (+)= sum over rows of x[row, n]; x is bf16 or fp32; rows are split over blockIdx.y, partials added atomically.
+template <typename T>
+__global__ void colsum_kernel(const T* __restrict__ x, long long ld, long long rows, int N, float* __restrict__ out) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const long long per = (rows + gridDim.y - 1) / gridDim.y;
+  const long long r0 = blockIdx.y * per, r1 = min(rows, r0 + per);
+  float acc = 0.f;
+  for (long long r = r0; r < r1; ++r) acc += static_cast<float>(x[r * ld + n]);
+  atomicAdd(out + n, acc);
+}
+
+// y = a + b (fp32), optional bf16 copy
+__global__ void add_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ y, __nv_bfloat16* __restrict__ yb, long long n) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = a[i] + (b ? b[i] : 0.f);
+  if (y) y[i] = v;
+  if (yb) yb[i] = __float2bfloat16(v);
+}
+
+}  // namespace rb
+
+using namespace rb;
+
+#define RB_CHECK_LAUNCH() RB_CUDA(cudaGetLastError())
+
+extern "C" int rb_stem_im2col(const float* img, void* out, int B, int H, int W, int H1, int W1, void* stream) {
+  const long long total = static_cast<long long>(B) * H1 * W1 * 20;
+  stem_im2col_kernel<<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(img, static_cast<uint4*>(out), B, H, W, H1, W1);
+  RB_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int rb_maxpool_3x3s2(const void* in, void* out, int B, int H1, int W1, int C, int H2, int W2, void* stream) {
+  if (C % 8) return rb_fail("rb_maxpool_3x3s2: C must be a multiple of 8");
+  const long long total = static_cast<long long>(B) * (H2 + 2) * (W2 + 2) * (C / 8);
+  maxpool_kernel<<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint4*>(in), static_cast<uint4*>(out), B, H1, W1, C / 8, H2, W2);
+  RB_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int rb_parity_split(const void* x, void* xs, int B, int H, int W, int C, int Ho, int Wo, void* stream) {
+  if (C % 8) return rb_fail("rb_parity_split: C must be a multiple of 8");
+  const long long total = 4ll * B * (Ho + 2) * (Wo + 2) * (C / 8);
+  parity_split_kernel<<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint4*>(x), static_cast<uint4*>(xs), B, H, W, C / 8, Ho + 2, Wo + 2);
+  RB_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int rb_parity_merge(const void* dxs, const void* add, const void* mask_src, void* dx, int B, int H, int W, int C, int Ho, int Wo, void* stream) {
+  if (C % 8) return rb_fail("rb_parity_merge: C must be a multiple of 8");
+  const long long total = static_cast<long long>(B) * (H + 2) * (W + 2) * (C / 8);
+  parity_merge_kernel<<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(dxs), static_cast<const uint4*>(add), static_cast<const uint4*>(mask_src), static_cast<uint4*>(dx), B, H, W, C / 8, Ho + 2, Wo + 2);
+  RB_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int rb_pack_conv(const float* w, int Cout, int Cin, int kh, int kw, const float* bn_w, const float* bn_b, const float* bn_rm,
+                            const float* bn_rv, float eps, const float* conv_bias, void* fwd, int ldk, void* dgr, float* scale_out, float* bias_out,
+                            void* stream) {
+  if (ldk < kh * kw * Cin) return rb_fail("rb_pack_conv: ldk too small");
+  const long long total = static_cast<long long>(Cout) * ldk;
+  pack_conv_kernel<<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(w, Cout, Cin, kh, kw, bn_w, bn_b, bn_rm, bn_rv, eps, conv_bias,
+                                                                                          static_cast<__nv_bfloat16*>(fwd), ldk, static_cast<__nv_bfloat16*>(dgr), scale_out, bias_out);
+  RB_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int rb_pack_linear(const float* w, int N, int K, void* wb, long long ldwb, void* wt, long long ldwt, void* stream) {
+  dim3 grid((K + 31) / 32, (N + 31) / 32);
+  pack_linear_kernel<<<grid, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(w, N, K, static_cast<__nv_bfloat16*>(wb), ldwb, static_cast<__nv_bfloat16*>(wt), ldwt);
+  RB_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int rb_unpack_conv_grad(const float* dwf, const float* scale, float* grad, int Cout, int Cin, int taps, void* stream) {
+  const long long total = static_cast<long long>(Cout) * Cin * taps;
+  unpack_conv_grad_kernel<<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(dwf, scale, grad, Cout, Cin, taps);
+  RB_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int rb_cast_bf16(const float* in, void* out, long long n, void* stream) {
+  if (n <= 0) return 0;
+  cast_bf16_kernel<<<blocks_for((n + 3) / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(in, static_cast<__nv_bfloat16*>(out), n);
+  RB_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int rb_colsum(const void* x, int is_bf16, long long ld, long long rows, int N, float* out, void* stream) {
+  if (rows <= 0 || N <= 0) return 0;
+  int ysplit = static_cast<int>(rows / 256);
+  ysplit = ysplit < 1 ? 1 : (ysplit > 64 ? 64 : ysplit);
+  dim3 grid((N + 127) / 128, ysplit);
+  if (is_bf16)
+    colsum_kernel<__nv_bfloat16><<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(x), ld, rows, N, out);
+  else
+    colsum_kernel<float><<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const float*>(x), ld, rows, N, out);
+  RB_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int rb_add(const float* a, const float* b, float* y, void* yb, long long n, void* stream) {
+  if (n <= 0) return 0;
+  add_kernel<<<blocks_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, b, y, static_cast<__nv_bfloat16*>(yb), n);
+  RB_CHECK_LAUNCH();
+  return 0;
+}

@@ -42,16 +42,18 @@ struct GemmKParams {
 
 __device__ __forceinline__ bool row_is_interior(const rb_geom& g, long long row) {
   if (g.mode == 0) return true;
-  int lo_u = 1, lo_v = 1;
-  if (g.mode == 2) {
-    int plane = static_cast<int>(row / g.Rs);
-    row -= static_cast<long long>(plane) * g.Rs;
-    lo_u = 1 - (plane >> 1);
-    lo_v = 1 - (plane & 1);
+  if (g.mode == 1) {
+    const int t = static_cast<int>(row % g.HpWp);
+    const int u = t / g.Wp, v = t - u * g.Wp;
+    return (u >= 1) && (u <= g.H) && (v >= 1) && (v <= g.W);
   }
-  int t = static_cast<int>(row % g.HpWp);
-  int u = t / g.Wp, v = t - u * g.Wp;
-  return (u >= lo_u) && (u < lo_u + g.H) && (v >= lo_v) && (v < lo_v + g.W);
+  // parity planes: cell (u,v) of plane (p,q) holds padded-input pixel (2u+p, 2v+q); interior iff 1 <= . <= H (resp. W)
+  const int plane = static_cast<int>(row / g.Rs);
+  row -= static_cast<long long>(plane) * g.Rs;
+  const int t = static_cast<int>(row % g.HpWp);
+  const int u = t / g.Wp, v = t - u * g.Wp;
+  const int y = 2 * u + (plane >> 1), x = 2 * v + (plane & 1);
+  return (y >= 1) && (y <= g.H) && (x >= 1) && (x <= g.W);
 }
 
 template <int BN, int MODE, int STAGES>

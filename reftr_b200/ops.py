@@ -66,3 +66,115 @@ def gemm(A, B, M, N, K, *, mode=0, taps=((0, 0),), bias=None, res=None, res32=No
         a.geom = geom
     _lib.check(_lib.lib().rb_gemm(C.byref(a), _stream()), "rb_gemm")
     return out if out is not None else out32
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# thin wrappers (argument order == include/reftr_b200.h)
+# ---------------------------------------------------------------------------------------------------------------
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _s():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def stem_im2col(img, out, B, H, W, H1, W1):
+    _lib.call("rb_stem_im2col", _p(img), _p(out), B, H, W, H1, W1, _s())
+
+
+def maxpool_3x3s2(x, out, B, H1, W1, C, H2, W2):
+    _lib.call("rb_maxpool_3x3s2", _p(x), _p(out), B, H1, W1, C, H2, W2, _s())
+
+
+def parity_split(x, xs, B, H, W, C, Ho, Wo):
+    _lib.call("rb_parity_split", _p(x), _p(xs), B, H, W, C, Ho, Wo, _s())
+
+
+def parity_merge(dxs, add, mask_src, dx, B, H, W, C, Ho, Wo):
+    _lib.call("rb_parity_merge", _p(dxs), _p(add), _p(mask_src), _p(dx), B, H, W, C, Ho, Wo, _s())
+
+
+def pack_conv(w, bn, conv_bias, fwd, ldk, dgr, scale_out, bias_out, eps=1e-5):
+    Cout, Cin, kh, kw = w.shape
+    bw, bb, brm, brv = bn if bn is not None else (None, None, None, None)
+    _lib.call("rb_pack_conv", _p(w), Cout, Cin, kh, kw, _p(bw), _p(bb), _p(brm), _p(brv), eps, _p(conv_bias), _p(fwd), ldk, _p(dgr),
+              _p(scale_out), _p(bias_out), _s())
+
+
+def pack_linear(w, wb, wt):
+    N, K = w.shape
+    assert w.is_contiguous()
+    _lib.call("rb_pack_linear", _p(w), N, K, _p(wb), wb.stride(0) if wb is not None else 0, _p(wt), wt.stride(0) if wt is not None else 0, _s())
+
+
+def unpack_conv_grad(dwf, scale, grad, Cout, Cin, taps):
+    _lib.call("rb_unpack_conv_grad", _p(dwf), _p(scale), _p(grad), Cout, Cin, taps, _s())
+
+
+def cast_bf16(x, out=None):
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    if out is None:
+        out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    _lib.call("rb_cast_bf16", _p(x), _p(out), x.numel(), _s())
+    return out
+
+
+def colsum(x, out, rows=None, N=None):
+    """out[N] += column sums of x [rows, N] (bf16 or fp32)."""
+    rows = x.shape[0] if rows is None else rows
+    N = x.shape[1] if N is None else N
+    _lib.call("rb_colsum", _p(x), int(x.dtype == torch.bfloat16), x.stride(0), rows, N, _p(out), _s())
+
+
+def add(a, b, y=None, yb=None):
+    _lib.call("rb_add", _p(a), _p(b), _p(y), _p(yb), a.numel(), _s())
+
+
+def layernorm_fwd(x, gamma, beta, rows, *, y32=None, yb=None, pos32=None, ypb=None, relu=False, mean=None, rstd=None, rowmap=(0, 0, 0),
+                  eps=1e-5):
+    _lib.call("rb_layernorm_fwd", _p(x), _p(gamma), _p(beta), rows, x.shape[-1], eps, _p(y32), _p(yb), _p(pos32), _p(ypb), int(relu),
+              _p(mean), _p(rstd), rowmap[0], rowmap[1], rowmap[2], _s())
+
+
+def layernorm_bwd(dy, x, gamma, mean, rstd, rows, *, dy2=None, y_relu=None, dx32=None, dxb=None, dgamma=None, dbeta=None, rowmap=(0, 0, 0)):
+    _lib.call("rb_layernorm_bwd", _p(dy), _p(dy2), _p(y_relu), _p(x), _p(gamma), _p(mean), _p(rstd), rows, x.shape[-1], _p(dx32), _p(dxb),
+              _p(dgamma), _p(dbeta), rowmap[0], rowmap[1], rowmap[2], _s())
+
+
+def groupnorm_tokens_fwd(x, gamma, beta, B, h, w, S, L, y32, yb, pos32, ypb, mean, rstd, eps=1e-5):
+    _lib.call("rb_groupnorm_tokens_fwd", _p(x), _p(gamma), _p(beta), B, h, w, S, L, eps, _p(y32), _p(yb), _p(pos32), _p(ypb), _p(mean),
+              _p(rstd), _s())
+
+
+def groupnorm_tokens_bwd(dy, dy2, x, gamma, mean, rstd, B, h, w, S, L, dx, dgamma, dbeta):
+    _lib.call("rb_groupnorm_tokens_bwd", _p(dy), _p(dy2), _p(x), _p(gamma), _p(mean), _p(rstd), B, h, w, S, L, _p(dx), _p(dgamma),
+              _p(dbeta), _s())
+
+
+def build_pos_mask(img_mask, B, H, W, h, w, sent_mask, L, lang_pos, token_type, level_embed, pos32, kpm):
+    assert img_mask.dtype == torch.bool and sent_mask.dtype == torch.int64
+    _lib.call("rb_build_pos_mask", _p(img_mask), B, H, W, h, w, _p(sent_mask), L, _p(lang_pos), _p(token_type), _p(level_embed), _p(pos32),
+              _p(kpm), _s())
+
+
+def embed_grad(dpos, B, S, L, d_lang_pos, d_token_type, d_level):
+    _lib.call("rb_embed_grad", _p(dpos), B, S, L, _p(d_lang_pos), _p(d_token_type), _p(d_level), _s())
+
+
+def attn_fwd(Q, K, V, kpm, O, LSE, B, H, Tq, Sk, scale):
+    _lib.call("rb_attn_fwd", _p(Q), _p(K), _p(V), _p(kpm), _p(O), _p(LSE), B, H, 32, Tq, Sk, Q.stride(0), K.stride(0), V.stride(0),
+              O.stride(0), scale, _s())
+
+
+def attn_bwd(Q, K, V, kpm, O, dO, LSE, dQ, dK, dV, Dbuf, B, H, Tq, Sk, scale):
+    _lib.call("rb_attn_bwd", _p(Q), _p(K), _p(V), _p(kpm), _p(O), _p(dO), _p(LSE), _p(dQ), _p(dK), _p(dV), _p(Dbuf), B, H, 32, Tq, Sk,
+              Q.stride(0), K.stride(0), V.stride(0), O.stride(0), dO.stride(0), dQ.stride(0), dK.stride(0), dV.stride(0), scale, _s())
+
+
+def qenc_pool_fwd(k, q, v, mask, B, L, n_ph, att, c):
+    _lib.call("rb_qenc_pool_fwd", _p(k), _p(q), _p(v), _p(mask), B, L, n_ph, _p(att), _p(c), _s())
+
+
+def qenc_pool_bwd(dc, k, q, v, att, B, L, n_ph, dk, dq, dv):
+    _lib.call("rb_qenc_pool_bwd", _p(dc), _p(k), _p(q), _p(v), _p(att), B, L, n_ph, _p(dk), _p(dq), _p(dv), _s())

@@ -1,0 +1,136 @@
+"""Packed (bf16, kernel-layout) copies of the fp32 master parameters, rebuilt lazily when a parameter's version changes
+(optimizer.step / load_state_dict bump ``Tensor._version``), never stored in the state_dict."""
+import torch
+
+from . import ops
+
+
+def _ver(*ts):
+    return tuple((t.data_ptr(), t._version) for t in ts if t is not None)
+
+
+class PackedConv:
+    """conv (+ FrozenBN) -> wf bf16 [Cout, ldk] with BN scale folded, wd bf16 [Cin, taps*Cout] (flipped taps) for dgrad,
+    scale / bias fp32 [Cout]."""
+
+    def __init__(self, conv, bn=None, need_dgrad=True, ldk=None):
+        self.conv, self.bn = conv, bn
+        w = conv.weight
+        self.Cout, self.Cin, self.kh, self.kw = w.shape
+        self.taps = self.kh * self.kw
+        self.K = self.taps * self.Cin
+        self.ldk = ldk or self.K
+        self.need_dgrad = need_dgrad
+        self.trainable = w.requires_grad
+        self._key = None
+        self.wf = self.wd = self.scale = self.bias = None
+
+    def refresh(self):
+        w = self.conv.weight
+        bn = None
+        if self.bn is not None:
+            bn = (self.bn.weight, self.bn.bias, self.bn.running_mean, self.bn.running_var)
+        cb = getattr(self.conv, "bias", None)
+        key = _ver(w, cb, *(bn or ()))
+        if key == self._key:
+            return
+        dev = w.device
+        if self.wf is None or self.wf.device != dev:
+            self.wf = torch.empty(self.Cout, self.ldk, dtype=torch.bfloat16, device=dev)
+            self.wd = torch.empty(self.Cin, self.taps * self.Cout, dtype=torch.bfloat16, device=dev) if self.need_dgrad else None
+            self.scale = torch.empty(self.Cout, dtype=torch.float32, device=dev)
+            self.bias = torch.empty(self.Cout, dtype=torch.float32, device=dev)
+        ops.pack_conv(w.detach(), bn, cb.detach() if cb is not None else None, self.wf, self.ldk, self.wd, self.scale, self.bias,
+                      eps=self.bn.eps if self.bn is not None else 1e-5)
+        self._key = key
+
+
+class PackedLinear:
+    """weight fp32 [N,K] -> wb bf16 [Npad,K], wt bf16 [K,Npad]; bias fp32 [Npad].  ``pad_to`` zero-pads the output dim
+    (used for the 4-wide box head so every pitch is a multiple of 16 bytes)."""
+
+    def __init__(self, weight, bias=None, pad_to=None):
+        self.weight, self.bias_p = weight, bias
+        self.N, self.K = weight.shape
+        self.Np = max(self.N, pad_to or 0)
+        self._key = None
+        self.wb = self.wt = self.bias = None
+
+    def refresh(self):
+        key = _ver(self.weight, self.bias_p)
+        if key == self._key:
+            return
+        dev = self.weight.device
+        if self.wb is None or self.wb.device != dev:
+            self.wb = torch.zeros(self.Np, self.K, dtype=torch.bfloat16, device=dev)
+            self.wt = torch.zeros(self.K, self.Np, dtype=torch.bfloat16, device=dev)
+            if self.Np != self.N:
+                self.bias = torch.zeros(self.Np, dtype=torch.float32, device=dev)
+        ops.pack_linear(self.weight.detach(), self.wb, self.wt)
+        if self.bias_p is not None:
+            if self.Np != self.N:
+                self.bias[:self.N].copy_(self.bias_p.detach())
+            else:
+                self.bias = self.bias_p.detach()
+        self._key = key
+
+
+class PackedStack:
+    """Row-blocks of several weights packed side by side: wb [n*Nblk, K] and wt [K, n*Nblk] (decoder cross-attention K / V
+    projections of all layers, so the memory is projected by ONE GEMM)."""
+
+    def __init__(self, weights, biases, row0, nrows):
+        self.weights, self.biases, self.row0, self.nrows = weights, biases, row0, nrows
+        self.K = weights[0].shape[1]
+        self.n = len(weights)
+        self._key = None
+        self.wb = self.wt = self.bias = None
+
+    def refresh(self):
+        key = _ver(*self.weights, *self.biases)
+        if key == self._key:
+            return
+        dev = self.weights[0].device
+        N = self.n * self.nrows
+        if self.wb is None or self.wb.device != dev:
+            self.wb = torch.empty(N, self.K, dtype=torch.bfloat16, device=dev)
+            self.wt = torch.empty(self.K, N, dtype=torch.bfloat16, device=dev)
+            self.bias = torch.empty(N, dtype=torch.float32, device=dev)
+        for i, (w, b) in enumerate(zip(self.weights, self.biases)):
+            sl = slice(i * self.nrows, (i + 1) * self.nrows)
+            ops.pack_linear(w.detach()[self.row0:self.row0 + self.nrows], self.wb[sl], self.wt[:, sl])
+            self.bias[sl].copy_(b.detach()[self.row0:self.row0 + self.nrows])
+        self._key = key
+
+
+class GradStore:
+    """One flat fp32 buffer per backward holding every hot-path parameter gradient (views are handed to autograd) plus a
+    scratch region for folded-layout 3x3 weight gradients.  A fresh zeroed buffer is taken for each backward so the views
+    autograd keeps in ``param.grad`` never alias the next step's accumulation."""
+
+    def __init__(self, named_params, scratch_sizes):
+        self.slots = {}
+        off = 0
+        for name, p in named_params:
+            self.slots[name] = (off, tuple(p.shape))
+            off += (p.numel() + 63) // 64 * 64
+        self.scratch = {}
+        for name, n in scratch_sizes.items():
+            self.scratch[name] = (off, n)
+            off += (n + 63) // 64 * 64
+        self.total = off
+        self.flat = None
+
+    def begin(self, device):
+        self.flat = torch.zeros(self.total, dtype=torch.float32, device=device)
+
+    def view(self, name):
+        off, shape = self.slots[name]
+        n = 1
+        for s in shape:
+            n *= s
+        return self.flat[off:off + n].view(shape)
+
+    def scratch_view(self, name):
+        off, n = self.scratch[name]
+        return self.flat[off:off + n]
