@@ -134,6 +134,18 @@ int rb_qenc_pool_fwd(const float* k, const float* q, const float* v, const void*
 int rb_qenc_pool_bwd(const float* dc, const float* k, const float* q, const float* v, const float* att, int B, int L, int n_ph, float* dk, float* dq,
                      float* dv, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Row-mapped glue (QueryEncoder.forward reftr_transformer.py:41-66; memory slicing :261-267).  A map is a HOST pointer
+ * to 4 ints {group, stride, inner, offset}: index(r) = (r / group) * stride + (r % group) * inner + offset
+ * (group == 0 or a NULL map: r + offset).
+ * ------------------------------------------------------------------------------------------------------------- */
+/* y[my(r), :D] = a[ma(r), :D] + b[mb(r), :D] (b nullable); fp32 in, fp32 (y32) and/or bf16 (yb) out */
+int rb_rows_add(const float* a, long long lda, const int* map_a, const float* b, long long ldb, const int* map_b, float* y32, long long ldy,
+                void* yb, long long ldyb, const int* map_y, long long rows, int D, void* stream);
+/* dst[md(r), :D] += src[ms(r), :D] (fp32 atomics) */
+int rb_rows_scatter_add(const float* src, long long lds, const int* map_src, float* dst, long long ldd, const int* map_dst, long long rows,
+                        int D, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -86,13 +86,20 @@ def lib():
     return _lib
 
 
+LAUNCHES = 0  # number of C-ABI kernel-launching calls made by this process (bench.py reports it)
+
+
 def call(name, *args):
     """Calls a C-ABI function; tensors are passed as data_ptr() ints or None; raises on a non-zero return."""
+    global LAUNCHES
+    LAUNCHES += 1
     rc = getattr(lib(), name)(*args)
     if rc != 0:
         raise RuntimeError(f"{name}: {lib().rb_last_error().decode()}")
 
 
 def check(rc, what):
+    global LAUNCHES
+    LAUNCHES += 1
     if rc != 0:
         raise RuntimeError(f"{what}: {lib().rb_last_error().decode()}")

@@ -1,0 +1,977 @@
+"""Forward / backward orchestration of the RefTR hot path on the C-ABI kernels (include/reftr_b200.h).
+
+``RefTREngine`` owns, per model: the packed bf16 weights (pack.py), a workspace of static device buffers (so the whole
+forward and the whole backward are CUDA-graph capturable: no allocation, no host sync, fixed addresses), and one flat
+fp32 gradient buffer.  ``HotPathFunction`` is the single autograd node through which the reference's nn.Module surface
+(modules.py) reaches it; BERT stays a HuggingFace module outside (third party in the reference).
+
+Reference call stack restated here: Joiner/Backbone (backbone.py:101-145) -> input_proj + GroupNorm
+(reftr_transformer.py:172-175) -> map_sentence / map_phrase (:201, :250) -> VLTransformer.encode (reftr.py:99-120) ->
+TransformerEncoderLayer.forward_post x N (transformer.py:168-181) -> QueryEncoder (reftr_transformer.py:41-66) ->
+TransformerDecoderLayer.forward_post x N (transformer.py:231-252, decoder.norm on every layer :131-138) -> bbox_embed
+(:287); segmentation adds MHAttentionMap + MaskHeadSmallConv (reftr_segmentation.py:152-175, :196-280).
+
+Layouts: backbone activations are "padded NHWC" bf16 matrices [B*(H+2)*(W+2), C] with an exactly-zero border, so every
+convolution is a GEMM over row-shifted copies of the same matrix; tokens are batch-major fp32/bf16 matrices
+[B*S, 256] (row b*S + s; language tokens first).  The residual stream, LayerNorm/GroupNorm statistics and softmax are
+fp32; bf16 appears only as tensor-core operands and as saved activations / activation gradients.
+"""
+import math
+import os
+
+import torch
+
+from . import ops
+from .pack import PackedConv, PackedLinear, PackedStack
+
+NH = 8      # heads
+DH = 32     # head dim
+D = 256     # model dim
+
+
+def _cdiv(a, b):
+    return (a + b - 1) // b
+
+
+class Grid:
+    """Geometry of a padded NHWC activation [B, H+2, W+2, C] viewed as a matrix with R rows."""
+
+    def __init__(self, B, H, W):
+        self.B, self.H, self.W = B, H, W
+        self.Hp, self.Wp = H + 2, W + 2
+        self.R = B * self.Hp * self.Wp
+        self.geom = ops.make_geom(1, self.Wp, self.Hp * self.Wp, H, W, 0)
+
+    def half(self):
+        return Grid(self.B, (self.H + 1) // 2, (self.W + 1) // 2)
+
+    def shifts(self):
+        """Row shift of tap (r, s) of a 3x3 / stride-1 / pad-1 convolution, r-major."""
+        return [(r - 1) * self.Wp + (s - 1) for r in range(3) for s in range(3)]
+
+    def s2_offsets(self):
+        """Row offset into the 4 parity planes (built on THIS grid = the stride-2 output grid) of tap (r, s)."""
+        offs = []
+        for r in range(3):
+            for s in range(3):
+                plane = 2 * (r & 1) + (s & 1)
+                du = (1 if r == 2 else 0) - 1
+                dv = (1 if s == 2 else 0) - 1
+                offs.append((plane, du * self.Wp + dv))
+        return offs
+
+
+class Workspace:
+    """Named static device buffers (allocated on first use, reused by every later step with the same shapes)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.bufs = {}
+
+    def get(self, name, shape, dtype=None, zero=False):
+        dtype = dtype or torch.bfloat16
+        shape = tuple(int(s) for s in shape)
+        t = self.bufs.get(name)
+        if t is None or tuple(t.shape) != shape or t.dtype != dtype:
+            if torch.cuda.is_available() and torch.cuda.is_current_stream_capturing():
+                raise RuntimeError(f"workspace buffer {name!r} {shape} would be allocated during CUDA-graph capture")
+            t = (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=self.device)
+            self.bufs[name] = t
+        return t
+
+    def nbytes(self):
+        return sum(t.numel() * t.element_size() for t in self.bufs.values())
+
+
+class _Block:
+    pass
+
+
+class RefTREngine:
+    def __init__(self, model):
+        self.model = model
+        self.seg = hasattr(model, "mask_head")
+        body = model.img_backbone[0].body
+        self.return_interm = model.img_backbone[0].return_interm_layers
+        # ---- packed weights -------------------------------------------------------------------------------------
+        self.stem = PackedConv(body.conv1, body.bn1, need_dgrad=False, ldk=160)
+        self.blocks = []
+        first_trainable = True
+        for li in range(1, 5):
+            for bi, bp in enumerate(getattr(body, f"layer{li}")):
+                b = _Block()
+                b.key = f"layer{li}.{bi}"
+                b.pname = f"img_backbone.0.body.layer{li}.{bi}"
+                b.stride, b.cin, b.width = bp.stride, bp.cin, bp.width
+                b.trainable = bp.conv1.weight.requires_grad
+                b.c1 = PackedConv(bp.conv1, bp.bn1, need_dgrad=b.trainable)
+                b.c2 = PackedConv(bp.conv2, bp.bn2, need_dgrad=b.trainable)
+                b.c3 = PackedConv(bp.conv3, bp.bn3, need_dgrad=b.trainable)
+                b.ds = PackedConv(bp.downsample[0], bp.downsample[1], need_dgrad=b.trainable) if bp.downsample is not None else None
+                b.need_gx = b.trainable and not first_trainable  # gradient stops at the first trainable block's input
+                if b.trainable:
+                    first_trainable = False
+                b.layer_end = bi == len(getattr(body, f"layer{li}")) - 1
+                b.layer = li
+                self.blocks.append(b)
+        self.iproj = PackedConv(model.input_proj[0][0], None, need_dgrad=True)
+        vt = model.vl_transformer
+        self.enc = []
+        for lay in vt.encoder.layers:
+            e = _Block()
+            e.inp = PackedLinear(lay.self_attn.in_proj_weight, lay.self_attn.in_proj_bias)
+            e.out = PackedLinear(lay.self_attn.out_proj.weight, lay.self_attn.out_proj.bias)
+            e.l1 = PackedLinear(lay.linear1.weight, lay.linear1.bias)
+            e.l2 = PackedLinear(lay.linear2.weight, lay.linear2.bias)
+            e.mod = lay
+            self.enc.append(e)
+        self.dec = []
+        for lay in vt.decoder.layers:
+            d = _Block()
+            d.sa = PackedLinear(lay.self_attn.in_proj_weight, lay.self_attn.in_proj_bias)
+            d.sa_out = PackedLinear(lay.self_attn.out_proj.weight, lay.self_attn.out_proj.bias)
+            d.ca = PackedLinear(lay.multihead_attn.in_proj_weight, lay.multihead_attn.in_proj_bias)
+            d.ca_out = PackedLinear(lay.multihead_attn.out_proj.weight, lay.multihead_attn.out_proj.bias)
+            d.l1 = PackedLinear(lay.linear1.weight, lay.linear1.bias)
+            d.l2 = PackedLinear(lay.linear2.weight, lay.linear2.bias)
+            d.mod = lay
+            self.dec.append(d)
+        caw = [lay.multihead_attn.in_proj_weight for lay in vt.decoder.layers]
+        cab = [lay.multihead_attn.in_proj_bias for lay in vt.decoder.layers]
+        self.kstack = PackedStack(caw, cab, D, D)
+        self.vstack = PackedStack(caw, cab, 2 * D, D)
+
+        def mlp(seq):
+            return [PackedLinear(seq[0].weight, seq[0].bias), PackedLinear(seq[4].weight, seq[4].bias)]
+        self.map_sentence = mlp(model.map_sentence)
+        self.map_phrase = mlp(model.map_phrase)
+        qe = model.query_encoder
+        self.qe_lin = [PackedLinear(m.weight, m.bias) for m in (qe.linear1, qe.linear2, qe.linear3)]
+        self.qe_fuse = mlp(qe.fuse_encoder_query)
+        self.qe_cout = PackedLinear(qe.context_out[0].weight, qe.context_out[0].bias)
+        bl = model.bbox_embed.layers
+        self.bbox = [PackedLinear(bl[0].weight, bl[0].bias), PackedLinear(bl[1].weight, bl[1].bias),
+                     PackedLinear(bl[2].weight, bl[2].bias, pad_to=64)]
+        self.packs = [self.stem, self.iproj, self.kstack, self.vstack] + self.map_sentence + self.map_phrase + self.qe_lin + \
+            self.qe_fuse + [self.qe_cout] + self.bbox
+        for b in self.blocks:
+            self.packs += [p for p in (b.c1, b.c2, b.c3, b.ds) if p is not None]
+        for e in self.enc:
+            self.packs += [e.inp, e.out, e.l1, e.l2]
+        for d in self.dec:
+            self.packs += [d.sa, d.sa_out, d.ca, d.ca_out, d.l1, d.l2]
+        if self.seg:
+            from .seg import SegHead
+            self.seghead = SegHead(self, model)
+            self.packs += self.seghead.packs
+        # ---- gradient store -------------------------------------------------------------------------------------
+        self.named = [(n, p) for n, p in model.named_parameters() if p.requires_grad and not n.startswith("lang_backbone.")]
+        self.pnames = {id(p): n for n, p in self.named}
+        self.slots = {}
+        off = 0
+        for n, p in self.named:
+            self.slots[n] = (off, tuple(p.shape))
+            off += _cdiv(p.numel(), 64) * 64
+        self.n_grad = off
+        self.scratch = {}
+        for b in self.blocks:
+            if b.trainable:
+                n = b.c2.Cout * 9 * b.c2.Cin
+                self.scratch[b.key + ".c2"] = (off, n)
+                off += _cdiv(n, 64) * 64
+        if self.seg:
+            off = self.seghead.reserve_scratch(self.scratch, off)
+        self.n_flat = off
+        self.gflat = None
+        self.ws = None
+        self.saved = {}
+        self._dev = None
+        self._sig = None
+        self._states = {}
+        self._cur = None
+        self.step_id = 0
+        self.use_graphs = os.environ.get("REFTR_B200_GRAPHS", "1") != "0"
+        self._graphs = {}
+        self.launches = 0
+
+    # ------------------------------------------------------------------------------------------------------------
+    def param_list(self):
+        return [p for _, p in self.named]
+
+    def _prepare(self, device):
+        """Re-packs weights whose master copy changed (optimizer step / load_state_dict) and drops captured graphs when
+        any parameter storage moved (graphs hold raw device addresses)."""
+        sig = tuple(p.data_ptr() for _, p in self.named)
+        if self._dev != device or sig != self._sig:
+            self._dev, self._sig = device, sig
+            self._states = {}
+            self.gflat = torch.zeros(self.n_flat, dtype=torch.float32, device=device)
+        for p in self.packs:
+            p.refresh()
+
+    # ------------------------------------------------------------------------------------------------------------
+    # step driver: eager on the first step of a shape, CUDA-graph capture on the second, replay afterwards
+    # ------------------------------------------------------------------------------------------------------------
+    MAX_GRAPHED_SHAPES = 3
+
+    def _state(self, key):
+        st = self._states.get(key)
+        if st is None:
+            graphed = self.use_graphs and self._dev.type == "cuda" and \
+                sum(1 for s in self._states.values() if s["graphed"]) < self.MAX_GRAPHED_SHAPES
+            if not graphed and "eager" in self._states:
+                st = self._states["eager"]  # all un-graphed shapes share one workspace
+            else:
+                st = dict(ws=Workspace(self._dev), graphed=graphed, fwd=None, bwd=None, nf=0, nb=0, fl=0, bl=0, saved=None, dims=None,
+                          outs=None, bouts=None)
+            self._states[key if graphed else "eager"] = st
+        return st
+
+    def run_forward(self, img, img_mask, sent_mask, mask_context, query_mask, n_ph, want_seg, sent_feat, pooled):
+        ops.require_device(img)
+        if next(self.model.parameters()).device != img.device:
+            raise RuntimeError("reftr_b200: model parameters and inputs are on different devices")
+        self._prepare(img.device)
+        self.step_id += 1
+        B, L = sent_feat.shape[:2]
+        T = n_ph * self.model.num_queries_per_phrase
+        key = (tuple(img.shape), L, n_ph, bool(want_seg), tuple(pooled.shape))
+        st = self._state(key)
+        self._cur = st
+        self.ws = ws = st["ws"]
+        args = (ws.get("in.img", img.shape, torch.float32), ws.get("in.imask", img_mask.shape, torch.bool),
+                ws.get("in.smask", [B, L], torch.int64), ws.get("in.mctx", [B, n_ph, L], torch.uint8), ws.get("in.qmask", [B, T], torch.uint8),
+                ws.get("in.sf", sent_feat.shape, torch.float32), ws.get("in.pl", [B * n_ph, pooled.shape[-1]], torch.float32))
+        for dst, src in zip(args, (img, img_mask, sent_mask, mask_context, query_mask, sent_feat, pooled)):
+            dst.copy_(src.reshape(dst.shape))
+        a = (args[0], args[1], args[2], args[3], args[4], n_ph, want_seg, args[5], args[6])
+        if st["fwd"] is not None:
+            self.saved, self.dims = st["saved"], st["dims"]
+            st["fwd"].replay()
+        elif st["graphed"] and st["nf"] >= 1:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                st["outs"] = self.forward(*a)
+            st["fwd"], st["saved"], st["dims"] = g, self.saved, self.dims
+            g.replay()
+        else:
+            n0 = ops.launch_count()
+            st["outs"] = self.forward(*a)
+            st["fl"] = ops.launch_count() - n0
+            st["saved"], st["dims"] = self.saved, self.dims
+        st["nf"] += 1
+        self.launches += st["fl"]
+        return st["outs"]
+
+    def run_backward(self, g_logits, g_masks, g_att):
+        st = self._cur
+        self.ws = ws = st["ws"]
+        self.saved, self.dims = st["saved"], st["dims"]
+        gl = ws.get("in.g_logits", g_logits.shape, torch.float32)
+        gl.copy_(g_logits)
+        gm = ga = None
+        if g_masks is not None:
+            gm = ws.get("in.g_masks", g_masks.shape, torch.float32)
+            gm.copy_(g_masks)
+            ga = ws.get("in.g_att", self.seghead.out_att.shape, torch.float32)
+            if g_att is None:
+                ga.zero_()
+            else:
+                ga.copy_(g_att)
+        if st["bwd"] is not None:
+            st["bwd"].replay()
+        elif st["graphed"] and st["fwd"] is not None and st["nb"] >= 1:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                st["bouts"] = self.backward(gl, gm, ga)
+            st["bwd"] = g
+            g.replay()
+        else:
+            n0 = ops.launch_count()
+            st["bouts"] = self.backward(gl, gm, ga)
+            st["bl"] = ops.launch_count() - n0
+        st["nb"] += 1
+        self.launches += st["bl"]
+        d_sent, d_pooled = st["bouts"]
+        # fresh storage per step: autograd may keep these as .grad of leaf tensors
+        return d_sent.clone(), d_pooled.clone(), self.gflat[:self.n_grad].clone()
+
+    def G(self, name_or_param):
+        n = name_or_param if isinstance(name_or_param, str) else self.pnames[id(name_or_param)]
+        off, shape = self.slots[n]
+        numel = 1
+        for s in shape:
+            numel *= s
+        return self.gflat[off:off + numel].view(shape)
+
+    def scratch_view(self, key):
+        off, n = self.scratch[key]
+        return self.gflat[off:off + n]
+
+    # ------------------------------------------------------------------------------------------------------------
+    # generic helpers
+    # ------------------------------------------------------------------------------------------------------------
+    @staticmethod
+    def _splits(M, N, taps, K):
+        bn = 128 if N >= 128 else 64
+        tiles = _cdiv(M, 128) * _cdiv(N, bn) * taps
+        kb = _cdiv(K, 64)
+        want = _cdiv(3 * 148, tiles)
+        return max(1, min(want, kb // 4 if kb >= 4 else 1))
+
+    def wgrad_linear(self, dY, X, gview, M, N, K):
+        """gview[M, N] += dY[:K, :M]^T X[:K, :N]   (TN GEMM, split-K, fp32 atomics)."""
+        ops.gemm(dY, X, M, N, K, mode=1, out32=gview, atomic=True, splits=self._splits(M, N, 1, K))
+
+    def wgrad_conv(self, pc, dY, X, K, key=None, b_offsets=None):
+        """Folded-layout weight gradient of a convolution; b_offsets = row offset of X per tap (None: 1x1, no shift)."""
+        g = self.G(pc.conv.weight)
+        Cout, Cin = pc.Cout, pc.Cin
+        if b_offsets is None or len(b_offsets) == 1:
+            gv = g.view(Cout, Cin)
+            ops.gemm(dY, X, Cout, Cin, K, mode=1, taps=[(0, b_offsets[0] if b_offsets else 0)], out32=gv, atomic=True,
+                     splits=self._splits(Cout, Cin, 1, K))
+            ops.unpack_conv_grad(gv, pc.scale, gv, Cout, Cin, 1)  # in-place x scale[co]  (FrozenBN fold)
+        else:
+            taps = len(b_offsets)
+            sc = self.scratch_view(key).view(Cout, taps * Cin)
+            ops.gemm(dY, X, Cout, Cin, K, mode=1, taps=[(0, o) for o in b_offsets], out32=sc, atomic=True,
+                     splits=self._splits(Cout, Cin, taps, K), out32_z_stride=Cin)
+            ops.unpack_conv_grad(sc, pc.scale, g, Cout, Cin, taps)
+
+    # ------------------------------------------------------------------------------------------------------------
+    # backbone
+    # ------------------------------------------------------------------------------------------------------------
+    def _block_fwd(self, b, x, g):
+        ws = self.ws
+        k, w, cin, cout = b.key, b.width, b.cin, 4 * b.width
+        a1 = ws.get(k + ".a1", [g.R, w])
+        ops.gemm(x, b.c1.wf, g.R, w, cin, bias=b.c1.bias, relu=True, out=a1, geom=g.geom)
+        a1s = xs = None
+        if b.stride == 1:
+            go = g
+            a2 = ws.get(k + ".a2", [go.R, w])
+            ops.gemm(a1, b.c2.wf, go.R, w, w, taps=[(s, t * w) for t, s in enumerate(g.shifts())], bias=b.c2.bias, relu=True,
+                     out=a2, geom=go.geom)
+        else:
+            go = g.half()
+            a1s = ws.get(k + ".a1s", [4 * go.R, w])
+            ops.parity_split(a1, a1s, g.B, g.H, g.W, w, go.H, go.W)
+            a2 = ws.get(k + ".a2", [go.R, w])
+            ops.gemm(a1s, b.c2.wf, go.R, w, w, taps=[(p * go.R + o, t * w) for t, (p, o) in enumerate(go.s2_offsets())],
+                     bias=b.c2.bias, relu=True, out=a2, geom=go.geom)
+        if b.ds is None:
+            idn = x
+        elif b.stride == 1:
+            idn = ws.get(k + ".idn", [go.R, cout])
+            ops.gemm(x, b.ds.wf, go.R, cout, cin, bias=b.ds.bias, out=idn, geom=go.geom)
+        else:
+            xs = ws.get(k + ".xs", [4 * go.R, cin])
+            ops.parity_split(x, xs, g.B, g.H, g.W, cin, go.H, go.W)
+            idn = ws.get(k + ".idn", [go.R, cout])
+            ops.gemm(xs, b.ds.wf, go.R, cout, cin, taps=[(3 * go.R - go.Wp - 1, 0)], bias=b.ds.bias, out=idn, geom=go.geom)
+        y = ws.get(k + ".y", [go.R, cout])
+        ops.gemm(a2, b.c3.wf, go.R, cout, w, bias=b.c3.bias, res=idn, relu=True, out=y, geom=go.geom)
+        self.saved[k] = (x, g, go, a1, a1s, a2, xs, y)
+        return y, go
+
+    def _block_bwd(self, b, gy, g_extra=None):
+        """gy: bf16 [go.R, cout], gradient w.r.t. the block's pre-ReLU output (already masked by y > 0).
+        Returns the gradient w.r.t. the pre-ReLU output of the previous block (or None when not needed)."""
+        ws = self.ws
+        k, w, cin, cout = b.key, b.width, b.cin, 4 * b.width
+        x, g, go, a1, a1s, a2, xs, _ = self.saved[k]
+        # conv3 (1x1)
+        self.wgrad_conv(b.c3, gy, a2, go.R)
+        d_a2 = ws.get(k + ".d_a2", [go.R, w])
+        ops.gemm(gy, b.c3.wd, go.R, w, cout, mask_src=a2, out=d_a2)
+        # conv2 (3x3)
+        d_a1 = ws.get(k + ".d_a1", [g.R, w])
+        if b.stride == 1:
+            sh = g.shifts()
+            self.wgrad_conv(b.c2, d_a2, a1, g.R, key=k + ".c2", b_offsets=sh)
+            ops.gemm(d_a2, b.c2.wd, g.R, w, w, taps=[(s, t * w) for t, s in enumerate(sh)], mask_src=a1, out=d_a1)
+        else:
+            so = go.s2_offsets()
+            self.wgrad_conv(b.c2, d_a2, a1s, go.R, key=k + ".c2", b_offsets=[p * go.R + o for p, o in so])
+            dxs = ws.get(k + ".dxs", [4 * go.R, w])
+            for P in range(4):
+                taps = [(-o, (8 - t) * w) for t, (p, o) in enumerate(so) if p == P]
+                ops.gemm(d_a2, b.c2.wd, go.R, w, w, taps=taps, out=dxs[P * go.R:(P + 1) * go.R])
+            ops.parity_merge(dxs, None, a1, d_a1, g.B, g.H, g.W, w, go.H, go.W)
+        # conv1 (1x1) and the identity path
+        self.wgrad_conv(b.c1, d_a1, x, g.R)
+        if b.ds is not None and b.stride == 2:
+            self.wgrad_conv(b.ds, gy, xs, go.R, b_offsets=[3 * go.R - go.Wp - 1])
+        elif b.ds is not None:
+            self.wgrad_conv(b.ds, gy, x, go.R)
+        if not b.need_gx:
+            return None
+        gx = ws.get(k + ".gx", [g.R, cin])
+        if b.ds is None:
+            ops.gemm(d_a1, b.c1.wd, g.R, cin, w, res=gy, mask_src=x, out=gx)
+        elif b.stride == 1:
+            t = ws.get(k + ".t", [g.R, cin])
+            ops.gemm(gy, b.ds.wd, g.R, cin, cout, res=g_extra, out=t)
+            ops.gemm(d_a1, b.c1.wd, g.R, cin, w, res=t, mask_src=x, out=gx)
+        else:
+            t = ws.get(k + ".t", [g.R, cin])
+            ops.gemm(d_a1, b.c1.wd, g.R, cin, w, res=g_extra, out=t)
+            dxs2 = ws.get(k + ".dxs_ds", [4 * go.R, cin], zero=True)  # planes 0..2 stay zero: the 1x1/s2 conv reads plane 3 only
+            ops.gemm(gy, b.ds.wd, go.R, cin, cout, taps=[(go.Wp + 1, 0)], out=dxs2[3 * go.R:])
+            ops.parity_merge(dxs2, t, x, gx, g.B, g.H, g.W, cin, go.H, go.W)
+        return gx
+
+    def _backbone_fwd(self, img):
+        ws = self.ws
+        B, _, H, W = img.shape
+        H1, W1 = (H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1
+        H2, W2 = (H1 + 2 - 3) // 2 + 1, (W1 + 2 - 3) // 2 + 1
+        col = ws.get("stem.col", [B * H1 * W1, 160])
+        ops.stem_im2col(img, col, B, H, W, H1, W1)
+        c1 = ws.get("stem.out", [B * H1 * W1, 64])
+        ops.gemm(col, self.stem.wf, B * H1 * W1, 64, 160, bias=self.stem.bias, relu=True, out=c1)
+        g = Grid(B, H2, W2)
+        x = ws.get("stem.pool", [g.R, 64])
+        ops.maxpool_3x3s2(c1, x, B, H1, W1, 64, H2, W2)
+        feats = {}
+        for b in self.blocks:
+            x, g = self._block_fwd(b, x, g)
+            if b.layer_end:
+                feats[b.layer] = (x, g)
+        return feats
+
+    def _backbone_bwd(self, gy, g_fpn):
+        """gy: masked gradient at the C5 output; g_fpn: {layer: unmasked bf16 gradient added at that layer's output}."""
+        for b in reversed(self.blocks):
+            if not b.trainable:
+                break
+            # a gradient arriving at a layer's output from the FPN adapters is injected where the NEXT layer's first
+            # block forms its input gradient; that block is processed before this one, so look it up by layer index
+            g_extra = g_fpn.get(b.layer - 1) if (b.ds is not None and b.need_gx) else None
+            gy = self._block_bwd(b, gy, g_extra)
+            if gy is None:
+                break
+
+    # ------------------------------------------------------------------------------------------------------------
+    # small fused pieces
+    # ------------------------------------------------------------------------------------------------------------
+    def _mlp_map_fwd(self, key, packs, seq, A, rows, K, *, y32, yb=None, ypb=None, pos32=None, rowmap=(0, 0, 0)):
+        """mlp_mapping (reftr_transformer.py:14-23): Linear -> LN -> ReLU -> [Dropout] -> Linear -> LN -> ReLU."""
+        ws = self.ws
+        y0 = ws.get(key + ".y0", [rows, D], torch.float32)
+        ops.gemm(A, packs[0].wb, rows, D, K, bias=packs[0].bias, out32=y0)
+        a1 = ws.get(key + ".a1", [rows, D], torch.float32)
+        a1b = ws.get(key + ".a1b", [rows, D])
+        m0, r0 = ws.get(key + ".m0", [rows], torch.float32), ws.get(key + ".r0", [rows], torch.float32)
+        ops.layernorm_fwd(y0, seq[1].weight, seq[1].bias, rows, y32=a1, yb=a1b, relu=True, mean=m0, rstd=r0, eps=seq[1].eps)
+        y1 = ws.get(key + ".y1", [rows, D], torch.float32)
+        ops.gemm(a1b, packs[1].wb, rows, D, D, bias=packs[1].bias, out32=y1)
+        m1, r1 = ws.get(key + ".m1", [rows], torch.float32), ws.get(key + ".r1", [rows], torch.float32)
+        ops.layernorm_fwd(y1, seq[5].weight, seq[5].bias, rows, y32=y32, yb=yb, pos32=pos32, ypb=ypb, relu=True, mean=m1, rstd=r1,
+                          rowmap=rowmap, eps=seq[5].eps)
+        self.saved[key] = (A, rows, K, y0, a1, a1b, m0, r0, y1, m1, r1, y32, rowmap)
+
+    def _mlp_map_bwd(self, key, packs, seq, dy, *, need_dA=True):
+        """dy: fp32 gradient w.r.t. the MLP output (read at the rows the forward wrote).  Returns fp32 dA [rows, K]."""
+        ws = self.ws
+        A, rows, K, y0, a1, a1b, m0, r0, y1, m1, r1, y32, rowmap = self.saved[key]
+        d1 = ws.get(key + ".d1", [rows, D], torch.float32)
+        d1b = ws.get(key + ".d1b", [rows, D])
+        ops.layernorm_bwd(dy, y1, seq[5].weight, m1, r1, rows, y_relu=y32, dx32=d1, dxb=d1b, dgamma=self.G(seq[5].weight),
+                          dbeta=self.G(seq[5].bias), rowmap=rowmap)
+        ops.colsum(d1, self.G(seq[4].bias))
+        self.wgrad_linear(d1b, a1b, self.G(seq[4].weight), D, D, rows)
+        da1 = ws.get(key + ".da1", [rows, D], torch.float32)
+        ops.gemm(d1b, packs[1].wt, rows, D, D, out32=da1)
+        d0 = ws.get(key + ".d0", [rows, D], torch.float32)
+        d0b = ws.get(key + ".d0b", [rows, D])
+        ops.layernorm_bwd(da1, y0, seq[1].weight, m0, r0, rows, y_relu=a1, dx32=d0, dxb=d0b, dgamma=self.G(seq[1].weight),
+                          dbeta=self.G(seq[1].bias))
+        ops.colsum(d0, self.G(seq[0].bias))
+        self.wgrad_linear(d0b, A, self.G(seq[0].weight), D, K, rows)
+        if not need_dA:
+            return None
+        dA = ws.get(key + ".dA", [rows, K], torch.float32)
+        ops.gemm(d0b, packs[0].wt, rows, K, D, out32=dA)
+        return dA
+
+    # ------------------------------------------------------------------------------------------------------------
+    # encoder layer (transformer.py:168-181)
+    # ------------------------------------------------------------------------------------------------------------
+    def _enc_fwd(self, l, e, x32, xb, xpb, kpm, pos32, B, S):
+        ws = self.ws
+        rows = B * S
+        k = f"enc{l}"
+        lay = e.mod
+        qkv = ws.get(k + ".qkv", [rows, 3 * D])
+        ops.gemm(xpb, e.inp.wb[:2 * D], rows, 2 * D, D, bias=e.inp.bias[:2 * D], out=qkv[:, :2 * D])
+        ops.gemm(xb, e.inp.wb[2 * D:], rows, D, D, bias=e.inp.bias[2 * D:], out=qkv[:, 2 * D:])
+        o = ws.get(k + ".o", [rows, D])
+        lse = ws.get(k + ".lse", [B, NH, S], torch.float32)
+        ops.attn_fwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], kpm, o, lse, B, NH, S, S, DH ** -0.5)
+        y1 = ws.get(k + ".y1", [rows, D], torch.float32)
+        ops.gemm(o, e.out.wb, rows, D, D, bias=e.out.bias, res32=x32, out32=y1)
+        x1 = ws.get(k + ".x1", [rows, D], torch.float32)
+        x1b = ws.get(k + ".x1b", [rows, D])
+        m1, r1 = ws.get(k + ".m1", [rows], torch.float32), ws.get(k + ".r1", [rows], torch.float32)
+        ops.layernorm_fwd(y1, lay.norm1.weight, lay.norm1.bias, rows, y32=x1, yb=x1b, mean=m1, rstd=r1, eps=lay.norm1.eps)
+        dff = e.l1.N
+        h = ws.get(k + ".h", [rows, dff])
+        ops.gemm(x1b, e.l1.wb, rows, dff, D, bias=e.l1.bias, relu=True, out=h)
+        y2 = ws.get(k + ".y2", [rows, D], torch.float32)
+        ops.gemm(h, e.l2.wb, rows, D, dff, bias=e.l2.bias, res32=x1, out32=y2)
+        xo = ws.get(k + ".xo", [rows, D], torch.float32)
+        xob = ws.get(k + ".xob", [rows, D])
+        xopb = ws.get(k + ".xopb", [rows, D])
+        m2, r2 = ws.get(k + ".m2", [rows], torch.float32), ws.get(k + ".r2", [rows], torch.float32)
+        ops.layernorm_fwd(y2, lay.norm2.weight, lay.norm2.bias, rows, y32=xo, yb=xob, pos32=pos32, ypb=xopb, mean=m2, rstd=r2,
+                          eps=lay.norm2.eps)
+        self.saved[k] = (xb, xpb, qkv, o, lse, y1, m1, r1, x1b, h, y2, m2, r2)
+        return xo, xob, xopb
+
+    def _ffn_bwd(self, key, lin1, lin2, mod, dy32, dyb, x_in_b, h, rows, out32):
+        """Shared by encoder and decoder: given dy (= gradient at the FFN's residual sum, fp32 + bf16), accumulates the
+        weight/bias gradients of linear1/linear2 and writes out32 = dy + d(FFN input)."""
+        ws = self.ws
+        dff = lin1.N
+        ops.colsum(dy32, self.G(mod.linear2.bias))
+        self.wgrad_linear(dyb, h, self.G(mod.linear2.weight), D, dff, rows)
+        dh = ws.get(key + ".dh", [rows, dff])
+        ops.gemm(dyb, lin2.wt, rows, dff, D, mask_src=h, out=dh)
+        ops.colsum(dh, self.G(mod.linear1.bias))
+        self.wgrad_linear(dh, x_in_b, self.G(mod.linear1.weight), dff, D, rows)
+        ops.gemm(dh, lin1.wt, rows, D, dff, res32=dy32, out32=out32)
+
+    def _enc_bwd(self, l, e, g, g_out, kpm, dpos, B, S):
+        """g: fp32 gradient w.r.t. the layer output; writes g_out = gradient w.r.t. the layer input; dpos += d(pos)."""
+        ws = self.ws
+        rows = B * S
+        k = f"enc{l}"
+        lay = e.mod
+        xb, xpb, qkv, o, lse, y1, m1, r1, x1b, h, y2, m2, r2 = self.saved[k]
+        dy2 = ws.get("encb.dy2", [rows, D], torch.float32)
+        dy2b = ws.get("encb.dy2b", [rows, D])
+        ops.layernorm_bwd(g, y2, lay.norm2.weight, m2, r2, rows, dx32=dy2, dxb=dy2b, dgamma=self.G(lay.norm2.weight),
+                          dbeta=self.G(lay.norm2.bias))
+        g1 = ws.get("encb.g1", [rows, D], torch.float32)
+        self._ffn_bwd("encb", e.l1, e.l2, lay, dy2, dy2b, x1b, h, rows, g1)
+        dy1 = ws.get("encb.dy1", [rows, D], torch.float32)
+        dy1b = ws.get("encb.dy1b", [rows, D])
+        ops.layernorm_bwd(g1, y1, lay.norm1.weight, m1, r1, rows, dx32=dy1, dxb=dy1b, dgamma=self.G(lay.norm1.weight),
+                          dbeta=self.G(lay.norm1.bias))
+        ops.colsum(dy1, self.G(lay.self_attn.out_proj.bias))
+        self.wgrad_linear(dy1b, o, self.G(lay.self_attn.out_proj.weight), D, D, rows)
+        do = ws.get("encb.do", [rows, D])
+        ops.gemm(dy1b, e.out.wt, rows, D, D, out=do)
+        dqkv = ws.get("encb.dqkv", [rows, 3 * D])
+        dbuf = ws.get("encb.dbuf", [B, NH, S], torch.float32)
+        ops.attn_bwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], kpm, o, do, lse, dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:], dbuf,
+                     B, NH, S, S, DH ** -0.5)
+        ops.colsum(dqkv, self.G(lay.self_attn.in_proj_bias))
+        gw = self.G(lay.self_attn.in_proj_weight)
+        self.wgrad_linear(dqkv[:, :2 * D], xpb, gw[:2 * D], 2 * D, D, rows)
+        self.wgrad_linear(dqkv[:, 2 * D:], xb, gw[2 * D:], D, D, rows)
+        ops.gemm(dqkv, e.inp.wt, rows, D, 3 * D, res32=dy1, out32=g_out)
+        ops.gemm(dqkv[:, :2 * D], e.inp.wt[:, :2 * D], rows, D, 2 * D, res32=dpos, out32=dpos)
+
+    # ------------------------------------------------------------------------------------------------------------
+    # query encoder (reftr_transformer.py:41-66)
+    # ------------------------------------------------------------------------------------------------------------
+    def _qenc_fwd(self, mem32, ph32, mctx, B, S, L, n_ph, n_q):
+        ws = self.ws
+        qe = self.model.query_encoder
+        rl, rp, T = B * L, B * n_ph, n_ph * n_q
+        ctx32 = ws.get("qe.ctx32", [rl, D], torch.float32)
+        ctxb = ws.get("qe.ctxb", [rl, D])
+        ops.rows_add(mem32, None, rl, D, y32=ctx32, yb=ctxb, map_a=(L, S, 1, 0))
+        cls_b = ctxb.view(B, L * D)[:, :D]  # post-encoder CLS token of every sample
+        k32 = ws.get("qe.k32", [B, D], torch.float32)
+        q32 = ws.get("qe.q32", [rl, D], torch.float32)
+        v32 = ws.get("qe.v32", [rl, D], torch.float32)
+        ops.gemm(cls_b, self.qe_lin[0].wb, B, D, D, bias=self.qe_lin[0].bias, out32=k32)
+        ops.gemm(ctxb, self.qe_lin[1].wb, rl, D, D, bias=self.qe_lin[1].bias, out32=q32)
+        ops.gemm(ctxb, self.qe_lin[2].wb, rl, D, D, bias=self.qe_lin[2].bias, out32=v32)
+        att = ws.get("qe.att", [B, n_ph, L], torch.float32)
+        c32 = ws.get("qe.c32", [rp, D], torch.float32)
+        ops.qenc_pool_fwd(k32, q32, v32, mctx, B, L, n_ph, att, c32)
+        cb = ws.get("qe.cb", [rp, D])
+        ops.cast_bf16(c32, cb)
+        co32 = ws.get("qe.co32", [rp, D], torch.float32)
+        ops.gemm(cb, self.qe_cout.wb, rp, D, D, bias=self.qe_cout.bias, out32=co32)
+        cn32 = ws.get("qe.cn32", [rp, D], torch.float32)
+        mc, rc = ws.get("qe.mc", [rp], torch.float32), ws.get("qe.rc", [rp], torch.float32)
+        ln = qe.context_out[1]
+        ops.layernorm_fwd(co32, ln.weight, ln.bias, rp, y32=cn32, mean=mc, rstd=rc, eps=ln.eps)
+        fin = ws.get("qe.fin", [rp, 2 * D])
+        ops.rows_add(cn32, mem32, rp, D, yb=fin[:, :D], map_b=(n_ph, S, 0, 0))   # + memory CLS token (residual, :58)
+        ops.rows_add(ph32, None, rp, D, yb=fin[:, D:])                            # cat([context, phrase]) (:60)
+        f32 = ws.get("qe.f32", [rp, D], torch.float32)
+        self._mlp_map_fwd("qe.fuse", self.qe_fuse, qe.fuse_encoder_query, fin, rp, 2 * D, y32=f32)
+        rt = B * T
+        tgt32 = ws.get("qe.tgt32", [rt, D], torch.float32)
+        tgtb = ws.get("qe.tgtb", [rt, D])
+        qpos32 = ws.get("qe.qpos32", [rt, D], torch.float32)
+        tqb = ws.get("qe.tqb", [rt, D])
+        qw = qe.query_embed.weight
+        ops.rows_add(f32, qw[:, :D], rt, D, y32=tgt32, yb=tgtb, map_a=(n_q, 1, 0, 0), map_b=(n_q, 0, 1, 0))
+        ops.rows_add(f32, qw[:, D:], rt, D, y32=qpos32, map_a=(n_q, 1, 0, 0), map_b=(n_q, 0, 1, 0))
+        ops.rows_add(tgt32, qpos32, rt, D, yb=tqb)
+        self.saved["qe"] = (ctxb, cls_b, k32, q32, v32, att, cb, co32, mc, rc, f32)
+        return tgt32, tgtb, qpos32, tqb
+
+    def _qenc_bwd(self, d_tgt, d_qpos, g_mem, mctx, B, S, L, n_ph, n_q):
+        """Adds the query encoder's gradient into g_mem (language rows) and returns fp32 d(phrase feats) [B*n_ph, 256]."""
+        ws = self.ws
+        qe = self.model.query_encoder
+        rl, rp, T = B * L, B * n_ph, n_ph * n_q
+        rt = B * T
+        ctxb, cls_b, k32, q32, v32, att, cb, co32, mc, rc, f32 = self.saved["qe"]
+        d_f = ws.get("qeb.d_f", [rp, D], torch.float32)
+        d_f.zero_()
+        ops.rows_scatter_add(d_tgt, d_f, rt, D, map_dst=(n_q, 1, 0, 0))
+        ops.rows_scatter_add(d_qpos, d_f, rt, D, map_dst=(n_q, 1, 0, 0))
+        gq = self.G(qe.query_embed.weight)
+        ops.rows_scatter_add(d_tgt, gq[:, :D], rt, D, map_dst=(n_q, 0, 1, 0))
+        ops.rows_scatter_add(d_qpos, gq[:, D:], rt, D, map_dst=(n_q, 0, 1, 0))
+        d_fin = self._mlp_map_bwd("qe.fuse", self.qe_fuse, qe.fuse_encoder_query, d_f)  # fp32 [rp, 512]
+        d_left = ws.get("qeb.d_left", [rp, D], torch.float32)
+        d_ph = ws.get("qeb.d_ph", [rp, D], torch.float32)
+        ops.rows_add(d_fin[:, :D], None, rp, D, y32=d_left)
+        ops.rows_add(d_fin[:, D:], None, rp, D, y32=d_ph)
+        ops.rows_scatter_add(d_left, g_mem, rp, D, map_dst=(n_ph, S, 0, 0))  # residual to the memory CLS token
+        ln = qe.context_out[1]
+        d_co = ws.get("qeb.d_co", [rp, D], torch.float32)
+        d_cob = ws.get("qeb.d_cob", [rp, D])
+        ops.layernorm_bwd(d_left, co32, ln.weight, mc, rc, rp, dx32=d_co, dxb=d_cob, dgamma=self.G(ln.weight), dbeta=self.G(ln.bias))
+        ops.colsum(d_co, self.G(qe.context_out[0].bias))
+        self.wgrad_linear(d_cob, cb, self.G(qe.context_out[0].weight), D, D, rp)
+        d_c = ws.get("qeb.d_c", [rp, D], torch.float32)
+        ops.gemm(d_cob, self.qe_cout.wt, rp, D, D, out32=d_c)
+        dk = ws.get("qeb.dk", [B, D], torch.float32)
+        dq = ws.get("qeb.dq", [rl, D], torch.float32)
+        dv = ws.get("qeb.dv", [rl, D], torch.float32)
+        ops.qenc_pool_bwd(d_c, k32, q32, v32, att, B, L, n_ph, dk, dq, dv)
+        dkb, dqb, dvb = ws.get("qeb.dkb", [B, D]), ws.get("qeb.dqb", [rl, D]), ws.get("qeb.dvb", [rl, D])
+        ops.cast_bf16(dk, dkb)
+        ops.cast_bf16(dq, dqb)
+        ops.cast_bf16(dv, dvb)
+        for lin, mod, d32, db, x, n in ((self.qe_lin[0], qe.linear1, dk, dkb, cls_b, B), (self.qe_lin[1], qe.linear2, dq, dqb, ctxb, rl),
+                                        (self.qe_lin[2], qe.linear3, dv, dvb, ctxb, rl)):
+            ops.colsum(d32, self.G(mod.bias))
+            self.wgrad_linear(db, x, self.G(mod.weight), D, D, n)
+        d_ctx = ws.get("qeb.d_ctx", [rl, D], torch.float32)
+        ops.gemm(dqb, self.qe_lin[1].wt, rl, D, D, out32=d_ctx)
+        ops.gemm(dvb, self.qe_lin[2].wt, rl, D, D, res32=d_ctx, out32=d_ctx)
+        d_cls = ws.get("qeb.d_cls", [B, D], torch.float32)
+        ops.gemm(dkb, self.qe_lin[0].wt, B, D, D, out32=d_cls)
+        ops.rows_scatter_add(d_ctx, g_mem, rl, D, map_dst=(L, S, 1, 0))
+        ops.rows_scatter_add(d_cls, g_mem, B, D, map_dst=(1, S, 0, 0))
+        return d_ph
+
+    # ------------------------------------------------------------------------------------------------------------
+    # decoder (transformer.py:114-143, :231-252)
+    # ------------------------------------------------------------------------------------------------------------
+    def _dec_fwd(self, tgt32, tgtb, qpos32, tqb, memb, mempb, kpm, qmask, B, S, T):
+        ws = self.ws
+        rows, rt = B * S, B * T
+        nl = len(self.dec)
+        vt = self.model.vl_transformer
+        kall = ws.get("dec.kall", [rows, nl * D])
+        vall = ws.get("dec.vall", [rows, nl * D])
+        ops.gemm(mempb, self.kstack.wb, rows, nl * D, D, bias=self.kstack.bias, out=kall)
+        ops.gemm(memb, self.vstack.wb, rows, nl * D, D, bias=self.vstack.bias, out=vall)
+        hs32 = ws.get("dec.hs32", [nl * rt, D], torch.float32)
+        hsb = ws.get("dec.hsb", [nl * rt, D])
+        mh, rh = ws.get("dec.mh", [nl * rt], torch.float32), ws.get("dec.rh", [nl * rt], torch.float32)
+        scale = DH ** -0.5
+        for l, d in enumerate(self.dec):
+            k = f"dec{l}"
+            lay = d.mod
+            # self attention over the T queries of a sample (key padding = query_mask)
+            qkv = ws.get(k + ".qkv", [rt, 3 * D])
+            ops.gemm(tqb, d.sa.wb[:2 * D], rt, 2 * D, D, bias=d.sa.bias[:2 * D], out=qkv[:, :2 * D])
+            ops.gemm(tgtb, d.sa.wb[2 * D:], rt, D, D, bias=d.sa.bias[2 * D:], out=qkv[:, 2 * D:])
+            o_s = ws.get(k + ".o_s", [rt, D])
+            lse_s = ws.get(k + ".lse_s", [B, NH, T], torch.float32)
+            ops.attn_fwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], qmask, o_s, lse_s, B, NH, T, T, scale)
+            y1 = ws.get(k + ".y1", [rt, D], torch.float32)
+            ops.gemm(o_s, d.sa_out.wb, rt, D, D, bias=d.sa_out.bias, res32=tgt32, out32=y1)
+            t1 = ws.get(k + ".t1", [rt, D], torch.float32)
+            t1qb = ws.get(k + ".t1qb", [rt, D])
+            m1, r1 = ws.get(k + ".m1", [rt], torch.float32), ws.get(k + ".r1", [rt], torch.float32)
+            ops.layernorm_fwd(y1, lay.norm1.weight, lay.norm1.bias, rt, y32=t1, pos32=qpos32, ypb=t1qb, mean=m1, rstd=r1, eps=lay.norm1.eps)
+            # cross attention: q = t1 + query_pos, k = memory + pos, v = memory
+            qc = ws.get(k + ".qc", [rt, D])
+            ops.gemm(t1qb, d.ca.wb[:D], rt, D, D, bias=d.ca.bias[:D], out=qc)
+            kl, vl = kall[:, l * D:(l + 1) * D], vall[:, l * D:(l + 1) * D]
+            o_c = ws.get(k + ".o_c", [rt, D])
+            lse_c = ws.get(k + ".lse_c", [B, NH, T], torch.float32)
+            ops.attn_fwd(qc, kl, vl, kpm, o_c, lse_c, B, NH, T, S, scale)
+            y2 = ws.get(k + ".y2", [rt, D], torch.float32)
+            ops.gemm(o_c, d.ca_out.wb, rt, D, D, bias=d.ca_out.bias, res32=t1, out32=y2)
+            t2 = ws.get(k + ".t2", [rt, D], torch.float32)
+            t2b = ws.get(k + ".t2b", [rt, D])
+            m2, r2 = ws.get(k + ".m2", [rt], torch.float32), ws.get(k + ".r2", [rt], torch.float32)
+            ops.layernorm_fwd(y2, lay.norm2.weight, lay.norm2.bias, rt, y32=t2, yb=t2b, mean=m2, rstd=r2, eps=lay.norm2.eps)
+            dff = d.l1.N
+            h = ws.get(k + ".h", [rt, dff])
+            ops.gemm(t2b, d.l1.wb, rt, dff, D, bias=d.l1.bias, relu=True, out=h)
+            y3 = ws.get(k + ".y3", [rt, D], torch.float32)
+            ops.gemm(h, d.l2.wb, rt, D, dff, bias=d.l2.bias, res32=t2, out32=y3)
+            t3 = ws.get(k + ".t3", [rt, D], torch.float32)
+            t3b = ws.get(k + ".t3b", [rt, D])
+            t3qb = ws.get(k + ".t3qb", [rt, D])
+            m3, r3 = ws.get(k + ".m3", [rt], torch.float32), ws.get(k + ".r3", [rt], torch.float32)
+            ops.layernorm_fwd(y3, lay.norm3.weight, lay.norm3.bias, rt, y32=t3, yb=t3b, pos32=qpos32, ypb=t3qb, mean=m3, rstd=r3,
+                              eps=lay.norm3.eps)
+            # shared final LayerNorm on every layer's output (return_intermediate, transformer.py:131-138)
+            sl = slice(l * rt, (l + 1) * rt)
+            ops.layernorm_fwd(t3, vt.decoder.norm.weight, vt.decoder.norm.bias, rt, y32=hs32[sl], yb=hsb[sl], mean=mh[sl], rstd=rh[sl],
+                              eps=vt.decoder.norm.eps)
+            self.saved[k] = (tgtb, tqb, qkv, o_s, lse_s, y1, m1, r1, t1qb, qc, o_c, lse_c, y2, m2, r2, t2b, h, y3, m3, r3, t3)
+            tgt32, tgtb, tqb = t3, t3b, t3qb
+        self.saved["dec"] = (kall, vall, mh, rh)
+        return hs32, hsb
+
+    def _dec_bwd(self, d_hs, memb, mempb, kpm, qmask, g_mem, dpos, B, S, T):
+        """d_hs: fp32 [nl*B*T, 256].  Writes g_mem (= d memory from the cross-attention V path + K path) and dpos
+        (= K path only); returns (d_tgt0, d_qpos) fp32 [B*T, 256]."""
+        ws = self.ws
+        rows, rt = B * S, B * T
+        nl = len(self.dec)
+        vt = self.model.vl_transformer
+        kall, vall, mh, rh = self.saved["dec"]
+        dkall = ws.get("decb.dkall", [rows, nl * D])
+        dvall = ws.get("decb.dvall", [rows, nl * D])
+        dqpos = ws.get("decb.dqpos", [rt, D], torch.float32)
+        dqpos.zero_()
+        gbuf = [ws.get("decb.gA", [rt, D], torch.float32), ws.get("decb.gB", [rt, D], torch.float32)]
+        g_next = None
+        scale = DH ** -0.5
+        for l in reversed(range(nl)):
+            d = self.dec[l]
+            k = f"dec{l}"
+            lay = d.mod
+            tgtb, tqb, qkv, o_s, lse_s, y1, m1, r1, t1qb, qc, o_c, lse_c, y2, m2, r2, t2b, h, y3, m3, r3, t3 = self.saved[k]
+            sl = slice(l * rt, (l + 1) * rt)
+            gh = ws.get("decb.gh", [rt, D], torch.float32)
+            ops.layernorm_bwd(d_hs[sl], t3, vt.decoder.norm.weight, mh[sl], rh[sl], rt, dx32=gh, dgamma=self.G(vt.decoder.norm.weight),
+                              dbeta=self.G(vt.decoder.norm.bias))
+            dy3 = ws.get("decb.dy3", [rt, D], torch.float32)
+            dy3b = ws.get("decb.dy3b", [rt, D])
+            ops.layernorm_bwd(gh, y3, lay.norm3.weight, m3, r3, rt, dy2=g_next, dx32=dy3, dxb=dy3b, dgamma=self.G(lay.norm3.weight),
+                              dbeta=self.G(lay.norm3.bias))
+            g2 = ws.get("decb.g2", [rt, D], torch.float32)
+            self._ffn_bwd("decb", d.l1, d.l2, lay, dy3, dy3b, t2b, h, rt, g2)
+            dy2 = ws.get("decb.dy2", [rt, D], torch.float32)
+            dy2b = ws.get("decb.dy2b", [rt, D])
+            ops.layernorm_bwd(g2, y2, lay.norm2.weight, m2, r2, rt, dx32=dy2, dxb=dy2b, dgamma=self.G(lay.norm2.weight),
+                              dbeta=self.G(lay.norm2.bias))
+            # cross attention
+            ops.colsum(dy2, self.G(lay.multihead_attn.out_proj.bias))
+            self.wgrad_linear(dy2b, o_c, self.G(lay.multihead_attn.out_proj.weight), D, D, rt)
+            do_c = ws.get("decb.do_c", [rt, D])
+            ops.gemm(dy2b, d.ca_out.wt, rt, D, D, out=do_c)
+            dqc = ws.get("decb.dqc", [rt, D])
+            dbuf = ws.get("decb.dbuf", [B, NH, T], torch.float32)
+            cs = slice(l * D, (l + 1) * D)
+            ops.attn_bwd(qc, kall[:, cs], vall[:, cs], kpm, o_c, do_c, lse_c, dqc, dkall[:, cs], dvall[:, cs], dbuf, B, NH, T, S, scale)
+            gw = self.G(lay.multihead_attn.in_proj_weight)
+            gb = self.G(lay.multihead_attn.in_proj_bias)
+            ops.colsum(dqc, gb[:D])
+            ops.colsum(dkall[:, cs], gb[D:2 * D])
+            ops.colsum(dvall[:, cs], gb[2 * D:])
+            self.wgrad_linear(dqc, t1qb, gw[:D], D, D, rt)
+            self.wgrad_linear(dkall[:, cs], mempb, gw[D:2 * D], D, D, rows)
+            self.wgrad_linear(dvall[:, cs], memb, gw[2 * D:], D, D, rows)
+            g1 = ws.get("decb.g1", [rt, D], torch.float32)
+            ops.gemm(dqc, d.ca.wt[:, :D], rt, D, D, res32=dy2, out32=g1)
+            ops.gemm(dqc, d.ca.wt[:, :D], rt, D, D, res32=dqpos, out32=dqpos)
+            dy1 = ws.get("decb.dy1", [rt, D], torch.float32)
+            dy1b = ws.get("decb.dy1b", [rt, D])
+            ops.layernorm_bwd(g1, y1, lay.norm1.weight, m1, r1, rt, dx32=dy1, dxb=dy1b, dgamma=self.G(lay.norm1.weight),
+                              dbeta=self.G(lay.norm1.bias))
+            # self attention
+            ops.colsum(dy1, self.G(lay.self_attn.out_proj.bias))
+            self.wgrad_linear(dy1b, o_s, self.G(lay.self_attn.out_proj.weight), D, D, rt)
+            do_s = ws.get("decb.do_s", [rt, D])
+            ops.gemm(dy1b, d.sa_out.wt, rt, D, D, out=do_s)
+            dqkv = ws.get("decb.dqkv", [rt, 3 * D])
+            ops.attn_bwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], qmask, o_s, do_s, lse_s, dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:],
+                         dbuf, B, NH, T, T, scale)
+            ops.colsum(dqkv, self.G(lay.self_attn.in_proj_bias))
+            gws = self.G(lay.self_attn.in_proj_weight)
+            self.wgrad_linear(dqkv[:, :2 * D], tqb, gws[:2 * D], 2 * D, D, rt)
+            self.wgrad_linear(dqkv[:, 2 * D:], tgtb, gws[2 * D:], D, D, rt)
+            g_prev = gbuf[l & 1]
+            ops.gemm(dqkv, d.sa.wt, rt, D, 3 * D, res32=dy1, out32=g_prev)
+            ops.gemm(dqkv[:, :2 * D], d.sa.wt[:, :2 * D], rt, D, 2 * D, res32=dqpos, out32=dqpos)
+            g_next = g_prev
+        # memory gradient of all layers' K / V projections in two GEMMs (K = nl*256)
+        ops.gemm(dkall, self.kstack.wt, rows, D, nl * D, out32=dpos)
+        ops.gemm(dvall, self.vstack.wt, rows, D, nl * D, res32=dpos, out32=g_mem)
+        return g_next, dqpos
+
+    # ------------------------------------------------------------------------------------------------------------
+    # top level
+    # ------------------------------------------------------------------------------------------------------------
+    def forward(self, img, img_mask, sent_mask, mask_context, query_mask, n_ph, want_seg, sent_feat, pooled):
+        """All tensor arguments are static workspace buffers staged by ``run_forward`` (fp32 image, bool image mask,
+        int64 sentence mask, u8 context / query masks, fp32 BERT features)."""
+        m = self.model
+        ws = self.ws
+        self.saved = {}
+        vt = m.vl_transformer
+        B, _, H, W = img.shape
+        L = sent_feat.shape[1]
+        n_q = m.num_queries_per_phrase
+        T = n_ph * n_q
+        if L > vt.max_lang_seq:
+            raise ValueError(f"sentence length {L} exceeds max_lang_seq {vt.max_lang_seq} (reftr.py:81)")
+        # ---- backbone (backbone.py:101-109) ---------------------------------------------------------------------
+        feats = self._backbone_fwd(img)
+        c5, g5 = feats[4]
+        h, w = g5.H, g5.W
+        S = L + h * w
+        rows = B * S
+        # ---- positions + key-padding mask (position_encoding.py:36-56, reftr.py:57-97) ---------------------------
+        pos32 = ws.get("pos32", [rows, D], torch.float32)
+        kpm = ws.get("kpm", [B, S], torch.uint8)
+        ops.build_pos_mask(img_mask, B, H, W, h, w, sent_mask, L, vt.lang_pos_embeddings.weight, vt.token_type_embeddings.weight,
+                           vt.level_embed, pos32, kpm)
+        mctx, qmask = mask_context, query_mask
+        # ---- input_proj + GroupNorm -> visual token rows (reftr_transformer.py:172-175, reftr.py:57) --------------
+        proj32 = ws.get("iproj.out", [g5.R, D], torch.float32)
+        ops.gemm(c5, self.iproj.wf, g5.R, D, 2048, bias=self.iproj.bias, out32=proj32)
+        x32 = ws.get("enc.x0", [rows, D], torch.float32)
+        xb = ws.get("enc.x0b", [rows, D])
+        xpb = ws.get("enc.x0pb", [rows, D])
+        gn = m.input_proj[0][1]
+        gmean, grstd = ws.get("iproj.mean", [B * 32], torch.float32), ws.get("iproj.rstd", [B * 32], torch.float32)
+        ops.groupnorm_tokens_fwd(proj32, gn.weight, gn.bias, B, h, w, S, L, x32, xb, pos32, xpb, gmean, grstd, eps=gn.eps)
+        # ---- language features -> language token rows (reftr_transformer.py:201, reftr.py:79-97) -------------------
+        sfb = ws.get("lang.sfb", [B * L, sent_feat.shape[-1]])
+        ops.cast_bf16(sent_feat.view(B * L, -1), sfb)
+        self._mlp_map_fwd("map_sentence", self.map_sentence, m.map_sentence, sfb, B * L, sfb.shape[1], y32=x32, yb=xb, ypb=xpb,
+                          pos32=pos32, rowmap=(L, S, 0))
+        plb = ws.get("lang.plb", [B * n_ph, pooled.shape[-1]])
+        ops.cast_bf16(pooled.view(B * n_ph, -1), plb)
+        ph32 = ws.get("lang.ph32", [B * n_ph, D], torch.float32)
+        self._mlp_map_fwd("map_phrase", self.map_phrase, m.map_phrase, plb, B * n_ph, plb.shape[1], y32=ph32)
+        # ---- encoder ------------------------------------------------------------------------------------------------
+        for l, e in enumerate(self.enc):
+            x32, xb, xpb = self._enc_fwd(l, e, x32, xb, xpb, kpm, pos32, B, S)
+        mem32, memb, mempb = x32, xb, xpb
+        # ---- query encoder + decoder + box head -------------------------------------------------------------------------
+        tgt32, tgtb, qpos32, tqb = self._qenc_fwd(mem32, ph32, mctx, B, S, L, n_ph, n_q)
+        hs32, hsb = self._dec_fwd(tgt32, tgtb, qpos32, tqb, memb, mempb, kpm, qmask, B, S, T)
+        nl = len(self.dec)
+        rh = nl * B * T
+        z0 = ws.get("bbox.z0", [rh, D])
+        z1 = ws.get("bbox.z1", [rh, D])
+        logits = ws.get("bbox.logits", [rh, 64], torch.float32)
+        ops.gemm(hsb, self.bbox[0].wb, rh, D, D, bias=self.bbox[0].bias, relu=True, out=z0)
+        ops.gemm(z0, self.bbox[1].wb, rh, D, D, bias=self.bbox[1].bias, relu=True, out=z1)
+        ops.gemm(z1, self.bbox[2].wb, rh, 64, D, bias=self.bbox[2].bias, out32=logits)
+        self.dims = (B, H, W, h, w, L, S, T, n_ph, n_q)
+        self.saved["top"] = (feats, c5, g5, pos32, kpm, mctx, qmask, proj32, gmean, grstd, mem32, memb, mempb, hs32, hsb, z0, z1)
+        outs = [logits[:, :4].reshape(nl, B, n_ph, n_q, 4)]
+        if want_seg:
+            outs += self.seghead.forward(feats, proj32, mem32, memb, hs32, hsb, kpm, B, h, w, L, S, T)
+        return outs
+
+    def backward(self, g_logits, g_masks=None, g_att=None):
+        """Returns (d_sent_feat [B, L, 768], d_pooled [B*n_ph, 768]); parameter gradients are left in ``self.gflat``."""
+        m = self.model
+        ws = self.ws
+        vt = m.vl_transformer
+        B, H, W, h, w, L, S, T, n_ph, n_q = self.dims
+        feats, c5, g5, pos32, kpm, mctx, qmask, proj32, gmean, grstd, mem32, memb, mempb, hs32, hsb, z0, z1 = self.saved["top"]
+        rows, rt = B * S, B * T
+        nl = len(self.dec)
+        rh = nl * rt
+        self.gflat.zero_()
+        # ---- box head (backbone.py:35-38) ---------------------------------------------------------------------------------
+        bl = m.bbox_embed.layers
+        gl = ws.get("bboxb.gl", [rh, 64], torch.float32, zero=True)
+        gl[:, :4].copy_(g_logits.reshape(rh, 4))
+        glb = ws.get("bboxb.glb", [rh, 64])
+        ops.cast_bf16(gl, glb)
+        ops.colsum(gl, self.G(bl[2].bias), rows=rh, N=4)
+        self.wgrad_linear(glb, z1, self.G(bl[2].weight), 4, D, rh)
+        dz1 = ws.get("bboxb.dz1", [rh, D])
+        ops.gemm(glb, self.bbox[2].wt, rh, D, 64, mask_src=z1, out=dz1)
+        ops.colsum(dz1, self.G(bl[1].bias))
+        self.wgrad_linear(dz1, z0, self.G(bl[1].weight), D, D, rh)
+        dz0 = ws.get("bboxb.dz0", [rh, D])
+        ops.gemm(dz1, self.bbox[1].wt, rh, D, D, mask_src=z0, out=dz0)
+        ops.colsum(dz0, self.G(bl[0].bias))
+        self.wgrad_linear(dz0, hsb, self.G(bl[0].weight), D, D, rh)
+        d_hs = ws.get("bboxb.d_hs", [rh, D], torch.float32)
+        ops.gemm(dz0, self.bbox[0].wt, rh, D, D, out32=d_hs)
+        g_mem = ws.get("bwd.g_mem", [rows, D], torch.float32)
+        dpos = ws.get("bwd.dpos", [rows, D], torch.float32)
+        g_fpn = {}
+        g_src = None
+        if g_masks is not None:
+            # segmentation head: adds into d_hs (last layer), returns d(memory visual rows), d(input_proj out), FPN grads
+            g_mem_seg, g_src, g_fpn = self.seghead.backward(g_masks, g_att, d_hs)
+        # ---- decoder + query encoder ----------------------------------------------------------------------------------------
+        d_tgt, d_qpos = self._dec_bwd(d_hs, memb, mempb, kpm, qmask, g_mem, dpos, B, S, T)
+        if g_masks is not None:
+            ops.rows_add(g_mem, g_mem_seg, rows, D, y32=g_mem)
+        d_ph = self._qenc_bwd(d_tgt, d_qpos, g_mem, mctx, B, S, L, n_ph, n_q)
+        d_pooled = self._mlp_map_bwd("map_phrase", self.map_phrase, m.map_phrase, d_ph)
+        # ---- encoder --------------------------------------------------------------------------------------------------------
+        gbuf = [ws.get("bwd.gA", [rows, D], torch.float32), ws.get("bwd.gB", [rows, D], torch.float32)]
+        g = g_mem
+        for l in reversed(range(len(self.enc))):
+            g_out = gbuf[l & 1]
+            self._enc_bwd(l, self.enc[l], g, g_out, kpm, dpos, B, S)
+            g = g_out
+        ops.embed_grad(dpos, B, S, L, self.G(vt.lang_pos_embeddings.weight), self.G(vt.token_type_embeddings.weight), self.G(vt.level_embed))
+        # ---- language rows -> map_sentence; visual rows -> GroupNorm -> input_proj -> backbone ---------------------------------------
+        d_sent = self._mlp_map_bwd("map_sentence", self.map_sentence, m.map_sentence, g)
+        gn = m.input_proj[0][1]
+        dproj = ws.get("iproj.dx", [g5.R, D], zero=True)
+        ops.groupnorm_tokens_bwd(g, g_src, proj32, gn.weight, gmean, grstd, B, h, w, S, L, dproj, self.G(gn.weight), self.G(gn.bias))
+        ops.colsum(dproj, self.G(m.input_proj[0][0].bias))
+        self.wgrad_conv(self.iproj, dproj, c5, g5.R)
+        if self.blocks[-1].trainable:
+            g5y = ws.get("iproj.gc5", [g5.R, 2048])
+            ops.gemm(dproj, self.iproj.wd, g5.R, 2048, D, res=g_fpn.get(4), mask_src=c5, out=g5y)
+            self._backbone_bwd(g5y, g_fpn)
+        return d_sent.view(B, L, -1), d_pooled
+
+
+class HotPathFunction(torch.autograd.Function):
+    """The single autograd node of the hot path.  Inputs that carry gradient: BERT's sentence features and pooled
+    phrase features, and every trainable hot-path parameter (so DistributedDataParallel's hooks fire as usual)."""
+
+    @staticmethod
+    def forward(ctx, eng, img, img_mask, sent_mask, mask_context, query_mask, n_ph, want_seg, sent_feat, pooled, *params):
+        outs = eng.run_forward(img, img_mask, sent_mask, mask_context, query_mask, n_ph, want_seg, sent_feat.detach(), pooled.detach())
+        ctx.eng = eng
+        ctx.n_params = len(params)
+        ctx.want_seg = want_seg
+        ctx.step = eng.step_id
+        outs = tuple(o.clone() for o in outs)
+        return outs
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        eng = ctx.eng
+        if ctx.step != eng.step_id:
+            raise RuntimeError("reftr_b200: backward() of a stale forward (the engine keeps activations of the LAST forward only)")
+        g_logits = gouts[0]
+        g_masks = gouts[1] if ctx.want_seg else None
+        g_att = gouts[2] if ctx.want_seg else None
+        if ctx.want_seg and g_masks is None:
+            g_masks = torch.zeros_like(eng.seghead.out_masks)
+        d_sent, d_pooled, flat = eng.run_backward(g_logits, g_masks, g_att)
+        grads = []
+        for n, p in eng.named:
+            off, shape = eng.slots[n]
+            grads.append(flat[off:off + p.numel()].view(shape))
+        return (None, None, None, None, None, None, None, None, d_sent, d_pooled, *grads)

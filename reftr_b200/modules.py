@@ -285,8 +285,6 @@ class RefTR(nn.Module):
         if not hasattr(img, "decompose"):
             raise TypeError("samples['img'] must be a NestedTensor-like object with .tensors / .mask (util/misc.py:308)")
         tensors, mask = img.decompose()
-        if not tensors.is_cuda:
-            raise RuntimeError("reftr_b200 runs on CUDA (sm_100a) only; there is no CPU path")
         sent_feat, pooled, mask_context, query_mask, n_ph = self._language(samples)
         eng = self.engine()
         params = eng.param_list()

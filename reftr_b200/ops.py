@@ -8,6 +8,17 @@ from . import _lib
 from ._lib import GemmArgs, Geom
 
 
+def require_device(t):
+    """The kernels exist for sm_100a only; there is no CPU or PyTorch fallback."""
+    if not t.is_cuda:
+        raise RuntimeError("reftr_b200 runs on CUDA (sm_100a) only: got a tensor on %s" % t.device)
+    _lib.lib()
+
+
+def launch_count():
+    return _lib.LAUNCHES
+
+
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -178,3 +189,26 @@ def qenc_pool_fwd(k, q, v, mask, B, L, n_ph, att, c):
 
 def qenc_pool_bwd(dc, k, q, v, att, B, L, n_ph, dk, dq, dv):
     _lib.call("rb_qenc_pool_bwd", _p(dc), _p(k), _p(q), _p(v), _p(att), B, L, n_ph, _p(dk), _p(dq), _p(dv), _s())
+
+
+def _map(m):
+    """(group, stride, inner, offset) -> host int[4] (kept alive by the caller's frame) or NULL."""
+    if m is None:
+        return None, None
+    arr = (C.c_int * 4)(*m)
+    return arr, C.addressof(arr)
+
+
+def rows_add(a, b, rows, D, *, y32=None, yb=None, map_a=None, map_b=None, map_y=None):
+    """y[my(r), :D] = a[ma(r), :D] + b[mb(r), :D]; tensors are 2-D fp32 views (pitch = stride(0))."""
+    ka, pa = _map(map_a)
+    kb, pb = _map(map_b)
+    ky, py = _map(map_y)
+    _lib.call("rb_rows_add", _p(a), a.stride(0), pa, _p(b), b.stride(0) if b is not None else 0, pb, _p(y32),
+              y32.stride(0) if y32 is not None else 0, _p(yb), yb.stride(0) if yb is not None else 0, py, rows, D, _s())
+
+
+def rows_scatter_add(src, dst, rows, D, *, map_src=None, map_dst=None):
+    ks, ps = _map(map_src)
+    kd, pd = _map(map_dst)
+    _lib.call("rb_rows_scatter_add", _p(src), src.stride(0), ps, _p(dst), dst.stride(0), pd, rows, D, _s())

@@ -1,0 +1,415 @@
+"""TEST INFRASTRUCTURE: a plain-PyTorch (CPU) emulation of the C-ABI kernels, op for op, following the semantics stated in
+include/reftr_b200.h.  It exists so that the HOST logic of the engine (reftr_b200/engine.py: buffer wiring, tap offsets,
+backward formulas) can be checked against the oracle on a machine without a GPU (``-m "not gpu"`` suite).  It is never
+imported by the product package; ``tests/test_engine_emulated.py`` swaps it in for ``reftr_b200.ops``.
+"""
+import math
+from collections import namedtuple
+
+import torch
+import torch.nn.functional as F
+
+Geom = namedtuple("Geom", "mode Wp HpWp H W Rs")
+_LAUNCHES = [0]
+# EXACT mode: "bf16" buffers are allocated as fp32 by the test (see test_engine_emulated.py) and nothing is rounded, so the
+# engine's wiring can be checked against the oracle to ~1e-5 instead of to bf16 noise.
+EXACT = [False]
+_BF = torch.bfloat16
+
+
+def _lp():
+    return torch.float32 if EXACT[0] else _BF
+
+
+def launch_count():
+    return _LAUNCHES[0]
+
+
+def make_geom(mode=0, Wp=0, HpWp=0, H=0, W=0, Rs=0):
+    return Geom(mode, Wp, HpWp, H, W, Rs)
+
+
+def _interior(geom, rows):
+    if geom is None or geom.mode == 0:
+        return torch.ones_like(rows, dtype=torch.bool)
+    assert geom.mode == 1
+    t = rows % geom.HpWp
+    u, v = t // geom.Wp, t % geom.Wp
+    return (u >= 1) & (u <= geom.H) & (v >= 1) & (v <= geom.W)
+
+
+def _rows(A, idx, ncols):
+    """A[idx, :ncols] with out-of-bounds rows / columns read as zero (TMA OOB fill)."""
+    out = torch.zeros(idx.numel(), ncols, dtype=torch.float32)
+    ok = (idx >= 0) & (idx < A.shape[0])
+    c = min(ncols, A.shape[1])
+    out[ok, :c] = A[idx[ok], :c].float()
+    return out
+
+
+def _cols(Bm, n, k0, K):
+    """B[:n, k0:k0+K] with zero fill."""
+    out = torch.zeros(n, K, dtype=torch.float32)
+    r = min(n, Bm.shape[0])
+    c1 = min(k0 + K, Bm.shape[1])
+    if c1 > k0:
+        out[:r, :c1 - k0] = Bm[:r, k0:c1].float()
+    return out
+
+
+def gemm(A, B, M, N, K, *, mode=0, taps=((0, 0),), bias=None, res=None, res32=None, mask_src=None, relu=False, out=None, out32=None,
+         atomic=False, splits=1, geom=None, out_row_off=0, out32_z_stride=0, block_n=0):
+    _LAUNCHES[0] += 1
+    assert A.dtype == _lp() and B.dtype == _lp() and A.stride(1) == 1 and B.stride(1) == 1
+    assert A.stride(0) % 8 == 0 and B.stride(0) % 8 == 0, "TMA pitch"
+    assert 1 <= len(taps) <= 16
+    m = torch.arange(M)
+    if mode == 0:
+        Kp = (K + 63) // 64 * 64  # the kernel always loads whole 64-wide k-blocks
+        acc = torch.zeros(M, N)
+        for ro, ko in taps:
+            acc += _rows(A, m + ro, Kp) @ _cols(B, N, ko, Kp).t()
+        assert not atomic
+        rows = m + out_row_off
+        v = acc
+        if bias is not None:
+            v = v + bias[:N].float()
+        if res is not None:
+            v = v + res[rows, :N].float()
+        if res32 is not None:
+            v = v + res32[rows, :N]
+        if relu:
+            v = v.clamp_min(0)
+        if mask_src is not None:
+            v = torch.where(mask_src[rows, :N].float() > 0, v, torch.zeros(()))
+        v = torch.where(_interior(geom, rows)[:, None], v, torch.zeros(()))
+        if out is not None:
+            out[rows, :N] = v.to(_lp())
+        if out32 is not None:
+            out32[rows, :N] = v
+    else:
+        assert atomic and out32 is not None
+        r = torch.arange((K + 63) // 64 * 64)
+        valid = (r < K).float()[:, None]
+        for z, (ro, bo) in enumerate(taps):
+            a = _rows(A, r + ro, M) * valid
+            b = _rows(B, r + bo, N) * valid
+            d = a.t() @ b
+            tgt = torch.as_strided(out32, (M, N), (out32.stride(-2), 1), out32.storage_offset() + z * out32_z_stride)
+            tgt += d
+    return out if out is not None else out32
+
+
+# ------------------------------------------------------------------------------------------------ backbone support
+def stem_im2col(img, out, B, H, W, H1, W1):
+    _LAUNCHES[0] += 1
+    cols = F.unfold(img, 7, padding=3, stride=2)  # [B, 3*49, H1*W1], row index c*49 + r*7 + s
+    cols = cols.view(B, 3, 49, H1 * W1).permute(0, 3, 2, 1).reshape(B * H1 * W1, 147)  # (r*7+s)*3 + c
+    out.zero_()
+    out[:, :147] = cols.to(_lp())
+
+
+def maxpool_3x3s2(x, out, B, H1, W1, C, H2, W2):
+    _LAUNCHES[0] += 1
+    p = F.max_pool2d(x.view(B, H1, W1, C).permute(0, 3, 1, 2).float(), 3, 2, 1)
+    o = out.view(B, H2 + 2, W2 + 2, C)
+    o.zero_()
+    o[:, 1:-1, 1:-1] = p.permute(0, 2, 3, 1).to(_lp())
+
+
+def parity_split(x, xs, B, H, W, C, Ho, Wo):
+    _LAUNCHES[0] += 1
+    xv = x.view(B, H + 2, W + 2, C)
+    o = xs.view(4, B, Ho + 2, Wo + 2, C)
+    o.zero_()
+    for p in range(2):
+        for q in range(2):
+            sub = xv[:, p::2, q::2]
+            o[2 * p + q, :, :sub.shape[1], :sub.shape[2]] = sub
+
+
+def parity_merge(dxs, add, mask_src, dx, B, H, W, C, Ho, Wo):
+    _LAUNCHES[0] += 1
+    s = dxs.view(4, B, Ho + 2, Wo + 2, C)
+    o = torch.zeros(B, H + 2, W + 2, C)
+    for p in range(2):
+        for q in range(2):
+            n0, n1 = o[:, p::2, q::2].shape[1:3]
+            o[:, p::2, q::2] = s[2 * p + q, :, :n0, :n1].float()
+    if add is not None:
+        o = o + add.view(B, H + 2, W + 2, C).float()
+    if mask_src is not None:
+        o = torch.where(mask_src.view(B, H + 2, W + 2, C).float() > 0, o, torch.zeros(()))
+    res = torch.zeros(B, H + 2, W + 2, C)
+    res[:, 1:-1, 1:-1] = o[:, 1:-1, 1:-1]
+    dx.view(B, H + 2, W + 2, C).copy_(res.to(_lp()))
+
+
+def pack_conv(w, bn, conv_bias, fwd, ldk, dgr, scale_out, bias_out, eps=1e-5):
+    _LAUNCHES[0] += 1
+    Cout, Cin, kh, kw = w.shape
+    if bn is not None:
+        bw, bb, rm, rv = bn
+        sc = bw * torch.rsqrt(rv + eps)
+        bi = bb - rm * sc
+    else:
+        sc = torch.ones(Cout)
+        bi = conv_bias.clone() if conv_bias is not None else torch.zeros(Cout)
+    if scale_out is not None:
+        scale_out.copy_(sc)
+    if bias_out is not None:
+        bias_out.copy_(bi)
+    wf = (w * sc.view(-1, 1, 1, 1)).permute(0, 2, 3, 1).reshape(Cout, kh * kw * Cin)
+    fwd.zero_()
+    fwd[:, :kh * kw * Cin] = wf.to(_lp())
+    if dgr is not None:
+        dgr.copy_((w * sc.view(-1, 1, 1, 1)).flip(2, 3).permute(1, 2, 3, 0).reshape(Cin, kh * kw * Cout).to(_lp()))
+
+
+def pack_linear(w, wb, wt):
+    _LAUNCHES[0] += 1
+    N, K = w.shape
+    if wb is not None:
+        wb[:N, :K] = w.to(_lp())
+    if wt is not None:
+        wt[:K, :N] = w.t().to(_lp())
+
+
+def unpack_conv_grad(dwf, scale, grad, Cout, Cin, taps):
+    _LAUNCHES[0] += 1
+    v = dwf.reshape(Cout, taps, Cin).permute(0, 2, 1).clone()
+    if scale is not None:
+        v = v * scale.view(-1, 1, 1)
+    grad.view(Cout, Cin, taps).copy_(v)
+
+
+def cast_bf16(x, out=None):
+    _LAUNCHES[0] += 1
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    if out is None:
+        out = torch.empty(x.shape, dtype=_lp())
+    out.view(-1).copy_(x.reshape(-1).to(_lp()))
+    return out
+
+
+def colsum(x, out, rows=None, N=None):
+    _LAUNCHES[0] += 1
+    rows = x.shape[0] if rows is None else rows
+    N = x.shape[1] if N is None else N
+    out.view(-1)[:N] += x[:rows, :N].float().sum(0)
+
+
+def add(a, b, y=None, yb=None):
+    _LAUNCHES[0] += 1
+    v = a + (b if b is not None else 0)
+    if y is not None:
+        y.copy_(v)
+    if yb is not None:
+        yb.copy_(v.to(_lp()))
+
+
+def _map3(rowmap, r):
+    g, s, o = rowmap
+    return (r // g) * s + (r % g) + o if g else r
+
+
+# ------------------------------------------------------------------------------------------------ normalisation
+def layernorm_fwd(x, gamma, beta, rows, *, y32=None, yb=None, pos32=None, ypb=None, relu=False, mean=None, rstd=None, rowmap=(0, 0, 0),
+                  eps=1e-5):
+    _LAUNCHES[0] += 1
+    xr = x[:rows].float()
+    mu = xr.mean(-1, keepdim=True)
+    var = ((xr - mu) ** 2).mean(-1, keepdim=True)
+    rs = torch.rsqrt(var + eps)
+    y = (xr - mu) * rs * gamma.detach() + beta.detach()
+    if relu:
+        y = y.clamp_min(0)
+    if mean is not None:
+        mean[:rows] = mu[:, 0]
+    if rstd is not None:
+        rstd[:rows] = rs[:, 0]
+    o = _map3(rowmap, torch.arange(rows))
+    if y32 is not None:
+        y32[o] = y
+    if yb is not None:
+        yb[o] = y.to(_lp())
+    if ypb is not None:
+        ypb[o] = (y + pos32[o]).to(_lp())
+
+
+def layernorm_bwd(dy, x, gamma, mean, rstd, rows, *, dy2=None, y_relu=None, dx32=None, dxb=None, dgamma=None, dbeta=None, rowmap=(0, 0, 0)):
+    _LAUNCHES[0] += 1
+    i = _map3(rowmap, torch.arange(rows))
+    d = dy[i].float()
+    if dy2 is not None:
+        d = d + dy2[i]
+    if y_relu is not None:
+        d = torch.where(y_relu[i] > 0, d, torch.zeros(()))
+    xh = (x[:rows] - mean[:rows, None]) * rstd[:rows, None]
+    if dgamma is not None:
+        dgamma += (d * xh).sum(0)
+    if dbeta is not None:
+        dbeta += d.sum(0)
+    g = d * gamma.detach()
+    dx = rstd[:rows, None] * (g - g.mean(-1, keepdim=True) - xh * (g * xh).mean(-1, keepdim=True))
+    if dx32 is not None:
+        dx32[:rows] = dx
+    if dxb is not None:
+        dxb[:rows] = dx.to(_lp())
+
+
+def groupnorm_tokens_fwd(x, gamma, beta, B, h, w, S, L, y32, yb, pos32, ypb, mean, rstd, eps=1e-5):
+    _LAUNCHES[0] += 1
+    xi = x.view(B, h + 2, w + 2, 256)[:, 1:-1, 1:-1].reshape(B, h * w, 32, 8)
+    mu = xi.mean((1, 3), keepdim=True)
+    var = (xi * xi).mean((1, 3), keepdim=True) - mu * mu
+    rs = torch.rsqrt(var.clamp_min(0) + eps)
+    mean.view(B, 32).copy_(mu.view(B, 32))
+    rstd.view(B, 32).copy_(rs.view(B, 32))
+    y = ((xi - mu) * rs).reshape(B, h * w, 256) * gamma.detach() + beta.detach()
+    y32.view(B, S, 256)[:, L:] = y
+    yb.view(B, S, 256)[:, L:] = y.to(_lp())
+    if ypb is not None:
+        ypb.view(B, S, 256)[:, L:] = (y + pos32.view(B, S, 256)[:, L:]).to(_lp())
+
+
+def groupnorm_tokens_bwd(dy, dy2, x, gamma, mean, rstd, B, h, w, S, L, dx, dgamma, dbeta):
+    _LAUNCHES[0] += 1
+    d = dy.view(B, S, 256)[:, L:]
+    if dy2 is not None:
+        d = d + dy2.view(B, S, 256)[:, L:]
+    xi = x.view(B, h + 2, w + 2, 256)[:, 1:-1, 1:-1].reshape(B, h * w, 32, 8)
+    xh = (xi - mean.view(B, 1, 32, 1)) * rstd.view(B, 1, 32, 1)
+    d4 = d.reshape(B, h * w, 32, 8)
+    dgamma += (d4 * xh).sum((0, 1)).reshape(256)
+    dbeta += d4.sum((0, 1)).reshape(256)
+    g = d4 * gamma.detach().view(1, 1, 32, 8)
+    n = h * w * 8
+    s1 = g.sum((1, 3), keepdim=True) / n
+    s2 = (g * xh).sum((1, 3), keepdim=True) / n
+    o = rstd.view(B, 1, 32, 1) * (g - s1 - xh * s2)
+    dx.view(B, h + 2, w + 2, 256)[:, 1:-1, 1:-1] = o.reshape(B, h, w, 256).to(_lp())
+
+
+def build_pos_mask(img_mask, B, H, W, h, w, sent_mask, L, lang_pos, token_type, level_embed, pos32, kpm):
+    _LAUNCHES[0] += 1
+    assert img_mask.dtype == torch.bool and sent_mask.dtype == torch.int64
+    S = L + h * w
+    ys = torch.clamp(torch.floor(torch.arange(h) * (H / h)).long(), max=H - 1)
+    xs = torch.clamp(torch.floor(torch.arange(w) * (W / w)).long(), max=W - 1)
+    m = img_mask[:, ys][:, :, xs]  # [B, h, w]
+    nm = ~m
+    ye = nm.cumsum(1, dtype=torch.float32)
+    xe = nm.cumsum(2, dtype=torch.float32)
+    ye = (ye - 0.5) / (ye[:, -1:, :] + 1e-6) * (2 * math.pi)
+    xe = (xe - 0.5) / (xe[:, :, -1:] + 1e-6) * (2 * math.pi)
+    i = torch.arange(128, dtype=torch.float32)
+    dim_t = 10000.0 ** (2 * (i // 2) / 128)
+    px, py = xe[..., None] / dim_t, ye[..., None] / dim_t
+    px = torch.stack((px[..., 0::2].sin(), px[..., 1::2].cos()), 4).flatten(3)
+    py = torch.stack((py[..., 0::2].sin(), py[..., 1::2].cos()), 4).flatten(3)
+    vis = torch.cat((py, px), 3).reshape(B, h * w, 256) + level_embed.detach()[0] + token_type.detach()[1]
+    p = pos32.view(B, S, 256)
+    p[:, L:] = vis
+    p[:, :L] = (lang_pos.detach()[:L] + token_type.detach()[0]).unsqueeze(0)
+    k = kpm.view(B, S)
+    k[:, :L] = (sent_mask == 0).to(torch.uint8)
+    k[:, L:] = m.reshape(B, h * w).to(torch.uint8)
+
+
+def embed_grad(dpos, B, S, L, d_lang_pos, d_token_type, d_level):
+    _LAUNCHES[0] += 1
+    d = dpos.view(B, S, 256)
+    d_lang_pos[:L] = d[:, :L].sum(0)
+    d_token_type[0] += d[:, :L].sum((0, 1))
+    vis = d[:, L:].sum((0, 1))
+    d_token_type[1] += vis
+    d_level[0] += vis
+
+
+# ------------------------------------------------------------------------------------------------ attention
+def _heads(t, B, n, H):
+    return t.float().reshape(B, n, H, 32).transpose(1, 2)
+
+
+def _attn(Q, K, V, kpm, B, H, Tq, Sk, scale):
+    q = _heads(Q[:, :H * 32], B, Tq, H) * scale
+    k = _heads(K[:, :H * 32], B, Sk, H)
+    v = _heads(V[:, :H * 32], B, Sk, H)
+    s = q @ k.transpose(-1, -2)
+    if kpm is not None:
+        s = s.masked_fill(kpm.view(B, 1, 1, Sk).bool(), float("-inf"))
+    return s, v
+
+
+def attn_fwd(Q, K, V, kpm, O, LSE, B, H, Tq, Sk, scale):
+    _LAUNCHES[0] += 1
+    s, v = _attn(Q, K, V, kpm, B, H, Tq, Sk, scale)
+    LSE.view(B, H, Tq).copy_(torch.logsumexp(s, -1))
+    o = (s.softmax(-1) @ v).transpose(1, 2).reshape(B * Tq, H * 32)
+    O[:, :H * 32] = o.to(_lp())
+
+
+def attn_bwd(Q, K, V, kpm, O, dO, LSE, dQ, dK, dV, Dbuf, B, H, Tq, Sk, scale):
+    _LAUNCHES[0] += 1
+    with torch.enable_grad():
+        q = Q[:, :H * 32].float().requires_grad_()
+        k = K[:, :H * 32].float().requires_grad_()
+        v = V[:, :H * 32].float().requires_grad_()
+        s, vh = _attn(q, k, v, kpm, B, H, Tq, Sk, scale)
+        o = (s.softmax(-1) @ vh).transpose(1, 2).reshape(B * Tq, H * 32)
+        o.backward(dO[:, :H * 32].float())
+    dQ[:, :H * 32] = q.grad.to(_lp())
+    dK[:, :H * 32] = k.grad.to(_lp())
+    dV[:, :H * 32] = v.grad.to(_lp())
+
+
+def qenc_pool_fwd(k, q, v, mask, B, L, n_ph, att, c):
+    _LAUNCHES[0] += 1
+    s = torch.bmm(k.view(B, 1, 256), q.view(B, L, 256).transpose(1, 2)).expand(-1, n_ph, -1)
+    a = s.masked_fill(mask.view(B, n_ph, L).bool(), float("-inf")).softmax(-1)
+    att.view(B, n_ph, L).copy_(a)
+    c.view(B, n_ph, 256).copy_(a @ v.view(B, L, 256))
+
+
+def qenc_pool_bwd(dc, k, q, v, att, B, L, n_ph, dk, dq, dv):
+    _LAUNCHES[0] += 1
+    a = att.view(B, n_ph, L)
+    d = dc.view(B, n_ph, 256)
+    datt = d @ v.view(B, L, 256).transpose(1, 2)
+    ds = a * (datt - (a * datt).sum(-1, keepdim=True))
+    dsl = ds.sum(1)  # [B, L]
+    dq.view(B, L, 256).copy_(dsl.unsqueeze(-1) * k.view(B, 1, 256))
+    dv.view(B, L, 256).copy_(a.transpose(1, 2) @ d)
+    dk.view(B, 256).copy_((dsl.unsqueeze(-1) * q.view(B, L, 256)).sum(1))
+
+
+# ------------------------------------------------------------------------------------------------ row-mapped glue
+def _map4(m, r):
+    if m is None:
+        return r
+    g, s, i, o = m
+    return (r // g) * s + (r % g) * i + o if g else r + o
+
+
+def rows_add(a, b, rows, D, *, y32=None, yb=None, map_a=None, map_b=None, map_y=None):
+    _LAUNCHES[0] += 1
+    r = torch.arange(rows)
+    v = a.detach()[_map4(map_a, r), :D].float()
+    if b is not None:
+        v = v + b.detach()[_map4(map_b, r), :D].float()
+    o = _map4(map_y, r)
+    if y32 is not None:
+        y32[o, :D] = v
+    if yb is not None:
+        yb[o, :D] = v.to(_lp())
+
+
+def rows_scatter_add(src, dst, rows, D, *, map_src=None, map_dst=None):
+    _LAUNCHES[0] += 1
+    r = torch.arange(rows)
+    dst[:, :D].index_add_(0, _map4(map_dst, r), src[_map4(map_src, r), :D])
+
+
+def require_device(t):
+    pass
