@@ -191,7 +191,7 @@ class RefTREngine:
         self._cur = None
         self.step_id = 0
         self.use_graphs = os.environ.get("REFTR_B200_GRAPHS", "1") != "0"
-        self._graphs = {}
+        self.force_eager = False  # bench.py: run the next steps launch by launch on the graphed workspace (profiling)
         self.launches = 0
 
     # ------------------------------------------------------------------------------------------------------------
@@ -245,7 +245,11 @@ class RefTREngine:
         for dst, src in zip(args, (img, img_mask, sent_mask, mask_context, query_mask, sent_feat, pooled)):
             dst.copy_(src.reshape(dst.shape))
         a = (args[0], args[1], args[2], args[3], args[4], n_ph, want_seg, args[5], args[6])
-        if st["fwd"] is not None:
+        if self.force_eager:
+            st["outs"] = self.forward(*a)
+            if st["fwd"] is None:
+                st["saved"], st["dims"] = self.saved, self.dims
+        elif st["fwd"] is not None:
             self.saved, self.dims = st["saved"], st["dims"]
             st["fwd"].replay()
         elif st["graphed"] and st["nf"] >= 1:
@@ -278,7 +282,9 @@ class RefTREngine:
                 ga.zero_()
             else:
                 ga.copy_(g_att)
-        if st["bwd"] is not None:
+        if self.force_eager:
+            st["bouts"] = self.backward(gl, gm, ga)
+        elif st["bwd"] is not None:
             st["bwd"].replay()
         elif st["graphed"] and st["fwd"] is not None and st["nb"] >= 1:
             g = torch.cuda.CUDAGraph()

@@ -8,6 +8,9 @@ from . import _lib
 from ._lib import GemmArgs, Geom
 
 
+PROFILE = None  # bench.py sets this to a list: every rb_gemm launch is then bracketed by CUDA events -> (start, end, flops)
+
+
 def require_device(t):
     """The kernels exist for sm_100a only; there is no CPU or PyTorch fallback."""
     if not t.is_cuda:
@@ -75,7 +78,14 @@ def gemm(A, B, M, N, K, *, mode=0, taps=((0, 0),), bias=None, res=None, res32=No
     a.atomic = int(atomic)
     if geom is not None:
         a.geom = geom
-    _lib.check(_lib.lib().rb_gemm(C.byref(a), _stream()), "rb_gemm")
+    if PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.check(_lib.lib().rb_gemm(C.byref(a), _stream()), "rb_gemm")
+        e1.record()
+        PROFILE.append((e0, e1, 2.0 * M * N * K * len(taps)))
+    else:
+        _lib.check(_lib.lib().rb_gemm(C.byref(a), _stream()), "rb_gemm")
     return out if out is not None else out32
 
 
