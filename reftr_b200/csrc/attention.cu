@@ -417,7 +417,7 @@ using namespace rb;
   if (dh != DH) return rb_fail(name ": only head_dim 32 is built (got %d)", dh);                            \
   if (Tq <= 0 || Sk <= 0 || B <= 0 || H <= 0) return rb_fail(name ": empty problem");
 
-extern "C" int rb_attn_fwd(const void* Q, const void* K, const void* V, const void* kpm, void* O, float* LSE, int B, int H, int dh, int Tq, int Sk,
+int rb::attn_fwd_simt(const void* Q, const void* K, const void* V, const void* kpm, void* O, float* LSE, int B, int H, int dh, int Tq, int Sk,
                            long long ldq, long long ldk, long long ldv, long long ldo, float scale, void* stream) {
   RB_ATTN_CHECK("rb_attn_fwd");
   if ((ldk % 8) || (ldv % 8)) return rb_fail("rb_attn_fwd: K/V pitch must be a multiple of 8 elements");
@@ -429,7 +429,7 @@ extern "C" int rb_attn_fwd(const void* Q, const void* K, const void* V, const vo
   return rb_fail("rb_attn_fwd: Sk = %d > 672 keys is not built yet", Sk);
 }
 
-extern "C" int rb_attn_bwd(const void* Q, const void* K, const void* V, const void* kpm, const void* O, const void* dO, const float* LSE, void* dQ, void* dK,
+int rb::attn_bwd_simt(const void* Q, const void* K, const void* V, const void* kpm, const void* O, const void* dO, const float* LSE, void* dQ, void* dK,
                            void* dV, float* Dbuf, int B, int H, int dh, int Tq, int Sk, long long ldq, long long ldk, long long ldv, long long ldo,
                            long long lddo, long long lddq, long long lddk, long long lddv, float scale, void* stream) {
   RB_ATTN_CHECK("rb_attn_bwd");

@@ -211,6 +211,49 @@ __global__ void colsum_kernel(const T* __restrict__ x, long long ld, long long r
   atomicAdd(out + n, acc);
 }
 
+// Vectorised variant: a block is 32 column-lanes (VEC columns each) x 8 row-lanes; each thread walks its rows with 4 independent
+// loads in flight, the 8 row-lanes are reduced in shared memory, one atomic per column per block.
+template <typename T, int VEC>
+__global__ void colsum_vec_kernel(const T* __restrict__ x, long long ld, long long rows, int N, float* __restrict__ out, int rows_per_block) {
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int n0 = (blockIdx.x * 32 + tx) * VEC;
+  const long long r0 = static_cast<long long>(blockIdx.y) * rows_per_block;
+  const long long r1 = min(rows, r0 + rows_per_block);
+  float acc[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
+  if (n0 < N) {
+    for (long long r = r0 + ty; r < r1; r += 32) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long rr = r + 8 * u;
+        if (rr < r1) {
+          if (sizeof(T) == 2) {
+            const uint4 v = *reinterpret_cast<const uint4*>(x + rr * ld + n0);
+            acc[0] += bf16_lo(v.x); acc[1] += bf16_hi(v.x); acc[2] += bf16_lo(v.y); acc[3] += bf16_hi(v.y);
+            acc[4 % VEC] += bf16_lo(v.z); acc[5 % VEC] += bf16_hi(v.z); acc[6 % VEC] += bf16_lo(v.w); acc[7 % VEC] += bf16_hi(v.w);
+          } else {
+            const float4 v = *reinterpret_cast<const float4*>(x + rr * ld + n0);
+            acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
+          }
+        }
+      }
+    }
+  }
+  __shared__ float red[8][32 * VEC + 1];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) red[ty][tx * VEC + i] = acc[i];
+  __syncthreads();
+  for (int c = threadIdx.x; c < 32 * VEC; c += blockDim.x) {
+    const int n = blockIdx.x * 32 * VEC + c;
+    if (n >= N) continue;
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += red[w][c];
+    atomicAdd(out + n, v);
+  }
+}
+
 // y = a + b (fp32), optional bf16 copy
 __global__ void add_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ y, __nv_bfloat16* __restrict__ yb, long long n) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -292,6 +335,20 @@ extern "C" int rb_cast_bf16(const float* in, void* out, long long n, void* strea
 
 extern "C" int rb_colsum(const void* x, int is_bf16, long long ld, long long rows, int N, float* out, void* stream) {
   if (rows <= 0 || N <= 0) return 0;
+  const int vec = is_bf16 ? 8 : 4;
+  if (N % vec == 0 && ld % vec == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    // rows per block: enough blocks to fill the machine, at least 64 rows each
+    const int gx = (N + 32 * vec - 1) / (32 * vec);
+    long long rpb = (rows * gx + 591) / 592;
+    rpb = rpb < 64 ? 64 : ((rpb + 31) / 32) * 32;
+    dim3 g(gx, static_cast<unsigned>((rows + rpb - 1) / rpb));
+    if (is_bf16)
+      colsum_vec_kernel<__nv_bfloat16, 8><<<g, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(x), ld, rows, N, out, static_cast<int>(rpb));
+    else
+      colsum_vec_kernel<float, 4><<<g, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const float*>(x), ld, rows, N, out, static_cast<int>(rpb));
+    RB_CHECK_LAUNCH();
+    return 0;
+  }
   int ysplit = static_cast<int>(rows / 256);
   ysplit = ysplit < 1 ? 1 : (ysplit > 64 ? 64 : ysplit);
   dim3 grid((N + 127) / 128, ysplit);

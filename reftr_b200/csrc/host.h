@@ -12,6 +12,12 @@ int rb_fail(const char* fmt, ...);
 // (box_inner*2 must be <= 128); out-of-bounds elements (including negative coordinates) read as zero.
 int make_tmap_2d(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t rows, uint64_t pitch_bytes, uint32_t box_inner,
                  uint32_t box_rows);
+// SIMT attention (attention.cu); the C-ABI entry points in attention_tc.cu fall back to these for short query counts
+int attn_fwd_simt(const void* Q, const void* K, const void* V, const void* kpm, void* O, float* LSE, int B, int H, int dh, int Tq, int Sk, long long ldq,
+                  long long ldk, long long ldv, long long ldo, float scale, void* stream);
+int attn_bwd_simt(const void* Q, const void* K, const void* V, const void* kpm, const void* O, const void* dO, const float* LSE, void* dQ, void* dK,
+                  void* dV, float* Dbuf, int B, int H, int dh, int Tq, int Sk, long long ldq, long long ldk, long long ldv, long long ldo,
+                  long long lddo, long long lddq, long long lddk, long long lddv, float scale, void* stream);
 }  // namespace rb
 
 #define RB_CUDA(expr)                                                                         \

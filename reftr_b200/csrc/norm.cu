@@ -128,10 +128,22 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ dy, const float* 
       *reinterpret_cast<uint4*>(dxb + row * LN_D + lane * 8) = p;
     }
   }
+  // block-level reduction of the per-warp partial dgamma / dbeta, then ONE atomic per column per block
+  __shared__ float red[2][8][LN_D + 8];
+  const int wib = threadIdx.x >> 5;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    if (dgamma) atomicAdd(dgamma + lane * 8 + i, dg[i]);
-    if (dbeta) atomicAdd(dbeta + lane * 8 + i, db[i]);
+    red[0][wib][lane * 8 + i] = dg[i];
+    red[1][wib][lane * 8 + i] = db[i];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * LN_D; c += blockDim.x) {
+    const int which = c / LN_D, col = c - which * LN_D;
+    float* dst = which ? dbeta : dgamma;
+    if (!dst) continue;
+    float v = 0.f;
+    for (int w = 0; w < warps_per_block; ++w) v += red[which][w][col];
+    atomicAdd(dst + col, v);
   }
 }
 
@@ -380,7 +392,7 @@ extern "C" int rb_layernorm_bwd(const float* dy, const float* dy2, const float* 
   if (rows <= 0) return 0;
   RowMap m{map_group, map_stride, map_offset};
   long long blocks = (rows + 7) / 8;
-  if (blocks > 296) blocks = 296;  // 2 per SM; each warp strides over rows so dgamma/dbeta atomics stay few
+  if (blocks > 148) blocks = 148;  // one per SM; warps stride over rows, dgamma/dbeta cost one atomic per column per block
   layernorm_bwd_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       dy, dy2, y_relu, x, gamma, mean, rstd, rows, dx32, static_cast<__nv_bfloat16*>(dxb), dgamma, dbeta, m);
   RB_CUDA(cudaGetLastError());

@@ -255,18 +255,16 @@ class RefTR(nn.Module):
         sentence, sentence_mask = samples["sentence"], samples["sentence_mask"]
         B, L = sentence.shape
         n_q = self.num_queries_per_phrase
-        prev = torch.backends.cuda.matmul.allow_tf32
-        if self.tf32_bert:
+        if self.tf32_bert and not torch.backends.cuda.matmul.allow_tf32:
+            # BERT is a third-party PyTorch module (reftr_transformer.py:8); its fp32 GEMMs run on the tensor cores in TF32,
+            # forward AND backward (autograd runs the backward outside any scope, so the switch is process-wide).
             torch.backends.cuda.matmul.allow_tf32 = True
-        try:
-            lo = self.lang_backbone(sentence, token_type_ids=None, attention_mask=sentence_mask)
-            sent_feat, pooled = lo[0], lo[1]
-            if "phrase" in samples:
-                ph, pm = samples["phrase"], samples["phrase_mask"]
-                n_ph = ph.size(1)
-                pooled = self.lang_backbone(ph.reshape(B * n_ph, -1), token_type_ids=None, attention_mask=pm.reshape(B * n_ph, -1))[1]
-        finally:
-            torch.backends.cuda.matmul.allow_tf32 = prev
+        lo = self.lang_backbone(sentence, token_type_ids=None, attention_mask=sentence_mask)
+        sent_feat, pooled = lo[0], lo[1]
+        if "phrase" in samples:
+            ph, pm = samples["phrase"], samples["phrase_mask"]
+            n_ph = ph.size(1)
+            pooled = self.lang_backbone(ph.reshape(B * n_ph, -1), token_type_ids=None, attention_mask=pm.reshape(B * n_ph, -1))[1]
         if "phrase" in samples:
             ar = torch.arange(L, device=sentence.device).view(1, 1, L)
             inside = (ar >= samples["phrase_pos_l"].unsqueeze(-1)) & (ar < samples["phrase_pos_r"].unsqueeze(-1))

@@ -91,7 +91,8 @@ def _attn_ref(q, k, v, kpm, H, scale):
     return (p @ vh).transpose(1, 2).reshape(B, Tq, d)
 
 
-@pytest.mark.parametrize("B,H,Tq,Sk", [(2, 8, 57, 57), (1, 8, 420, 420), (3, 8, 1, 77), (2, 8, 5, 5), (1, 8, 300, 665), (2, 8, 3, 420)])
+@pytest.mark.parametrize("B,H,Tq,Sk", [(2, 8, 57, 57), (1, 8, 420, 420), (3, 8, 1, 77), (2, 8, 5, 5), (1, 8, 300, 665), (2, 8, 3, 420),
+                                        (2, 8, 64, 64), (3, 8, 128, 200), (2, 8, 420, 420), (2, 8, 665, 665), (2, 8, 100, 7)])
 def test_attention_fwd_bwd(B, H, Tq, Sk):
     from reftr_b200 import ops
     d = H * 32
@@ -214,3 +215,15 @@ def test_stem_maxpool_parity_pack():
     ops.colsum(x, cs)
     assert _rel(cs, x.sum(0)) < 1e-5
     assert torch.equal(ops.cast_bf16(x), x.bfloat16())
+
+
+@pytest.mark.parametrize("rows,N,dt", [(6720, 256, torch.bfloat16), (6720, 768, torch.bfloat16), (107584, 128, torch.bfloat16), (321, 2048, torch.bfloat16),
+                                       (6720, 256, torch.float32), (96, 4, torch.float32), (33, 72, torch.float32)])
+def test_colsum(rows, N, dt):
+    from reftr_b200 import ops
+    ld = 64 if N == 4 else N
+    x = torch.randn(rows, ld, device=dev).to(dt)
+    out = torch.ones(N, device=dev)
+    ops.colsum(x, out, rows=rows, N=N)
+    ref = 1 + x[:, :N].float().sum(0)
+    assert (out - ref).abs().max().item() < 2e-3 * max(1.0, ref.abs().max().item())
