@@ -33,24 +33,42 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-int make_tmap_2d(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t rows, uint64_t pitch_bytes, uint32_t box_inner,
-                 uint32_t box_rows) {
+static int make_tmap_2d_impl(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t rows, uint64_t pitch_bytes, uint32_t box_inner,
+                             uint32_t box_rows, CUtensorMapDataType dt, uint32_t esize) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return rb_fail("cuTensorMapEncodeTiled not available (no CUDA driver?)");
   cuuint64_t dims[2] = {inner, rows};
   cuuint64_t strides[1] = {pitch_bytes};
   cuuint32_t box[2] = {box_inner, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUtensorMapSwizzle sw = box_inner * 2 >= 128 ? CU_TENSOR_MAP_SWIZZLE_128B
-                          : box_inner * 2 >= 64 ? CU_TENSOR_MAP_SWIZZLE_64B
-                                                : CU_TENSOR_MAP_SWIZZLE_32B;
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  const uint32_t row_bytes = box_inner * esize;
+  CUtensorMapSwizzle sw = row_bytes >= 128 ? CU_TENSOR_MAP_SWIZZLE_128B : row_bytes >= 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+  CUresult r = enc(out, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
-    return rb_fail("cuTensorMapEncodeTiled failed (%d): inner=%llu rows=%llu pitch=%llu box=%ux%u ptr=%p", static_cast<int>(r),
+    return rb_fail("cuTensorMapEncodeTiled failed (%d): inner=%llu rows=%llu pitch=%llu box=%ux%u esize=%u ptr=%p", static_cast<int>(r),
                    static_cast<unsigned long long>(inner), static_cast<unsigned long long>(rows),
-                   static_cast<unsigned long long>(pitch_bytes), box_inner, box_rows, ptr);
+                   static_cast<unsigned long long>(pitch_bytes), box_inner, box_rows, esize, ptr);
   return 0;
+}
+
+int make_tmap_2d(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t rows, uint64_t pitch_bytes, uint32_t box_inner,
+                 uint32_t box_rows) {
+  return make_tmap_2d_impl(out, ptr, inner, rows, pitch_bytes, box_inner, box_rows, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2);
+}
+
+int make_tmap_2d_f32(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t rows, uint64_t pitch_bytes, uint32_t box_inner,
+                     uint32_t box_rows) {
+  return make_tmap_2d_impl(out, ptr, inner, rows, pitch_bytes, box_inner, box_rows, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4);
+}
+
+int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
 }
 
 }  // namespace rb

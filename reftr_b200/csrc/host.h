@@ -12,6 +12,10 @@ int rb_fail(const char* fmt, ...);
 // (box_inner*2 must be <= 128); out-of-bounds elements (including negative coordinates) read as zero.
 int make_tmap_2d(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t rows, uint64_t pitch_bytes, uint32_t box_inner,
                  uint32_t box_rows);
+// same for an fp32 tensor (box_inner * 4 bytes <= 128; swizzle chosen by the box row bytes: 128 -> 128B, 64 -> 64B, else 32B)
+int make_tmap_2d_f32(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t rows, uint64_t pitch_bytes, uint32_t box_inner,
+                     uint32_t box_rows);
+int sm_count();
 // SIMT attention (attention.cu); the C-ABI entry points in attention_tc.cu fall back to these for short query counts
 int attn_fwd_simt(const void* Q, const void* K, const void* V, const void* kpm, void* O, float* LSE, int B, int H, int dh, int Tq, int Sk, long long ldq,
                   long long ldk, long long ldv, long long ldo, float scale, void* stream);
