@@ -1,0 +1,542 @@
+// tcgen05 GEMM / implicit-GEMM convolution for sm_100a -- persistent, warp-specialised, TMA in and TMA out.
+//
+// One CTA per SM walks a static list of 128 x BN output tiles (BN = 64..256, chosen per problem at run time).
+// Warp roles (352 threads):
+//   warp 0      : TMA producer for the main loop (one elected lane) -- STAGES-deep ring of {A tile, B tile} in shared memory
+//   warp 1      : TMEM allocator + MMA issuer (one elected lane issues tcgen05.mma); the accumulator is DOUBLE-BUFFERED in
+//                 TMEM (2 x BN columns) so the main loop of tile i+1 overlaps the epilogue of tile i
+//   warps 2..9  : epilogue, two teams of 4 warps that take alternate 64-column chunks -- tcgen05.ld the accumulator (one
+//                 thread per output row), fused bias / residual / ReLU / ReLU-mask / border-zero; results are staged in shared
+//                 memory (128B-swizzled, bank-conflict free) and written with TMA bulk stores (bf16 and/or fp32), or added
+//                 with vector fp32 reductions (red.global.add.v4.f32) in split-K mode
+//   warp 10     : TMA producer for the epilogue INPUTS (bf16 residual, fp32 residual, ReLU-mask source), 64-column chunks
+//                 prefetched through a small ring, so that the epilogue never waits on a dependent global load
+// All global traffic is therefore bulk, asynchronous and 128-byte coalesced; what bounds the HBM-bound layers is the
+// number of bytes in flight (ring depths), not the number of resident warps.
+//
+// mode NT: A [rows, K] and B [N, K] are K-major; tiles are [128|BN rows] x 64 k (128 B per row), 128B-swizzled by TMA.
+//          Convolution taps are row shifts of A (padded-NHWC layout, see include/reftr_b200.h).
+// mode TN: the contraction runs over rows (pixels/tokens): A [rows, M] and B [rows, N] are "MN-major"; tiles are
+//          64 rows x 64 channels boxes, consumed through MN-major UMMA descriptors (no transposes anywhere).
+#include "common.cuh"
+#include "host.h"
+
+#include <string.h>
+
+namespace rb {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int GEMM_THREADS = 352;
+constexpr int MAX_STAGES = 8;
+constexpr int MAX_EIN = 6;
+constexpr int A_BYTES = BM * BK * 2;
+constexpr int SMEM_LIMIT = 232448;  // 227 KB opt-in maximum per CTA
+
+struct GemmKParams {
+  int mode;
+  int M, N;
+  int kblocks;  // NT: k-blocks per tap; TN: total row-blocks
+  int taps;
+  int a_rowoff[16];
+  int b_koff[16];
+  int splits;
+  int bn, stages;
+  int tiles_m, tiles_n, tiles_total;
+  long long out_row_off;
+  const float* bias;
+  float* out32;  // atomic mode only (otherwise TMA store)
+  long long ldo32;
+  long long out32_z_stride;
+  int relu, atomic;
+  int has_out, has_out32, has_res, has_res32, has_mask;
+  int ein_slots, out_slots;
+  uint32_t stage_bytes;                                  // A_BYTES + bn * 128
+  uint32_t off_ein, ein_slot_bytes, ein_off_mask, ein_off_res32;
+  uint32_t off_out, out_slot_bytes, out_off_f32;         // out_slots per team, 2 teams
+  uint32_t off_bars;
+  rb_geom geom;
+};
+
+__device__ __forceinline__ bool row_is_interior(const rb_geom& g, long long row) {
+  if (g.mode == 0) return true;
+  if (g.mode == 1) {
+    const int t = static_cast<int>(row % g.HpWp);
+    const int u = t / g.Wp, v = t - u * g.Wp;
+    return (u >= 1) && (u <= g.H) && (v >= 1) && (v <= g.W);
+  }
+  // parity planes: cell (u,v) of plane (p,q) holds padded-input pixel (2u+p, 2v+q); interior iff 1 <= . <= H (resp. W)
+  const int plane = static_cast<int>(row / g.Rs);
+  row -= static_cast<long long>(plane) * g.Rs;
+  const int t = static_cast<int>(row % g.HpWp);
+  const int u = t / g.Wp, v = t - u * g.Wp;
+  const int y = 2 * u + (plane >> 1), x = 2 * v + (plane & 1);
+  return (y >= 1) && (y <= g.H) && (x >= 1) && (x <= g.W);
+}
+
+struct TileCoord {
+  int m0, n0, z_tap, it_begin, n_it;
+};
+
+__device__ __forceinline__ TileCoord tile_coord(const GemmKParams& p, int t) {
+  TileCoord c;
+  const int tn = t % p.tiles_n;
+  int rest = t / p.tiles_n;
+  const int tm = rest % p.tiles_m;
+  const int z = rest / p.tiles_m;
+  c.m0 = tm * BM;
+  c.n0 = tn * p.bn;
+  if (p.mode == 0) {
+    c.z_tap = 0;
+    c.it_begin = 0;
+    c.n_it = p.taps * p.kblocks;
+  } else {
+    c.z_tap = z / p.splits;
+    const int split = z - c.z_tap * p.splits;
+    const int per = (p.kblocks + p.splits - 1) / p.splits;
+    c.it_begin = split * per;
+    const int it_end = min(p.kblocks, c.it_begin + per);
+    c.n_it = it_end - c.it_begin;  // may be <= 0: every role skips such a tile
+  }
+  return c;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
+                 const __grid_constant__ CUtensorMap tmOut32, const __grid_constant__ CUtensorMap tmRes, const __grid_constant__ CUtensorMap tmRes32,
+                 const __grid_constant__ CUtensorMap tmMask, const __grid_constant__ GemmKParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_bars);
+  uint64_t* full = bars;                       // [MAX_STAGES]
+  uint64_t* empty = bars + MAX_STAGES;         // [MAX_STAGES]
+  uint64_t* acc_full = bars + 2 * MAX_STAGES;  // [2]
+  uint64_t* acc_empty = acc_full + 2;          // [2]
+  uint64_t* ein_full = acc_empty + 2;          // [MAX_EIN]
+  uint64_t* ein_empty = ein_full + MAX_EIN;    // [MAX_EIN]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ein_empty + MAX_EIN);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int bn = p.bn;
+  const bool has_ein = p.has_res | p.has_res32 | p.has_mask;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], 8);
+    }
+    for (int s = 0; s < MAX_EIN; ++s) {
+      mbar_init(&ein_full[s], 1);
+      mbar_init(&ein_empty[s], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------------------------------ main-loop producer
+    if (lane == 0) {
+      const uint32_t tx_bytes = p.stage_bytes;
+      int i = 0;  // global k-iteration counter (ring position)
+      for (int t = blockIdx.x; t < p.tiles_total; t += gridDim.x) {
+        const TileCoord c = tile_coord(p, t);
+        for (int k = 0; k < c.n_it; ++k, ++i) {
+          const int s = i % p.stages;
+          const uint32_t ph = (i / p.stages) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_expect_tx(&full[s], tx_bytes);
+          uint8_t* a_dst = smem + s * p.stage_bytes;
+          uint8_t* b_dst = a_dst + A_BYTES;
+          const int it = c.it_begin + k;
+          if (MODE == 0) {
+            const int tap = it / p.kblocks;
+            const int kc = it - tap * p.kblocks;
+            tma_load_2d(a_dst, &tmA, &full[s], kc * BK, c.m0 + p.a_rowoff[tap]);
+            tma_load_2d(b_dst, &tmB, &full[s], p.b_koff[tap] + kc * BK, c.n0);
+          } else {
+            const int r0 = it * BK;
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j) tma_load_2d(a_dst + j * 8192, &tmA, &full[s], c.m0 + 64 * j, r0 + p.a_rowoff[c.z_tap]);
+            for (int j = 0; j < bn / 64; ++j) tma_load_2d(b_dst + j * 8192, &tmB, &full[s], c.n0 + 64 * j, r0 + p.b_koff[c.z_tap]);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(BM, bn, MODE, MODE);
+      int i = 0, tcount = 0;
+      for (int t = blockIdx.x; t < p.tiles_total; t += gridDim.x) {
+        const TileCoord c = tile_coord(p, t);
+        if (c.n_it <= 0) continue;
+        const int as = tcount & 1;
+        mbar_wait(&acc_empty[as], ((tcount >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * bn;
+        for (int k = 0; k < c.n_it; ++k, ++i) {
+          const int s = i % p.stages;
+          const uint32_t ph = (i / p.stages) & 1;
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(smem + s * p.stage_bytes);
+          const uint32_t b_base = a_base + A_BYTES;
+#pragma unroll
+          for (int kk = 0; kk < BK / 16; ++kk) {
+            uint64_t ad, bd;
+            if (MODE == 0) {
+              ad = umma_smem_desc(a_base + kk * 32, 16, 1024, SWZ_128B);
+              bd = umma_smem_desc(b_base + kk * 32, 16, 1024, SWZ_128B);
+            } else {
+              ad = umma_smem_desc(a_base + kk * 2048, 8192, 1024, SWZ_128B);
+              bd = umma_smem_desc(b_base + kk * 2048, 8192, 1024, SWZ_128B);
+            }
+            umma_bf16_ss(d_tmem, ad, bd, idesc, (k | kk) != 0);
+          }
+          umma_commit(&empty[s]);
+        }
+        umma_commit(&acc_full[as]);
+        ++tcount;
+      }
+    }
+    __syncwarp();
+  } else if (warp == 10) {
+    // ------------------------------------------------------------------------------------------ epilogue-input producer
+    if (lane == 0 && has_ein && !p.atomic) {
+      const uint32_t tx = (p.has_res ? 16384u : 0u) + (p.has_mask ? 16384u : 0u) + (p.has_res32 ? 32768u : 0u);
+      int g = 0;
+      for (int t = blockIdx.x; t < p.tiles_total; t += gridDim.x) {
+        const TileCoord c = tile_coord(p, t);
+        if (c.n_it <= 0) continue;
+        for (int ch = 0; ch < bn / 64; ++ch, ++g) {
+          const int col0 = c.n0 + ch * 64;
+          if (col0 >= p.N) { g += bn / 64 - ch; break; }
+          const int s = g % p.ein_slots;
+          mbar_wait(&ein_empty[s], ((g / p.ein_slots) & 1) ^ 1);
+          mbar_expect_tx(&ein_full[s], tx);
+          uint8_t* dst = smem + p.off_ein + s * p.ein_slot_bytes;
+          if (p.has_res) tma_load_2d(dst, &tmRes, &ein_full[s], col0, c.m0);
+          if (p.has_mask) tma_load_2d(dst + p.ein_off_mask, &tmMask, &ein_full[s], col0, c.m0);
+          if (p.has_res32) {
+            tma_load_2d(dst + p.ein_off_res32, &tmRes32, &ein_full[s], col0, c.m0);
+            tma_load_2d(dst + p.ein_off_res32 + 16384, &tmRes32, &ein_full[s], col0 + 32, c.m0);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------------------------------ epilogue (2 teams)
+    const int team = (warp - 2) >> 2;
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+    const bool store_thread = (threadIdx.x == 64 + team * 128);
+    const int sw128 = r & 7;
+    const bool use_ein = has_ein && !p.atomic;
+    int tcount = 0, g = 0, o = 0;
+    for (int t = blockIdx.x; t < p.tiles_total; t += gridDim.x) {
+      const TileCoord c = tile_coord(p, t);
+      if (c.n_it <= 0) continue;
+      const int as = tcount & 1;
+      const long long gm = static_cast<long long>(c.m0) + r;
+      const bool row_ok = gm < p.M;
+      const long long orow = gm + p.out_row_off;
+      const bool interior = row_ok && row_is_interior(p.geom, orow);
+      mbar_wait(&acc_full[as], (tcount >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int ch = 0; ch < bn / 64; ++ch, ++g) {
+        const int col0 = c.n0 + ch * 64;
+        if (col0 >= p.N) { g += bn / 64 - ch; break; }
+        if ((g & 1) != team) continue;
+        const uint8_t* ein = nullptr;
+        int es = 0;
+        if (use_ein) {
+          es = g % p.ein_slots;
+          mbar_wait(&ein_full[es], (g / p.ein_slots) & 1);
+          ein = smem + p.off_ein + es * p.ein_slot_bytes;
+        }
+        uint8_t* oslot = smem + p.off_out + (team * p.out_slots + (o % p.out_slots)) * p.out_slot_bytes;
+        ++o;
+        if (!p.atomic) {
+          if (store_thread) {  // the store that last used this slot has finished reading it
+            if (p.out_slots == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
+          }
+          named_bar_sync(1 + team, 128);
+        }
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+          const int hc0 = col0 + half * 32;
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + lane_addr + as * bn + ch * 64 + half * 32, v);
+          tmem_ld_wait();
+          if (hc0 >= p.N) continue;  // warp-uniform
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if (p.atomic) {
+            if (row_ok) {
+              float* dst = p.out32 + static_cast<long long>(c.z_tap) * p.out32_z_stride + orow * p.ldo32 + hc0;
+              if (hc0 + 32 <= p.N && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) red_add_v4(dst + 4 * j, f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (hc0 + j < p.N) atomicAdd(dst + j, f[j]);
+              }
+            }
+            continue;
+          }
+          if (p.bias) {
+            if (hc0 + 32 <= p.N) {
+              const float4* b4 = reinterpret_cast<const float4*>(p.bias + hc0);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 b = __ldg(b4 + j);
+                f[4 * j] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (hc0 + j < p.N) f[j] += __ldg(p.bias + hc0 + j);
+            }
+          }
+          if (p.has_res) {
+            const uint8_t* row = ein + r * 128;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 tt = *reinterpret_cast<const uint4*>(row + (((half * 4 + j) ^ sw128) << 4));
+              f[8 * j] += bf16_lo(tt.x); f[8 * j + 1] += bf16_hi(tt.x); f[8 * j + 2] += bf16_lo(tt.y); f[8 * j + 3] += bf16_hi(tt.y);
+              f[8 * j + 4] += bf16_lo(tt.z); f[8 * j + 5] += bf16_hi(tt.z); f[8 * j + 6] += bf16_lo(tt.w); f[8 * j + 7] += bf16_hi(tt.w);
+            }
+          }
+          if (p.has_res32) {
+            const uint8_t* row = ein + p.ein_off_res32 + half * 16384 + r * 128;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 b = *reinterpret_cast<const float4*>(row + ((j ^ sw128) << 4));
+              f[4 * j] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+          }
+          if (p.has_mask) {
+            const uint8_t* row = ein + p.ein_off_mask + r * 128;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 tt = *reinterpret_cast<const uint4*>(row + (((half * 4 + j) ^ sw128) << 4));
+              const uint32_t w[4] = {tt.x, tt.y, tt.z, tt.w};
+#pragma unroll
+              for (int ee = 0; ee < 4; ++ee) {
+                if (!(bf16_lo(w[ee]) > 0.f)) f[8 * j + 2 * ee] = 0.f;
+                if (!(bf16_hi(w[ee]) > 0.f)) f[8 * j + 2 * ee + 1] = 0.f;
+              }
+            }
+          }
+          if (!interior) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = 0.f;
+          }
+          if (p.has_out) {
+            uint8_t* row = oslot + r * 128;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 tt;
+              tt.x = pack_bf16x2(f[8 * j], f[8 * j + 1]); tt.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
+              tt.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]); tt.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+              *reinterpret_cast<uint4*>(row + (((half * 4 + j) ^ sw128) << 4)) = tt;
+            }
+          }
+          if (p.has_out32) {
+            uint8_t* row = oslot + p.out_off_f32 + half * 16384 + r * 128;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<float4*>(row + ((j ^ sw128) << 4)) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+          }
+        }
+        if (p.atomic) continue;
+        if (ein) {  // this warp is done with the input slot
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&ein_empty[es]);
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1 + team, 128);
+        if (store_thread) {
+          if (p.has_out) tma_store_2d(&tmOut, oslot, col0, c.m0);
+          if (p.has_out32) {
+            tma_store_2d(&tmOut32, oslot + p.out_off_f32, col0, c.m0);
+            if (col0 + 32 < p.N) tma_store_2d(&tmOut32, oslot + p.out_off_f32 + 16384, col0 + 32, c.m0);
+          }
+          tma_store_commit();
+        }
+      }
+      // every TMEM read of this accumulator stage by this warp has completed (tcgen05.wait::ld): release it
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[as]);
+      ++tcount;
+    }
+    if (store_thread) tma_store_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+}  // namespace rb
+
+using namespace rb;
+
+static int pick_bn(int N, long long tiles_mz, long long k_iters, int nsm) {
+  // cost model (arbitrary time units): waves x (fixed per-tile latency + part that grows with the tile width and the main-loop
+  // length).  Few waves matter most for small problems; wide tiles re-read A less and amortise the epilogue barriers.
+  const int cands[3] = {256, 128, 64};
+  int best = 64;
+  double best_cost = 1e300;
+  for (int bn : cands) {
+    if (bn >= 2 * N && bn > 64) continue;  // more than half of the tile would be padding
+    const long long tiles = tiles_mz * ((N + bn - 1) / bn);
+    const long long waves = (tiles + nsm - 1) / nsm;
+    const double tile_cost = 1.0 + (bn / 64) * (0.1 + 0.02 * static_cast<double>(k_iters));
+    const double cost = static_cast<double>(waves) * tile_cost;
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
+  }
+  return best;
+}
+
+extern "C" int rb_gemm(const rb_gemm_args* a, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!a || !a->A || !a->B) return rb_fail("rb_gemm: null operand");
+  if (a->M <= 0 || a->N <= 0 || a->K <= 0) return rb_fail("rb_gemm: empty problem (M,N,K must be > 0)");
+  if (a->taps < 1 || a->taps > 16) return rb_fail("rb_gemm: taps must be in [1,16]");
+  if ((a->lda % 8) || (a->ldb % 8)) return rb_fail("rb_gemm: operand row pitch must be a multiple of 8 elements (16 B) for TMA");
+  if ((reinterpret_cast<uintptr_t>(a->A) & 15) || (reinterpret_cast<uintptr_t>(a->B) & 15)) return rb_fail("rb_gemm: operands must be 16-byte aligned");
+  if (!a->out && !a->out32) return rb_fail("rb_gemm: no output");
+  if (a->atomic && !a->out32) return rb_fail("rb_gemm: atomic accumulation needs out32");
+  if (a->mode != 0 && a->mode != 1) return rb_fail("rb_gemm: mode must be 0 (NT) or 1 (TN)");
+  if (a->mode == 1 && !a->atomic && (a->taps != 1 || a->splits > 1)) return rb_fail("rb_gemm: TN mode with several taps / splits needs atomic accumulation");
+  if (a->out && ((a->ldo % 8) || (reinterpret_cast<uintptr_t>(a->out) & 15))) return rb_fail("rb_gemm: out must be 16-byte aligned with pitch % 8 == 0");
+  if (a->out32 && !a->atomic && ((a->ldo32 % 4) || (reinterpret_cast<uintptr_t>(a->out32) & 15))) return rb_fail("rb_gemm: out32 must be 16-byte aligned with pitch % 4 == 0");
+  if (a->res && ((a->ldres % 8) || (reinterpret_cast<uintptr_t>(a->res) & 15))) return rb_fail("rb_gemm: res alignment");
+  if (a->res32 && ((a->ldres32 % 4) || (reinterpret_cast<uintptr_t>(a->res32) & 15))) return rb_fail("rb_gemm: res32 alignment");
+  if (a->mask_src && ((a->ldmask % 8) || (reinterpret_cast<uintptr_t>(a->mask_src) & 15))) return rb_fail("rb_gemm: mask_src alignment");
+  if (a->bias && (reinterpret_cast<uintptr_t>(a->bias) & 15)) return rb_fail("rb_gemm: bias must be 16-byte aligned");
+
+  GemmKParams kp;
+  memset(&kp, 0, sizeof(kp));
+  kp.mode = a->mode;
+  kp.M = a->M; kp.N = a->N; kp.taps = a->taps; kp.splits = a->splits < 1 ? 1 : a->splits;
+  for (int i = 0; i < 16; ++i) { kp.a_rowoff[i] = a->a_rowoff[i]; kp.b_koff[i] = a->b_koff[i]; }
+  kp.out_row_off = a->out_row_off;
+  kp.bias = a->bias;
+  kp.relu = a->relu; kp.atomic = a->atomic; kp.geom = a->geom;
+  kp.kblocks = (a->K + BK - 1) / BK;
+  const int nsm = sm_count();
+  const long long tiles_m = (a->M + BM - 1) / BM;
+  const long long k_iters = a->mode == 0 ? static_cast<long long>(a->taps) * kp.kblocks : (kp.kblocks + kp.splits - 1) / kp.splits;
+  int bn = a->block_n ? a->block_n : pick_bn(a->N, tiles_m * (a->mode == 1 ? a->taps * kp.splits : 1), k_iters, nsm);
+  if (bn == 32) bn = 64;
+  if (bn != 64 && bn != 128 && bn != 256) return rb_fail("rb_gemm: unsupported block_n %d", bn);
+  kp.bn = bn;
+  kp.tiles_m = static_cast<int>(tiles_m);
+  kp.tiles_n = (a->N + bn - 1) / bn;
+  const long long total = tiles_m * kp.tiles_n * (a->mode == 1 ? a->taps * kp.splits : 1);
+  if (total > 0x7fffffffLL) return rb_fail("rb_gemm: too many tiles");
+  kp.tiles_total = static_cast<int>(total);
+  if (a->atomic) {
+    kp.out32 = a->out32; kp.ldo32 = a->ldo32; kp.out32_z_stride = a->out32_z_stride;
+  } else {
+    kp.has_out = a->out != nullptr; kp.has_out32 = a->out32 != nullptr;
+    kp.has_res = a->res != nullptr; kp.has_res32 = a->res32 != nullptr; kp.has_mask = a->mask_src != nullptr;
+  }
+  // ---- shared-memory plan --------------------------------------------------------------------------------------
+  kp.stage_bytes = A_BYTES + bn * 128;
+  const bool has_ein = kp.has_res || kp.has_res32 || kp.has_mask;
+  kp.ein_off_mask = kp.has_res ? 16384 : 0;
+  kp.ein_off_res32 = kp.ein_off_mask + (kp.has_mask ? 16384 : 0);
+  kp.ein_slot_bytes = kp.ein_off_res32 + (kp.has_res32 ? 32768 : 0);
+  kp.out_off_f32 = kp.has_out ? 16384 : 0;
+  kp.out_slot_bytes = kp.out_off_f32 + (kp.has_out32 ? 32768 : 0);
+  const uint32_t bars_bytes = 512;
+  // short main loops do not need a deep ring: the room goes to the epilogue rings instead (HBM-bound 1x1 convolutions, where
+  // the residual / mask stream is as large as the output)
+  const int want_stages = k_iters * 2 < 4 ? 4 : static_cast<int>(k_iters * 2 > MAX_STAGES ? MAX_STAGES : k_iters * 2);
+  int stages = 0;
+  kp.ein_slots = 0;
+  kp.out_slots = 2;
+  for (int pass = 0; pass < 2 && stages < 2; ++pass) {
+    kp.out_slots = 2 - pass;  // second pass: one staging slot per team
+    const long long fixed = 2LL * kp.out_slots * kp.out_slot_bytes + bars_bytes + 1024 /* alignment slack */;
+    if (has_ein) {
+      for (int slots = MAX_EIN; slots >= 2; --slots) {
+        const long long room = static_cast<long long>(SMEM_LIMIT) - fixed - static_cast<long long>(slots) * kp.ein_slot_bytes;
+        stages = room > 0 ? static_cast<int>(room / kp.stage_bytes) : 0;
+        kp.ein_slots = slots;
+        if (stages >= 3 || (stages >= 2 && stages >= want_stages)) break;
+      }
+    } else {
+      stages = static_cast<int>((SMEM_LIMIT - fixed) / kp.stage_bytes);
+    }
+  }
+  if (stages > want_stages) stages = want_stages;
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  if (stages < 2) return rb_fail("rb_gemm: shared-memory plan failed (bn=%d)", bn);
+  kp.stages = stages;
+  kp.off_ein = stages * kp.stage_bytes;
+  kp.off_out = kp.off_ein + kp.ein_slots * kp.ein_slot_bytes;
+  kp.off_bars = kp.off_out + 2 * kp.out_slots * kp.out_slot_bytes;
+  const int smem_bytes = static_cast<int>(kp.off_bars + bars_bytes + 1024);
+  if (smem_bytes > SMEM_LIMIT) return rb_fail("rb_gemm: shared-memory plan exceeds the limit (%d B)", smem_bytes);
+
+  // ---- tensor maps ---------------------------------------------------------------------------------------------
+  CUtensorMap tmA, tmB, tmOut, tmOut32, tmRes, tmRes32, tmMask;
+  if (a->mode == 0) {
+    if (make_tmap_2d(&tmA, a->A, static_cast<uint64_t>(a->a_cols), static_cast<uint64_t>(a->a_rows), a->lda * 2, 64, BM)) return 1;
+    if (make_tmap_2d(&tmB, a->B, static_cast<uint64_t>(a->b_cols), static_cast<uint64_t>(a->b_rows), a->ldb * 2, 64, bn)) return 1;
+  } else {
+    if (make_tmap_2d(&tmA, a->A, static_cast<uint64_t>(a->a_cols), static_cast<uint64_t>(a->a_rows), a->lda * 2, 64, 64)) return 1;
+    if (make_tmap_2d(&tmB, a->B, static_cast<uint64_t>(a->b_cols), static_cast<uint64_t>(a->b_rows), a->ldb * 2, 64, 64)) return 1;
+  }
+  tmOut = tmA; tmOut32 = tmA; tmRes = tmA; tmRes32 = tmA; tmMask = tmA;  // placeholders for unused maps
+  const uint64_t M64 = static_cast<uint64_t>(a->M), N64 = static_cast<uint64_t>(a->N);
+  if (kp.has_out && make_tmap_2d(&tmOut, static_cast<const __nv_bfloat16*>(a->out) + a->out_row_off * a->ldo, N64, M64, a->ldo * 2, 64, BM)) return 1;
+  if (kp.has_out32 && make_tmap_2d_f32(&tmOut32, a->out32 + a->out_row_off * a->ldo32, N64, M64, a->ldo32 * 4, 32, BM)) return 1;
+  if (kp.has_res && make_tmap_2d(&tmRes, static_cast<const __nv_bfloat16*>(a->res) + a->out_row_off * a->ldres, N64, M64, a->ldres * 2, 64, BM)) return 1;
+  if (kp.has_res32 && make_tmap_2d_f32(&tmRes32, a->res32 + a->out_row_off * a->ldres32, N64, M64, a->ldres32 * 4, 32, BM)) return 1;
+  if (kp.has_mask && make_tmap_2d(&tmMask, static_cast<const __nv_bfloat16*>(a->mask_src) + a->out_row_off * a->ldmask, N64, M64, a->ldmask * 2, 64, BM)) return 1;
+
+  static bool configured[2] = {false, false};
+  const int grid = kp.tiles_total < nsm ? kp.tiles_total : nsm;
+  if (a->mode == 0) {
+    if (!configured[0]) {
+      RB_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+      configured[0] = true;
+    }
+    umma_gemm_kernel<0><<<grid, GEMM_THREADS, smem_bytes, st>>>(tmA, tmB, tmOut, tmOut32, tmRes, tmRes32, tmMask, kp);
+  } else {
+    if (!configured[1]) {
+      RB_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+      configured[1] = true;
+    }
+    umma_gemm_kernel<1><<<grid, GEMM_THREADS, smem_bytes, st>>>(tmA, tmB, tmOut, tmOut32, tmRes, tmRes32, tmMask, kp);
+  }
+  RB_CUDA(cudaGetLastError());
+  return 0;
+}
