@@ -1,0 +1,105 @@
+"""Data-parallel host logic on CPU (gloo, world_size 2): the module wrapped in DistributedDataParallel, exactly as
+main_vg.py:293-296 wraps the reference, must produce the full-batch gradients when every rank runs half of the batch.
+The CUDA kernels are replaced by their torch emulation (tests/emu_ops.py, EXACT fp32 mode) so that the check isolates
+the wiring: one autograd node handing every parameter gradient to DDP's hooks, bucketed all-reduce, averaging."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _patch_emulated():
+    sys.path.insert(0, HERE)
+    sys.path.insert(0, os.path.dirname(HERE))
+    import emu_ops
+    import reftr_b200.engine as engine
+    import reftr_b200.pack as pack
+
+    class Fp32Proxy:
+        def __getattr__(self, name):
+            return torch.float32 if name == "bfloat16" else getattr(torch, name)
+
+    for m in (engine, pack):
+        m.ops = emu_ops
+        m.torch = Fp32Proxy()
+    emu_ops.EXACT[0] = True
+
+
+def _slice_samples(s, lo, hi):
+    from reftr_b200.synthetic import ImageList
+    out = {}
+    for k, v in s.items():
+        out[k] = ImageList(v.tensors[lo:hi], v.mask[lo:hi]) if k == "img" else v[lo:hi]
+    return out
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.set_num_threads(max(1, (os.cpu_count() or 2) // world))
+    _patch_emulated()
+    from oracle.cases import CASES
+    from oracle.reftr_oracle import total_box_loss
+    from reftr_b200.synthetic import synthetic_samples, synthetic_targets
+    from util_build import build_candidate
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    case = CASES["cfg1_box"]
+    model = build_candidate(case)
+    ddp = torch.nn.parallel.DistributedDataParallel(model)
+    B = case["inputs"]["B"]
+    per = B // world
+    s = _slice_samples(synthetic_samples(**case["inputs"]), rank * per, (rank + 1) * per)
+    tgt = synthetic_targets(B)[rank * per:(rank + 1) * per]
+    total_box_loss(ddp(s), tgt).backward()
+    names = ["bbox_embed.layers.0.weight", "vl_transformer.encoder.layers.0.linear1.weight", "img_backbone.0.body.layer3.1.conv2.weight",
+             "input_proj.0.0.weight", "lang_backbone.encoder.layer.0.attention.self.query.weight", "vl_transformer.level_embed"]
+    params = dict(model.named_parameters())
+    if rank == 0:
+        q.put({n: params[n].grad.detach().numpy().copy() for n in names})
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(900)
+def test_ddp_world2_matches_full_batch():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=800)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    # single process, full batch
+    _patch_emulated()
+    from oracle.cases import CASES
+    from oracle.reftr_oracle import total_box_loss
+    from reftr_b200.synthetic import synthetic_samples, synthetic_targets
+    from util_build import build_candidate
+    import emu_ops
+    try:
+        case = CASES["cfg1_box"]
+        model = build_candidate(case)
+        total_box_loss(model(synthetic_samples(**case["inputs"])), synthetic_targets(case["inputs"]["B"])).backward()
+        params = dict(model.named_parameters())
+        for n, g in got.items():
+            ref = params[n].grad
+            g = torch.from_numpy(g)
+            err = ((g - ref).norm() / (ref.norm() + 1e-12)).item()
+            assert err < 1e-3, (n, err)
+    finally:
+        emu_ops.EXACT[0] = False
+        import importlib
+        import reftr_b200.engine as engine
+        import reftr_b200.pack as pack
+        from reftr_b200 import ops as real_ops
+        for m in (engine, pack):
+            m.ops = real_ops
+            m.torch = torch
