@@ -29,7 +29,7 @@ constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int GEMM_THREADS = 352;
 constexpr int MAX_STAGES = 8;
-constexpr int MAX_EIN = 6;
+constexpr int MAX_EIN = 8;
 constexpr int A_BYTES = BM * BK * 2;
 constexpr int SMEM_LIMIT = 232448;  // 227 KB opt-in maximum per CTA
 
@@ -270,20 +270,21 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_wait(&ein_full[es], (g / p.ein_slots) & 1);
           ein = smem + p.off_ein + es * p.ein_slot_bytes;
         }
-        uint8_t* oslot = smem + p.off_out + (team * p.out_slots + (o % p.out_slots)) * p.out_slot_bytes;
+        const bool two_slots = p.out_slots == 2;
+        uint8_t* oslot = smem + p.off_out + (team * p.out_slots + (two_slots ? (o & 1) : 0)) * p.out_slot_bytes;
         ++o;
-        if (!p.atomic) {
-          if (store_thread) {  // the store that last used this slot has finished reading it
-            if (p.out_slots == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
-          }
+        if (!p.atomic && !two_slots) {
+          if (store_thread) tma_store_wait_read<0>();  // the previous store of this team has finished reading the slot
           named_bar_sync(1 + team, 128);
         }
-#pragma unroll 1
+        uint32_t vv[2][32];
+        tmem_ld_32x32(tmem_base + lane_addr + as * bn + ch * 64, vv[0]);
+        tmem_ld_32x32(tmem_base + lane_addr + as * bn + ch * 64 + 32, vv[1]);
+        tmem_ld_wait();
+#pragma unroll
         for (int half = 0; half < 2; ++half) {
           const int hc0 = col0 + half * 32;
-          uint32_t v[32];
-          tmem_ld_32x32(tmem_base + lane_addr + as * bn + ch * 64 + half * 32, v);
-          tmem_ld_wait();
+          const uint32_t (&v)[32] = vv[half];
           if (hc0 >= p.N) continue;  // warp-uniform
           float f[32];
 #pragma unroll
@@ -377,6 +378,9 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (lane == 0) mbar_arrive(&ein_empty[es]);
         }
         fence_proxy_async_smem();
+        // two slots: the store issued one chunk ago must have read ITS slot before the next chunk overwrites it; checking that
+        // here (instead of before writing) needs a single barrier per chunk
+        if (two_slots && store_thread) tma_store_wait_read<0>();
         named_bar_sync(1 + team, 128);
         if (store_thread) {
           if (p.has_out) tma_store_2d(&tmOut, oslot, col0, c.m0);
@@ -452,6 +456,8 @@ extern "C" int rb_gemm(const rb_gemm_args* a, void* stream) {
   const long long tiles_m = (a->M + BM - 1) / BM;
   const long long k_iters = a->mode == 0 ? static_cast<long long>(a->taps) * kp.kblocks : (kp.kblocks + kp.splits - 1) / kp.splits;
   int bn = a->block_n ? a->block_n : pick_bn(a->N, tiles_m * (a->mode == 1 ? a->taps * kp.splits : 1), k_iters, nsm);
+  // output/residual-dominated problems (short main loop + epilogue inputs): narrower tiles leave room for a deep input ring
+  if (!a->block_n && bn == 256 && !a->atomic && (a->res || a->res32 || a->mask_src) && k_iters <= 4) bn = 128;
   if (bn == 32) bn = 64;
   if (bn != 64 && bn != 128 && bn != 256) return rb_fail("rb_gemm: unsupported block_n %d", bn);
   kp.bn = bn;
@@ -483,16 +489,19 @@ extern "C" int rb_gemm(const rb_gemm_args* a, void* stream) {
   kp.out_slots = 2;
   for (int pass = 0; pass < 2 && stages < 2; ++pass) {
     kp.out_slots = 2 - pass;  // second pass: one staging slot per team
-    const long long fixed = 2LL * kp.out_slots * kp.out_slot_bytes + bars_bytes + 1024 /* alignment slack */;
+    const long long room = static_cast<long long>(SMEM_LIMIT) - (2LL * kp.out_slots * kp.out_slot_bytes + bars_bytes + 1024 /* alignment slack */);
     if (has_ein) {
-      for (int slots = MAX_EIN; slots >= 2; --slots) {
-        const long long room = static_cast<long long>(SMEM_LIMIT) - fixed - static_cast<long long>(slots) * kp.ein_slot_bytes;
-        stages = room > 0 ? static_cast<int>(room / kp.stage_bytes) : 0;
-        kp.ein_slots = slots;
-        if (stages >= 3 || (stages >= 2 && stages >= want_stages)) break;
-      }
+      // the epilogue-input ring is what keeps HBM busy when the main loop is short: give it up to MAX_EIN slots after a minimal
+      // main-loop ring, then hand what is left back to the main loop
+      const int min_stages = want_stages < 3 ? want_stages : (k_iters <= 2 ? 2 : 3);
+      long long slots = (room - static_cast<long long>(min_stages) * kp.stage_bytes) / kp.ein_slot_bytes;
+      if (slots > MAX_EIN) slots = MAX_EIN;
+      if (slots < 2) slots = 2;
+      kp.ein_slots = static_cast<int>(slots);
+      const long long left = room - slots * kp.ein_slot_bytes;
+      stages = left > 0 ? static_cast<int>(left / kp.stage_bytes) : 0;
     } else {
-      stages = static_cast<int>((SMEM_LIMIT - fixed) / kp.stage_bytes);
+      stages = static_cast<int>(room / kp.stage_bytes);
     }
   }
   if (stages > want_stages) stages = want_stages;
