@@ -146,6 +146,34 @@ int rb_rows_add(const float* a, long long lda, const int* map_a, const float* b,
 int rb_rows_scatter_add(const float* src, long long lds, const int* map_src, float* dst, long long ldd, const int* map_dst, long long rows,
                         int D, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Segmentation head (reftr_segmentation.py:152-175, :196-207 MHAttentionMap, :243-280 MaskHeadSmallConv).
+ * Grids are padded NHWC (see top); `ld` is the pixel pitch in elements, `col0` the first channel touched.
+ * ------------------------------------------------------------------------------------------------------------- */
+/* visual token rows b*S+L+p of tok fp32 [B*S, C] -> interior pixels of grid bf16, channels [col0, col0+C)  (:166, :243 cat) */
+int rb_tokens_to_grid(const float* tok, int B, int S, int L, int h, int w, int C, void* grid, long long ld, int col0, void* stream);
+/* reverse: dtok[b*S+L+p, :C] = grid[pixel, col0:col0+C] (fp32; language rows are not touched) */
+int rb_grid_to_tokens(const void* grid, long long ld, int col0, int B, int S, int L, int h, int w, int C, float* dtok, void* stream);
+/* MHAttentionMap: q fp32 [B,256] (q_linear output), k fp32 [B*S,256] (k_linear output, visual rows used), kpm u8 [B,S];
+ * logits[b,n,p] = scale * <q[b,32n:32n+32], k[b*S+L+p, 32n:32n+32]>, masked where kpm, softmax over (n,p) jointly;
+ * att fp32 [B,8,hw]; also written as bf16 into grid channels [col0, col0+8) */
+int rb_attn_map_fwd(const float* q, const float* k, const void* kpm, int B, int S, int L, int hw, int w, float scale, float* att, void* grid,
+                    long long ld, int col0, void* stream);
+/* d(att) = datt_ext (nullable, fp32 [B,8,hw]) + grid gradient channels [col0, col0+8) (bf16); dq fp32 [B,256]; dk fp32 [B*S,256]
+ * (language rows written as zero) */
+int rb_attn_map_bwd(const float* datt_ext, const void* dgrid, long long ld, int col0, const float* att, const float* q, const float* k, int B, int S,
+                    int L, int hw, int w, float scale, float* dq, float* dk, void* stream);
+/* nn.GroupNorm(G, C) (+ReLU) over the interior of a padded NHWC fp32 grid [B,H+2,W+2,C] -> bf16 grid (border written as zero) */
+int rb_groupnorm_nhwc_fwd(const float* x, const float* gamma, const float* beta, int B, int H, int W, int C, int G, float eps, int relu, void* y,
+                          float* mean, float* rstd, void* stream);
+/* dy, y bf16 grids (y > 0 is the ReLU mask when relu), x fp32 grid -> dx bf16 grid (border zero); dgamma/dbeta accumulated */
+int rb_groupnorm_nhwc_bwd(const void* dy, const void* y, const float* x, const float* gamma, const float* mean, const float* rstd, int B, int H, int W,
+                          int C, int G, int relu, void* dx, float* dgamma, float* dbeta, void* stream);
+/* y = cur + nearest_upsample(lo) (F.interpolate(mode="nearest") to cur's size, :256-274); bf16 grids, C % 8 == 0 */
+int rb_upsample_add(const void* lo, const void* cur, void* y, int B, int h, int w, int H, int W, int C, void* stream);
+/* dlo[b,sy,sx,:] = sum of dy over the pixels that read (sy,sx) */
+int rb_upsample_bwd(const void* dy, void* dlo, int B, int h, int w, int H, int W, int C, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -222,3 +222,38 @@ def rows_scatter_add(src, dst, rows, D, *, map_src=None, map_dst=None):
     ks, ps = _map(map_src)
     kd, pd = _map(map_dst)
     _lib.call("rb_rows_scatter_add", _p(src), src.stride(0), ps, _p(dst), dst.stride(0), pd, rows, D, _s())
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# segmentation head
+# ---------------------------------------------------------------------------------------------------------------
+def tokens_to_grid(tok, B, S, L, h, w, C, grid, col0):
+    _lib.call("rb_tokens_to_grid", _p(tok), B, S, L, h, w, C, _p(grid), grid.stride(0), col0, _s())
+
+
+def grid_to_tokens(grid, col0, B, S, L, h, w, C, dtok):
+    _lib.call("rb_grid_to_tokens", _p(grid), grid.stride(0), col0, B, S, L, h, w, C, _p(dtok), _s())
+
+
+def attn_map_fwd(q, k, kpm, B, S, L, hw, w, scale, att, grid, col0):
+    _lib.call("rb_attn_map_fwd", _p(q), _p(k), _p(kpm), B, S, L, hw, w, scale, _p(att), _p(grid), grid.stride(0), col0, _s())
+
+
+def attn_map_bwd(datt_ext, dgrid, col0, att, q, k, B, S, L, hw, w, scale, dq, dk):
+    _lib.call("rb_attn_map_bwd", _p(datt_ext), _p(dgrid), dgrid.stride(0), col0, _p(att), _p(q), _p(k), B, S, L, hw, w, scale, _p(dq), _p(dk), _s())
+
+
+def groupnorm_nhwc_fwd(x, gamma, beta, B, H, W, C, G, y, mean, rstd, relu=True, eps=1e-5):
+    _lib.call("rb_groupnorm_nhwc_fwd", _p(x), _p(gamma), _p(beta), B, H, W, C, G, eps, int(relu), _p(y), _p(mean), _p(rstd), _s())
+
+
+def groupnorm_nhwc_bwd(dy, y, x, gamma, mean, rstd, B, H, W, C, G, dx, dgamma, dbeta, relu=True):
+    _lib.call("rb_groupnorm_nhwc_bwd", _p(dy), _p(y), _p(x), _p(gamma), _p(mean), _p(rstd), B, H, W, C, G, int(relu), _p(dx), _p(dgamma), _p(dbeta), _s())
+
+
+def upsample_add(lo, cur, y, B, h, w, H, W, C):
+    _lib.call("rb_upsample_add", _p(lo), _p(cur), _p(y), B, h, w, H, W, C, _s())
+
+
+def upsample_bwd(dy, dlo, B, h, w, H, W, C):
+    _lib.call("rb_upsample_bwd", _p(dy), _p(dlo), B, h, w, H, W, C, _s())

@@ -413,3 +413,101 @@ def rows_scatter_add(src, dst, rows, D, *, map_src=None, map_dst=None):
 
 def require_device(t):
     pass
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# segmentation head
+# ---------------------------------------------------------------------------------------------------------------
+def tokens_to_grid(tok, B, S, L, h, w, C, grid, col0):
+    _LAUNCHES[0] += 1
+    g = grid.view(B, h + 2, w + 2, -1)
+    g[:, 1:-1, 1:-1, col0:col0 + C] = tok.view(B, S, C)[:, L:].reshape(B, h, w, C).to(_lp())
+
+
+def grid_to_tokens(grid, col0, B, S, L, h, w, C, dtok):
+    _LAUNCHES[0] += 1
+    g = grid.view(B, h + 2, w + 2, -1)
+    dtok.view(B, S, C)[:, L:] = g[:, 1:-1, 1:-1, col0:col0 + C].reshape(B, h * w, C).float()
+
+
+def attn_map_fwd(q, k, kpm, B, S, L, hw, w, scale, att, grid, col0):
+    _LAUNCHES[0] += 1
+    qh = q.view(B, 8, 32) * scale
+    kh = k.view(B, S, 8, 32)[:, L:]
+    lg = torch.einsum("bnc,bpnc->bnp", qh, kh)
+    lg = lg.masked_fill(kpm.view(B, S)[:, L:].bool()[:, None, :], float("-inf"))
+    a = torch.softmax(lg.reshape(B, -1), -1).view(B, 8, hw)
+    att.copy_(a)
+    h = hw // w
+    grid.view(B, h + 2, w + 2, -1)[:, 1:-1, 1:-1, col0:col0 + 8] = a.permute(0, 2, 1).reshape(B, h, w, 8).to(_lp())
+
+
+def attn_map_bwd(datt_ext, dgrid, col0, att, q, k, B, S, L, hw, w, scale, dq, dk):
+    _LAUNCHES[0] += 1
+    h = hw // w
+    d = dgrid.view(B, h + 2, w + 2, -1)[:, 1:-1, 1:-1, col0:col0 + 8].reshape(B, hw, 8).permute(0, 2, 1).float()
+    if datt_ext is not None:
+        d = d + datt_ext.view(B, 8, hw)
+    a = att.view(B, 8, hw)
+    dl = a * (d - (a * d).sum((1, 2), keepdim=True)) * scale
+    kh = k.view(B, S, 8, 32)[:, L:]
+    dq.view(B, 8, 32).copy_(torch.einsum("bnp,bpnc->bnc", dl, kh))
+    dk.view(B, S, 8, 32)[:, :L] = 0
+    dk.view(B, S, 8, 32)[:, L:] = torch.einsum("bnp,bnc->bpnc", dl, q.view(B, 8, 32))
+
+
+def groupnorm_nhwc_fwd(x, gamma, beta, B, H, W, C, G, y, mean, rstd, relu=True, eps=1e-5):
+    _LAUNCHES[0] += 1
+    xi = x.view(B, H + 2, W + 2, C)[:, 1:-1, 1:-1].reshape(B, H * W, G, C // G)
+    mu = xi.mean((1, 3), keepdim=True)
+    var = (xi * xi).mean((1, 3), keepdim=True) - mu * mu
+    rs = torch.rsqrt(var.clamp_min(0) + eps)
+    mean.view(B, G).copy_(mu.view(B, G))
+    rstd.view(B, G).copy_(rs.view(B, G))
+    o = ((xi - mu) * rs).reshape(B, H, W, C) * gamma.detach() + beta.detach()
+    if relu:
+        o = o.clamp_min(0)
+    yv = y.view(B, H + 2, W + 2, C)
+    yv.zero_()
+    yv[:, 1:-1, 1:-1] = o.to(_lp())
+
+
+def groupnorm_nhwc_bwd(dy, y, x, gamma, mean, rstd, B, H, W, C, G, dx, dgamma, dbeta, relu=True):
+    _LAUNCHES[0] += 1
+    Cg = C // G
+    d = dy.view(B, H + 2, W + 2, C)[:, 1:-1, 1:-1].float()
+    if relu:
+        d = d * (y.view(B, H + 2, W + 2, C)[:, 1:-1, 1:-1].float() > 0)
+    xi = x.view(B, H + 2, W + 2, C)[:, 1:-1, 1:-1].reshape(B, H * W, G, Cg)
+    xh = (xi - mean.view(B, 1, G, 1)) * rstd.view(B, 1, G, 1)
+    d4 = d.reshape(B, H * W, G, Cg)
+    dgamma += (d4 * xh).sum((0, 1)).reshape(C)
+    dbeta += d4.sum((0, 1)).reshape(C)
+    g = d4 * gamma.detach().view(1, 1, G, Cg)
+    n = H * W * Cg
+    s1 = g.sum((1, 3), keepdim=True) / n
+    s2 = (g * xh).sum((1, 3), keepdim=True) / n
+    o = rstd.view(B, 1, G, 1) * (g - s1 - xh * s2)
+    dv = dx.view(B, H + 2, W + 2, C)
+    dv.zero_()
+    dv[:, 1:-1, 1:-1] = o.reshape(B, H, W, C).to(_lp())
+
+
+def upsample_add(lo, cur, y, B, h, w, H, W, C):
+    _LAUNCHES[0] += 1
+    l = lo.view(B, h + 2, w + 2, C)[:, 1:-1, 1:-1].permute(0, 3, 1, 2).float()
+    up = F.interpolate(l, size=(H, W), mode="nearest").permute(0, 2, 3, 1)
+    yv = y.view(B, H + 2, W + 2, C)
+    yv.zero_()
+    yv[:, 1:-1, 1:-1] = (up + cur.view(B, H + 2, W + 2, C)[:, 1:-1, 1:-1].float()).to(_lp())
+
+
+def upsample_bwd(dy, dlo, B, h, w, H, W, C):
+    _LAUNCHES[0] += 1
+    with torch.enable_grad():
+        l = torch.zeros(B, C, h, w, requires_grad=True)
+        up = F.interpolate(l, size=(H, W), mode="nearest")
+    up.backward(dy.view(B, H + 2, W + 2, C)[:, 1:-1, 1:-1].permute(0, 3, 1, 2).float())
+    dv = dlo.view(B, h + 2, w + 2, C)
+    dv.zero_()
+    dv[:, 1:-1, 1:-1] = l.grad.permute(0, 2, 3, 1).to(_lp())
