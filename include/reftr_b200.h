@@ -174,6 +174,32 @@ int rb_upsample_add(const void* lo, const void* cur, void* y, int B, int h, int 
 /* dlo[b,sy,sx,:] = sum of dy over the pixels that read (sy,sx) */
 int rb_upsample_bwd(const void* dy, void* dlo, int B, int h, int w, int H, int W, int C, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * BERT-base language backbone (HuggingFace BertModel as called at reftr_transformer.py:200, :217; third party in the
+ * reference).  Its linear layers run on rb_gemm; these are the remaining pieces.
+ * ------------------------------------------------------------------------------------------------------------- */
+/* BertEmbeddings before LayerNorm: out[r,:] = word[ids[r]] + pos[r % L] + type0   (token_type_ids = 0, position_ids = arange(L)) */
+int rb_bert_embed_fwd(const long long* ids, long long rows, int L, int D, const float* word, const float* pos, const float* type0, float* out, void* stream);
+/* scatter-add of d [rows, D] into the three embedding tables' gradients (any of them nullable) */
+int rb_bert_embed_bwd(const float* d, const long long* ids, long long rows, int L, int D, float* dword, float* dpos, float* dtype0, void* stream);
+/* nn.LayerNorm over D = 768 / 1024 wide rows: fp32 in, fp32 and/or bf16 out, saves mean / rstd */
+int rb_ln_wide_fwd(const float* x, const float* gamma, const float* beta, long long rows, int D, float eps, float* y32, void* yb, float* mean, float* rstd,
+                   void* stream);
+int rb_ln_wide_bwd(const float* dy, const float* dy2, const float* x, const float* gamma, const float* mean, const float* rstd, long long rows, int D,
+                   float* dx32, void* dxb, float* dgamma, float* dbeta, void* stream);
+/* exact (erf) GELU on bf16, n % 8 == 0; backward takes the PRE-activation x */
+int rb_gelu_fwd(const void* x, void* y, long long n, void* stream);
+int rb_gelu_bwd(const void* dy, const void* x, void* dx, long long n, void* stream);
+/* BertPooler activation */
+int rb_tanh_fwd(const float* x, float* y, long long n, void* stream);
+int rb_tanh_bwd(const float* dy, const float* y, float* dx, void* dxb, long long n, void* stream);
+/* BertSelfAttention core, head_dim 64, S <= 128 tokens: Q,K,V bf16 [B*S, ld] (head h at columns [64h, 64h+64)), mask u8 [B,S]
+ * (1 = ignore key); P fp32 [B,H,S,S] is saved for the backward */
+int rb_attn_small_fwd(const void* Q, const void* K, const void* V, const void* mask, void* O, float* P, int B, int H, int dh, int S, long long ldq,
+                      long long ldk, long long ldv, long long ldo, float scale, void* stream);
+int rb_attn_small_bwd(const void* Q, const void* K, const void* V, const void* dO, const float* P, void* dQ, void* dK, void* dV, int B, int H, int dh, int S,
+                      long long ldq, long long ldk, long long ldv, long long lddo, long long lddq, long long lddk, long long lddv, float scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

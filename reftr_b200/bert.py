@@ -1,0 +1,167 @@
+"""BERT-base (HuggingFace ``BertModel``) forward / backward on the C-ABI kernels -- SURVEY.md 8(f) row N1.
+
+The reference calls ``self.lang_backbone(sentence, token_type_ids=None, attention_mask=sentence_mask)`` (reftr_transformer.py:200)
+and, for multi-phrase inputs, once more on the phrases (:217), taking ``[0]`` (sequence output) and ``[1]`` (pooler output).
+The HF module stays the PARAMETER CONTAINER (state_dict keys ``lang_backbone.*`` unchanged); this class restates its math:
+BertEmbeddings (word + position + token-type-0, LayerNorm eps 1e-12) -> N x [self-attention (12 heads x 64, additive key mask),
+dense + residual + LayerNorm, dense + exact GELU, dense + residual + LayerNorm] -> pooler (dense on token 0, tanh).
+Residual stream and LayerNorm statistics are fp32; GEMM operands bf16 (as in the rest of the hot path).
+"""
+import torch
+
+from . import ops
+from .pack import PackedLinear, PackedStack
+
+
+class _L:
+    pass
+
+
+class BertEngine:
+    @staticmethod
+    def eligible(bert):
+        cfg = getattr(bert, "config", None)
+        if cfg is None or type(bert).__name__ != "BertModel":
+            return False
+        ok = cfg.hidden_act == "gelu" and cfg.hidden_size in (768, 1024) and cfg.hidden_size // cfg.num_attention_heads == 64
+        ok = ok and getattr(cfg, "position_embedding_type", None) in (None, "absolute") and getattr(bert, "pooler", None) is not None
+        flags = {p.requires_grad for p in bert.parameters()}
+        return ok and len(flags) == 1  # all trainable or all frozen
+
+    def __init__(self, eng, bert):
+        self.eng, self.bert = eng, bert
+        cfg = bert.config
+        self.D, self.H, self.FF, self.eps = cfg.hidden_size, cfg.num_attention_heads, cfg.intermediate_size, cfg.layer_norm_eps
+        self.trainable = all(p.requires_grad for p in bert.parameters())
+        self.layers = []
+        self.packs = []
+        for lay in bert.encoder.layer:
+            a = lay.attention
+            l = _L()
+            l.mod = lay
+            l.qkv = PackedStack([a.self.query.weight, a.self.key.weight, a.self.value.weight],
+                                [a.self.query.bias, a.self.key.bias, a.self.value.bias], 0, self.D)
+            l.o = PackedLinear(a.output.dense.weight, a.output.dense.bias)
+            l.i = PackedLinear(lay.intermediate.dense.weight, lay.intermediate.dense.bias)
+            l.o2 = PackedLinear(lay.output.dense.weight, lay.output.dense.bias)
+            self.layers.append(l)
+            self.packs += [l.qkv, l.o, l.i, l.o2]
+        self.pool = PackedLinear(bert.pooler.dense.weight, bert.pooler.dense.bias)
+        self.packs.append(self.pool)
+        self.saved = {}
+
+    # ------------------------------------------------------------------------------------------------------------
+    def forward(self, tag, ids, mask_u8, Bn, L):
+        """ids int64 [Bn, L], mask_u8 [Bn, L] (1 = padding key).  Returns (seq fp32 [Bn*L, D], seq bf16, pooled fp32 [Bn, D])."""
+        eng, ws, bert = self.eng, self.eng.ws, self.bert
+        D, H, FF = self.D, self.H, self.FF
+        if L > bert.config.max_position_embeddings:
+            raise ValueError(f"{L} tokens exceed BERT's {bert.config.max_position_embeddings} positions")
+        rows = Bn * L
+        f32 = torch.float32
+        emb = bert.embeddings
+        e32 = ws.get(f"bert.{tag}.emb", [rows, D], f32)
+        ops.bert_embed_fwd(ids, L, emb.word_embeddings.weight, emb.position_embeddings.weight, emb.token_type_embeddings.weight[0], e32)
+        x32, xb = ws.get(f"bert.{tag}.x0", [rows, D], f32), ws.get(f"bert.{tag}.x0b", [rows, D])
+        me, re_ = ws.get(f"bert.{tag}.me", [rows], f32), ws.get(f"bert.{tag}.re", [rows], f32)
+        ops.ln_wide_fwd(e32, emb.LayerNorm.weight, emb.LayerNorm.bias, rows, y32=x32, yb=xb, mean=me, rstd=re_, eps=self.eps)
+        scale = 64 ** -0.5
+        per_layer = []
+        for li, l in enumerate(self.layers):
+            k = f"bert.{tag}.{li}"
+            lay = l.mod
+            qkv = ws.get(k + ".qkv", [rows, 3 * D])
+            ops.gemm(xb, l.qkv.wb, rows, 3 * D, D, bias=l.qkv.bias, out=qkv)
+            ctx = ws.get(k + ".ctx", [rows, D])
+            P = ws.get(k + ".P", [Bn, H, L, L], f32)
+            ops.attn_small_fwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], mask_u8, ctx, P, Bn, H, L, scale)
+            y1 = ws.get(k + ".y1", [rows, D], f32)
+            ops.gemm(ctx, l.o.wb, rows, D, D, bias=l.o.bias, res32=x32, out32=y1)
+            x1, x1b = ws.get(k + ".x1", [rows, D], f32), ws.get(k + ".x1b", [rows, D])
+            m1, r1 = ws.get(k + ".m1", [rows], f32), ws.get(k + ".r1", [rows], f32)
+            ln1 = lay.attention.output.LayerNorm
+            ops.ln_wide_fwd(y1, ln1.weight, ln1.bias, rows, y32=x1, yb=x1b, mean=m1, rstd=r1, eps=self.eps)
+            hpre, h = ws.get(k + ".hpre", [rows, FF]), ws.get(k + ".h", [rows, FF])
+            ops.gemm(x1b, l.i.wb, rows, FF, D, bias=l.i.bias, out=hpre)
+            ops.gelu_fwd(hpre, h)
+            y2 = ws.get(k + ".y2", [rows, D], f32)
+            ops.gemm(h, l.o2.wb, rows, D, FF, bias=l.o2.bias, res32=x1, out32=y2)
+            xo, xob = ws.get(k + ".xo", [rows, D], f32), ws.get(k + ".xob", [rows, D])
+            m2, r2 = ws.get(k + ".m2", [rows], f32), ws.get(k + ".r2", [rows], f32)
+            ln2 = lay.output.LayerNorm
+            ops.ln_wide_fwd(y2, ln2.weight, ln2.bias, rows, y32=xo, yb=xob, mean=m2, rstd=r2, eps=self.eps)
+            per_layer.append((xb, qkv, ctx, P, y1, m1, r1, x1b, hpre, h, y2, m2, r2))
+            x32, xb = xo, xob
+        cls_b = xb.view(Bn, L * D)[:, :D]  # token 0 of every sequence (row pitch L*D)
+        ppre = ws.get(f"bert.{tag}.ppre", [Bn, D], f32)
+        ops.gemm(cls_b, self.pool.wb, Bn, D, D, bias=self.pool.bias, out32=ppre)
+        pooled = ws.get(f"bert.{tag}.pooled", [Bn, D], f32)
+        ops.tanh_fwd(ppre, pooled)
+        self.saved[tag] = (ids, mask_u8, Bn, L, e32, me, re_, per_layer, cls_b, pooled)
+        return x32, xb, pooled
+
+    # ------------------------------------------------------------------------------------------------------------
+    def backward(self, tag, d_seq, d_pooled):
+        """d_seq fp32 [Bn*L, D] or None, d_pooled fp32 [Bn, D] or None; parameter gradients are accumulated into the engine's
+        flat gradient buffer (the sentence and the phrase invocation share the weights)."""
+        if not self.trainable:
+            return
+        eng, ws, bert = self.eng, self.eng.ws, self.bert
+        G = eng.G
+        D, H, FF = self.D, self.H, self.FF
+        ids, mask_u8, Bn, L, e32, me, re_, per_layer, cls_b, pooled = self.saved[tag]
+        rows = Bn * L
+        f32 = torch.float32
+        gbuf = [ws.get(f"bertb.{tag}.gA", [rows, D], f32), ws.get(f"bertb.{tag}.gB", [rows, D], f32)]
+        g = gbuf[0]
+        if d_seq is None:
+            g.zero_()
+        else:
+            g.copy_(d_seq.reshape(rows, D))
+        if d_pooled is not None:
+            dpre = ws.get(f"bertb.{tag}.dpre", [Bn, D], f32)
+            dpreb = ws.get(f"bertb.{tag}.dpreb", [Bn, D])
+            ops.tanh_bwd(d_pooled.reshape(Bn, D), pooled, dx=dpre, dxb=dpreb)
+            ops.colsum(dpre, G(bert.pooler.dense.bias))
+            eng.wgrad_linear(dpreb, cls_b, G(bert.pooler.dense.weight), D, D, Bn)
+            dcls = ws.get(f"bertb.{tag}.dcls", [Bn, D], f32)
+            ops.gemm(dpreb, self.pool.wt, Bn, D, D, out32=dcls)
+            ops.rows_scatter_add(dcls, g, Bn, D, map_dst=(1, L, 0, 0))
+        scale = 64 ** -0.5
+        for li in reversed(range(len(self.layers))):
+            l = self.layers[li]
+            lay = l.mod
+            a = lay.attention
+            xb, qkv, ctx, P, y1, m1, r1, x1b, hpre, h, y2, m2, r2 = per_layer[li]
+            ln1, ln2 = a.output.LayerNorm, lay.output.LayerNorm
+            dy2, dy2b = ws.get(f"bertb.{tag}.dy2", [rows, D], f32), ws.get(f"bertb.{tag}.dy2b", [rows, D])
+            ops.ln_wide_bwd(g, y2, ln2.weight, m2, r2, rows, dx32=dy2, dxb=dy2b, dgamma=G(ln2.weight), dbeta=G(ln2.bias))
+            ops.colsum(dy2, G(lay.output.dense.bias))
+            eng.wgrad_linear(dy2b, h, G(lay.output.dense.weight), D, FF, rows)
+            dh = ws.get(f"bertb.{tag}.dh", [rows, FF])
+            ops.gemm(dy2b, l.o2.wt, rows, FF, D, out=dh)
+            dhp = ws.get(f"bertb.{tag}.dhp", [rows, FF])
+            ops.gelu_bwd(dh, hpre, dhp)
+            ops.colsum(dhp, G(lay.intermediate.dense.bias))
+            eng.wgrad_linear(dhp, x1b, G(lay.intermediate.dense.weight), FF, D, rows)
+            g1 = ws.get(f"bertb.{tag}.g1", [rows, D], f32)
+            ops.gemm(dhp, l.i.wt, rows, D, FF, res32=dy2, out32=g1)
+            dy1, dy1b = ws.get(f"bertb.{tag}.dy1", [rows, D], f32), ws.get(f"bertb.{tag}.dy1b", [rows, D])
+            ops.ln_wide_bwd(g1, y1, ln1.weight, m1, r1, rows, dx32=dy1, dxb=dy1b, dgamma=G(ln1.weight), dbeta=G(ln1.bias))
+            ops.colsum(dy1, G(a.output.dense.bias))
+            eng.wgrad_linear(dy1b, ctx, G(a.output.dense.weight), D, D, rows)
+            dctx = ws.get(f"bertb.{tag}.dctx", [rows, D])
+            ops.gemm(dy1b, l.o.wt, rows, D, D, out=dctx)
+            dqkv = ws.get(f"bertb.{tag}.dqkv", [rows, 3 * D])
+            ops.attn_small_bwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], dctx, P, dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:], Bn, H, L, scale)
+            for j, lin in enumerate((a.self.query, a.self.key, a.self.value)):
+                sl = dqkv[:, j * D:(j + 1) * D]
+                ops.colsum(sl, G(lin.bias))
+                eng.wgrad_linear(sl, xb, G(lin.weight), D, D, rows)
+            g_in = gbuf[1] if g is gbuf[0] else gbuf[0]
+            ops.gemm(dqkv, l.qkv.wt, rows, D, 3 * D, res32=dy1, out32=g_in)
+            g = g_in
+        emb = bert.embeddings
+        de = ws.get(f"bertb.{tag}.de", [rows, D], f32)
+        ops.ln_wide_bwd(g, e32, emb.LayerNorm.weight, me, re_, rows, dx32=de, dgamma=G(emb.LayerNorm.weight), dbeta=G(emb.LayerNorm.bias))
+        ops.bert_embed_bwd(de, ids, L, G(emb.word_embeddings.weight), G(emb.position_embeddings.weight), G(emb.token_type_embeddings.weight)[0])

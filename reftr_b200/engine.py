@@ -164,8 +164,15 @@ class RefTREngine:
             from .seg import SegHead
             self.seghead = SegHead(self, model)
             self.packs += self.seghead.packs
+        # ---- language backbone: BERT on the same kernels when it is a plain HF BertModel, else it stays PyTorch
+        from .bert import BertEngine
+        self.bert = None
+        if os.environ.get("REFTR_B200_NATIVE_BERT", "1") != "0" and BertEngine.eligible(model.lang_backbone):
+            self.bert = BertEngine(self, model.lang_backbone)
+            self.packs += self.bert.packs
         # ---- gradient store -------------------------------------------------------------------------------------
-        self.named = [(n, p) for n, p in model.named_parameters() if p.requires_grad and not n.startswith("lang_backbone.")]
+        self.named = [(n, p) for n, p in model.named_parameters()
+                      if p.requires_grad and (self.bert is not None or not n.startswith("lang_backbone."))]
         self.pnames = {id(p): n for n, p in self.named}
         self.slots = {}
         off = 0
@@ -227,24 +234,41 @@ class RefTREngine:
             self._states[key if graphed else "eager"] = st
         return st
 
-    def run_forward(self, img, img_mask, sent_mask, mask_context, query_mask, n_ph, want_seg, sent_feat, pooled):
+    def run_forward(self, img, img_mask, sent_mask, mask_context, query_mask, n_ph, want_seg, sent_feat, pooled, sent_ids=None, ph_ids=None,
+                    ph_mask=None):
+        """Language input is either BERT's outputs (``sent_feat`` [B,L,768], ``pooled`` [B*n_ph,768]; BERT ran in PyTorch) or,
+        when BERT runs on our kernels (``self.bert``), the token ids: ``sent_ids`` [B,L] and optionally ``ph_ids`` / ``ph_mask``
+        [B,n_ph,Lp] of the multi-phrase configs."""
         ops.require_device(img)
         if next(self.model.parameters()).device != img.device:
             raise RuntimeError("reftr_b200: model parameters and inputs are on different devices")
         self._prepare(img.device)
         self.step_id += 1
-        B, L = sent_feat.shape[:2]
+        native = self.bert is not None
+        B, L = sent_mask.shape[:2]
         T = n_ph * self.model.num_queries_per_phrase
-        key = (tuple(img.shape), L, n_ph, bool(want_seg), tuple(pooled.shape))
+        Lp = ph_ids.shape[-1] if (native and ph_ids is not None) else 0
+        key = (tuple(img.shape), L, n_ph, bool(want_seg), native, Lp)
         st = self._state(key)
         self._cur = st
         self.ws = ws = st["ws"]
-        args = (ws.get("in.img", img.shape, torch.float32), ws.get("in.imask", img_mask.shape, torch.bool),
-                ws.get("in.smask", [B, L], torch.int64), ws.get("in.mctx", [B, n_ph, L], torch.uint8), ws.get("in.qmask", [B, T], torch.uint8),
-                ws.get("in.sf", sent_feat.shape, torch.float32), ws.get("in.pl", [B * n_ph, pooled.shape[-1]], torch.float32))
-        for dst, src in zip(args, (img, img_mask, sent_mask, mask_context, query_mask, sent_feat, pooled)):
+        args = [ws.get("in.img", img.shape, torch.float32), ws.get("in.imask", img_mask.shape, torch.bool),
+                ws.get("in.smask", [B, L], torch.int64), ws.get("in.mctx", [B, n_ph, L], torch.uint8), ws.get("in.qmask", [B, T], torch.uint8)]
+        srcs = [img, img_mask, sent_mask, mask_context, query_mask]
+        if native:
+            args += [ws.get("in.sids", [B, L], torch.int64), ws.get("in.lmask", [B, L], torch.uint8)]
+            srcs += [sent_ids, sent_mask == 0]
+            if Lp:
+                args += [ws.get("in.pids", [B * n_ph, Lp], torch.int64), ws.get("in.pmask", [B * n_ph, Lp], torch.uint8)]
+                srcs += [ph_ids, ph_mask == 0]
+            lang = ("ids",) + tuple(args[5:])
+        else:
+            args += [ws.get("in.sf", sent_feat.shape, torch.float32), ws.get("in.pl", [B * n_ph, pooled.shape[-1]], torch.float32)]
+            srcs += [sent_feat, pooled]
+            lang = ("feat",) + tuple(args[5:])
+        for dst, src in zip(args, srcs):
             dst.copy_(src.reshape(dst.shape))
-        a = (args[0], args[1], args[2], args[3], args[4], n_ph, want_seg, args[5], args[6])
+        a = (args[0], args[1], args[2], args[3], args[4], n_ph, want_seg, lang)
         if self.force_eager:
             st["outs"] = self.forward(*a)
             if st["fwd"] is None:
@@ -300,6 +324,8 @@ class RefTREngine:
         self.launches += st["bl"]
         d_sent, d_pooled = st["bouts"]
         # fresh storage per step: autograd may keep these as .grad of leaf tensors
+        if self.bert is not None:
+            return None, None, self.gflat[:self.n_grad].clone()
         return d_sent.clone(), d_pooled.clone(), self.gflat[:self.n_grad].clone()
 
     def G(self, name_or_param):
@@ -822,15 +848,16 @@ class RefTREngine:
     # ------------------------------------------------------------------------------------------------------------
     # top level
     # ------------------------------------------------------------------------------------------------------------
-    def forward(self, img, img_mask, sent_mask, mask_context, query_mask, n_ph, want_seg, sent_feat, pooled):
+    def forward(self, img, img_mask, sent_mask, mask_context, query_mask, n_ph, want_seg, lang):
         """All tensor arguments are static workspace buffers staged by ``run_forward`` (fp32 image, bool image mask,
-        int64 sentence mask, u8 context / query masks, fp32 BERT features)."""
+        int64 sentence mask, u8 context / query masks; ``lang`` = ("feat", BERT features, pooled) or ("ids", token ids, key mask,
+        [phrase ids, phrase key mask]))."""
         m = self.model
         ws = self.ws
         self.saved = {}
         vt = m.vl_transformer
         B, _, H, W = img.shape
-        L = sent_feat.shape[1]
+        L = sent_mask.shape[1]
         n_q = m.num_queries_per_phrase
         T = n_ph * n_q
         if L > vt.max_lang_seq:
@@ -857,8 +884,14 @@ class RefTREngine:
         gmean, grstd = ws.get("iproj.mean", [B * 32], torch.float32), ws.get("iproj.rstd", [B * 32], torch.float32)
         ops.groupnorm_tokens_fwd(proj32, gn.weight, gn.bias, B, h, w, S, L, x32, xb, pos32, xpb, gmean, grstd, eps=gn.eps)
         # ---- language features -> language token rows (reftr_transformer.py:201, reftr.py:79-97) -------------------
-        sfb = ws.get("lang.sfb", [B * L, sent_feat.shape[-1]])
-        ops.cast_bf16(sent_feat.view(B * L, -1), sfb)
+        if lang[0] == "ids":  # BERT on our kernels (reftr_transformer.py:200, :215-217)
+            _, sfb, pooled = self.bert.forward("s", lang[1], lang[2], B, L)
+            if len(lang) > 3:
+                _, _, pooled = self.bert.forward("p", lang[3], lang[4], B * n_ph, lang[3].shape[1])
+        else:
+            sent_feat, pooled = lang[1], lang[2]
+            sfb = ws.get("lang.sfb", [B * L, sent_feat.shape[-1]])
+            ops.cast_bf16(sent_feat.view(B * L, -1), sfb)
         self._mlp_map_fwd("map_sentence", self.map_sentence, m.map_sentence, sfb, B * L, sfb.shape[1], y32=x32, yb=xb, ypb=xpb,
                           pos32=pos32, rowmap=(L, S, 0))
         plb = ws.get("lang.plb", [B * n_ph, pooled.shape[-1]])
@@ -880,7 +913,7 @@ class RefTREngine:
         ops.gemm(hsb, self.bbox[0].wb, rh, D, D, bias=self.bbox[0].bias, relu=True, out=z0)
         ops.gemm(z0, self.bbox[1].wb, rh, D, D, bias=self.bbox[1].bias, relu=True, out=z1)
         ops.gemm(z1, self.bbox[2].wb, rh, 64, D, bias=self.bbox[2].bias, out32=logits)
-        self.dims = (B, H, W, h, w, L, S, T, n_ph, n_q)
+        self.dims = (B, H, W, h, w, L, S, T, n_ph, n_q, lang[0] == "ids", len(lang) > 3)
         self.saved["top"] = (feats, c5, g5, pos32, kpm, mctx, qmask, proj32, gmean, grstd, mem32, memb, mempb, hs32, hsb, z0, z1)
         outs = [logits[:, :4].reshape(nl, B, n_ph, n_q, 4)]
         if want_seg:
@@ -892,7 +925,7 @@ class RefTREngine:
         m = self.model
         ws = self.ws
         vt = m.vl_transformer
-        B, H, W, h, w, L, S, T, n_ph, n_q = self.dims
+        B, H, W, h, w, L, S, T, n_ph, n_q, native_bert, has_phrases = self.dims
         feats, c5, g5, pos32, kpm, mctx, qmask, proj32, gmean, grstd, mem32, memb, mempb, hs32, hsb, z0, z1 = self.saved["top"]
         rows, rt = B * S, B * T
         nl = len(self.dec)
@@ -948,6 +981,12 @@ class RefTREngine:
             g5y = ws.get("iproj.gc5", [g5.R, 2048])
             ops.gemm(dproj, self.iproj.wd, g5.R, 2048, D, res=g_fpn.get(4), mask_src=c5, out=g5y)
             self._backbone_bwd(g5y, g_fpn)
+        if native_bert:
+            if has_phrases:
+                self.bert.backward("p", None, d_pooled)
+                self.bert.backward("s", d_sent, None)
+            else:
+                self.bert.backward("s", d_sent, d_pooled)
         return d_sent.view(B, L, -1), d_pooled
 
 
@@ -956,8 +995,10 @@ class HotPathFunction(torch.autograd.Function):
     phrase features, and every trainable hot-path parameter (so DistributedDataParallel's hooks fire as usual)."""
 
     @staticmethod
-    def forward(ctx, eng, img, img_mask, sent_mask, mask_context, query_mask, n_ph, want_seg, sent_feat, pooled, *params):
-        outs = eng.run_forward(img, img_mask, sent_mask, mask_context, query_mask, n_ph, want_seg, sent_feat.detach(), pooled.detach())
+    def forward(ctx, eng, img, img_mask, sent_mask, mask_context, query_mask, n_ph, want_seg, sent_feat, pooled, sent_ids, ph_ids, ph_mask, *params):
+        outs = eng.run_forward(img, img_mask, sent_mask, mask_context, query_mask, n_ph, want_seg,
+                               sent_feat.detach() if sent_feat is not None else None, pooled.detach() if pooled is not None else None,
+                               sent_ids, ph_ids, ph_mask)
         ctx.eng = eng
         ctx.n_params = len(params)
         ctx.want_seg = want_seg
@@ -980,4 +1021,4 @@ class HotPathFunction(torch.autograd.Function):
         for n, p in eng.named:
             off, shape = eng.slots[n]
             grads.append(flat[off:off + p.numel()].view(shape))
-        return (None, None, None, None, None, None, None, None, d_sent, d_pooled, *grads)
+        return (None, None, None, None, None, None, None, None, d_sent, d_pooled, None, None, None, *grads)

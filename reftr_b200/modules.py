@@ -255,6 +255,8 @@ class RefTR(nn.Module):
         sentence, sentence_mask = samples["sentence"], samples["sentence_mask"]
         B, L = sentence.shape
         n_q = self.num_queries_per_phrase
+        if self.engine().bert is not None:  # BERT runs inside the engine on the C-ABI kernels; only the masks are built here
+            return self._language_masks(samples) + (None, None)
         if self.tf32_bert and not torch.backends.cuda.matmul.allow_tf32:
             # BERT is a third-party PyTorch module (reftr_transformer.py:8); its fp32 GEMMs run on the tensor cores in TF32,
             # forward AND backward (autograd runs the backward outside any scope, so the switch is process-wide).
@@ -265,7 +267,16 @@ class RefTR(nn.Module):
             ph, pm = samples["phrase"], samples["phrase_mask"]
             n_ph = ph.size(1)
             pooled = self.lang_backbone(ph.reshape(B * n_ph, -1), token_type_ids=None, attention_mask=pm.reshape(B * n_ph, -1))[1]
+        return self._language_masks(samples) + (sent_feat, pooled)
+
+    def _language_masks(self, samples):
+        """phrase / context masks of reftr_transformer.py:206-248, vectorised (no host syncs)."""
+        sentence, sentence_mask = samples["sentence"], samples["sentence_mask"]
+        B, L = sentence.shape
+        n_q = self.num_queries_per_phrase
         if "phrase" in samples:
+            pm = samples["phrase_mask"]
+            n_ph = samples["phrase"].size(1)
             ar = torch.arange(L, device=sentence.device).view(1, 1, L)
             inside = (ar >= samples["phrase_pos_l"].unsqueeze(-1)) & (ar < samples["phrase_pos_r"].unsqueeze(-1))
             mask_context = ~inside
@@ -276,18 +287,20 @@ class RefTR(nn.Module):
             ar = torch.arange(L, device=sentence.device).view(1, L)
             mask_context = (sentence_mask.to(torch.bool).logical_not() | (ar == 0) | (ar == (slen - 1).view(B, 1))).view(B, 1, L)
             query_mask = torch.zeros((B, 1), dtype=torch.bool, device=sentence.device)
-        return sent_feat, pooled, mask_context, query_mask, n_ph
+        return mask_context, query_mask, n_ph
 
     def _hot_path(self, samples, want_seg=False):
         img = samples["img"]
         if not hasattr(img, "decompose"):
             raise TypeError("samples['img'] must be a NestedTensor-like object with .tensors / .mask (util/misc.py:308)")
         tensors, mask = img.decompose()
-        sent_feat, pooled, mask_context, query_mask, n_ph = self._language(samples)
+        mask_context, query_mask, n_ph, sent_feat, pooled = self._language(samples)
         eng = self.engine()
         params = eng.param_list()
+        ph_ids = samples.get("phrase") if isinstance(samples, dict) else None
+        ph_mask = samples.get("phrase_mask") if ph_ids is not None else None
         outs = HotPathFunction.apply(eng, tensors, mask, samples["sentence_mask"], mask_context, query_mask, n_ph, want_seg,
-                                     sent_feat, pooled, *params)
+                                     sent_feat, pooled, samples["sentence"], ph_ids, ph_mask, *params)
         return outs, query_mask, n_ph
 
     def forward(self, samples):

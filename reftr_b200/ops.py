@@ -257,3 +257,48 @@ def upsample_add(lo, cur, y, B, h, w, H, W, C):
 
 def upsample_bwd(dy, dlo, B, h, w, H, W, C):
     _lib.call("rb_upsample_bwd", _p(dy), _p(dlo), B, h, w, H, W, C, _s())
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# BERT
+# ---------------------------------------------------------------------------------------------------------------
+def bert_embed_fwd(ids, L, word, pos, type0, out):
+    assert ids.dtype == torch.int64 and ids.is_contiguous()
+    _lib.call("rb_bert_embed_fwd", _p(ids), ids.numel(), L, word.shape[1], _p(word), _p(pos), _p(type0), _p(out), _s())
+
+
+def bert_embed_bwd(d, ids, L, dword, dpos, dtype0):
+    _lib.call("rb_bert_embed_bwd", _p(d), _p(ids), ids.numel(), L, d.shape[1], _p(dword), _p(dpos), _p(dtype0), _s())
+
+
+def ln_wide_fwd(x, gamma, beta, rows, *, y32=None, yb=None, mean=None, rstd=None, eps=1e-12):
+    _lib.call("rb_ln_wide_fwd", _p(x), _p(gamma), _p(beta), rows, x.shape[-1], eps, _p(y32), _p(yb), _p(mean), _p(rstd), _s())
+
+
+def ln_wide_bwd(dy, x, gamma, mean, rstd, rows, *, dy2=None, dx32=None, dxb=None, dgamma=None, dbeta=None):
+    _lib.call("rb_ln_wide_bwd", _p(dy), _p(dy2), _p(x), _p(gamma), _p(mean), _p(rstd), rows, x.shape[-1], _p(dx32), _p(dxb), _p(dgamma), _p(dbeta), _s())
+
+
+def gelu_fwd(x, y):
+    _lib.call("rb_gelu_fwd", _p(x), _p(y), x.numel(), _s())
+
+
+def gelu_bwd(dy, x, dx):
+    _lib.call("rb_gelu_bwd", _p(dy), _p(x), _p(dx), x.numel(), _s())
+
+
+def tanh_fwd(x, y):
+    _lib.call("rb_tanh_fwd", _p(x), _p(y), x.numel(), _s())
+
+
+def tanh_bwd(dy, y, dx=None, dxb=None):
+    _lib.call("rb_tanh_bwd", _p(dy), _p(y), _p(dx), _p(dxb), y.numel(), _s())
+
+
+def attn_small_fwd(Q, K, V, mask, O, P, B, H, S, scale):
+    _lib.call("rb_attn_small_fwd", _p(Q), _p(K), _p(V), _p(mask), _p(O), _p(P), B, H, 64, S, Q.stride(0), K.stride(0), V.stride(0), O.stride(0), scale, _s())
+
+
+def attn_small_bwd(Q, K, V, dO, P, dQ, dK, dV, B, H, S, scale):
+    _lib.call("rb_attn_small_bwd", _p(Q), _p(K), _p(V), _p(dO), _p(P), _p(dQ), _p(dK), _p(dV), B, H, 64, S, Q.stride(0), K.stride(0), V.stride(0),
+              dO.stride(0), dQ.stride(0), dK.stride(0), dV.stride(0), scale, _s())

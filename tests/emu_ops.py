@@ -511,3 +511,114 @@ def upsample_bwd(dy, dlo, B, h, w, H, W, C):
     dv = dlo.view(B, h + 2, w + 2, C)
     dv.zero_()
     dv[:, 1:-1, 1:-1] = l.grad.permute(0, 2, 3, 1).to(_lp())
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# BERT
+# ---------------------------------------------------------------------------------------------------------------
+def bert_embed_fwd(ids, L, word, pos, type0, out):
+    _LAUNCHES[0] += 1
+    rows = ids.numel()
+    t = torch.arange(rows) % L
+    out.copy_(word.detach()[ids.reshape(-1)] + pos.detach()[t] + type0.detach().reshape(1, -1))
+
+
+def bert_embed_bwd(d, ids, L, dword, dpos, dtype0):
+    _LAUNCHES[0] += 1
+    rows = ids.numel()
+    t = torch.arange(rows) % L
+    if dword is not None:
+        dword.index_add_(0, ids.reshape(-1), d)
+    if dpos is not None:
+        dpos.index_add_(0, t, d)
+    if dtype0 is not None:
+        dtype0 += d.sum(0).reshape(dtype0.shape)
+
+
+def ln_wide_fwd(x, gamma, beta, rows, *, y32=None, yb=None, mean=None, rstd=None, eps=1e-12):
+    _LAUNCHES[0] += 1
+    xx = x[:rows]
+    mu = xx.mean(-1, keepdim=True)
+    var = ((xx - mu) ** 2).mean(-1, keepdim=True)
+    rs = torch.rsqrt(var + eps)
+    y = (xx - mu) * rs * gamma.detach() + beta.detach()
+    if mean is not None:
+        mean[:rows] = mu.flatten()
+        rstd[:rows] = rs.flatten()
+    if y32 is not None:
+        y32[:rows] = y
+    if yb is not None:
+        yb[:rows] = y.to(_lp())
+
+
+def ln_wide_bwd(dy, x, gamma, mean, rstd, rows, *, dy2=None, dx32=None, dxb=None, dgamma=None, dbeta=None):
+    _LAUNCHES[0] += 1
+    d = dy[:rows] if dy2 is None else dy[:rows] + dy2[:rows]
+    xh = (x[:rows] - mean[:rows, None]) * rstd[:rows, None]
+    if dgamma is not None:
+        dgamma += (d * xh).sum(0)
+    if dbeta is not None:
+        dbeta += d.sum(0)
+    g = d * gamma.detach()
+    s1 = g.mean(-1, keepdim=True)
+    s2 = (g * xh).mean(-1, keepdim=True)
+    dx = rstd[:rows, None] * (g - s1 - xh * s2)
+    if dx32 is not None:
+        dx32[:rows] = dx
+    if dxb is not None:
+        dxb[:rows] = dx.to(_lp())
+
+
+def gelu_fwd(x, y):
+    _LAUNCHES[0] += 1
+    y.copy_(F.gelu(x.float()).to(_lp()))
+
+
+def gelu_bwd(dy, x, dx):
+    _LAUNCHES[0] += 1
+    xf = x.float()
+    g = 0.5 * (1 + torch.erf(xf / math.sqrt(2))) + xf * torch.exp(-0.5 * xf * xf) / math.sqrt(2 * math.pi)
+    dx.copy_((dy.float() * g).to(_lp()))
+
+
+def tanh_fwd(x, y):
+    _LAUNCHES[0] += 1
+    y.copy_(torch.tanh(x))
+
+
+def tanh_bwd(dy, y, dx=None, dxb=None):
+    _LAUNCHES[0] += 1
+    v = dy * (1 - y * y)
+    if dx is not None:
+        dx.copy_(v)
+    if dxb is not None:
+        dxb.copy_(v.to(_lp()))
+
+
+def attn_small_fwd(Q, K, V, mask, O, P, B, H, S, scale):
+    _LAUNCHES[0] += 1
+    q = Q.float().reshape(B, S, H, 64).transpose(1, 2) * scale
+    k = K.float().reshape(B, S, H, 64).transpose(1, 2)
+    v = V.float().reshape(B, S, H, 64).transpose(1, 2)
+    s = q @ k.transpose(-1, -2)
+    if mask is not None:
+        s = s.masked_fill(mask.view(B, 1, 1, S).bool(), float("-inf"))
+    p = torch.softmax(s, -1)
+    P.view(B, H, S, S).copy_(p)
+    O.copy_((p @ v).transpose(1, 2).reshape(B * S, H * 64).to(_lp()))
+
+
+def attn_small_bwd(Q, K, V, dO, P, dQ, dK, dV, B, H, S, scale):
+    _LAUNCHES[0] += 1
+    q = Q.float().reshape(B, S, H, 64).transpose(1, 2)
+    k = K.float().reshape(B, S, H, 64).transpose(1, 2)
+    v = V.float().reshape(B, S, H, 64).transpose(1, 2)
+    do = dO.float().reshape(B, S, H, 64).transpose(1, 2)
+    p = P.view(B, H, S, S)
+    dv = p.transpose(-1, -2) @ do
+    dp = do @ v.transpose(-1, -2)
+    ds = p * (dp - (dp * p).sum(-1, keepdim=True)) * scale
+    dq = ds @ k
+    dk = ds.transpose(-1, -2) @ q
+    for dst, src in ((dQ, dq), (dK, dk), (dV, dv)):
+        dst.copy_(src.transpose(1, 2).reshape(B * S, H * 64).to(_lp()))

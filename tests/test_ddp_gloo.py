@@ -17,14 +17,16 @@ def _patch_emulated():
     sys.path.insert(0, HERE)
     sys.path.insert(0, os.path.dirname(HERE))
     import emu_ops
+    import reftr_b200.bert as bert
     import reftr_b200.engine as engine
     import reftr_b200.pack as pack
+    import reftr_b200.seg as seg
 
     class Fp32Proxy:
         def __getattr__(self, name):
             return torch.float32 if name == "bfloat16" else getattr(torch, name)
 
-    for m in (engine, pack):
+    for m in (engine, pack, bert, seg):
         m.ops = emu_ops
         m.torch = Fp32Proxy()
     emu_ops.EXACT[0] = True
@@ -97,9 +99,11 @@ def test_ddp_world2_matches_full_batch():
     finally:
         emu_ops.EXACT[0] = False
         import importlib
+        import reftr_b200.bert as bert
         import reftr_b200.engine as engine
         import reftr_b200.pack as pack
+        import reftr_b200.seg as seg
         from reftr_b200 import ops as real_ops
-        for m in (engine, pack):
+        for m in (engine, pack, bert, seg):
             m.ops = real_ops
             m.torch = torch

@@ -24,7 +24,8 @@ class _TorchFp32Proxy:
 def _modules():
     import reftr_b200.engine as engine
     import reftr_b200.pack as pack
-    mods = [engine, pack]
+    import reftr_b200.bert as bert
+    mods = [engine, pack, bert]
     try:
         import reftr_b200.seg as seg
         mods.append(seg)
