@@ -255,7 +255,7 @@ def main():
     out = dict(base, value=value, ms_per_step=ms / a.steps, dtype="bf16",
                config={"workload": "cfg2: ResNet-50 + 6+6-layer RefTR box model, 640x640, 20-token phrase, bs16 per GPU, aux_loss",
                        "global_batch": world * B, "parallelism": f"dp{world}", "mode": "eval+grad (dropout inactive), fwd+criterion+bwd, no optimizer",
-                       "bert": "HF BertModel (third party in the reference) in PyTorch, TF32 matmul",
+                       "bert": "BERT-base on the same C-ABI kernels (bf16 operands, fp32 residual/LN), inside the step graphs",
                        "l2": "per-step working set (saved activations, several GB) far exceeds the 126 MB L2; no explicit flush"},
                e2e={"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": nbytes(s_host, t_host), "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / a.steps},

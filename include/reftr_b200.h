@@ -200,6 +200,15 @@ int rb_attn_small_fwd(const void* Q, const void* K, const void* V, const void* m
 int rb_attn_small_bwd(const void* Q, const void* K, const void* V, const void* dO, const float* P, void* dQ, void* dK, void* dV, int B, int H, int dh, int S,
                       long long ldq, long long ldk, long long ldv, long long lddo, long long lddq, long long lddk, long long lddv, float scale, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Criterion (models/criterion.py:113-153, :189-201; util/box_ops.py): L1 + GIoU of paired cxcywh boxes for all decoder layers
+ * at once.  boxes fp32 [n_layers, N, 4], tgt fp32 [N, 4], valid u8 [N] (nullable: all valid).  losses fp32 [n_layers, 2] =
+ * (sum |p - t|, sum (1 - giou)) * inv_norm (inv_norm_dev, a device scalar, overrides inv_norm when non-NULL);
+ * dl1 / dgiou fp32 [n_layers, N, 4] = gradients of the two terms w.r.t. boxes (already times inv_norm).
+ * ------------------------------------------------------------------------------------------------------------- */
+int rb_box_loss(const float* boxes, const float* tgt, const void* valid, int n_layers, int N, float inv_norm, const float* inv_norm_dev, float* losses,
+                float* dl1, float* dgiou, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

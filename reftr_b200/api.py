@@ -51,6 +51,12 @@ def _weight_dict(args, keys):
 
 
 def _reference_classes():
+    """Criterion / post-processor classes.  Default: the restatements in reftr_b200/criterion.py (same constructor, weight_dict,
+    loss keys and values as the reference's; sync-free and with all box losses in one kernel).  REFTR_B200_REF_CRITERION=1 uses
+    the reference's own classes when its ``models`` package is importable."""
+    if os.environ.get("REFTR_B200_REF_CRITERION") != "1":
+        from .criterion import CriterionVGMultiPhrase, CriterionVGOnePhraseSeg, PostProcessSegm, PostProcessVGMultiPhrase
+        return CriterionVGMultiPhrase, PostProcessVGMultiPhrase, CriterionVGOnePhraseSeg, PostProcessSegm
     try:
         from models.criterion import CriterionVGMultiPhrase
         from models.post_process import PostProcessVGMultiPhrase

@@ -47,11 +47,56 @@ def sigmoid_focal_loss(inputs, targets, num_boxes, alpha=0.25, gamma=2):  # mode
     return loss.mean(1).sum() / num_boxes
 
 
+class _FusedBoxLoss(torch.autograd.Function):
+    """L1 + GIoU for every decoder layer in ONE kernel (rb_box_loss); the kernel also emits d(loss)/d(boxes), so the backward is
+    two broadcast multiplies."""
+
+    @staticmethod
+    def forward(ctx, boxes_all, tgt, valid, inv_norm, inv_norm_dev):
+        from . import ops
+        nl, N = boxes_all.shape[0], boxes_all.shape[1]
+        losses = torch.empty(nl, 2, dtype=torch.float32, device=boxes_all.device)
+        dl1, dgiou = torch.empty_like(boxes_all), torch.empty_like(boxes_all)
+        ops.box_loss(boxes_all, tgt, valid, inv_norm, inv_norm_dev, losses, dl1, dgiou)
+        ctx.save_for_backward(dl1, dgiou)
+        return losses
+
+    @staticmethod
+    def backward(ctx, g):
+        dl1, dgiou = ctx.saved_tensors
+        nl = dl1.shape[0]
+        return torch.addcmul(dl1 * g[:, 0].view(nl, 1, 1), dgiou, g[:, 1].view(nl, 1, 1)), None, None, None, None
+
+
 class CriterionVGMultiPhrase(nn.Module):
     def __init__(self, weight_dict, losses):
         super().__init__()
         self.weight_dict = weight_dict
         self.losses = losses
+
+    def _fused_boxes(self, outputs, targets, num_boxes):
+        """All layers' box losses from ``outputs["_boxes_all"]`` ([n_layers, B, n_ph, k, 4], last layer last) -- sync-free."""
+        allb = outputs["_boxes_all"]
+        nl, b, n_ph, k, _ = allb.shape
+        tgt = torch.cat([t["boxes"] for t in targets], dim=0).to(torch.float32)
+        valid = None
+        if tgt.shape[0] != b * n_ph:  # padded phrases: scatter the valid targets to their (sample, phrase) slots
+            pm = outputs["phrase_mask"].view(b, n_ph, k)[:, :, 0].reshape(b * n_ph)
+            full = torch.zeros(b * n_ph, 4, dtype=torch.float32, device=allb.device)
+            full.masked_scatter_(pm.unsqueeze(-1).expand(-1, 4), tgt)
+            tgt = full
+            valid = pm.unsqueeze(-1).expand(-1, k).reshape(-1).to(torch.uint8).contiguous()
+        tgt = tgt.unsqueeze(1).expand(-1, k, -1).reshape(b * n_ph * k, 4).contiguous()
+        if torch.is_tensor(num_boxes):
+            inv, inv_dev = 0.0, (1.0 / (num_boxes.to(torch.float32) * k)).reshape(1).contiguous()
+        else:
+            inv, inv_dev = 1.0 / (num_boxes * k), None
+        L = _FusedBoxLoss.apply(allb.reshape(nl, b * n_ph * k, 4).contiguous(), tgt, valid, inv, inv_dev)
+        losses = {"loss_bbox": L[nl - 1, 0], "loss_giou": L[nl - 1, 1]}
+        for i in range(nl - 1):
+            losses[f"loss_bbox_{i}"] = L[i, 0]
+            losses[f"loss_giou_{i}"] = L[i, 1]
+        return losses
 
     def loss_boxes(self, outputs, targets, num_boxes):  # criterion.py:113-153
         src = outputs["pred_boxes"]
@@ -78,12 +123,20 @@ class CriterionVGMultiPhrase(nn.Module):
     def forward(self, outputs, targets):  # criterion.py:166-202
         num_boxes = float(sum(len(t["labels"]) for t in targets))
         if torch.distributed.is_available() and torch.distributed.is_initialized():
+            # the reference calls .item() here (criterion.py:180): a host sync per step.  The count stays a device scalar instead.
             nb = torch.as_tensor([num_boxes], dtype=torch.float, device=outputs["pred_boxes"].device)
             torch.distributed.all_reduce(nb)
-            num_boxes = torch.clamp(nb / torch.distributed.get_world_size(), min=1).item()
+            num_boxes = torch.clamp(nb / torch.distributed.get_world_size(), min=1)[0]
         else:
             num_boxes = max(num_boxes, 1.0)
         losses = {}
+        fused = "_boxes_all" in outputs and outputs["_boxes_all"].is_cuda and "boxes" in self.losses
+        if fused:
+            losses.update(self._fused_boxes(outputs, targets, num_boxes))
+            for loss in self.losses:
+                if loss != "boxes":
+                    losses.update(self.get_loss(loss, outputs, targets, num_boxes))
+            return losses
         for loss in self.losses:
             losses.update(self.get_loss(loss, outputs, targets, num_boxes))
         for i, aux in enumerate(outputs.get("aux_outputs", [])):

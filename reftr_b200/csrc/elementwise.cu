@@ -366,3 +366,77 @@ extern "C" int rb_add(const float* a, const float* b, float* y, void* yb, long l
   RB_CHECK_LAUNCH();
   return 0;
 }
+
+// ------------------------------------------------------------------------------------------------ fused box losses
+// L1 + GIoU of paired cxcywh boxes for all decoder layers at once (criterion.py:113-153, :189-201; box_ops.py:9-13, :52-77),
+// forward values and the gradient w.r.t. the predicted boxes in one pass.
+namespace rb {
+__global__ void box_loss_kernel(const float* __restrict__ boxes, const float* __restrict__ tgt, const uint8_t* __restrict__ valid, int n_layers, int N,
+                                float inv_norm, const float* __restrict__ inv_norm_dev, float* __restrict__ losses, float* __restrict__ dl1,
+                                float* __restrict__ dgiou) {
+  const int layer = blockIdx.y;
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const float inv = inv_norm_dev ? *inv_norm_dev : inv_norm;
+  float l1 = 0.f, lg = 0.f;
+  if (n < N) {
+    const long long o = (static_cast<long long>(layer) * N + n) * 4;
+    float g1[4] = {0.f, 0.f, 0.f, 0.f}, gg[4] = {0.f, 0.f, 0.f, 0.f};
+    if (!valid || valid[n]) {
+      const float4 p = *reinterpret_cast<const float4*>(boxes + o);
+      const float4 t = *reinterpret_cast<const float4*>(tgt + static_cast<long long>(n) * 4);
+      const float pv[4] = {p.x, p.y, p.z, p.w}, tv[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float d = pv[i] - tv[i];
+        l1 += fabsf(d);
+        g1[i] = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+      }
+      const float a[4] = {p.x - 0.5f * p.z, p.y - 0.5f * p.w, p.x + 0.5f * p.z, p.y + 0.5f * p.w};
+      const float b[4] = {t.x - 0.5f * t.z, t.y - 0.5f * t.w, t.x + 0.5f * t.z, t.y + 0.5f * t.w};
+      const float Aa = (a[2] - a[0]) * (a[3] - a[1]), Ab = (b[2] - b[0]) * (b[3] - b[1]);
+      const float w0 = fmaxf(fminf(a[2], b[2]) - fmaxf(a[0], b[0]), 0.f), w1 = fmaxf(fminf(a[3], b[3]) - fmaxf(a[1], b[1]), 0.f);
+      const float I = w0 * w1, U = Aa + Ab - I;
+      const float c0 = fmaxf(fmaxf(a[2], b[2]) - fminf(a[0], b[0]), 0.f), c1 = fmaxf(fmaxf(a[3], b[3]) - fminf(a[1], b[1]), 0.f);
+      const float C = c0 * c1;
+      const float giou = I / U - (C - U) / C;
+      lg = 1.f - giou;
+      // derivatives w.r.t. the corners a0..a3
+      const float dAa[4] = {-(a[3] - a[1]), -(a[2] - a[0]), (a[3] - a[1]), (a[2] - a[0])};
+      const float dI[4] = {(w0 > 0.f && a[0] > b[0]) ? -w1 : 0.f, (w1 > 0.f && a[1] > b[1]) ? -w0 : 0.f, (w0 > 0.f && a[2] < b[2]) ? w1 : 0.f,
+                           (w1 > 0.f && a[3] < b[3]) ? w0 : 0.f};
+      const float dC[4] = {(a[0] < b[0]) ? -c1 : 0.f, (a[1] < b[1]) ? -c0 : 0.f, (a[2] > b[2]) ? c1 : 0.f, (a[3] > b[3]) ? c0 : 0.f};
+      float da[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float dU = dAa[i] - dI[i];
+        const float diou = (dI[i] * U - I * dU) / (U * U);
+        const float dgi = diou + (dU * C - U * dC[i]) / (C * C);
+        da[i] = -dgi;  // d(1 - giou)
+      }
+      gg[0] = da[0] + da[2];
+      gg[1] = da[1] + da[3];
+      gg[2] = 0.5f * (da[2] - da[0]);
+      gg[3] = 0.5f * (da[3] - da[1]);
+    }
+    *reinterpret_cast<float4*>(dl1 + o) = make_float4(g1[0] * inv, g1[1] * inv, g1[2] * inv, g1[3] * inv);
+    *reinterpret_cast<float4*>(dgiou + o) = make_float4(gg[0] * inv, gg[1] * inv, gg[2] * inv, gg[3] * inv);
+  }
+  l1 = warp_sum(l1);
+  lg = warp_sum(lg);
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(losses + layer * 2, l1 * inv);
+    atomicAdd(losses + layer * 2 + 1, lg * inv);
+  }
+}
+}  // namespace rb
+
+extern "C" int rb_box_loss(const float* boxes, const float* tgt, const void* valid, int n_layers, int N, float inv_norm, const float* inv_norm_dev,
+                           float* losses, float* dl1, float* dgiou, void* stream) {
+  if (n_layers <= 0 || N <= 0) return 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  RB_CUDA(cudaMemsetAsync(losses, 0, sizeof(float) * 2 * n_layers, st));
+  rb::box_loss_kernel<<<dim3((N + 127) / 128, n_layers), 128, 0, st>>>(boxes, tgt, static_cast<const uint8_t*>(valid), n_layers, N, inv_norm, inv_norm_dev, losses,
+                                                                     dl1, dgiou);
+  RB_CHECK_LAUNCH();
+  return 0;
+}

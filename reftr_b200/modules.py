@@ -311,6 +311,7 @@ class RefTR(nn.Module):
         out = {"pred_boxes": coord[-1], "phrase_mask": pm}
         if self.aux_loss:
             out["aux_outputs"] = [{"pred_boxes": b, "phrase_mask": pm} for b in coord[:-1]]
+            out["_boxes_all"] = coord  # every layer's boxes in one tensor: lets reftr_b200's criterion fuse all box losses
         return out
 
 

@@ -302,3 +302,8 @@ def attn_small_fwd(Q, K, V, mask, O, P, B, H, S, scale):
 def attn_small_bwd(Q, K, V, dO, P, dQ, dK, dV, B, H, S, scale):
     _lib.call("rb_attn_small_bwd", _p(Q), _p(K), _p(V), _p(dO), _p(P), _p(dQ), _p(dK), _p(dV), B, H, 64, S, Q.stride(0), K.stride(0), V.stride(0),
               dO.stride(0), dQ.stride(0), dK.stride(0), dV.stride(0), scale, _s())
+
+
+def box_loss(boxes, tgt, valid, inv_norm, inv_norm_dev, losses, dl1, dgiou):
+    n_layers, N = boxes.shape[0], boxes.shape[1]
+    _lib.call("rb_box_loss", _p(boxes), _p(tgt), _p(valid), n_layers, N, float(inv_norm), _p(inv_norm_dev), _p(losses), _p(dl1), _p(dgiou), _s())

@@ -227,3 +227,39 @@ def test_colsum(rows, N, dt):
     ops.colsum(x, out, rows=rows, N=N)
     ref = 1 + x[:, :N].float().sum(0)
     assert (out - ref).abs().max().item() < 2e-3 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("padded", [False, True])
+def test_fused_box_criterion_matches_torch(padded):
+    """rb_box_loss (all layers, L1 + GIoU, values and gradients) against the plain-torch restatement of criterion.py:113-153."""
+    from reftr_b200.criterion import CriterionVGMultiPhrase
+    nl, B, n_ph, k = 6, 5, 3, 2
+    g = torch.Generator().manual_seed(0)
+    c = 0.25 + 0.5 * torch.rand(nl, B, n_ph, k, 2, generator=g)
+    wh = 0.05 + 0.4 * torch.rand(nl, B, n_ph, k, 2, generator=g)
+    boxes = torch.cat([c, wh], -1).to(dev)
+    pm = torch.ones(B, n_ph * k, dtype=torch.bool, device=dev)
+    if padded:
+        pm.view(B, n_ph, k)[1, 2] = False
+        pm.view(B, n_ph, k)[3, 1:] = False
+    targets = []
+    for b in range(B):
+        nv = int(pm.view(B, n_ph, k)[b, :, 0].sum().item())
+        t = torch.cat([0.3 + 0.4 * torch.rand(nv, 2, generator=g), 0.1 + 0.3 * torch.rand(nv, 2, generator=g)], -1).to(dev)
+        targets.append({"boxes": t, "labels": [0] * nv})
+    wd = {"loss_bbox": 1.0, "loss_giou": 1.0}
+    crit = CriterionVGMultiPhrase(wd, ["boxes"])
+    res = {}
+    for fused in (False, True):
+        bx = boxes.clone().requires_grad_()
+        out = {"pred_boxes": bx[-1], "phrase_mask": pm, "aux_outputs": [{"pred_boxes": x, "phrase_mask": pm} for x in bx[:-1]]}
+        if fused:
+            out["_boxes_all"] = bx
+        ld = crit(out, targets)
+        w = torch.linspace(0.5, 1.5, len(ld)).tolist()
+        sum(v * wi for v, wi in zip((ld[k_] for k_ in sorted(ld)), w)).backward()
+        res[fused] = ({k_: v.item() for k_, v in ld.items()}, bx.grad.clone())
+    assert set(res[True][0]) == set(res[False][0]) and len(res[True][0]) == 2 * nl
+    for k_, v in res[False][0].items():
+        assert abs(res[True][0][k_] - v) < 1e-5 * max(1.0, abs(v)), (k_, res[True][0][k_], v)
+    assert (res[True][1] - res[False][1]).abs().max().item() < 1e-5
