@@ -77,6 +77,9 @@ int rb_gemm(const rb_gemm_args* args, void* stream);
  * ------------------------------------------------------------------------------------------------------------- */
 /* img fp32 NCHW [B,3,H,W] -> out bf16 [B*H1*W1, 160]: im2col of the 7x7/2 pad-3 stem, column (r*7+s)*3+c, 147.. zero */
 int rb_stem_im2col(const float* img, void* out, int B, int H, int W, int H1, int W1, void* stream);
+/* the whole stem in one kernel: 7x7/2 pad-3 conv 3->64 (+ folded FrozenBN bias + ReLU), im2col built in shared memory;
+ * img fp32 NCHW, wf = rb_pack_conv output bf16 [64, ldk] (column (r*7+s)*3+c), out bf16 NHWC [B*H1*W1, 64] */
+int rb_stem_conv(const float* img, const void* wf, int ldk, const float* bias, void* out, int B, int H, int W, int H1, int W1, void* stream);
 /* in bf16 NHWC [B,H1,W1,C] -> out padded NHWC [B,H2+2,W2+2,C]; 3x3 stride 2 pad 1 max-pool */
 int rb_maxpool_3x3s2(const void* in, void* out, int B, int H1, int W1, int C, int H2, int W2, void* stream);
 /* padded NHWC [B,H+2,W+2,C] <-> 4 parity planes [4,B,Ho+2,Wo+2,C] (see header comment); merge = backward of split,

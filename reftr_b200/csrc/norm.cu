@@ -306,42 +306,57 @@ __global__ void build_pos_mask_kernel(const uint8_t* __restrict__ img_mask, int 
                                       float* __restrict__ pos32, uint8_t* __restrict__ kpm) {
   const int b = blockIdx.x;
   const int S = L + h * w;
+  const int hw = h * w;
   extern __shared__ uint8_t sm[];
-  uint8_t* nm = sm;  // not_mask [h*w]
+  uint8_t* nm = sm;                                                        // not_mask [hw]
+  float* ey = reinterpret_cast<float*>(sm + ((hw + 15) & ~15));            // normalised y_embed [hw]
+  float* ex = ey + hw;                                                     // normalised x_embed [hw]
   const float sh = static_cast<float>(H) / h, sw = static_cast<float>(W) / w;
-  for (int p = threadIdx.x; p < h * w; p += blockDim.x) {
+  const bool first = blockIdx.y == 0;
+  for (int p = threadIdx.x; p < hw; p += blockDim.x) {
     const int yy = p / w, xx = p - yy * w;
     const int ys = min(static_cast<int>(floorf(yy * sh)), H - 1), xs = min(static_cast<int>(floorf(xx * sw)), W - 1);
     const uint8_t m = img_mask[(static_cast<long long>(b) * H + ys) * W + xs];
     nm[p] = m ? 0 : 1;
-    kpm[static_cast<long long>(b) * S + L + p] = m ? 1 : 0;
+    if (first) kpm[static_cast<long long>(b) * S + L + p] = m ? 1 : 0;
   }
-  for (int l = threadIdx.x; l < L; l += blockDim.x) kpm[static_cast<long long>(b) * S + l] = sent_mask[static_cast<long long>(b) * L + l] ? 0 : 1;
-  __syncthreads();
-  for (int i = threadIdx.x; i < L * LN_D; i += blockDim.x) {
-    const int l = i / LN_D, c = i - l * LN_D;
-    pos32[(static_cast<long long>(b) * S + l) * LN_D + c] = lang_pos[l * LN_D + c] + token_type[c];
-  }
-  const float two_pi = 6.283185307179586f;
-  for (int i = threadIdx.x; i < h * w * LN_D; i += blockDim.x) {
-    const int p = i / LN_D, c = i - p * LN_D;
-    const int yy = p / w, xx = p - yy * w;
-    float e, tot;
-    if (c < 128) {  // pos_y: cumsum over rows
-      int cs = 0, all = 0;
-      for (int t = 0; t < h; ++t) { all += nm[t * w + xx]; if (t <= yy) cs = all; }
-      e = static_cast<float>(cs); tot = static_cast<float>(all);
-    } else {
-      int cs = 0, all = 0;
-      for (int t = 0; t < w; ++t) { all += nm[yy * w + t]; if (t <= xx) cs = all; }
-      e = static_cast<float>(cs); tot = static_cast<float>(all);
+  if (first) {
+    for (int l = threadIdx.x; l < L; l += blockDim.x) kpm[static_cast<long long>(b) * S + l] = sent_mask[static_cast<long long>(b) * L + l] ? 0 : 1;
+    for (int i = threadIdx.x; i < L * LN_D; i += blockDim.x) {
+      const int l = i / LN_D, c = i - l * LN_D;
+      pos32[(static_cast<long long>(b) * S + l) * LN_D + c] = lang_pos[l * LN_D + c] + token_type[c];
     }
-    e = (e - 0.5f) / (tot + 1e-6f) * two_pi;
-    const int ci = c & 127;
-    const float dim_t = powf(10000.f, static_cast<float>(2 * (ci / 2)) / 128.f);
+  }
+  __syncthreads();
+  const float two_pi = 6.283185307179586f;
+  // cumulative sums of not_mask along y (one thread per column) and along x (one thread per row), normalised to 2*pi
+  for (int t = threadIdx.x; t < w + h; t += blockDim.x) {
+    if (t < w) {
+      int all = 0;
+      for (int yy = 0; yy < h; ++yy) all += nm[yy * w + t];
+      int cs = 0;
+      for (int yy = 0; yy < h; ++yy) { cs += nm[yy * w + t]; ey[yy * w + t] = (static_cast<float>(cs) - 0.5f) / (static_cast<float>(all) + 1e-6f) * two_pi; }
+    } else {
+      const int yy = t - w;
+      int all = 0;
+      for (int xx = 0; xx < w; ++xx) all += nm[yy * w + xx];
+      int cs = 0;
+      for (int xx = 0; xx < w; ++xx) { cs += nm[yy * w + xx]; ex[yy * w + xx] = (static_cast<float>(cs) - 0.5f) / (static_cast<float>(all) + 1e-6f) * two_pi; }
+    }
+  }
+  __syncthreads();
+  // this CTA's slice of the visual tokens; thread = channel
+  const int per = (hw + gridDim.y - 1) / gridDim.y;
+  const int p0 = blockIdx.y * per, p1 = min(hw, p0 + per);
+  const int c = threadIdx.x;  // blockDim.x == LN_D
+  const int ci = c & 127;
+  const float dim_t = powf(10000.f, static_cast<float>(2 * (ci / 2)) / 128.f);
+  const float add = level_embed[c] + token_type[LN_D + c];
+  for (int p = p0; p < p1; ++p) {
+    const float e = (c < 128) ? ey[p] : ex[p];
     const float a = e / dim_t;
     const float v = (ci & 1) ? cosf(a) : sinf(a);
-    pos32[(static_cast<long long>(b) * S + L + p) * LN_D + c] = v + level_embed[c] + token_type[LN_D + c];
+    pos32[(static_cast<long long>(b) * S + L + p) * LN_D + c] = v + add;
   }
 }
 
@@ -417,7 +432,9 @@ extern "C" int rb_groupnorm_tokens_bwd(const float* dy, const float* dy2, const 
 
 extern "C" int rb_build_pos_mask(const void* img_mask, int B, int H, int W, int h, int w, const long long* sent_mask, int L, const float* lang_pos,
                                  const float* token_type, const float* level_embed, float* pos32, void* kpm, void* stream) {
-  build_pos_mask_kernel<<<B, 256, h * w, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint8_t*>(img_mask), H, W, h, w, sent_mask, L, lang_pos,
+  const size_t smem = ((static_cast<size_t>(h) * w + 15) & ~static_cast<size_t>(15)) + 2 * static_cast<size_t>(h) * w * sizeof(float);
+  if (smem > 48 * 1024) return rb_fail("rb_build_pos_mask: %d x %d tokens exceed the shared-memory plan", h, w);
+  build_pos_mask_kernel<<<dim3(B, 10), LN_D, smem, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint8_t*>(img_mask), H, W, h, w, sent_mask, L, lang_pos,
                                                                             token_type, level_embed, pos32, static_cast<uint8_t*>(kpm));
   RB_CUDA(cudaGetLastError());
   return 0;

@@ -324,9 +324,16 @@ class RefTREngine:
         self.launches += st["bl"]
         d_sent, d_pooled = st["bouts"]
         # fresh storage per step: autograd may keep these as .grad of leaf tensors
+        flat = self.gflat[:self.n_grad].clone()
+        if getattr(self.model, "engine_allreduce", False) and torch.distributed.is_available() and torch.distributed.is_initialized():
+            world = torch.distributed.get_world_size()
+            if world > 1:
+                # the data-parallel exchange of the path: ONE all-reduce over the flat gradient buffer, then the mean
+                torch.distributed.all_reduce(flat)
+                flat.mul_(1.0 / world)
         if self.bert is not None:
-            return None, None, self.gflat[:self.n_grad].clone()
-        return d_sent.clone(), d_pooled.clone(), self.gflat[:self.n_grad].clone()
+            return None, None, flat
+        return d_sent.clone(), d_pooled.clone(), flat
 
     def G(self, name_or_param):
         n = name_or_param if isinstance(name_or_param, str) else self.pnames[id(name_or_param)]
@@ -459,10 +466,8 @@ class RefTREngine:
         B, _, H, W = img.shape
         H1, W1 = (H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1
         H2, W2 = (H1 + 2 - 3) // 2 + 1, (W1 + 2 - 3) // 2 + 1
-        col = ws.get("stem.col", [B * H1 * W1, 160])
-        ops.stem_im2col(img, col, B, H, W, H1, W1)
         c1 = ws.get("stem.out", [B * H1 * W1, 64])
-        ops.gemm(col, self.stem.wf, B * H1 * W1, 64, 160, bias=self.stem.bias, relu=True, out=c1)
+        ops.stem_conv(img, self.stem.wf, self.stem.bias, c1, B, H, W, H1, W1)  # conv1 + bn1 + relu, im2col in shared memory
         g = Grid(B, H2, W2)
         x = ws.get("stem.pool", [g.R, 64])
         ops.maxpool_3x3s2(c1, x, B, H1, W1, 64, H2, W2)

@@ -236,6 +236,25 @@ class RefTR(nn.Module):
         nn.init.constant_(self.input_proj[0][0].bias, 0)
         self.tf32_bert = True
         self._engine = None
+        self._mark_ddp_ignored()
+
+    def _mark_ddp_ignored(self):
+        """Data-parallel gradients: the engine produces every hot-path gradient in ONE flat fp32 buffer, so it all-reduces that
+        buffer itself (one NCCL call, no bucket copies; engine.run_backward) instead of letting DistributedDataParallel re-bucket
+        ~700 tensors.  DDP (main_vg.py:293-296) is told to skip those parameters through its documented-by-use
+        ``_ddp_params_and_buffers_to_ignore`` attribute; one tiny parameter stays with DDP because it refuses a module without
+        any (its second averaging of an already-averaged gradient is the identity)."""
+        import os
+        from .bert import BertEngine
+        if os.environ.get("REFTR_B200_GRAD_ALLREDUCE", "engine") != "engine":
+            self._ddp_params_and_buffers_to_ignore = []
+            self.engine_allreduce = False
+            return
+        native_bert = os.environ.get("REFTR_B200_NATIVE_BERT", "1") != "0" and BertEngine.eligible(self.lang_backbone)
+        keep = "vl_transformer.level_embed"
+        self._ddp_params_and_buffers_to_ignore = [n for n, p in self.named_parameters()
+                                                  if p.requires_grad and n != keep and (native_bert or not n.startswith("lang_backbone."))]
+        self.engine_allreduce = True
 
     # -- checkpoint helpers of the reference -----------------------------------------------------------------
     def init_from_pretrained_detr(self, state_dict):  # reftr_transformer.py:137-146
@@ -333,6 +352,7 @@ class RefTRSeg(RefTR):
         self.bbox_attention = MHAttentionMapParams(d, h)
         self.mask_head = MaskHeadParams(d * 2 + h, [1024, 512, 256], d)
         self.cem_loss = False
+        self._mark_ddp_ignored()
 
     def init_from_pretrained(self, pretrained_state_dict):  # reftr_segmentation.py:66-74
         missing, unexpected = self.load_state_dict(pretrained_state_dict, strict=False)

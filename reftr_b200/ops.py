@@ -104,6 +104,10 @@ def stem_im2col(img, out, B, H, W, H1, W1):
     _lib.call("rb_stem_im2col", _p(img), _p(out), B, H, W, H1, W1, _s())
 
 
+def stem_conv(img, wf, bias, out, B, H, W, H1, W1):
+    _lib.call("rb_stem_conv", _p(img), _p(wf), wf.stride(0), _p(bias), _p(out), B, H, W, H1, W1, _s())
+
+
 def maxpool_3x3s2(x, out, B, H1, W1, C, H2, W2):
     _lib.call("rb_maxpool_3x3s2", _p(x), _p(out), B, H1, W1, C, H2, W2, _s())
 

@@ -109,6 +109,14 @@ def stem_im2col(img, out, B, H, W, H1, W1):
     out[:, :147] = cols.to(_lp())
 
 
+def stem_conv(img, wf, bias, out, B, H, W, H1, W1):
+    _LAUNCHES[0] += 1
+    w = wf[:, :147].float().reshape(64, 7, 7, 3).permute(0, 3, 1, 2)
+    x = img if EXACT[0] else img.to(_BF).float()
+    y = F.relu(F.conv2d(x, w, bias, stride=2, padding=3))
+    out.copy_(y.permute(0, 2, 3, 1).reshape(B * H1 * W1, 64).to(_lp()))
+
+
 def maxpool_3x3s2(x, out, B, H1, W1, C, H2, W2):
     _LAUNCHES[0] += 1
     p = F.max_pool2d(x.view(B, H1, W1, C).permute(0, 3, 1, 2).float(), 3, 2, 1)

@@ -263,3 +263,18 @@ def test_fused_box_criterion_matches_torch(padded):
     for k_, v in res[False][0].items():
         assert abs(res[True][0][k_] - v) < 1e-5 * max(1.0, abs(v)), (k_, res[True][0][k_], v)
     assert (res[True][1] - res[False][1]).abs().max().item() < 1e-5
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 64, 96), (1, 224, 224), (2, 50, 70)])
+def test_stem_conv_fused(B, H, W):
+    from reftr_b200 import ops
+    H1, W1 = (H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1
+    img = torch.randn(B, 3, H, W, device=dev)
+    w = torch.randn(64, 3, 7, 7, device=dev) * 0.1
+    bias = torch.randn(64, device=dev) * 0.1
+    wf = torch.zeros(64, 160, device=dev, dtype=torch.bfloat16)
+    wf[:, :147] = w.permute(0, 2, 3, 1).reshape(64, 147).bfloat16()
+    out = torch.empty(B * H1 * W1, 64, device=dev, dtype=torch.bfloat16)
+    ops.stem_conv(img, wf, bias, out, B, H, W, H1, W1)
+    ref = F.relu(F.conv2d(img.bfloat16().float(), w.bfloat16().float(), bias, stride=2, padding=3)).permute(0, 2, 3, 1).reshape(B * H1 * W1, 64)
+    assert _rel(out, ref) < 1e-2
