@@ -9,7 +9,8 @@ Under torchrun (N > 1) the model is wrapped in DistributedDataParallel (NCCL gra
 
   value : inputs already resident in HBM when the timed region starts
   e2e   : the same step through the public API (build_reftr -> model(samples) -> criterion -> backward) with the batch in
-          pinned HOST memory: H2D copy of the inputs and D2H read of the loss inside the timed region, every step
+          pinned HOST memory: H2D copy of the inputs (prefetched on a side stream, as engine_vg.py's data_prefetcher does) and
+          D2H read of the loss inside the timed region, every step
   roofline : the tcgen05 GEMM / implicit-conv kernel (dominant kernel), timed live with CUDA events launch by launch in an
           extra eager pass after the timed region: algorithmic FLOPs of those launches / their summed duration
   cpu_baseline : the fp32 oracle (oracle/reftr_oracle.py, a restatement of the reference) on the host cores, rank 0, N=1
@@ -157,6 +158,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "stock-gpu"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--diag", default="", help="diagnostics only: 'noddp' = no DDP wrapper (engine all-reduce only); 'replicas' = no exchange at all")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -193,7 +195,9 @@ def main():
         model, crit, _ = build_ours(device)
         model.eval()  # dropout inactive (parity mode); gradients flow.  Stated in config.mode.
     net = model
-    if world > 1:
+    if a.diag == "replicas":
+        model.engine_allreduce = False
+    if world > 1 and not a.diag:
         net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local])
 
     s_host, t_host = host_batch(B, pinned=True)
@@ -212,8 +216,29 @@ def main():
         loss.backward()
         return loss
 
+    # e2e: the batch lives in pinned host memory; every step copies ITS inputs host->device and reads its loss back.  The copy of
+    # step i+1 is issued on a side stream while step i computes, exactly what the reference's data_prefetcher does
+    # (engine_vg.py:234-291: side CUDA stream + record_stream).
+    copy_stream = torch.cuda.Stream(device=device)
+    pending = {}
+
+    def prefetch():
+        with torch.cuda.stream(copy_stream):
+            s, t = to_device(s_host, t_host, device)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        pending["next"] = (s, t, ev)
+
     def step_e2e():
-        s, t = to_device(s_host, t_host, device)
+        if "next" not in pending:
+            prefetch()
+        s, t, ev = pending.pop("next")
+        torch.cuda.current_stream().wait_event(ev)
+        for v in s.values():
+            for x in ((v.tensors, v.mask) if hasattr(v, "tensors") else (v,)):
+                x.record_stream(torch.cuda.current_stream())
+        t.record_stream(torch.cuda.current_stream())
+        prefetch()  # next step's inputs, overlapped with this step's compute
         net.zero_grad(set_to_none=True)
         loss = loss_of(net(s), t)
         loss.backward()

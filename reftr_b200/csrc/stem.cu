@@ -51,13 +51,25 @@ stem_conv_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restric
   }
   // ---- input patch -------------------------------------------------------------------------------------------------
   const int iy0 = 2 * oy0 - 3, ix0 = 2 * ox0 - 3;
-  for (int i = tid; i < 3 * ST_PH * ST_PW; i += 128) {
+  constexpr int PATCH_N = 3 * ST_PH * ST_PW, PATCH_IT = (PATCH_N + 127) / 128;
+  float pv[PATCH_IT];
+#pragma unroll
+  for (int it = 0; it < PATCH_IT; ++it) {  // all loads in flight before the first store
+    const int i = tid + it * 128;
     const int c = i / (ST_PH * ST_PW), rem = i - c * (ST_PH * ST_PW);
     const int py = rem / ST_PW, px = rem - py * ST_PW;
     const int iy = iy0 + py, ix = ix0 + px;
-    float v = 0.f;
-    if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(img + ((static_cast<long long>(b) * 3 + c) * H + iy) * W + ix);
-    patch[(c * ST_PH + py) * ST_PWP + px] = v;
+    pv[it] = 0.f;
+    if (i < PATCH_N && iy >= 0 && iy < H && ix >= 0 && ix < W) pv[it] = __ldg(img + ((static_cast<long long>(b) * 3 + c) * H + iy) * W + ix);
+  }
+#pragma unroll
+  for (int it = 0; it < PATCH_IT; ++it) {
+    const int i = tid + it * 128;
+    if (i < PATCH_N) {
+      const int c = i / (ST_PH * ST_PW), rem = i - c * (ST_PH * ST_PW);
+      const int py = rem / ST_PW, px = rem - py * ST_PW;
+      patch[(c * ST_PH + py) * ST_PWP + px] = pv[it];
+    }
   }
   __syncthreads();
   // ---- im2col row of this thread, written in the swizzled layout -------------------------------------------------------

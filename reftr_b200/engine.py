@@ -198,6 +198,8 @@ class RefTREngine:
         self._cur = None
         self.step_id = 0
         self.use_graphs = os.environ.get("REFTR_B200_GRAPHS", "1") != "0"
+        self._tracked = [t for t in list(model.parameters()) + list(model.buffers())]
+        self._vsig, self._pack_dev = None, None
         self.force_eager = False  # bench.py: run the next steps launch by launch on the graphed workspace (profiling)
         self.launches = 0
 
@@ -211,10 +213,15 @@ class RefTREngine:
         sig = tuple(p.data_ptr() for _, p in self.named)
         if self._dev != device or sig != self._sig:
             self._dev, self._sig = device, sig
+            self._vsig = None
             self._states = {}
             self.gflat = torch.zeros(self.n_flat, dtype=torch.float32, device=device)
-        for p in self.packs:
-            p.refresh()
+        # cheap change detection first (one tuple compare); the per-pack refresh walk only runs when something moved
+        vsig = tuple(t._version for t in self._tracked)
+        if vsig != self._vsig or device != self._pack_dev:
+            for p in self.packs:
+                p.refresh()
+            self._vsig, self._pack_dev = tuple(t._version for t in self._tracked), device
 
     # ------------------------------------------------------------------------------------------------------------
     # step driver: eager on the first step of a shape, CUDA-graph capture on the second, replay afterwards

@@ -254,6 +254,11 @@ class RefTR(nn.Module):
         keep = "vl_transformer.level_embed"
         self._ddp_params_and_buffers_to_ignore = [n for n, p in self.named_parameters()
                                                   if p.requires_grad and n != keep and (native_bert or not n.startswith("lang_backbone."))]
+        # FrozenBatchNorm statistics never change (backbone.py:43-80) and are identical on every rank (same checkpoint): keep DDP's
+        # per-forward buffer broadcast away from them -- it would bump their version counters and force a re-pack of every folded
+        # convolution weight on every step.
+        # (the same holds for the only other buffers of the model, BERT's constant position / token-type id tables)
+        self._ddp_params_and_buffers_to_ignore += [n for n, _ in self.named_buffers()]
         self.engine_allreduce = True
 
     # -- checkpoint helpers of the reference -----------------------------------------------------------------
