@@ -122,7 +122,7 @@ class BertEngine:
             dpre = ws.get(f"bertb.{tag}.dpre", [Bn, D], f32)
             dpreb = ws.get(f"bertb.{tag}.dpreb", [Bn, D])
             ops.tanh_bwd(d_pooled.reshape(Bn, D), pooled, dx=dpre, dxb=dpreb)
-            ops.colsum(dpre, G(bert.pooler.dense.bias))
+            eng.colsum(dpre, G(bert.pooler.dense.bias))
             eng.wgrad_linear(dpreb, cls_b, G(bert.pooler.dense.weight), D, D, Bn)
             dcls = ws.get(f"bertb.{tag}.dcls", [Bn, D], f32)
             ops.gemm(dpreb, self.pool.wt, Bn, D, D, out32=dcls)
@@ -134,29 +134,29 @@ class BertEngine:
             a = lay.attention
             xb, qkv, ctx, P, y1, m1, r1, x1b, hpre, h, y2, m2, r2 = per_layer[li]
             ln1, ln2 = a.output.LayerNorm, lay.output.LayerNorm
-            dy2, dy2b = ws.get(f"bertb.{tag}.dy2", [rows, D], f32), ws.get(f"bertb.{tag}.dy2b", [rows, D])
+            dy2, dy2b = ws.get(f"bertb.{tag}.{li}.dy2", [rows, D], f32), ws.get(f"bertb.{tag}.{li}.dy2b", [rows, D])
             ops.ln_wide_bwd(g, y2, ln2.weight, m2, r2, rows, dx32=dy2, dxb=dy2b, dgamma=G(ln2.weight), dbeta=G(ln2.bias))
-            ops.colsum(dy2, G(lay.output.dense.bias))
+            eng.colsum(dy2, G(lay.output.dense.bias))
             eng.wgrad_linear(dy2b, h, G(lay.output.dense.weight), D, FF, rows)
-            dh = ws.get(f"bertb.{tag}.dh", [rows, FF])
+            dh = ws.get(f"bertb.{tag}.{li}.dh", [rows, FF])
             ops.gemm(dy2b, l.o2.wt, rows, FF, D, out=dh)
-            dhp = ws.get(f"bertb.{tag}.dhp", [rows, FF])
+            dhp = ws.get(f"bertb.{tag}.{li}.dhp", [rows, FF])
             ops.gelu_bwd(dh, hpre, dhp)
-            ops.colsum(dhp, G(lay.intermediate.dense.bias))
+            eng.colsum(dhp, G(lay.intermediate.dense.bias))
             eng.wgrad_linear(dhp, x1b, G(lay.intermediate.dense.weight), FF, D, rows)
-            g1 = ws.get(f"bertb.{tag}.g1", [rows, D], f32)
+            g1 = ws.get(f"bertb.{tag}.{li}.g1", [rows, D], f32)
             ops.gemm(dhp, l.i.wt, rows, D, FF, res32=dy2, out32=g1)
-            dy1, dy1b = ws.get(f"bertb.{tag}.dy1", [rows, D], f32), ws.get(f"bertb.{tag}.dy1b", [rows, D])
+            dy1, dy1b = ws.get(f"bertb.{tag}.{li}.dy1", [rows, D], f32), ws.get(f"bertb.{tag}.{li}.dy1b", [rows, D])
             ops.ln_wide_bwd(g1, y1, ln1.weight, m1, r1, rows, dx32=dy1, dxb=dy1b, dgamma=G(ln1.weight), dbeta=G(ln1.bias))
-            ops.colsum(dy1, G(a.output.dense.bias))
+            eng.colsum(dy1, G(a.output.dense.bias))
             eng.wgrad_linear(dy1b, ctx, G(a.output.dense.weight), D, D, rows)
-            dctx = ws.get(f"bertb.{tag}.dctx", [rows, D])
+            dctx = ws.get(f"bertb.{tag}.{li}.dctx", [rows, D])
             ops.gemm(dy1b, l.o.wt, rows, D, D, out=dctx)
-            dqkv = ws.get(f"bertb.{tag}.dqkv", [rows, 3 * D])
+            dqkv = ws.get(f"bertb.{tag}.{li}.dqkv", [rows, 3 * D])
             ops.attn_small_bwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], dctx, P, dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:], Bn, H, L, scale)
             for j, lin in enumerate((a.self.query, a.self.key, a.self.value)):
                 sl = dqkv[:, j * D:(j + 1) * D]
-                ops.colsum(sl, G(lin.bias))
+                eng.colsum(sl, G(lin.bias))
                 eng.wgrad_linear(sl, xb, G(lin.weight), D, D, rows)
             g_in = gbuf[1] if g is gbuf[0] else gbuf[0]
             ops.gemm(dqkv, l.qkv.wt, rows, D, 3 * D, res32=dy1, out32=g_in)
@@ -164,4 +164,5 @@ class BertEngine:
         emb = bert.embeddings
         de = ws.get(f"bertb.{tag}.de", [rows, D], f32)
         ops.ln_wide_bwd(g, e32, emb.LayerNorm.weight, me, re_, rows, dx32=de, dgamma=G(emb.LayerNorm.weight), dbeta=G(emb.LayerNorm.bias))
-        ops.bert_embed_bwd(de, ids, L, G(emb.word_embeddings.weight), G(emb.position_embeddings.weight), G(emb.token_type_embeddings.weight)[0])
+        with eng._off():
+            ops.bert_embed_bwd(de, ids, L, G(emb.word_embeddings.weight), G(emb.position_embeddings.weight), G(emb.token_type_embeddings.weight)[0])

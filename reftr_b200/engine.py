@@ -198,6 +198,8 @@ class RefTREngine:
         self._cur = None
         self.step_id = 0
         self.use_graphs = os.environ.get("REFTR_B200_GRAPHS", "1") != "0"
+        self.use_side = os.environ.get("REFTR_B200_SIDE_STREAM", "1") != "0"
+        self._side, self._side_used = None, False
         self._tracked = [t for t in list(model.parameters()) + list(model.buffers())]
         self._vsig, self._pack_dev = None, None
         self.force_eager = False  # bench.py: run the next steps launch by launch on the graphed workspace (profiling)
@@ -365,12 +367,46 @@ class RefTREngine:
         want = _cdiv(3 * 148, tiles)
         return max(1, min(want, kb // 4 if kb >= 4 else 1))
 
+    # ------------------------------------------------------------------------------------------------------------
+    # Off-critical-path work.  In the backward pass the chain of INPUT gradients is the critical path; weight gradients, bias
+    # gradients (column sums) and embedding scatters only feed the flat gradient buffer.  They are launched on a side stream
+    # (forked after the kernel that produced their operand, joined at the end of the backward), so the hundreds of small,
+    # latency-bound launches overlap the main chain -- inside the captured CUDA graph they become parallel branches.
+    # Backward scratch buffers are per layer for that reason (a later layer must not overwrite an operand still being read).
+    # ------------------------------------------------------------------------------------------------------------
+    def _off(self):
+        import contextlib
+        if not self.use_side or self._dev is None or self._dev.type != "cuda":
+            return contextlib.nullcontext()
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self._dev)
+        ev = torch.cuda.Event()
+        ev.record()  # on the main (current) stream: everything launched so far is visible to the side stream
+        self._side.wait_event(ev)
+        self._side_used = True
+        return torch.cuda.stream(self._side)
+
+    def _join_side(self):
+        if self._side_used:
+            torch.cuda.current_stream().wait_stream(self._side)
+            self._side_used = False
+
+    def colsum(self, x, out, rows=None, N=None):
+        """Bias gradient: out[N] += column sums of x (off the critical path)."""
+        with self._off():
+            ops.colsum(x, out, rows=rows, N=N)
+
     def wgrad_linear(self, dY, X, gview, M, N, K):
-        """gview[M, N] += dY[:K, :M]^T X[:K, :N]   (TN GEMM, split-K, fp32 atomics)."""
-        ops.gemm(dY, X, M, N, K, mode=1, out32=gview, atomic=True, splits=self._splits(M, N, 1, K))
+        """gview[M, N] += dY[:K, :M]^T X[:K, :N]   (TN GEMM, split-K, fp32 atomics; off the critical path)."""
+        with self._off():
+            ops.gemm(dY, X, M, N, K, mode=1, out32=gview, atomic=True, splits=self._splits(M, N, 1, K))
 
     def wgrad_conv(self, pc, dY, X, K, key=None, b_offsets=None):
         """Folded-layout weight gradient of a convolution; b_offsets = row offset of X per tap (None: 1x1, no shift)."""
+        with self._off():
+            self._wgrad_conv(pc, dY, X, K, key, b_offsets)
+
+    def _wgrad_conv(self, pc, dY, X, K, key=None, b_offsets=None):
         g = self.G(pc.conv.weight)
         Cout, Cin = pc.Cout, pc.Cin
         if b_offsets is None or len(b_offsets) == 1:
@@ -524,7 +560,7 @@ class RefTREngine:
         d1b = ws.get(key + ".d1b", [rows, D])
         ops.layernorm_bwd(dy, y1, seq[5].weight, m1, r1, rows, y_relu=y32, dx32=d1, dxb=d1b, dgamma=self.G(seq[5].weight),
                           dbeta=self.G(seq[5].bias), rowmap=rowmap)
-        ops.colsum(d1, self.G(seq[4].bias))
+        self.colsum(d1, self.G(seq[4].bias))
         self.wgrad_linear(d1b, a1b, self.G(seq[4].weight), D, D, rows)
         da1 = ws.get(key + ".da1", [rows, D], torch.float32)
         ops.gemm(d1b, packs[1].wt, rows, D, D, out32=da1)
@@ -532,7 +568,7 @@ class RefTREngine:
         d0b = ws.get(key + ".d0b", [rows, D])
         ops.layernorm_bwd(da1, y0, seq[1].weight, m0, r0, rows, y_relu=a1, dx32=d0, dxb=d0b, dgamma=self.G(seq[1].weight),
                           dbeta=self.G(seq[1].bias))
-        ops.colsum(d0, self.G(seq[0].bias))
+        self.colsum(d0, self.G(seq[0].bias))
         self.wgrad_linear(d0b, A, self.G(seq[0].weight), D, K, rows)
         if not need_dA:
             return None
@@ -579,11 +615,11 @@ class RefTREngine:
         weight/bias gradients of linear1/linear2 and writes out32 = dy + d(FFN input)."""
         ws = self.ws
         dff = lin1.N
-        ops.colsum(dy32, self.G(mod.linear2.bias))
+        self.colsum(dy32, self.G(mod.linear2.bias))
         self.wgrad_linear(dyb, h, self.G(mod.linear2.weight), D, dff, rows)
         dh = ws.get(key + ".dh", [rows, dff])
         ops.gemm(dyb, lin2.wt, rows, dff, D, mask_src=h, out=dh)
-        ops.colsum(dh, self.G(mod.linear1.bias))
+        self.colsum(dh, self.G(mod.linear1.bias))
         self.wgrad_linear(dh, x_in_b, self.G(mod.linear1.weight), dff, D, rows)
         ops.gemm(dh, lin1.wt, rows, D, dff, res32=dy32, out32=out32)
 
@@ -594,25 +630,25 @@ class RefTREngine:
         k = f"enc{l}"
         lay = e.mod
         xb, xpb, qkv, o, lse, y1, m1, r1, x1b, h, y2, m2, r2 = self.saved[k]
-        dy2 = ws.get("encb.dy2", [rows, D], torch.float32)
-        dy2b = ws.get("encb.dy2b", [rows, D])
+        dy2 = ws.get(f"encb{l}.dy2", [rows, D], torch.float32)
+        dy2b = ws.get(f"encb{l}.dy2b", [rows, D])
         ops.layernorm_bwd(g, y2, lay.norm2.weight, m2, r2, rows, dx32=dy2, dxb=dy2b, dgamma=self.G(lay.norm2.weight),
                           dbeta=self.G(lay.norm2.bias))
-        g1 = ws.get("encb.g1", [rows, D], torch.float32)
-        self._ffn_bwd("encb", e.l1, e.l2, lay, dy2, dy2b, x1b, h, rows, g1)
-        dy1 = ws.get("encb.dy1", [rows, D], torch.float32)
-        dy1b = ws.get("encb.dy1b", [rows, D])
+        g1 = ws.get(f"encb{l}.g1", [rows, D], torch.float32)
+        self._ffn_bwd(f"encb{l}", e.l1, e.l2, lay, dy2, dy2b, x1b, h, rows, g1)
+        dy1 = ws.get(f"encb{l}.dy1", [rows, D], torch.float32)
+        dy1b = ws.get(f"encb{l}.dy1b", [rows, D])
         ops.layernorm_bwd(g1, y1, lay.norm1.weight, m1, r1, rows, dx32=dy1, dxb=dy1b, dgamma=self.G(lay.norm1.weight),
                           dbeta=self.G(lay.norm1.bias))
-        ops.colsum(dy1, self.G(lay.self_attn.out_proj.bias))
+        self.colsum(dy1, self.G(lay.self_attn.out_proj.bias))
         self.wgrad_linear(dy1b, o, self.G(lay.self_attn.out_proj.weight), D, D, rows)
-        do = ws.get("encb.do", [rows, D])
+        do = ws.get(f"encb{l}.do", [rows, D])
         ops.gemm(dy1b, e.out.wt, rows, D, D, out=do)
-        dqkv = ws.get("encb.dqkv", [rows, 3 * D])
-        dbuf = ws.get("encb.dbuf", [B, NH, S], torch.float32)
+        dqkv = ws.get(f"encb{l}.dqkv", [rows, 3 * D])
+        dbuf = ws.get(f"encb{l}.dbuf", [B, NH, S], torch.float32)
         ops.attn_bwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], kpm, o, do, lse, dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:], dbuf,
                      B, NH, S, S, DH ** -0.5)
-        ops.colsum(dqkv, self.G(lay.self_attn.in_proj_bias))
+        self.colsum(dqkv, self.G(lay.self_attn.in_proj_bias))
         gw = self.G(lay.self_attn.in_proj_weight)
         self.wgrad_linear(dqkv[:, :2 * D], xpb, gw[:2 * D], 2 * D, D, rows)
         self.wgrad_linear(dqkv[:, 2 * D:], xb, gw[2 * D:], D, D, rows)
@@ -676,8 +712,9 @@ class RefTREngine:
         ops.rows_scatter_add(d_tgt, d_f, rt, D, map_dst=(n_q, 1, 0, 0))
         ops.rows_scatter_add(d_qpos, d_f, rt, D, map_dst=(n_q, 1, 0, 0))
         gq = self.G(qe.query_embed.weight)
-        ops.rows_scatter_add(d_tgt, gq[:, :D], rt, D, map_dst=(n_q, 0, 1, 0))
-        ops.rows_scatter_add(d_qpos, gq[:, D:], rt, D, map_dst=(n_q, 0, 1, 0))
+        with self._off():
+            ops.rows_scatter_add(d_tgt, gq[:, :D], rt, D, map_dst=(n_q, 0, 1, 0))
+            ops.rows_scatter_add(d_qpos, gq[:, D:], rt, D, map_dst=(n_q, 0, 1, 0))
         d_fin = self._mlp_map_bwd("qe.fuse", self.qe_fuse, qe.fuse_encoder_query, d_f)  # fp32 [rp, 512]
         d_left = ws.get("qeb.d_left", [rp, D], torch.float32)
         d_ph = ws.get("qeb.d_ph", [rp, D], torch.float32)
@@ -688,7 +725,7 @@ class RefTREngine:
         d_co = ws.get("qeb.d_co", [rp, D], torch.float32)
         d_cob = ws.get("qeb.d_cob", [rp, D])
         ops.layernorm_bwd(d_left, co32, ln.weight, mc, rc, rp, dx32=d_co, dxb=d_cob, dgamma=self.G(ln.weight), dbeta=self.G(ln.bias))
-        ops.colsum(d_co, self.G(qe.context_out[0].bias))
+        self.colsum(d_co, self.G(qe.context_out[0].bias))
         self.wgrad_linear(d_cob, cb, self.G(qe.context_out[0].weight), D, D, rp)
         d_c = ws.get("qeb.d_c", [rp, D], torch.float32)
         ops.gemm(d_cob, self.qe_cout.wt, rp, D, D, out32=d_c)
@@ -702,7 +739,7 @@ class RefTREngine:
         ops.cast_bf16(dv, dvb)
         for lin, mod, d32, db, x, n in ((self.qe_lin[0], qe.linear1, dk, dkb, cls_b, B), (self.qe_lin[1], qe.linear2, dq, dqb, ctxb, rl),
                                         (self.qe_lin[2], qe.linear3, dv, dvb, ctxb, rl)):
-            ops.colsum(d32, self.G(mod.bias))
+            self.colsum(d32, self.G(mod.bias))
             self.wgrad_linear(db, x, self.G(mod.weight), D, D, n)
         d_ctx = ws.get("qeb.d_ctx", [rl, D], torch.float32)
         ops.gemm(dqb, self.qe_lin[1].wt, rl, D, D, out32=d_ctx)
@@ -799,52 +836,52 @@ class RefTREngine:
             lay = d.mod
             tgtb, tqb, qkv, o_s, lse_s, y1, m1, r1, t1qb, qc, o_c, lse_c, y2, m2, r2, t2b, h, y3, m3, r3, t3 = self.saved[k]
             sl = slice(l * rt, (l + 1) * rt)
-            gh = ws.get("decb.gh", [rt, D], torch.float32)
+            gh = ws.get(f"decb{l}.gh", [rt, D], torch.float32)
             ops.layernorm_bwd(d_hs[sl], t3, vt.decoder.norm.weight, mh[sl], rh[sl], rt, dx32=gh, dgamma=self.G(vt.decoder.norm.weight),
                               dbeta=self.G(vt.decoder.norm.bias))
-            dy3 = ws.get("decb.dy3", [rt, D], torch.float32)
-            dy3b = ws.get("decb.dy3b", [rt, D])
+            dy3 = ws.get(f"decb{l}.dy3", [rt, D], torch.float32)
+            dy3b = ws.get(f"decb{l}.dy3b", [rt, D])
             ops.layernorm_bwd(gh, y3, lay.norm3.weight, m3, r3, rt, dy2=g_next, dx32=dy3, dxb=dy3b, dgamma=self.G(lay.norm3.weight),
                               dbeta=self.G(lay.norm3.bias))
-            g2 = ws.get("decb.g2", [rt, D], torch.float32)
-            self._ffn_bwd("decb", d.l1, d.l2, lay, dy3, dy3b, t2b, h, rt, g2)
-            dy2 = ws.get("decb.dy2", [rt, D], torch.float32)
-            dy2b = ws.get("decb.dy2b", [rt, D])
+            g2 = ws.get(f"decb{l}.g2", [rt, D], torch.float32)
+            self._ffn_bwd(f"decb{l}", d.l1, d.l2, lay, dy3, dy3b, t2b, h, rt, g2)
+            dy2 = ws.get(f"decb{l}.dy2", [rt, D], torch.float32)
+            dy2b = ws.get(f"decb{l}.dy2b", [rt, D])
             ops.layernorm_bwd(g2, y2, lay.norm2.weight, m2, r2, rt, dx32=dy2, dxb=dy2b, dgamma=self.G(lay.norm2.weight),
                               dbeta=self.G(lay.norm2.bias))
             # cross attention
-            ops.colsum(dy2, self.G(lay.multihead_attn.out_proj.bias))
+            self.colsum(dy2, self.G(lay.multihead_attn.out_proj.bias))
             self.wgrad_linear(dy2b, o_c, self.G(lay.multihead_attn.out_proj.weight), D, D, rt)
-            do_c = ws.get("decb.do_c", [rt, D])
+            do_c = ws.get(f"decb{l}.do_c", [rt, D])
             ops.gemm(dy2b, d.ca_out.wt, rt, D, D, out=do_c)
-            dqc = ws.get("decb.dqc", [rt, D])
-            dbuf = ws.get("decb.dbuf", [B, NH, T], torch.float32)
+            dqc = ws.get(f"decb{l}.dqc", [rt, D])
+            dbuf = ws.get(f"decb{l}.dbuf", [B, NH, T], torch.float32)
             cs = slice(l * D, (l + 1) * D)
             ops.attn_bwd(qc, kall[:, cs], vall[:, cs], kpm, o_c, do_c, lse_c, dqc, dkall[:, cs], dvall[:, cs], dbuf, B, NH, T, S, scale)
             gw = self.G(lay.multihead_attn.in_proj_weight)
             gb = self.G(lay.multihead_attn.in_proj_bias)
-            ops.colsum(dqc, gb[:D])
-            ops.colsum(dkall[:, cs], gb[D:2 * D])
-            ops.colsum(dvall[:, cs], gb[2 * D:])
+            self.colsum(dqc, gb[:D])
+            self.colsum(dkall[:, cs], gb[D:2 * D])
+            self.colsum(dvall[:, cs], gb[2 * D:])
             self.wgrad_linear(dqc, t1qb, gw[:D], D, D, rt)
             self.wgrad_linear(dkall[:, cs], mempb, gw[D:2 * D], D, D, rows)
             self.wgrad_linear(dvall[:, cs], memb, gw[2 * D:], D, D, rows)
-            g1 = ws.get("decb.g1", [rt, D], torch.float32)
+            g1 = ws.get(f"decb{l}.g1", [rt, D], torch.float32)
             ops.gemm(dqc, d.ca.wt[:, :D], rt, D, D, res32=dy2, out32=g1)
             ops.gemm(dqc, d.ca.wt[:, :D], rt, D, D, res32=dqpos, out32=dqpos)
-            dy1 = ws.get("decb.dy1", [rt, D], torch.float32)
-            dy1b = ws.get("decb.dy1b", [rt, D])
+            dy1 = ws.get(f"decb{l}.dy1", [rt, D], torch.float32)
+            dy1b = ws.get(f"decb{l}.dy1b", [rt, D])
             ops.layernorm_bwd(g1, y1, lay.norm1.weight, m1, r1, rt, dx32=dy1, dxb=dy1b, dgamma=self.G(lay.norm1.weight),
                               dbeta=self.G(lay.norm1.bias))
             # self attention
-            ops.colsum(dy1, self.G(lay.self_attn.out_proj.bias))
+            self.colsum(dy1, self.G(lay.self_attn.out_proj.bias))
             self.wgrad_linear(dy1b, o_s, self.G(lay.self_attn.out_proj.weight), D, D, rt)
-            do_s = ws.get("decb.do_s", [rt, D])
+            do_s = ws.get(f"decb{l}.do_s", [rt, D])
             ops.gemm(dy1b, d.sa_out.wt, rt, D, D, out=do_s)
-            dqkv = ws.get("decb.dqkv", [rt, 3 * D])
+            dqkv = ws.get(f"decb{l}.dqkv", [rt, 3 * D])
             ops.attn_bwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], qmask, o_s, do_s, lse_s, dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:],
                          dbuf, B, NH, T, T, scale)
-            ops.colsum(dqkv, self.G(lay.self_attn.in_proj_bias))
+            self.colsum(dqkv, self.G(lay.self_attn.in_proj_bias))
             gws = self.G(lay.self_attn.in_proj_weight)
             self.wgrad_linear(dqkv[:, :2 * D], tqb, gws[:2 * D], 2 * D, D, rt)
             self.wgrad_linear(dqkv[:, 2 * D:], tgtb, gws[2 * D:], D, D, rt)
@@ -949,15 +986,15 @@ class RefTREngine:
         gl[:, :4].copy_(g_logits.reshape(rh, 4))
         glb = ws.get("bboxb.glb", [rh, 64])
         ops.cast_bf16(gl, glb)
-        ops.colsum(gl, self.G(bl[2].bias), rows=rh, N=4)
+        self.colsum(gl, self.G(bl[2].bias), rows=rh, N=4)
         self.wgrad_linear(glb, z1, self.G(bl[2].weight), 4, D, rh)
         dz1 = ws.get("bboxb.dz1", [rh, D])
         ops.gemm(glb, self.bbox[2].wt, rh, D, 64, mask_src=z1, out=dz1)
-        ops.colsum(dz1, self.G(bl[1].bias))
+        self.colsum(dz1, self.G(bl[1].bias))
         self.wgrad_linear(dz1, z0, self.G(bl[1].weight), D, D, rh)
         dz0 = ws.get("bboxb.dz0", [rh, D])
         ops.gemm(dz1, self.bbox[1].wt, rh, D, D, mask_src=z0, out=dz0)
-        ops.colsum(dz0, self.G(bl[0].bias))
+        self.colsum(dz0, self.G(bl[0].bias))
         self.wgrad_linear(dz0, hsb, self.G(bl[0].weight), D, D, rh)
         d_hs = ws.get("bboxb.d_hs", [rh, D], torch.float32)
         ops.gemm(dz0, self.bbox[0].wt, rh, D, D, out32=d_hs)
@@ -981,13 +1018,14 @@ class RefTREngine:
             g_out = gbuf[l & 1]
             self._enc_bwd(l, self.enc[l], g, g_out, kpm, dpos, B, S)
             g = g_out
-        ops.embed_grad(dpos, B, S, L, self.G(vt.lang_pos_embeddings.weight), self.G(vt.token_type_embeddings.weight), self.G(vt.level_embed))
+        with self._off():
+            ops.embed_grad(dpos, B, S, L, self.G(vt.lang_pos_embeddings.weight), self.G(vt.token_type_embeddings.weight), self.G(vt.level_embed))
         # ---- language rows -> map_sentence; visual rows -> GroupNorm -> input_proj -> backbone ---------------------------------------
         d_sent = self._mlp_map_bwd("map_sentence", self.map_sentence, m.map_sentence, g)
         gn = m.input_proj[0][1]
         dproj = ws.get("iproj.dx", [g5.R, D], zero=True)
         ops.groupnorm_tokens_bwd(g, g_src, proj32, gn.weight, gmean, grstd, B, h, w, S, L, dproj, self.G(gn.weight), self.G(gn.bias))
-        ops.colsum(dproj, self.G(m.input_proj[0][0].bias))
+        self.colsum(dproj, self.G(m.input_proj[0][0].bias))
         self.wgrad_conv(self.iproj, dproj, c5, g5.R)
         if self.blocks[-1].trainable:
             g5y = ws.get("iproj.gc5", [g5.R, 2048])
@@ -999,6 +1037,7 @@ class RefTREngine:
                 self.bert.backward("s", d_sent, None)
             else:
                 self.bert.backward("s", d_sent, d_pooled)
+        self._join_side()
         return d_sent.view(B, L, -1), d_pooled
 
 

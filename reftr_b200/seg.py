@@ -148,7 +148,7 @@ class SegHead:
         y4 = sv[4][3]
         b8 = ws.get("segb.b8", [Cp], torch.float32)
         b8.zero_()
-        ops.colsum(dl, b8)
+        ops.colsum(dl, b8)  # (tiny; stays on the main stream: b8 is consumed right below)
         G(mh.out_lay.bias).add_(b8[:1])
         sc = eng.scratch_view("seg.out").view(Cp, 9 * self.out.Cin)
         sh = g2.shifts()
@@ -167,7 +167,7 @@ class SegHead:
             xin, g, c32, y, mean, rstd = sv[i][:6]
             dc = ws.get(f"segb.dc{i}", [g.R, pc.Cout])
             ops.groupnorm_nhwc_bwd(dy, y, c32, gn.weight, mean, rstd, B, g.H, g.W, pc.Cout, gn.num_groups, dc, G(gn.weight), G(gn.bias), relu=True)
-            ops.colsum(dc, G(lay.bias))
+            eng.colsum(dc, G(lay.bias))
             shg = g.shifts()
             eng.wgrad_conv(pc, dc, xin, g.R, key=f"seg.lay{i + 1}", b_offsets=shg)
             dxin = ws.get(f"segb.dxin{i}", [g.R, pc.Cin])
@@ -178,7 +178,7 @@ class SegHead:
                 adm = getattr(mh, f"adapter{j + 1}")
                 glo, f = sv[i][6], sv[i][7]
                 layer = (3, 2, 1)[j]
-                ops.colsum(dxin, G(adm.bias))
+                eng.colsum(dxin, G(adm.bias))
                 eng.wgrad_conv(ad, dxin, f, g.R)
                 first_trainable_layer = min(b.layer for b in eng.blocks if b.trainable) if any(b.trainable for b in eng.blocks) else 99
                 if layer >= first_trainable_layer:  # gradient into the backbone feature (C2 = frozen layer1 output: none)
@@ -202,12 +202,12 @@ class SegHead:
         ba = m.bbox_attention
         dkb = ws.get("segb.dkb", [rows, D])
         ops.cast_bf16(dk, dkb)
-        ops.colsum(dk, G(ba.k_linear.bias))
+        eng.colsum(dk, G(ba.k_linear.bias))
         eng.wgrad_linear(dkb, memb, G(ba.k_linear.weight), D, D, rows)
         ops.gemm(dkb, self.k.wt, rows, D, D, res32=g_mem, out32=g_mem)
         dqb = ws.get("segb.dqb", [B, D])
         ops.cast_bf16(dq, dqb)
-        ops.colsum(dq, G(ba.q_linear.bias))
+        eng.colsum(dq, G(ba.q_linear.bias))
         eng.wgrad_linear(dqb, hs_last, G(ba.q_linear.weight), D, D, B)
         d_last = d_hs[(nl - 1) * B:nl * B]
         ops.gemm(dqb, self.q.wt, B, D, D, res32=d_last, out32=d_last)
