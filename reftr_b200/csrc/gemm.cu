@@ -149,28 +149,37 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ------------------------------------------------------------------------------------------ main-loop producer
     if (lane == 0) {
       const uint32_t tx_bytes = p.stage_bytes;
-      int i = 0;  // global k-iteration counter (ring position)
+      int s = 0;         // ring position
+      uint32_t ph = 0;   // ring phase
       for (int t = blockIdx.x; t < p.tiles_total; t += gridDim.x) {
         const TileCoord c = tile_coord(p, t);
-        for (int k = 0; k < c.n_it; ++k, ++i) {
-          const int s = i % p.stages;
-          const uint32_t ph = (i / p.stages) & 1;
+        // incremental (tap, k-block) counters: this single thread is instruction-bound, so no divisions in the loop
+        int tap = 0, kc = 0;
+        if (MODE == 0 && c.it_begin) { tap = c.it_begin / p.kblocks; kc = c.it_begin - tap * p.kblocks; }
+        int row_a = c.m0 + (MODE == 0 ? p.a_rowoff[tap] : 0), col_b = (MODE == 0 ? p.b_koff[tap] : 0);
+        int r0 = c.it_begin * BK;
+        const int ra = (MODE == 1) ? p.a_rowoff[c.z_tap] : 0, rb = (MODE == 1) ? p.b_koff[c.z_tap] : 0;
+        for (int k = 0; k < c.n_it; ++k) {
           mbar_wait(&empty[s], ph ^ 1);
           mbar_expect_tx(&full[s], tx_bytes);
           uint8_t* a_dst = smem + s * p.stage_bytes;
           uint8_t* b_dst = a_dst + A_BYTES;
-          const int it = c.it_begin + k;
           if (MODE == 0) {
-            const int tap = it / p.kblocks;
-            const int kc = it - tap * p.kblocks;
-            tma_load_2d(a_dst, &tmA, &full[s], kc * BK, c.m0 + p.a_rowoff[tap]);
-            tma_load_2d(b_dst, &tmB, &full[s], p.b_koff[tap] + kc * BK, c.n0);
+            tma_load_2d(a_dst, &tmA, &full[s], kc * BK, row_a);
+            tma_load_2d(b_dst, &tmB, &full[s], col_b + kc * BK, c.n0);
+            if (++kc == p.kblocks) {
+              kc = 0;
+              ++tap;
+              row_a = c.m0 + p.a_rowoff[tap & 15];
+              col_b = p.b_koff[tap & 15];
+            }
           } else {
-            const int r0 = it * BK;
 #pragma unroll
-            for (int j = 0; j < BM / 64; ++j) tma_load_2d(a_dst + j * 8192, &tmA, &full[s], c.m0 + 64 * j, r0 + p.a_rowoff[c.z_tap]);
-            for (int j = 0; j < bn / 64; ++j) tma_load_2d(b_dst + j * 8192, &tmB, &full[s], c.n0 + 64 * j, r0 + p.b_koff[c.z_tap]);
+            for (int j = 0; j < BM / 64; ++j) tma_load_2d(a_dst + j * 8192, &tmA, &full[s], c.m0 + 64 * j, r0 + ra);
+            for (int j = 0; j < bn / 64; ++j) tma_load_2d(b_dst + j * 8192, &tmB, &full[s], c.n0 + 64 * j, r0 + rb);
+            r0 += BK;
           }
+          if (++s == p.stages) { s = 0; ph ^= 1; }
         }
       }
     }
@@ -179,7 +188,14 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ------------------------------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_bf16(BM, bn, MODE, MODE);
-      int i = 0, tcount = 0;
+      // The issuing thread is instruction-bound (one thread, dependent issue): descriptors are formed by ADDING 16-byte-unit
+      // offsets to a base descriptor (the start-address field is the low 14 bits; shared memory is < 256 KB so no carry-out).
+      const uint32_t smem_base = smem_u32(smem);
+      const uint64_t a_desc0 = (MODE == 0) ? umma_smem_desc(smem_base, 16, 1024, SWZ_128B) : umma_smem_desc(smem_base, 8192, 1024, SWZ_128B);
+      const uint32_t stage_units = p.stage_bytes >> 4, b_units = A_BYTES >> 4;
+      constexpr uint32_t kstep = (MODE == 0 ? 32 : 2048) >> 4;
+      int s = 0, tcount = 0;
+      uint32_t ph = 0;
       for (int t = blockIdx.x; t < p.tiles_total; t += gridDim.x) {
         const TileCoord c = tile_coord(p, t);
         if (c.n_it <= 0) continue;
@@ -187,26 +203,16 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_wait(&acc_empty[as], ((tcount >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * bn;
-        for (int k = 0; k < c.n_it; ++k, ++i) {
-          const int s = i % p.stages;
-          const uint32_t ph = (i / p.stages) & 1;
+        for (int k = 0; k < c.n_it; ++k) {
           mbar_wait(&full[s], ph);
           tc_fence_after();
-          const uint32_t a_base = smem_u32(smem + s * p.stage_bytes);
-          const uint32_t b_base = a_base + A_BYTES;
+          const uint64_t ad = a_desc0 + static_cast<uint64_t>(s * stage_units);
+          const uint64_t bd = ad + b_units;
+          umma_bf16_ss(d_tmem, ad, bd, idesc, k != 0);
 #pragma unroll
-          for (int kk = 0; kk < BK / 16; ++kk) {
-            uint64_t ad, bd;
-            if (MODE == 0) {
-              ad = umma_smem_desc(a_base + kk * 32, 16, 1024, SWZ_128B);
-              bd = umma_smem_desc(b_base + kk * 32, 16, 1024, SWZ_128B);
-            } else {
-              ad = umma_smem_desc(a_base + kk * 2048, 8192, 1024, SWZ_128B);
-              bd = umma_smem_desc(b_base + kk * 2048, 8192, 1024, SWZ_128B);
-            }
-            umma_bf16_ss(d_tmem, ad, bd, idesc, (k | kk) != 0);
-          }
+          for (int kk = 1; kk < BK / 16; ++kk) umma_bf16_ss(d_tmem, ad + kk * kstep, bd + kk * kstep, idesc, 1);
           umma_commit(&empty[s]);
+          if (++s == p.stages) { s = 0; ph ^= 1; }
         }
         umma_commit(&acc_full[as]);
         ++tcount;
