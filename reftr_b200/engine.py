@@ -200,6 +200,7 @@ class RefTREngine:
         self.use_graphs = os.environ.get("REFTR_B200_GRAPHS", "1") != "0"
         self.use_side = os.environ.get("REFTR_B200_SIDE_STREAM", "1") != "0"
         self._side, self._side_used = None, False
+        self._side2, self._side2_used = None, False
         self._tracked = [t for t in list(model.parameters()) + list(model.buffers())]
         self._vsig, self._pack_dev = None, None
         self.force_eager = False  # bench.py: run the next steps launch by launch on the graphed workspace (profiling)
@@ -385,6 +386,25 @@ class RefTREngine:
         self._side.wait_event(ev)
         self._side_used = True
         return torch.cuda.stream(self._side)
+
+    def _branch(self):
+        """A second side stream for a whole independent CHAIN (BERT forward next to the conv backbone, BERT backward next to the
+        backbone backward); ``_join_branch`` must be called on the main stream before the chain's results are consumed."""
+        import contextlib
+        if not self.use_side or self._dev is None or self._dev.type != "cuda":
+            return contextlib.nullcontext()
+        if self._side2 is None:
+            self._side2 = torch.cuda.Stream(device=self._dev)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._side2.wait_event(ev)
+        self._side2_used = True
+        return torch.cuda.stream(self._side2)
+
+    def _join_branch(self):
+        if self._side2_used:
+            torch.cuda.current_stream().wait_stream(self._side2)
+            self._side2_used = False
 
     def _join_side(self):
         if self._side_used:
@@ -911,6 +931,12 @@ class RefTREngine:
         T = n_ph * n_q
         if L > vt.max_lang_seq:
             raise ValueError(f"sentence length {L} exceeds max_lang_seq {vt.max_lang_seq} (reftr.py:81)")
+        # ---- language backbone first, on a branch stream: it is independent of the conv backbone and latency-bound ---------
+        if lang[0] == "ids":  # BERT on our kernels (reftr_transformer.py:200, :215-217)
+            with self._branch():
+                _, sfb, pooled = self.bert.forward("s", lang[1], lang[2], B, L)
+                if len(lang) > 3:
+                    _, _, pooled = self.bert.forward("p", lang[3], lang[4], B * n_ph, lang[3].shape[1])
         # ---- backbone (backbone.py:101-109) ---------------------------------------------------------------------
         feats = self._backbone_fwd(img)
         c5, g5 = feats[4]
@@ -933,10 +959,8 @@ class RefTREngine:
         gmean, grstd = ws.get("iproj.mean", [B * 32], torch.float32), ws.get("iproj.rstd", [B * 32], torch.float32)
         ops.groupnorm_tokens_fwd(proj32, gn.weight, gn.bias, B, h, w, S, L, x32, xb, pos32, xpb, gmean, grstd, eps=gn.eps)
         # ---- language features -> language token rows (reftr_transformer.py:201, reftr.py:79-97) -------------------
-        if lang[0] == "ids":  # BERT on our kernels (reftr_transformer.py:200, :215-217)
-            _, sfb, pooled = self.bert.forward("s", lang[1], lang[2], B, L)
-            if len(lang) > 3:
-                _, _, pooled = self.bert.forward("p", lang[3], lang[4], B * n_ph, lang[3].shape[1])
+        if lang[0] == "ids":
+            self._join_branch()
         else:
             sent_feat, pooled = lang[1], lang[2]
             sfb = ws.get("lang.sfb", [B * L, sent_feat.shape[-1]])
@@ -1022,6 +1046,13 @@ class RefTREngine:
             ops.embed_grad(dpos, B, S, L, self.G(vt.lang_pos_embeddings.weight), self.G(vt.token_type_embeddings.weight), self.G(vt.level_embed))
         # ---- language rows -> map_sentence; visual rows -> GroupNorm -> input_proj -> backbone ---------------------------------------
         d_sent = self._mlp_map_bwd("map_sentence", self.map_sentence, m.map_sentence, g)
+        if native_bert:  # BERT's backward chain runs next to the backbone backward (independent of it)
+            with self._branch():
+                if has_phrases:
+                    self.bert.backward("p", None, d_pooled)
+                    self.bert.backward("s", d_sent, None)
+                else:
+                    self.bert.backward("s", d_sent, d_pooled)
         gn = m.input_proj[0][1]
         dproj = ws.get("iproj.dx", [g5.R, D], zero=True)
         ops.groupnorm_tokens_bwd(g, g_src, proj32, gn.weight, gmean, grstd, B, h, w, S, L, dproj, self.G(gn.weight), self.G(gn.bias))
@@ -1031,12 +1062,7 @@ class RefTREngine:
             g5y = ws.get("iproj.gc5", [g5.R, 2048])
             ops.gemm(dproj, self.iproj.wd, g5.R, 2048, D, res=g_fpn.get(4), mask_src=c5, out=g5y)
             self._backbone_bwd(g5y, g_fpn)
-        if native_bert:
-            if has_phrases:
-                self.bert.backward("p", None, d_pooled)
-                self.bert.backward("s", d_sent, None)
-            else:
-                self.bert.backward("s", d_sent, d_pooled)
+        self._join_branch()
         self._join_side()
         return d_sent.view(B, L, -1), d_pooled
 
