@@ -238,10 +238,10 @@ def main():
             for x in ((v.tensors, v.mask) if hasattr(v, "tensors") else (v,)):
                 x.record_stream(torch.cuda.current_stream())
         t.record_stream(torch.cuda.current_stream())
-        prefetch()  # next step's inputs, overlapped with this step's compute
-        net.zero_grad(set_to_none=True)
         loss = loss_of(net(s), t)
+        prefetch()  # next step's inputs: the copy overlaps this step's compute
         loss.backward()
+        net.zero_grad(set_to_none=True)  # (where optimizer.zero_grad() sits in a training loop: after the update, before logging)
         return loss.item()  # D2H read of the step's result
 
     def barrier():
@@ -275,6 +275,17 @@ def main():
         step_e2e()
     ms_e2e = timed(step_e2e, a.steps)
 
+    # host-side cost of one step (diagnostic): time to enqueue a whole step without any sync, and time until the forward is enqueued
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    net.zero_grad(set_to_none=True)
+    o_ = net(s_dev)
+    t1 = time.perf_counter()
+    loss_of(o_, t_dev).backward()
+    t2 = time.perf_counter()
+    torch.cuda.synchronize()
+    host_ms = {"enqueue_fwd_ms": (t1 - t0) * 1e3, "enqueue_step_ms": (t2 - t0) * 1e3}
+
     value = world * B * a.steps / ms * 1e3
     e2e = world * B * a.steps / ms_e2e * 1e3
     out = dict(base, value=value, ms_per_step=ms / a.steps, dtype="bf16",
@@ -284,7 +295,7 @@ def main():
                        "l2": "per-step working set (saved activations, several GB) far exceeds the 126 MB L2; no explicit flush"},
                e2e={"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": nbytes(s_host, t_host), "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / a.steps},
-               gpu_launches=launches, clocks=clocks)
+               gpu_launches=launches, clocks=clocks, host=host_ms)
     if a.impl == "stock-gpu":
         out["impl"] = "stock-gpu"
         out["dtype"] = "f32 (cuDNN TF32 conv, fp32 matmul: PyTorch defaults)"

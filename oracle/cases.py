@@ -40,6 +40,11 @@ CASES = {
         flags=_COMMON + ["--enc_layers", "1", "--dec_layers", "2", "--reftr_type", "transformer"],
         oracle_kw=dict(enc=1, dec=2, dropout=0.0, aux_loss=True), seg=False, bert_layers=2, wseed=5,
         inputs=dict(B=2, H=160, W=160, L=16, n_valid=12, n_ph=3), grad_filter=_gf),
+    # BASELINE.json configs[4] architecture: ResNet-101 backbone (23 layer3 blocks), longer phrase
+    "r101_box": dict(
+        flags=_COMMON + ["--enc_layers", "1", "--dec_layers", "1", "--backbone", "resnet101"],
+        oracle_kw=dict(enc=1, dec=1, dropout=0.0, aux_loss=True, backbone="resnet101"), seg=False, bert_layers=2, wseed=9,
+        inputs=dict(B=1, H=160, W=128, L=40, n_valid=33), grad_filter=_gf),
     # segmentation model (reftr_segmentation.py)
     "seg": dict(
         flags=_COMMON + ["--enc_layers", "1", "--dec_layers", "1", "--masks"],

@@ -7,8 +7,9 @@ from reftr_b200.modules import BackboneParams, Joiner, PositionEmbeddingSine, Re
 from reftr_b200.synthetic import synthetic_weights
 
 
-def build_candidate(case, device="cpu", backbone="resnet50", bert=None):
+def build_candidate(case, device="cpu", backbone=None, bert=None):
     kw = case["oracle_kw"]
+    backbone = backbone or kw.get("backbone", "resnet50")
     torch.manual_seed(1234)
     bert = bert if bert is not None else BertModel(bert_config(case))
     seg = case["seg"]
