@@ -36,6 +36,10 @@ WORKLOAD = dict(B=16, H=640, W=640, L=20)
 METRIC = "samples/sec fwd+bwd (640x640, 20-tok phrase, bs16/GPU)"
 
 
+CONFIG = {"workload": "cfg2: ResNet-50 + 6+6-layer RefTR box model, 640x640, 20-token phrase, bs16 per GPU, aux_loss",
+          "mode": "eval+grad (dropout inactive), fwd+criterion+bwd, no optimizer"}
+
+
 def peaks():
     try:
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
@@ -175,7 +179,7 @@ def main():
         rate, threads, sec = oracle_cpu_rate(bs, a.steps, a.warmup)
         sample = f"fp32 oracle fwd+loss+bwd on host CPU, {bs} samples of the cfg2 workload per step (640x640, L=20), {threads} threads"
         out = dict(base, impl="reference", value=rate, ms_per_step=sec * 1e3, dtype="f32",
-                   config={"workload": "cfg2: R50 + 6+6 RefTR, 640x640, L=20", "batch_per_step": bs, "mode": "eval+grad (dropout inactive)"},
+                   config=dict(CONFIG, global_batch=bs, parallelism="cpu", sample=sample),
                    cpu_baseline={"value": rate, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample},
                    e2e={"value": rate, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, gpu_launches=0)
         print(json.dumps(out))
@@ -289,8 +293,7 @@ def main():
     value = world * B * a.steps / ms * 1e3
     e2e = world * B * a.steps / ms_e2e * 1e3
     out = dict(base, value=value, ms_per_step=ms / a.steps, dtype="bf16",
-               config={"workload": "cfg2: ResNet-50 + 6+6-layer RefTR box model, 640x640, 20-token phrase, bs16 per GPU, aux_loss",
-                       "global_batch": world * B, "parallelism": f"dp{world}", "mode": "eval+grad (dropout inactive), fwd+criterion+bwd, no optimizer",
+               config={"workload": CONFIG["workload"], "global_batch": world * B, "parallelism": f"dp{world}", "mode": CONFIG["mode"],
                        "bert": "BERT-base on the same C-ABI kernels (bf16 operands, fp32 residual/LN), inside the step graphs",
                        "l2": "per-step working set (saved activations, several GB) far exceeds the 126 MB L2; no explicit flush"},
                e2e={"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": nbytes(s_host, t_host), "d2h_bytes_per_step": 4,
