@@ -289,6 +289,8 @@ def main():
     t2 = time.perf_counter()
     torch.cuda.synchronize()
     host_ms = {"enqueue_fwd_ms": (t1 - t0) * 1e3, "enqueue_step_ms": (t2 - t0) * 1e3}
+    if eng is not None:
+        host_ms.update({k: round(v, 3) for k, v in getattr(eng, "host_ms", {}).items()})
 
     value = world * B * a.steps / ms * 1e3
     e2e = world * B * a.steps / ms_e2e * 1e3

@@ -124,7 +124,8 @@ class CriterionVGMultiPhrase(nn.Module):
         num_boxes = float(sum(len(t["labels"]) for t in targets))
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             # the reference calls .item() here (criterion.py:180): a host sync per step.  The count stays a device scalar instead.
-            nb = torch.as_tensor([num_boxes], dtype=torch.float, device=outputs["pred_boxes"].device)
+            # torch.full = a fill kernel; torch.as_tensor([..], device=cuda) would be a pageable H2D copy, i.e. a host sync
+            nb = torch.full((1,), num_boxes, dtype=torch.float, device=outputs["pred_boxes"].device)
             torch.distributed.all_reduce(nb)
             num_boxes = torch.clamp(nb / torch.distributed.get_world_size(), min=1)[0]
         else:

@@ -333,14 +333,21 @@ class RefTREngine:
         st["nb"] += 1
         self.launches += st["bl"]
         d_sent, d_pooled = st["bouts"]
+        import time as _t
+        _t0 = _t.perf_counter()
         # fresh storage per step: autograd may keep these as .grad of leaf tensors
         flat = self.gflat[:self.n_grad].clone()
+        _t1 = _t.perf_counter()
         if getattr(self.model, "engine_allreduce", False) and torch.distributed.is_available() and torch.distributed.is_initialized():
             world = torch.distributed.get_world_size()
             if world > 1:
                 # the data-parallel exchange of the path: ONE all-reduce over the flat gradient buffer, then the mean
-                torch.distributed.all_reduce(flat)
-                flat.mul_(1.0 / world)
+                if torch.distributed.get_backend() == "nccl":
+                    torch.distributed.all_reduce(flat, op=torch.distributed.ReduceOp.AVG)  # mean inside the collective
+                else:
+                    torch.distributed.all_reduce(flat)
+                    flat.mul_(1.0 / world)
+        self.host_ms = {"clone": (_t1 - _t0) * 1e3, "allreduce": (_t.perf_counter() - _t1) * 1e3}
         if self.bert is not None:
             return None, None, flat
         return d_sent.clone(), d_pooled.clone(), flat
@@ -1093,9 +1100,13 @@ class HotPathFunction(torch.autograd.Function):
         g_att = gouts[2] if ctx.want_seg else None
         if ctx.want_seg and g_masks is None:
             g_masks = torch.zeros_like(eng.seghead.out_masks)
+        import time as _t
+        _t0 = _t.perf_counter()
         d_sent, d_pooled, flat = eng.run_backward(g_logits, g_masks, g_att)
+        _t1 = _t.perf_counter()
         grads = []
         for n, p in eng.named:
             off, shape = eng.slots[n]
             grads.append(flat[off:off + p.numel()].view(shape))
+        eng.host_ms.update({"run_backward": (_t1 - _t0) * 1e3, "views": (_t.perf_counter() - _t1) * 1e3})
         return (None, None, None, None, None, None, None, None, d_sent, d_pooled, None, None, None, *grads)
