@@ -32,6 +32,7 @@ if ROOT not in sys.path:
 import torch  # noqa: E402
 
 GF_FWD_BWD = 207.83  # algorithmic GFLOP per sample, fwd+bwd, config 2 (FlopCounterMode on the reference)
+GF_BY_WORKLOAD = {"cfg2": 207.83, "cfg3": 220.77, "cfg4": 304.78, "cfg5": 616.74}
 WORKLOAD = dict(B=16, H=640, W=640, L=20)
 METRIC = "samples/sec fwd+bwd (640x640, 20-tok phrase, bs16/GPU)"
 
@@ -84,12 +85,20 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
 
 
-def build_ours(device):
+WORKLOADS = {  # name -> (flag list key, synthetic input shape)
+    "cfg2": ("cfg2_box_r50", dict(B=16, H=640, W=640, L=20)),
+    "cfg3": ("cfg3_seg_r50", dict(B=8, H=640, W=640, L=20)),
+    "cfg4": ("cfg4_flickr", dict(B=32, H=640, W=640, L=90, n_valid=30, n_ph=5)),
+    "cfg5": ("cfg5_r101", dict(B=16, H=800, W=800, L=40)),
+}
+
+
+def build_ours(device, workload="cfg2"):
     os.environ.setdefault("REFTR_B200_RANDOM_BERT", "1")  # no network / HF cache on the box: random-init BERT-base
     from reftr_b200 import build_reftr
     from reftr_b200.args import CONFIG_FLAGS, parse
     from reftr_b200.synthetic import synthetic_weights
-    args = parse(CONFIG_FLAGS["cfg2_box_r50"] + ["--device", str(device)])
+    args = parse(CONFIG_FLAGS[WORKLOADS[workload][0]] + ["--device", str(device)])
     torch.manual_seed(0)
     model, criterion, _ = build_reftr(args)
     synthetic_weights(model, seed=0)
@@ -107,10 +116,12 @@ def build_oracle_model(device):
     return model.to(device)
 
 
-def host_batch(B, pinned):
+def host_batch(B, pinned, shape=None):
     from reftr_b200.synthetic import ImageList, synthetic_samples, synthetic_targets
-    s = synthetic_samples(B, WORKLOAD["H"], WORKLOAD["W"], WORKLOAD["L"])
-    tgt = synthetic_targets(B)
+    shape = dict(shape or WORKLOAD)
+    shape["B"] = B
+    s = synthetic_samples(**shape)
+    tgt = synthetic_targets(B, max(shape.get("n_ph", 0), 1))
     if pinned:
         s = {k: (ImageList(v.tensors.pin_memory(), v.mask.pin_memory()) if k == "img" else v.pin_memory()) for k, v in s.items()}
         tgt = tgt.pin_memory()
@@ -123,8 +134,15 @@ def to_device(s, tgt, device):
     return d, t
 
 
-def targets_list(tgt):
-    return [{"boxes": b, "labels": [0] * b.shape[0]} for b in tgt]
+def targets_list(tgt, masks=False):
+    # multi-phrase synthetic samples end with one empty pad phrase (reftr_b200/synthetic.py): it has no target box
+    out = [{"boxes": (b if b.shape[0] == 1 else b[:-1]), "labels": [0] * (b.shape[0] if b.shape[0] == 1 else b.shape[0] - 1)} for b in tgt]
+    if masks:  # cfg3: one random-rectangle mask per sample at image resolution
+        for i, t in enumerate(out):
+            m = torch.zeros(1, 640, 640, dtype=torch.bool, device=tgt.device)
+            m[:, 100 + 10 * i:400, 150:500 - 10 * i] = True
+            t["masks"] = m
+    return out
 
 
 def nbytes(s, tgt):
@@ -162,6 +180,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "stock-gpu"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "cfg5"],
+                    help="cfg2 (default, the metric's configuration); cfg3 = +mask head bs8; cfg4 = Flickr multi-phrase L=90 n_ph=5 bs32; "
+                         "cfg5 = ResNet-101 800x800 L=40 (bs16 here)")
     ap.add_argument("--diag", default="", help="diagnostics only: 'noddp' = no DDP wrapper (engine all-reduce only); 'replicas' = no exchange at all")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -196,7 +217,7 @@ def main():
         model = build_oracle_model(device).eval()
         crit = None
     else:
-        model, crit, _ = build_ours(device)
+        model, crit, _ = build_ours(device, a.workload)
         model.eval()  # dropout inactive (parity mode); gradients flow.  Stated in config.mode.
     net = model
     if a.diag == "replicas":
@@ -204,14 +225,16 @@ def main():
     if world > 1 and not a.diag:
         net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local])
 
-    s_host, t_host = host_batch(B, pinned=True)
+    wl_shape = WORKLOADS[a.workload][1]
+    B = wl_shape["B"]
+    s_host, t_host = host_batch(B, pinned=True, shape=wl_shape)
     s_dev, t_dev = to_device(s_host, t_host, device)
     torch.cuda.synchronize()
 
     def loss_of(out, tgt):
         if crit is None:
             return total_box_loss(out, tgt)
-        ld = crit(out, targets_list(tgt))
+        ld = crit(out, targets_list(tgt, masks=a.workload == "cfg3"))
         return sum(ld[k] * crit.weight_dict[k] for k in ld if k in crit.weight_dict)
 
     def step_resident():
@@ -295,7 +318,7 @@ def main():
     value = world * B * a.steps / ms * 1e3
     e2e = world * B * a.steps / ms_e2e * 1e3
     out = dict(base, value=value, ms_per_step=ms / a.steps, dtype="bf16",
-               config={"workload": CONFIG["workload"], "global_batch": world * B, "parallelism": f"dp{world}", "mode": CONFIG["mode"],
+               config={"workload": CONFIG["workload"] if a.workload == "cfg2" else f"{a.workload} (NOT the metric's configuration): {wl_shape}", "global_batch": world * B, "parallelism": f"dp{world}", "mode": CONFIG["mode"],
                        "bert": "BERT-base on the same C-ABI kernels (bf16 operands, fp32 residual/LN), inside the step graphs",
                        "l2": "per-step working set (saved activations, several GB) far exceeds the 126 MB L2; no explicit flush"},
                e2e={"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": nbytes(s_host, t_host), "d2h_bytes_per_step": 4,
@@ -305,9 +328,10 @@ def main():
         out["impl"] = "stock-gpu"
         out["dtype"] = "f32 (cuDNN TF32 conv, fp32 matmul: PyTorch defaults)"
     # whole-step roofline: algorithmic FLOPs of the reference graph (BERT included) over the sustained tensor peak
-    out["step_roofline"] = {"bound": "tensor", "achieved": value * GF_FWD_BWD / 1e3 / world, "peak": pk["bf16_tflops_sustained"],
-                            "unit": "TFLOP/s", "frac": value * GF_FWD_BWD / 1e3 / world / pk["bf16_tflops_sustained"],
-                            "peak_source": pk_src + " (sustained)", "gflop_per_sample": GF_FWD_BWD}
+    gf = GF_BY_WORKLOAD[a.workload]
+    out["step_roofline"] = {"bound": "tensor", "achieved": value * gf / 1e3 / world, "peak": pk["bf16_tflops_sustained"],
+                            "unit": "TFLOP/s", "frac": value * gf / 1e3 / world / pk["bf16_tflops_sustained"],
+                            "peak_source": pk_src + " (sustained)", "gflop_per_sample": gf}
 
     if a.impl == "ours":
         # ---- dominant kernel (tcgen05 GEMM / implicit conv) ---------------------------------------------------------------

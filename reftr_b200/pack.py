@@ -101,36 +101,3 @@ class PackedStack:
             ops.pack_linear(w.detach()[self.row0:self.row0 + self.nrows], self.wb[sl], self.wt[:, sl])
             self.bias[sl].copy_(b.detach()[self.row0:self.row0 + self.nrows])
         self._key = key
-
-
-class GradStore:
-    """One flat fp32 buffer per backward holding every hot-path parameter gradient (views are handed to autograd) plus a
-    scratch region for folded-layout 3x3 weight gradients.  A fresh zeroed buffer is taken for each backward so the views
-    autograd keeps in ``param.grad`` never alias the next step's accumulation."""
-
-    def __init__(self, named_params, scratch_sizes):
-        self.slots = {}
-        off = 0
-        for name, p in named_params:
-            self.slots[name] = (off, tuple(p.shape))
-            off += (p.numel() + 63) // 64 * 64
-        self.scratch = {}
-        for name, n in scratch_sizes.items():
-            self.scratch[name] = (off, n)
-            off += (n + 63) // 64 * 64
-        self.total = off
-        self.flat = None
-
-    def begin(self, device):
-        self.flat = torch.zeros(self.total, dtype=torch.float32, device=device)
-
-    def view(self, name):
-        off, shape = self.slots[name]
-        n = 1
-        for s in shape:
-            n *= s
-        return self.flat[off:off + n].view(shape)
-
-    def scratch_view(self, name):
-        off, n = self.scratch[name]
-        return self.flat[off:off + n]
