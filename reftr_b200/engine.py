@@ -798,11 +798,17 @@ class RefTREngine:
             lay = d.mod
             # self attention over the T queries of a sample (key padding = query_mask)
             qkv = ws.get(k + ".qkv", [rt, 3 * D])
-            ops.gemm(tqb, d.sa.wb[:2 * D], rt, 2 * D, D, bias=d.sa.bias[:2 * D], out=qkv[:, :2 * D])
-            ops.gemm(tgtb, d.sa.wb[2 * D:], rt, D, D, bias=d.sa.bias[2 * D:], out=qkv[:, 2 * D:])
-            o_s = ws.get(k + ".o_s", [rt, D])
             lse_s = ws.get(k + ".lse_s", [B, NH, T], torch.float32)
-            ops.attn_fwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], qmask, o_s, lse_s, B, NH, T, T, scale)
+            if T == 1:
+                # one query per sample (every RES/REC config): the self-attention softmax runs over a single key, so its output is
+                # exactly the value projection; q / k projections, the attention kernel and their (exactly zero) gradients are skipped
+                o_s = qkv[:, 2 * D:]
+                ops.gemm(tgtb, d.sa.wb[2 * D:], rt, D, D, bias=d.sa.bias[2 * D:], out=o_s)
+            else:
+                ops.gemm(tqb, d.sa.wb[:2 * D], rt, 2 * D, D, bias=d.sa.bias[:2 * D], out=qkv[:, :2 * D])
+                ops.gemm(tgtb, d.sa.wb[2 * D:], rt, D, D, bias=d.sa.bias[2 * D:], out=qkv[:, 2 * D:])
+                o_s = ws.get(k + ".o_s", [rt, D])
+                ops.attn_fwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], qmask, o_s, lse_s, B, NH, T, T, scale)
             y1 = ws.get(k + ".y1", [rt, D], torch.float32)
             ops.gemm(o_s, d.sa_out.wb, rt, D, D, bias=d.sa_out.bias, res32=tgt32, out32=y1)
             t1 = ws.get(k + ".t1", [rt, D], torch.float32)
@@ -905,16 +911,21 @@ class RefTREngine:
             self.wgrad_linear(dy1b, o_s, self.G(lay.self_attn.out_proj.weight), D, D, rt)
             do_s = ws.get(f"decb{l}.do_s", [rt, D])
             ops.gemm(dy1b, d.sa_out.wt, rt, D, D, out=do_s)
-            dqkv = ws.get(f"decb{l}.dqkv", [rt, 3 * D])
-            ops.attn_bwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], qmask, o_s, do_s, lse_s, dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:],
-                         dbuf, B, NH, T, T, scale)
-            self.colsum(dqkv, self.G(lay.self_attn.in_proj_bias))
-            gws = self.G(lay.self_attn.in_proj_weight)
-            self.wgrad_linear(dqkv[:, :2 * D], tqb, gws[:2 * D], 2 * D, D, rt)
-            self.wgrad_linear(dqkv[:, 2 * D:], tgtb, gws[2 * D:], D, D, rt)
             g_prev = gbuf[l & 1]
-            ops.gemm(dqkv, d.sa.wt, rt, D, 3 * D, res32=dy1, out32=g_prev)
-            ops.gemm(dqkv[:, :2 * D], d.sa.wt[:, :2 * D], rt, D, 2 * D, res32=dqpos, out32=dqpos)
+            gws = self.G(lay.self_attn.in_proj_weight)
+            if T == 1:  # d(value projection) = d(attention output); q / k receive no gradient
+                self.colsum(do_s, self.G(lay.self_attn.in_proj_bias)[2 * D:])
+                self.wgrad_linear(do_s, tgtb, gws[2 * D:], D, D, rt)
+                ops.gemm(do_s, d.sa.wt[:, 2 * D:], rt, D, D, res32=dy1, out32=g_prev)
+            else:
+                dqkv = ws.get(f"decb{l}.dqkv", [rt, 3 * D])
+                ops.attn_bwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], qmask, o_s, do_s, lse_s, dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:],
+                             dbuf, B, NH, T, T, scale)
+                self.colsum(dqkv, self.G(lay.self_attn.in_proj_bias))
+                self.wgrad_linear(dqkv[:, :2 * D], tqb, gws[:2 * D], 2 * D, D, rt)
+                self.wgrad_linear(dqkv[:, 2 * D:], tgtb, gws[2 * D:], D, D, rt)
+                ops.gemm(dqkv, d.sa.wt, rt, D, 3 * D, res32=dy1, out32=g_prev)
+                ops.gemm(dqkv[:, :2 * D], d.sa.wt[:, :2 * D], rt, D, 2 * D, res32=dqpos, out32=dqpos)
             g_next = g_prev
         # memory gradient of all layers' K / V projections in two GEMMs (K = nl*256)
         ops.gemm(dkall, self.kstack.wt, rows, D, nl * D, out32=dpos)
