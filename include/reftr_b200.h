@@ -86,6 +86,11 @@ int rb_maxpool_3x3s2(const void* in, void* out, int B, int H1, int W1, int C, in
  * with optional addend `add` (padded layout) and ReLU mask `mask_src` (padded layout, keep where > 0) */
 int rb_parity_split(const void* x, void* xs, int B, int H, int W, int C, int Ho, int Wo, void* stream);
 int rb_parity_merge(const void* dxs, const void* add, const void* mask_src, void* dx, int B, int H, int W, int C, int Ho, int Wo, void* stream);
+/* single-plane variants for the 1x1 / stride-2 downsample convolution (torchvision Bottleneck.downsample), which reads plane 3
+ * only: split produces just that plane's [B,Ho+2,Wo+2,C] block; merge treats the three other planes as zero */
+int rb_parity_split_plane(const void* x, void* xs_plane, int B, int H, int W, int C, int Ho, int Wo, int plane, void* stream);
+int rb_parity_merge_plane(const void* dxs_plane, int plane, const void* add, const void* mask_src, void* dx, int B, int H, int W, int C, int Ho, int Wo,
+                          void* stream);
 /* conv weight fp32 OIHW (+ FrozenBN buffers or conv bias) -> bf16 [Cout, ldk] ((r,s,ci) columns, BN scale folded),
  * flipped/transposed dgrad copy bf16 [Cin, kh*kw*Cout] (nullable), per-channel scale and bias (fp32, nullable) */
 int rb_pack_conv(const float* w, int Cout, int Cin, int kh, int kw, const float* bn_w, const float* bn_b, const float* bn_rm, const float* bn_rv,

@@ -72,12 +72,13 @@ __global__ void maxpool_kernel(const uint4* __restrict__ in, uint4* __restrict__
 
 // ------------------------------------------------------------------------------------------------ parity split / merge
 // x padded [B,H+2,W+2,C] -> xs [4,B,Hs,Ws,C] (Hs=Ho+2, Ws=Wo+2); plane (p,q) cell (u,v) = x[2u+p, 2v+q] or 0.
-__global__ void parity_split_kernel(const uint4* __restrict__ x, uint4* __restrict__ xs, int B, int H, int W, int C8, int Hs, int Ws) {
+// only_plane < 0: all four planes (xs = [4, ...]); otherwise only that plane is produced (xs = that plane's [B, Hs, Ws, C] block)
+__global__ void parity_split_kernel(const uint4* __restrict__ x, uint4* __restrict__ xs, int B, int H, int W, int C8, int Hs, int Ws, int only_plane) {
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long per_plane = static_cast<long long>(B) * Hs * Ws * C8;
-  if (idx >= 4 * per_plane) return;
-  const int plane = static_cast<int>(idx / per_plane);
-  long long r = idx - plane * per_plane;
+  if (idx >= (only_plane < 0 ? 4 : 1) * per_plane) return;
+  const int plane = only_plane < 0 ? static_cast<int>(idx / per_plane) : only_plane;
+  long long r = only_plane < 0 ? idx - plane * per_plane : idx;
   const int c = static_cast<int>(r % C8); r /= C8;
   const int v = static_cast<int>(r % Ws); r /= Ws;
   const int u = static_cast<int>(r % Hs);
@@ -89,8 +90,9 @@ __global__ void parity_split_kernel(const uint4* __restrict__ x, uint4* __restri
 }
 
 // dx[b,y,x,:] = relu_mask(dxs[plane(y&1,x&1), b, y>>1, x>>1, :] (+ add[b,y,x,:])) on interior pixels, 0 on the border.
+// only_plane >= 0: dxs is that single plane's block and the three other planes are zero
 __global__ void parity_merge_kernel(const uint4* __restrict__ dxs, const uint4* __restrict__ add, const uint4* __restrict__ mask_src,
-                                    uint4* __restrict__ dx, int B, int H, int W, int C8, int Hs, int Ws) {
+                                    uint4* __restrict__ dx, int B, int H, int W, int C8, int Hs, int Ws, int only_plane) {
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int Hp = H + 2, Wp = W + 2;
   const long long total = static_cast<long long>(B) * Hp * Wp * C8;
@@ -102,7 +104,9 @@ __global__ void parity_merge_kernel(const uint4* __restrict__ dxs, const uint4* 
   uint4 o = make_uint4(0, 0, 0, 0);
   if (y >= 1 && y <= H && xx >= 1 && xx <= W) {
     const int plane = ((y & 1) << 1) | (xx & 1);
-    const uint4 t = __ldg(dxs + (((static_cast<long long>(plane) * B + b) * Hs + (y >> 1)) * Ws + (xx >> 1)) * C8 + c);
+    uint4 t = make_uint4(0, 0, 0, 0);
+    if (only_plane < 0) t = __ldg(dxs + (((static_cast<long long>(plane) * B + b) * Hs + (y >> 1)) * Ws + (xx >> 1)) * C8 + c);
+    else if (plane == only_plane) t = __ldg(dxs + ((static_cast<long long>(b) * Hs + (y >> 1)) * Ws + (xx >> 1)) * C8 + c);
     float f[8] = {bf16_lo(t.x), bf16_hi(t.x), bf16_lo(t.y), bf16_hi(t.y), bf16_lo(t.z), bf16_hi(t.z), bf16_lo(t.w), bf16_hi(t.w)};
     if (add) {
       const uint4 a = __ldg(add + idx);
@@ -287,7 +291,27 @@ extern "C" int rb_maxpool_3x3s2(const void* in, void* out, int B, int H1, int W1
 extern "C" int rb_parity_split(const void* x, void* xs, int B, int H, int W, int C, int Ho, int Wo, void* stream) {
   if (C % 8) return rb_fail("rb_parity_split: C must be a multiple of 8");
   const long long total = 4ll * B * (Ho + 2) * (Wo + 2) * (C / 8);
-  parity_split_kernel<<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint4*>(x), static_cast<uint4*>(xs), B, H, W, C / 8, Ho + 2, Wo + 2);
+  parity_split_kernel<<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint4*>(x), static_cast<uint4*>(xs), B, H, W, C / 8, Ho + 2, Wo + 2, -1);
+  RB_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int rb_parity_split_plane(const void* x, void* xs_plane, int B, int H, int W, int C, int Ho, int Wo, int plane, void* stream) {
+  if (C % 8) return rb_fail("rb_parity_split_plane: C must be a multiple of 8");
+  if (plane < 0 || plane > 3) return rb_fail("rb_parity_split_plane: plane must be 0..3");
+  const long long total = static_cast<long long>(B) * (Ho + 2) * (Wo + 2) * (C / 8);
+  parity_split_kernel<<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint4*>(x), static_cast<uint4*>(xs_plane), B, H, W, C / 8, Ho + 2, Wo + 2, plane);
+  RB_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int rb_parity_merge_plane(const void* dxs_plane, int plane, const void* add, const void* mask_src, void* dx, int B, int H, int W, int C, int Ho, int Wo,
+                                     void* stream) {
+  if (C % 8) return rb_fail("rb_parity_merge_plane: C must be a multiple of 8");
+  if (plane < 0 || plane > 3) return rb_fail("rb_parity_merge_plane: plane must be 0..3");
+  const long long total = static_cast<long long>(B) * (H + 2) * (W + 2) * (C / 8);
+  parity_merge_kernel<<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(dxs_plane), static_cast<const uint4*>(add), static_cast<const uint4*>(mask_src), static_cast<uint4*>(dx), B, H, W, C / 8, Ho + 2, Wo + 2, plane);
   RB_CHECK_LAUNCH();
   return 0;
 }
@@ -296,7 +320,7 @@ extern "C" int rb_parity_merge(const void* dxs, const void* add, const void* mas
   if (C % 8) return rb_fail("rb_parity_merge: C must be a multiple of 8");
   const long long total = static_cast<long long>(B) * (H + 2) * (W + 2) * (C / 8);
   parity_merge_kernel<<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const uint4*>(dxs), static_cast<const uint4*>(add), static_cast<const uint4*>(mask_src), static_cast<uint4*>(dx), B, H, W, C / 8, Ho + 2, Wo + 2);
+      static_cast<const uint4*>(dxs), static_cast<const uint4*>(add), static_cast<const uint4*>(mask_src), static_cast<uint4*>(dx), B, H, W, C / 8, Ho + 2, Wo + 2, -1);
   RB_CHECK_LAUNCH();
   return 0;
 }

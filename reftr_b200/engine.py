@@ -475,10 +475,11 @@ class RefTREngine:
             idn = ws.get(k + ".idn", [go.R, cout])
             ops.gemm(x, b.ds.wf, go.R, cout, cin, bias=b.ds.bias, out=idn, geom=go.geom)
         else:
-            xs = ws.get(k + ".xs", [4 * go.R, cin])
-            ops.parity_split(x, xs, g.B, g.H, g.W, cin, go.H, go.W)
+            # the 1x1 / stride-2 downsample reads input pixels (2i+1, 2j+1) of the padded grid only = parity plane 3
+            xs = ws.get(k + ".xs3", [go.R, cin])
+            ops.parity_split_plane(x, xs, g.B, g.H, g.W, cin, go.H, go.W, 3)
             idn = ws.get(k + ".idn", [go.R, cout])
-            ops.gemm(xs, b.ds.wf, go.R, cout, cin, taps=[(3 * go.R - go.Wp - 1, 0)], bias=b.ds.bias, out=idn, geom=go.geom)
+            ops.gemm(xs, b.ds.wf, go.R, cout, cin, taps=[(-go.Wp - 1, 0)], bias=b.ds.bias, out=idn, geom=go.geom)
         y = ws.get(k + ".y", [go.R, cout])
         ops.gemm(a2, b.c3.wf, go.R, cout, w, bias=b.c3.bias, res=idn, relu=True, out=y, geom=go.geom)
         self.saved[k] = (x, g, go, a1, a1s, a2, xs, y)
@@ -511,7 +512,7 @@ class RefTREngine:
         # conv1 (1x1) and the identity path
         self.wgrad_conv(b.c1, d_a1, x, g.R)
         if b.ds is not None and b.stride == 2:
-            self.wgrad_conv(b.ds, gy, xs, go.R, b_offsets=[3 * go.R - go.Wp - 1])
+            self.wgrad_conv(b.ds, gy, xs, go.R, b_offsets=[-go.Wp - 1])
         elif b.ds is not None:
             self.wgrad_conv(b.ds, gy, x, go.R)
         if not b.need_gx:
@@ -526,9 +527,9 @@ class RefTREngine:
         else:
             t = ws.get(k + ".t", [g.R, cin])
             ops.gemm(d_a1, b.c1.wd, g.R, cin, w, res=g_extra, out=t)
-            dxs2 = ws.get(k + ".dxs_ds", [4 * go.R, cin], zero=True)  # planes 0..2 stay zero: the 1x1/s2 conv reads plane 3 only
-            ops.gemm(gy, b.ds.wd, go.R, cin, cout, taps=[(go.Wp + 1, 0)], out=dxs2[3 * go.R:])
-            ops.parity_merge(dxs2, t, x, gx, g.B, g.H, g.W, cin, go.H, go.W)
+            dxs2 = ws.get(k + ".dxs_ds3", [go.R, cin])  # gradient w.r.t. parity plane 3 (the only plane the 1x1/s2 conv reads)
+            ops.gemm(gy, b.ds.wd, go.R, cin, cout, taps=[(go.Wp + 1, 0)], out=dxs2)
+            ops.parity_merge_plane(dxs2, 3, t, x, gx, g.B, g.H, g.W, cin, go.H, go.W)
         return gx
 
     def _backbone_fwd(self, img):

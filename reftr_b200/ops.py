@@ -121,6 +121,14 @@ def parity_merge(dxs, add, mask_src, dx, B, H, W, C, Ho, Wo):
     _lib.call("rb_parity_merge", _p(dxs), _p(add), _p(mask_src), _p(dx), B, H, W, C, Ho, Wo, _s())
 
 
+def parity_split_plane(x, xs_plane, B, H, W, C, Ho, Wo, plane):
+    _lib.call("rb_parity_split_plane", _p(x), _p(xs_plane), B, H, W, C, Ho, Wo, plane, _s())
+
+
+def parity_merge_plane(dxs_plane, plane, add, mask_src, dx, B, H, W, C, Ho, Wo):
+    _lib.call("rb_parity_merge_plane", _p(dxs_plane), plane, _p(add), _p(mask_src), _p(dx), B, H, W, C, Ho, Wo, _s())
+
+
 def pack_conv(w, bn, conv_bias, fwd, ldk, dgr, scale_out, bias_out, eps=1e-5):
     Cout, Cin, kh, kw = w.shape
     bw, bb, brm, brv = bn if bn is not None else (None, None, None, None)

@@ -136,6 +136,21 @@ def parity_split(x, xs, B, H, W, C, Ho, Wo):
             o[2 * p + q, :, :sub.shape[1], :sub.shape[2]] = sub
 
 
+def parity_split_plane(x, xs_plane, B, H, W, C, Ho, Wo, plane):
+    _LAUNCHES[0] += 1
+    xv = x.view(B, H + 2, W + 2, C)
+    o = xs_plane.view(B, Ho + 2, Wo + 2, C)
+    o.zero_()
+    sub = xv[:, (plane >> 1)::2, (plane & 1)::2]
+    o[:, :sub.shape[1], :sub.shape[2]] = sub
+
+
+def parity_merge_plane(dxs_plane, plane, add, mask_src, dx, B, H, W, C, Ho, Wo):
+    full = torch.zeros(4, B, Ho + 2, Wo + 2, C, dtype=dxs_plane.dtype)
+    full[plane] = dxs_plane.view(B, Ho + 2, Wo + 2, C)
+    parity_merge(full.view(-1, C), add, mask_src, dx, B, H, W, C, Ho, Wo)
+
+
 def parity_merge(dxs, add, mask_src, dx, B, H, W, C, Ho, Wo):
     _LAUNCHES[0] += 1
     s = dxs.view(4, B, Ho + 2, Wo + 2, C)
