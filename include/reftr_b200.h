@@ -33,6 +33,21 @@ typedef struct {
   int Rs;   /* rows per plane (mode 2) */
 } rb_geom;
 
+/* Counter-based dropout (nn.Dropout / the attention-probability dropout of nn.MultiheadAttention in train mode;
+ * transformer.py:151, :154-160, :211-223, reftr_transformer.py:19, HF BertModel).  Nothing is stored: the keep decision of
+ * element (row, col) of a site's logical [rows, cols] tensor is recomputed wherever it is needed (forward and backward) as
+ *     key  = mix32(lo32(seed) ^ mix32(hi32(seed) + site * 0x9E3779B9))
+ *     word = mix32((row * ((cols + 1) / 2) + col / 2) * 0x9E3779B1 + key)
+ *     keep = ((word >> 16 * (col & 1)) & 0xFFFF) >= thr,   thr = round(p * 65536);  kept values are scaled by 65536 / (65536 - thr)
+ * with mix32(x): x ^= x >> 16; x *= 0x21f0aaad; x ^= x >> 15; x *= 0x735a2d97; x ^= x >> 15.
+ * `seed` is a DEVICE pointer to one uint64 that the host rewrites between steps (so a captured CUDA graph draws a new mask
+ * on every replay); the struct itself is passed by HOST pointer, NULL (or seed == NULL, or p <= 0) = no dropout. */
+typedef struct {
+  const void* seed;
+  int site;
+  float p;
+} rb_dropout;
+
 /* Generic tensor-core GEMM / implicit-GEMM convolution (tcgen05.mma, TMA operands, fp32 accumulate in TMEM).
  *
  * mode 0 ("NT"): D[m, n] = sum_tap sum_k A[m + a_rowoff[tap], k] * B[n, b_koff[tap] + k]
@@ -45,6 +60,10 @@ typedef struct {
  * Epilogue (mode 0, and mode 1 when atomic=0): v = acc + bias[n] + res[row, n] + res32[row, n];
  *      relu; v = mask_src[row, n] > 0 ? v : 0; rows that are padding per `geom` -> 0; written as bf16 (out)
  *      and/or fp32 (out32).  row = m + out_row_off for out/res/mask_src addressing and geometry.
+ *      With `drop`: v = res + res32 + dropout(relu?(acc + bias)) (the residual dropouts and the FFN dropout of
+ *      transformer.py:176-179); the site's logical tensor is [rows, N >> drop_gshift] with element (row, n >> drop_gshift), so
+ *      drop_gshift = 5 drops whole 32-wide heads (attention-probability dropout of a single-key softmax).  `mask_scale`
+ *      (0 = 1) multiplies the values that mask_src keeps (backward of ReLU followed by dropout).
  */
 typedef struct {
   int mode;
@@ -67,6 +86,9 @@ typedef struct {
   int relu;
   int atomic;
   rb_geom geom;
+  const rb_dropout* drop; /* HOST pointer, nullable */
+  int drop_gshift;
+  float mask_scale;
 } rb_gemm_args;
 
 int rb_gemm(const rb_gemm_args* args, void* stream);
@@ -111,9 +133,13 @@ int rb_add(const float* a, const float* b, float* y, void* yb, long long n, void
  * ------------------------------------------------------------------------------------------------------------- */
 /* nn.LayerNorm(256) (+ optional ReLU, reftr_transformer.py:14-23): fp32 in, fp32 / bf16 / bf16(+pos) out, saves mean, rstd */
 int rb_layernorm_fwd(const float* x, const float* gamma, const float* beta, long long rows, int D, float eps, float* y32, void* yb, const float* pos32,
-                     void* ypb, int relu, float* mean, float* rstd, int map_group, int map_stride, int map_offset, void* stream);
-int rb_layernorm_bwd(const float* dy, const float* dy2, const float* y_relu, const float* x, const float* gamma, const float* mean, const float* rstd,
-                     long long rows, int D, float* dx32, void* dxb, float* dgamma, float* dbeta, int map_group, int map_stride, int map_offset, void* stream);
+                     void* ypb, int relu, float* mean, float* rstd, int map_group, int map_stride, int map_offset, const rb_dropout* drop, void* stream);
+/* y_relu > 0 is the ReLU (and, after a dropout, the keep) mask of the forward output, kept gradients are multiplied by relu_scale;
+ * `dxb_drop` applies the dropout of the layer that FED this LayerNorm's residual sum to the bf16 copy dxb only (dx32 stays the
+ * undropped residual gradient) */
+int rb_layernorm_bwd(const float* dy, const float* dy2, const float* y_relu, float relu_scale, const float* x, const float* gamma, const float* mean,
+                     const float* rstd, long long rows, int D, float* dx32, void* dxb, float* dgamma, float* dbeta, int map_group, int map_stride,
+                     int map_offset, const rb_dropout* dxb_drop, void* stream);
 /* input_proj GroupNorm(32,256) (reftr_transformer.py:121-125) fused with flatten/transpose/concat (reftr.py:57,115-117):
  * x fp32 padded NHWC [B,h+2,w+2,256] -> token rows b*S+L+p of y32 / yb / ypb */
 int rb_groupnorm_tokens_fwd(const float* x, const float* gamma, const float* beta, int B, int h, int w, int S, int L, float eps, float* y32, void* yb,
@@ -132,11 +158,12 @@ int rb_embed_grad(const float* dpos, int B, int S, int L, float* d_lang_pos, flo
  * Q [B*Tq, ldq], K/V [B*Sk, ld], head h at columns [32h, 32h+32); kpm [B,Sk] u8 (1 = ignore, nullable);
  * LSE, Dbuf fp32 [B,H,Tq].  scale multiplies q before QK^T as torch does.
  * ------------------------------------------------------------------------------------------------------------- */
+/* `drop`: dropout on the softmax probabilities (logical tensor [B*H*Tq, Sk]); LSE stays that of the undropped softmax */
 int rb_attn_fwd(const void* Q, const void* K, const void* V, const void* kpm, void* O, float* LSE, int B, int H, int dh, int Tq, int Sk, long long ldq,
-                long long ldk, long long ldv, long long ldo, float scale, void* stream);
+                long long ldk, long long ldv, long long ldo, float scale, const rb_dropout* drop, void* stream);
 int rb_attn_bwd(const void* Q, const void* K, const void* V, const void* kpm, const void* O, const void* dO, const float* LSE, void* dQ, void* dK, void* dV,
                 float* Dbuf, int B, int H, int dh, int Tq, int Sk, long long ldq, long long ldk, long long ldv, long long ldo, long long lddo, long long lddq,
-                long long lddk, long long lddv, float scale, void* stream);
+                long long lddk, long long lddv, float scale, const rb_dropout* drop, void* stream);
 /* QueryEncoder attended pooling (reftr_transformer.py:47-55): k [B,256], q,v [B*L,256] fp32, mask [B,n_ph,L] u8 */
 int rb_qenc_pool_fwd(const float* k, const float* q, const float* v, const void* mask, int B, int L, int n_ph, float* att, float* c, void* stream);
 int rb_qenc_pool_bwd(const float* dc, const float* k, const float* q, const float* v, const float* att, int B, int L, int n_ph, float* dk, float* dq,
@@ -191,10 +218,12 @@ int rb_bert_embed_fwd(const long long* ids, long long rows, int L, int D, const 
 /* scatter-add of d [rows, D] into the three embedding tables' gradients (any of them nullable) */
 int rb_bert_embed_bwd(const float* d, const long long* ids, long long rows, int L, int D, float* dword, float* dpos, float* dtype0, void* stream);
 /* nn.LayerNorm over D = 768 / 1024 wide rows: fp32 in, fp32 and/or bf16 out, saves mean / rstd */
+/* `drop` (BertEmbeddings.dropout): applied to both outputs */
 int rb_ln_wide_fwd(const float* x, const float* gamma, const float* beta, long long rows, int D, float eps, float* y32, void* yb, float* mean, float* rstd,
-                   void* stream);
+                   const rb_dropout* drop, void* stream);
+/* `dy_drop`: the forward output had this dropout (dy + dy2 is masked and scaled first); `dxb_drop`: as in rb_layernorm_bwd */
 int rb_ln_wide_bwd(const float* dy, const float* dy2, const float* x, const float* gamma, const float* mean, const float* rstd, long long rows, int D,
-                   float* dx32, void* dxb, float* dgamma, float* dbeta, void* stream);
+                   float* dx32, void* dxb, float* dgamma, float* dbeta, const rb_dropout* dy_drop, const rb_dropout* dxb_drop, void* stream);
 /* exact (erf) GELU on bf16, n % 8 == 0; backward takes the PRE-activation x */
 int rb_gelu_fwd(const void* x, void* y, long long n, void* stream);
 int rb_gelu_bwd(const void* dy, const void* x, void* dx, long long n, void* stream);
@@ -204,9 +233,10 @@ int rb_tanh_bwd(const float* dy, const float* y, float* dx, void* dxb, long long
 /* BertSelfAttention core, head_dim 64, S <= 128 tokens: Q,K,V bf16 [B*S, ld] (head h at columns [64h, 64h+64)), mask u8 [B,S]
  * (1 = ignore key); P fp32 [B,H,S,S] is saved for the backward */
 int rb_attn_small_fwd(const void* Q, const void* K, const void* V, const void* mask, void* O, float* P, int B, int H, int dh, int S, long long ldq,
-                      long long ldk, long long ldv, long long ldo, float scale, void* stream);
+                      long long ldk, long long ldv, long long ldo, float scale, const rb_dropout* drop, void* stream);
 int rb_attn_small_bwd(const void* Q, const void* K, const void* V, const void* dO, const float* P, void* dQ, void* dK, void* dV, int B, int H, int dh, int S,
-                      long long ldq, long long ldk, long long ldv, long long lddo, long long lddq, long long lddk, long long lddv, float scale, void* stream);
+                      long long ldq, long long ldk, long long ldv, long long lddo, long long lddq, long long lddk, long long lddv, float scale,
+                      const rb_dropout* drop, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Criterion (models/criterion.py:113-153, :189-201; util/box_ops.py): L1 + GIoU of paired cxcywh boxes for all decoder layers

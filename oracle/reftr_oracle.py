@@ -33,6 +33,39 @@ from torch import nn
 
 
 # --------------------------------------------------------------------------------------
+# Dropout (train mode).  The reference draws its masks from torch's generator (nn.Dropout,
+# F.dropout inside nn.MultiheadAttention); the CUDA path draws them from its own counter-based
+# generator, so mask-for-mask parity in train mode needs the SAME masks on both sides: tests
+# install DROPOUT_HOOK(x, p, tag, kind) -> dropped x, where `tag` names the site the way
+# reftr_b200/engine.py does and `kind` says how x is laid out ("rows": [..., d] flattened
+# row-major; "seq": [S, B, d] sequence-first; "attn": [B*h, T, S]).  Without a hook this is
+# F.dropout, i.e. the reference's behaviour.  DROP_CTX["bert"] tells a hooked HF BertModel
+# which invocation ("s" sentence / "p" phrases) is running.
+# --------------------------------------------------------------------------------------
+DROPOUT_HOOK = None
+DROP_CTX = {"bert": "s"}
+
+
+def _dropout(x, p, training, tag, kind):
+    if not training or p <= 0.0:
+        return x
+    if DROPOUT_HOOK is not None:
+        return DROPOUT_HOOK(x, p, tag, kind)
+    return F.dropout(x, p, True)
+
+
+class TaggedDropout(nn.Module):
+    """nn.Dropout(p) with a site tag (no parameters: the state_dict is unchanged)."""
+
+    def __init__(self, p, tag):
+        super().__init__()
+        self.p, self.tag = p, tag
+
+    def forward(self, x):
+        return _dropout(x, self.p, self.training, self.tag, "rows")
+
+
+# --------------------------------------------------------------------------------------
 # Backbone: FrozenBatchNorm2d + torchvision Bottleneck ResNet (backbone.py:43-121)
 # --------------------------------------------------------------------------------------
 class FrozenBN(nn.Module):
@@ -180,9 +213,9 @@ class Joiner(nn.Sequential):
 # F.multi_head_attention_forward; called from transformer.py:174/:239/:243)
 # --------------------------------------------------------------------------------------
 class MHA(nn.Module):
-    def __init__(self, d, h, dropout=0.0):
+    def __init__(self, d, h, dropout=0.0, tag=""):
         super().__init__()
-        self.d, self.h, self.p = d, h, dropout
+        self.d, self.h, self.p, self.tag = d, h, dropout, tag
         self.in_proj_weight = nn.Parameter(torch.empty(3 * d, d))
         self.in_proj_bias = nn.Parameter(torch.zeros(3 * d))
         self.out_proj = nn.Linear(d, d)
@@ -204,7 +237,7 @@ class MHA(nn.Module):
             m = key_padding_mask.view(B, 1, 1, S).expand(-1, h, -1, -1).reshape(B * h, 1, S)
             attn = attn.masked_fill(m, float("-inf"))
         attn = F.softmax(attn, dim=-1)
-        attn = F.dropout(attn, self.p, self.training)
+        attn = _dropout(attn, self.p, self.training, self.tag, "attn")
         out = torch.bmm(attn, v).transpose(0, 1).reshape(T, B, d)
         return self.out_proj(out)
 
@@ -212,51 +245,53 @@ class MHA(nn.Module):
 class EncoderLayer(nn.Module):
     """transformer.py:146-181 (forward_post)."""
 
-    def __init__(self, d, h, dff, dropout):
+    def __init__(self, d, h, dff, dropout, tag=""):
         super().__init__()
-        self.self_attn = MHA(d, h, dropout)
+        self.self_attn = MHA(d, h, dropout, tag + ".attn")
         self.linear1 = nn.Linear(d, dff)
         self.linear2 = nn.Linear(dff, d)
         self.norm1 = nn.LayerNorm(d)
         self.norm2 = nn.LayerNorm(d)
-        self.p = dropout
+        self.p, self.tag = dropout, tag
 
     def forward(self, src, mask, pos):
+        t, tr = self.tag, self.training
         q = k = src + pos
         src2 = self.self_attn(q, k, src, key_padding_mask=mask)
-        src = self.norm1(src + F.dropout(src2, self.p, self.training))
-        src2 = self.linear2(F.dropout(F.relu(self.linear1(src)), self.p, self.training))
-        return self.norm2(src + F.dropout(src2, self.p, self.training))
+        src = self.norm1(src + _dropout(src2, self.p, tr, t + ".drop1", "seq"))
+        src2 = self.linear2(_dropout(F.relu(self.linear1(src)), self.p, tr, t + ".ffn", "seq"))
+        return self.norm2(src + _dropout(src2, self.p, tr, t + ".drop2", "seq"))
 
 
 class DecoderLayer(nn.Module):
     """transformer.py:206-252 (forward_post)."""
 
-    def __init__(self, d, h, dff, dropout):
+    def __init__(self, d, h, dff, dropout, tag=""):
         super().__init__()
-        self.self_attn = MHA(d, h, dropout)
-        self.multihead_attn = MHA(d, h, dropout)
+        self.self_attn = MHA(d, h, dropout, tag + ".sa")
+        self.multihead_attn = MHA(d, h, dropout, tag + ".ca")
         self.linear1 = nn.Linear(d, dff)
         self.linear2 = nn.Linear(dff, d)
         self.norm1 = nn.LayerNorm(d)
         self.norm2 = nn.LayerNorm(d)
         self.norm3 = nn.LayerNorm(d)
-        self.p = dropout
+        self.p, self.tag = dropout, tag
 
     def forward(self, tgt, memory, tgt_mask, memory_mask, pos, query_pos):
+        t, tr = self.tag, self.training
         q = k = tgt + query_pos
         tgt2 = self.self_attn(q, k, tgt, key_padding_mask=tgt_mask)
-        tgt = self.norm1(tgt + F.dropout(tgt2, self.p, self.training))
+        tgt = self.norm1(tgt + _dropout(tgt2, self.p, tr, t + ".drop1", "seq"))
         tgt2 = self.multihead_attn(tgt + query_pos, memory + pos, memory, key_padding_mask=memory_mask)
-        tgt = self.norm2(tgt + F.dropout(tgt2, self.p, self.training))
-        tgt2 = self.linear2(F.dropout(F.relu(self.linear1(tgt)), self.p, self.training))
-        return self.norm3(tgt + F.dropout(tgt2, self.p, self.training))
+        tgt = self.norm2(tgt + _dropout(tgt2, self.p, tr, t + ".drop2", "seq"))
+        tgt2 = self.linear2(_dropout(F.relu(self.linear1(tgt)), self.p, tr, t + ".ffn", "seq"))
+        return self.norm3(tgt + _dropout(tgt2, self.p, tr, t + ".drop3", "seq"))
 
 
 class Encoder(nn.Module):
     def __init__(self, d, h, dff, dropout, n):
         super().__init__()
-        self.layers = nn.ModuleList([EncoderLayer(d, h, dff, dropout) for _ in range(n)])
+        self.layers = nn.ModuleList([EncoderLayer(d, h, dff, dropout, f"enc{i}") for i in range(n)])
 
     def forward(self, src, mask, pos):  # transformer.py:89-102 (norm is None for post-LN)
         for layer in self.layers:
@@ -267,7 +302,7 @@ class Encoder(nn.Module):
 class Decoder(nn.Module):
     def __init__(self, d, h, dff, dropout, n):
         super().__init__()
-        self.layers = nn.ModuleList([DecoderLayer(d, h, dff, dropout) for _ in range(n)])
+        self.layers = nn.ModuleList([DecoderLayer(d, h, dff, dropout, f"dec{i}") for i in range(n)])
         self.norm = nn.LayerNorm(d)
 
     def forward(self, tgt, memory, tgt_mask, memory_mask, pos, query_pos):
@@ -320,8 +355,8 @@ class VLTransformer(nn.Module):
 # --------------------------------------------------------------------------------------
 # RefTR top module (reftr_transformer.py:14-304)
 # --------------------------------------------------------------------------------------
-def mlp_mapping(i, o):  # reftr_transformer.py:14-23
-    return nn.Sequential(nn.Linear(i, o), nn.LayerNorm(o), nn.ReLU(), nn.Dropout(0.1),
+def mlp_mapping(i, o, tag=""):  # reftr_transformer.py:14-23
+    return nn.Sequential(nn.Linear(i, o), nn.LayerNorm(o), nn.ReLU(), TaggedDropout(0.1, tag + ".drop"),
                          nn.Linear(o, o), nn.LayerNorm(o), nn.ReLU())
 
 
@@ -349,7 +384,7 @@ class QueryEncoder(nn.Module):
         self.linear1 = nn.Linear(d, d)
         self.linear2 = nn.Linear(d, d)
         self.linear3 = nn.Linear(d, d)
-        self.fuse_encoder_query = mlp_mapping(d * 2, d)
+        self.fuse_encoder_query = mlp_mapping(d * 2, d, "qe.fuse")
         self.context_out = nn.Sequential(nn.Linear(d, d), nn.LayerNorm(d))
 
     def forward(self, ctx, phrase, mask_ctx):
@@ -378,8 +413,8 @@ class RefTROracle(nn.Module):
         self.num_queries_per_phrase = n_q
         self.hidden_dim = d
         self.bbox_embed = MLP(d, d, 4, 3)
-        self.map_sentence = mlp_mapping(lang_backbone.config.hidden_size, d)
-        self.map_phrase = mlp_mapping(lang_backbone.config.hidden_size, d)
+        self.map_sentence = mlp_mapping(lang_backbone.config.hidden_size, d, "map_sentence")
+        self.map_phrase = mlp_mapping(lang_backbone.config.hidden_size, d, "map_phrase")
         self.query_encoder = QueryEncoder(n_q, d)
         self.input_proj = nn.ModuleList([nn.Sequential(nn.Conv2d(2048, d, 1), nn.GroupNorm(32, d))])
         self.aux_loss = aux_loss
@@ -393,6 +428,7 @@ class RefTROracle(nn.Module):
         feats, masks, pos = self.img_backbone(img, mask)
         src = self.input_proj[0](feats[-1])  # reftr_transformer.py:172-175
         sentence, sentence_mask = samples["sentence"], samples["sentence_mask"]
+        DROP_CTX["bert"] = "s"
         lang_out = self.lang_backbone(sentence, token_type_ids=None, attention_mask=sentence_mask)
         sent_feat, sent_pooled = lang_out[0], lang_out[1]
         sent_feat = self.map_sentence(sent_feat)
@@ -400,6 +436,7 @@ class RefTROracle(nn.Module):
         if "phrase" in samples:  # reftr_transformer.py:206-238
             phrases, phrase_masks = samples["phrase"], samples["phrase_mask"]
             n_ph = phrases.size(1)
+            DROP_CTX["bert"] = "p"
             pooled = self.lang_backbone(phrases.view(B * n_ph, -1), token_type_ids=None,
                                         attention_mask=phrase_masks.view(B * n_ph, -1))[1]
             L = sentence_mask.size(1)

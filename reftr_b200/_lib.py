@@ -14,6 +14,11 @@ class Geom(C.Structure):
     _fields_ = [("mode", C.c_int), ("Wp", C.c_int), ("HpWp", C.c_int), ("H", C.c_int), ("W", C.c_int), ("Rs", C.c_int)]
 
 
+class Dropout(C.Structure):
+    """rb_dropout: device pointer to the uint64 seed, site id, drop probability."""
+    _fields_ = [("seed", C.c_void_p), ("site", C.c_int), ("p", C.c_float)]
+
+
 class GemmArgs(C.Structure):
     _fields_ = [
         ("mode", C.c_int),
@@ -36,6 +41,9 @@ class GemmArgs(C.Structure):
         ("relu", C.c_int),
         ("atomic", C.c_int),
         ("geom", Geom),
+        ("drop", C.c_void_p),
+        ("drop_gshift", C.c_int),
+        ("mask_scale", C.c_float),
     ]
 
 

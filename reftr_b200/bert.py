@@ -46,6 +46,7 @@ class BertEngine:
             l.o2 = PackedLinear(lay.output.dense.weight, lay.output.dense.bias)
             self.layers.append(l)
             self.packs += [l.qkv, l.o, l.i, l.o2]
+        self.p_hidden, self.p_attn = float(cfg.hidden_dropout_prob), float(cfg.attention_probs_dropout_prob)
         self.pool = PackedLinear(bert.pooler.dense.weight, bert.pooler.dense.bias)
         self.packs.append(self.pool)
         self.saved = {}
@@ -64,7 +65,9 @@ class BertEngine:
         ops.bert_embed_fwd(ids, L, emb.word_embeddings.weight, emb.position_embeddings.weight, emb.token_type_embeddings.weight[0], e32)
         x32, xb = ws.get(f"bert.{tag}.x0", [rows, D], f32), ws.get(f"bert.{tag}.x0b", [rows, D])
         me, re_ = ws.get(f"bert.{tag}.me", [rows], f32), ws.get(f"bert.{tag}.re", [rows], f32)
-        ops.ln_wide_fwd(e32, emb.LayerNorm.weight, emb.LayerNorm.bias, rows, y32=x32, yb=xb, mean=me, rstd=re_, eps=self.eps)
+        # train mode: BertEmbeddings.dropout, attention_probs dropout, BertSelfOutput / BertOutput dropouts (HF modeling_bert)
+        ops.ln_wide_fwd(e32, emb.LayerNorm.weight, emb.LayerNorm.bias, rows, y32=x32, yb=xb, mean=me, rstd=re_, eps=self.eps,
+                        drop=eng.drop(f"bert.{tag}.emb", self.p_hidden))
         scale = 64 ** -0.5
         per_layer = []
         for li, l in enumerate(self.layers):
@@ -74,9 +77,9 @@ class BertEngine:
             ops.gemm(xb, l.qkv.wb, rows, 3 * D, D, bias=l.qkv.bias, out=qkv)
             ctx = ws.get(k + ".ctx", [rows, D])
             P = ws.get(k + ".P", [Bn, H, L, L], f32)
-            ops.attn_small_fwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], mask_u8, ctx, P, Bn, H, L, scale)
+            ops.attn_small_fwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], mask_u8, ctx, P, Bn, H, L, scale, drop=eng.drop(k + ".attn", self.p_attn))
             y1 = ws.get(k + ".y1", [rows, D], f32)
-            ops.gemm(ctx, l.o.wb, rows, D, D, bias=l.o.bias, res32=x32, out32=y1)
+            ops.gemm(ctx, l.o.wb, rows, D, D, bias=l.o.bias, res32=x32, out32=y1, drop=eng.drop(k + ".drop1", self.p_hidden))
             x1, x1b = ws.get(k + ".x1", [rows, D], f32), ws.get(k + ".x1b", [rows, D])
             m1, r1 = ws.get(k + ".m1", [rows], f32), ws.get(k + ".r1", [rows], f32)
             ln1 = lay.attention.output.LayerNorm
@@ -85,7 +88,7 @@ class BertEngine:
             ops.gemm(x1b, l.i.wb, rows, FF, D, bias=l.i.bias, out=hpre)
             ops.gelu_fwd(hpre, h)
             y2 = ws.get(k + ".y2", [rows, D], f32)
-            ops.gemm(h, l.o2.wb, rows, D, FF, bias=l.o2.bias, res32=x1, out32=y2)
+            ops.gemm(h, l.o2.wb, rows, D, FF, bias=l.o2.bias, res32=x1, out32=y2, drop=eng.drop(k + ".drop2", self.p_hidden))
             xo, xob = ws.get(k + ".xo", [rows, D], f32), ws.get(k + ".xob", [rows, D])
             m2, r2 = ws.get(k + ".m2", [rows], f32), ws.get(k + ".r2", [rows], f32)
             ln2 = lay.output.LayerNorm
@@ -135,8 +138,10 @@ class BertEngine:
             xb, qkv, ctx, P, y1, m1, r1, x1b, hpre, h, y2, m2, r2 = per_layer[li]
             ln1, ln2 = a.output.LayerNorm, lay.output.LayerNorm
             dy2, dy2b = ws.get(f"bertb.{tag}.{li}.dy2", [rows, D], f32), ws.get(f"bertb.{tag}.{li}.dy2b", [rows, D])
-            ops.ln_wide_bwd(g, y2, ln2.weight, m2, r2, rows, dx32=dy2, dxb=dy2b, dgamma=G(ln2.weight), dbeta=G(ln2.bias))
-            eng.colsum(dy2, G(lay.output.dense.bias))
+            k = f"bert.{tag}.{li}"
+            dr1, dr2 = eng.drop(k + ".drop1", self.p_hidden), eng.drop(k + ".drop2", self.p_hidden)
+            ops.ln_wide_bwd(g, y2, ln2.weight, m2, r2, rows, dx32=dy2, dxb=dy2b, dgamma=G(ln2.weight), dbeta=G(ln2.bias), dxb_drop=dr2)
+            eng.colsum(dy2b if dr2 is not None else dy2, G(lay.output.dense.bias))
             eng.wgrad_linear(dy2b, h, G(lay.output.dense.weight), D, FF, rows)
             dh = ws.get(f"bertb.{tag}.{li}.dh", [rows, FF])
             ops.gemm(dy2b, l.o2.wt, rows, FF, D, out=dh)
@@ -147,13 +152,14 @@ class BertEngine:
             g1 = ws.get(f"bertb.{tag}.{li}.g1", [rows, D], f32)
             ops.gemm(dhp, l.i.wt, rows, D, FF, res32=dy2, out32=g1)
             dy1, dy1b = ws.get(f"bertb.{tag}.{li}.dy1", [rows, D], f32), ws.get(f"bertb.{tag}.{li}.dy1b", [rows, D])
-            ops.ln_wide_bwd(g1, y1, ln1.weight, m1, r1, rows, dx32=dy1, dxb=dy1b, dgamma=G(ln1.weight), dbeta=G(ln1.bias))
-            eng.colsum(dy1, G(a.output.dense.bias))
+            ops.ln_wide_bwd(g1, y1, ln1.weight, m1, r1, rows, dx32=dy1, dxb=dy1b, dgamma=G(ln1.weight), dbeta=G(ln1.bias), dxb_drop=dr1)
+            eng.colsum(dy1b if dr1 is not None else dy1, G(a.output.dense.bias))
             eng.wgrad_linear(dy1b, ctx, G(a.output.dense.weight), D, D, rows)
             dctx = ws.get(f"bertb.{tag}.{li}.dctx", [rows, D])
             ops.gemm(dy1b, l.o.wt, rows, D, D, out=dctx)
             dqkv = ws.get(f"bertb.{tag}.{li}.dqkv", [rows, 3 * D])
-            ops.attn_small_bwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], dctx, P, dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:], Bn, H, L, scale)
+            ops.attn_small_bwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], dctx, P, dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:], Bn, H, L, scale,
+                               drop=eng.drop(k + ".attn", self.p_attn))
             for j, lin in enumerate((a.self.query, a.self.key, a.self.value)):
                 sl = dqkv[:, j * D:(j + 1) * D]
                 eng.colsum(sl, G(lin.bias))
@@ -163,6 +169,7 @@ class BertEngine:
             g = g_in
         emb = bert.embeddings
         de = ws.get(f"bertb.{tag}.de", [rows, D], f32)
-        ops.ln_wide_bwd(g, e32, emb.LayerNorm.weight, me, re_, rows, dx32=de, dgamma=G(emb.LayerNorm.weight), dbeta=G(emb.LayerNorm.bias))
+        ops.ln_wide_bwd(g, e32, emb.LayerNorm.weight, me, re_, rows, dx32=de, dgamma=G(emb.LayerNorm.weight), dbeta=G(emb.LayerNorm.bias),
+                        dy_drop=eng.drop(f"bert.{tag}.emb", self.p_hidden))
         with eng._off():
             ops.bert_embed_bwd(de, ids, L, G(emb.word_embeddings.weight), G(emb.position_embeddings.weight), G(emb.token_type_embeddings.weight)[0])

@@ -71,8 +71,10 @@ template <int SCH, int NWARPS>
 __global__ void __launch_bounds__(NWARPS * 32)
 attn_fwd_kernel(const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16* __restrict__ K, const __nv_bfloat16* __restrict__ V,
                 const uint8_t* __restrict__ kpm, __nv_bfloat16* __restrict__ O, float* __restrict__ LSE, int H, int Tq, int Sk, long long ldq,
-                long long ldk, long long ldv, long long ldo, float scale, int q_per_block) {
+                long long ldk, long long ldv, long long ldo, float scale, int q_per_block, DropK drop) {
   constexpr int SP = SCH * 32;
+  const uint32_t dkey = drop.seed ? drop_key(drop) : 0u;
+  const uint32_t wpr = static_cast<uint32_t>((Sk + 1) >> 1);
   extern __shared__ __align__(16) uint8_t smem[];
   uint32_t* Kt2 = reinterpret_cast<uint32_t*>(smem);                          // [16][SP]
   __nv_bfloat16* Vs = reinterpret_cast<__nv_bfloat16*>(Kt2 + 16 * SP);        // [SP][32]
@@ -110,11 +112,14 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16* __rest
       m = warp_max(m);
       if (m == -INFINITY) m = 0.f;  // every key masked: the reference yields NaN; we yield zeros
       float acc = 0.f;
+      const uint32_t wrow = (static_cast<uint32_t>(blockIdx.y) * Tq + (t0 + q)) * wpr;
 #pragma unroll
       for (int c = 0; c < SCH; ++c) {
         const float e = __expf(s[q][c] - m);
         acc += e;
-        myps[q * SP + lane + 32 * c] = e;
+        const int j = lane + 32 * c;
+        // dropout on the probabilities: the row sum stays that of the undropped softmax; 1/(1-p) is folded into `inv` below
+        myps[q * SP + j] = (drop.seed && !drop_keep(drop_word(dkey, wrow + (j >> 1)), j & 1, drop.thr)) ? 0.f : e;
       }
       mx[q] = m;
       sum[q] = warp_sum(acc);
@@ -126,7 +131,7 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16* __rest
     for (int q = 0; q < NQ; ++q) {
       const int t = t0 + q;
       if (t < q_end) {
-        const float inv = sum[q] > 0.f ? 1.f / sum[q] : 0.f;
+        const float inv = sum[q] > 0.f ? drop.scale / sum[q] : 0.f;
         O[(static_cast<long long>(b) * Tq + t) * ldo + h * DH + lane] = __float2bfloat16(acc[q] * inv);
         if (lane == 0 && LSE) LSE[(static_cast<long long>(b) * H + h) * Tq + t] = mx[q] + __logf(fmaxf(sum[q], 1e-30f));
       }
@@ -141,8 +146,10 @@ __global__ void __launch_bounds__(NWARPS * 32)
 attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16* __restrict__ K, const __nv_bfloat16* __restrict__ V,
                    const uint8_t* __restrict__ kpm, const __nv_bfloat16* __restrict__ O, const __nv_bfloat16* __restrict__ dO,
                    const float* __restrict__ LSE, __nv_bfloat16* __restrict__ dQ, float* __restrict__ Dbuf, int H, int Tq, int Sk, long long ldq,
-                   long long ldk, long long ldv, long long ldo, long long lddo, long long lddq, float scale, int q_per_block) {
+                   long long ldk, long long ldv, long long ldo, long long lddo, long long lddq, float scale, int q_per_block, DropK drop) {
   constexpr int SP = SCH * 32;
+  const uint32_t dkey = drop.seed ? drop_key(drop) : 0u;
+  const uint32_t wpr = static_cast<uint32_t>((Sk + 1) >> 1);
   extern __shared__ __align__(16) uint8_t smem[];
   uint32_t* Kt2 = reinterpret_cast<uint32_t*>(smem);
   uint32_t* Vt2 = Kt2 + 16 * SP;
@@ -186,12 +193,17 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16* __r
     dot_phase<SCH>(myq, Kt2, SP, lane, s);
     dot_phase<SCH>(mydo, Vt2, SP, lane, dp);
 #pragma unroll
-    for (int q = 0; q < NQ; ++q)
+    for (int q = 0; q < NQ; ++q) {
+      const uint32_t wrow = (static_cast<uint32_t>(blockIdx.y) * Tq + (t0 + q)) * wpr;
 #pragma unroll
       for (int c = 0; c < SCH; ++c) {
-        const float p = msk[lane + 32 * c] ? 0.f : __expf(s[q][c] - lse[q]);
-        myps[q * SP + lane + 32 * c] = p * (dp[q][c] - Dq[q]) * scale;
+        const int j = lane + 32 * c;
+        const float p = msk[j] ? 0.f : __expf(s[q][c] - lse[q]);
+        float dpv = dp[q][c];  // gradient w.r.t. the DROPPED probabilities -> w.r.t. the softmax output
+        if (drop.seed) dpv = drop_keep(drop_word(dkey, wrow + (j >> 1)), j & 1, drop.thr) ? dpv * drop.scale : 0.f;
+        myps[q * SP + j] = p * (dpv - Dq[q]) * scale;
       }
+    }
     __syncwarp();
     float acc[NQ];
     mix_phase(myps, SP, Ks, n4, lane, acc);
@@ -210,8 +222,10 @@ __global__ void __launch_bounds__(NWARPS * 32)
 attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16* __restrict__ K, const __nv_bfloat16* __restrict__ V,
                     const uint8_t* __restrict__ kpm, const __nv_bfloat16* __restrict__ dO, const float* __restrict__ LSE, const float* __restrict__ Dbuf,
                     __nv_bfloat16* __restrict__ dK, __nv_bfloat16* __restrict__ dV, int H, int Tq, int Sk, long long ldq, long long ldk, long long ldv,
-                    long long lddo, long long lddk, long long lddv, float scale, int k_per_block) {
+                    long long lddo, long long lddk, long long lddv, float scale, int k_per_block, DropK drop) {
   constexpr int TP = TCH * 32;
+  const uint32_t dkey = drop.seed ? drop_key(drop) : 0u;
+  const uint32_t wpr = static_cast<uint32_t>((Sk + 1) >> 1);
   extern __shared__ __align__(16) uint8_t smem[];
   uint32_t* Qt2 = reinterpret_cast<uint32_t*>(smem);
   uint32_t* dOt2 = Qt2 + 16 * TP;
@@ -260,8 +274,13 @@ attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16* __
       for (int c = 0; c < TCH; ++c) {
         const int t = lane + 32 * c;
         const float p = dead[q] ? 0.f : __expf(s[q][c] - lse_s[t]);
-        myp[q * TP + t] = p;
-        myds[q * TP + t] = p * (dp[q][c] - D_s[t]) * scale;
+        float mk = 1.f;
+        if (drop.seed) {
+          const int j = j0 + q;
+          mk = drop_keep(drop_word(dkey, (static_cast<uint32_t>(blockIdx.y) * Tq + t) * wpr + (j >> 1)), j & 1, drop.thr) ? drop.scale : 0.f;
+        }
+        myp[q * TP + t] = p * mk;                                   // dV uses the dropped probabilities
+        myds[q * TP + t] = p * (dp[q][c] * mk - D_s[t]) * scale;
       }
     __syncwarp();
     float accv[NQ], acck[NQ];
@@ -359,7 +378,7 @@ __global__ void qenc_pool_bwd_kernel(const float* __restrict__ dc, const float* 
 // ------------------------------------------------------------------------------------------------ host dispatch
 template <int SCH>
 static int launch_fwd(const void* Q, const void* K, const void* V, const void* kpm, void* O, float* LSE, int B, int H, int Tq, int Sk, long long ldq,
-                      long long ldk, long long ldv, long long ldo, float scale, cudaStream_t st) {
+                      long long ldk, long long ldv, long long ldo, float scale, DropK drop, cudaStream_t st) {
   constexpr int NW = 8, SP = SCH * 32;
   constexpr int SMEM = 16 * SP * 4 + SP * DH * 2 + NW * NQ * SP * 4 + NW * NQ * DH * 4 + SP;
   auto kern = attn_fwd_kernel<SCH, NW>;
@@ -368,7 +387,7 @@ static int launch_fwd(const void* Q, const void* K, const void* V, const void* k
   const int qpb = 64;
   kern<<<dim3((Tq + qpb - 1) / qpb, B * H), NW * 32, SMEM, st>>>(static_cast<const __nv_bfloat16*>(Q), static_cast<const __nv_bfloat16*>(K),
                                                               static_cast<const __nv_bfloat16*>(V), static_cast<const uint8_t*>(kpm),
-                                                              static_cast<__nv_bfloat16*>(O), LSE, H, Tq, Sk, ldq, ldk, ldv, ldo, scale, qpb);
+                                                              static_cast<__nv_bfloat16*>(O), LSE, H, Tq, Sk, ldq, ldk, ldv, ldo, scale, qpb, drop);
   RB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -376,7 +395,7 @@ static int launch_fwd(const void* Q, const void* K, const void* V, const void* k
 template <int SCH>
 static int launch_dq(const void* Q, const void* K, const void* V, const void* kpm, const void* O, const void* dO, const float* LSE, void* dQ, float* Dbuf,
                      int B, int H, int Tq, int Sk, long long ldq, long long ldk, long long ldv, long long ldo, long long lddo, long long lddq, float scale,
-                     cudaStream_t st) {
+                     DropK drop, cudaStream_t st) {
   constexpr int NW = 8, SP = SCH * 32;
   constexpr int SMEM = 2 * 16 * SP * 4 + SP * DH * 2 + NW * NQ * SP * 4 + NW * 2 * NQ * DH * 4 + SP;
   auto kern = attn_bwd_dq_kernel<SCH, NW>;
@@ -386,7 +405,7 @@ static int launch_dq(const void* Q, const void* K, const void* V, const void* kp
   kern<<<dim3((Tq + qpb - 1) / qpb, B * H), NW * 32, SMEM, st>>>(
       static_cast<const __nv_bfloat16*>(Q), static_cast<const __nv_bfloat16*>(K), static_cast<const __nv_bfloat16*>(V), static_cast<const uint8_t*>(kpm),
       static_cast<const __nv_bfloat16*>(O), static_cast<const __nv_bfloat16*>(dO), LSE, static_cast<__nv_bfloat16*>(dQ), Dbuf, H, Tq, Sk, ldq, ldk, ldv,
-      ldo, lddo, lddq, scale, qpb);
+      ldo, lddo, lddq, scale, qpb, drop);
   RB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -394,7 +413,7 @@ static int launch_dq(const void* Q, const void* K, const void* V, const void* kp
 template <int TCH, int NW>
 static int launch_dkv(const void* Q, const void* K, const void* V, const void* kpm, const void* dO, const float* LSE, const float* Dbuf, void* dK, void* dV,
                       int B, int H, int Tq, int Sk, long long ldq, long long ldk, long long ldv, long long lddo, long long lddk, long long lddv, float scale,
-                      cudaStream_t st) {
+                      DropK drop, cudaStream_t st) {
   constexpr int TP = TCH * 32;
   constexpr int SMEM = 2 * 16 * TP * 4 + 2 * TP * DH * 2 + NW * 2 * NQ * TP * 4 + NW * 2 * NQ * DH * 4 + 2 * TP * 4;
   auto kern = attn_bwd_dkv_kernel<TCH, NW>;
@@ -404,7 +423,7 @@ static int launch_dkv(const void* Q, const void* K, const void* V, const void* k
   kern<<<dim3((Sk + kpb - 1) / kpb, B * H), NW * 32, SMEM, st>>>(
       static_cast<const __nv_bfloat16*>(Q), static_cast<const __nv_bfloat16*>(K), static_cast<const __nv_bfloat16*>(V), static_cast<const uint8_t*>(kpm),
       static_cast<const __nv_bfloat16*>(dO), LSE, Dbuf, static_cast<__nv_bfloat16*>(dK), static_cast<__nv_bfloat16*>(dV), H, Tq, Sk, ldq, ldk, ldv, lddo,
-      lddk, lddv, scale, kpb);
+      lddk, lddv, scale, kpb, drop);
   RB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -418,34 +437,36 @@ using namespace rb;
   if (Tq <= 0 || Sk <= 0 || B <= 0 || H <= 0) return rb_fail(name ": empty problem");
 
 int rb::attn_fwd_simt(const void* Q, const void* K, const void* V, const void* kpm, void* O, float* LSE, int B, int H, int dh, int Tq, int Sk,
-                           long long ldq, long long ldk, long long ldv, long long ldo, float scale, void* stream) {
+                           long long ldq, long long ldk, long long ldv, long long ldo, float scale, const rb_dropout* drop, void* stream) {
   RB_ATTN_CHECK("rb_attn_fwd");
+  const DropK dk = make_dropk(drop);
   if ((ldk % 8) || (ldv % 8)) return rb_fail("rb_attn_fwd: K/V pitch must be a multiple of 8 elements");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (Sk <= 32) return launch_fwd<1>(Q, K, V, kpm, O, LSE, B, H, Tq, Sk, ldq, ldk, ldv, ldo, scale, st);
-  if (Sk <= 128) return launch_fwd<4>(Q, K, V, kpm, O, LSE, B, H, Tq, Sk, ldq, ldk, ldv, ldo, scale, st);
-  if (Sk <= 448) return launch_fwd<14>(Q, K, V, kpm, O, LSE, B, H, Tq, Sk, ldq, ldk, ldv, ldo, scale, st);
-  if (Sk <= 672) return launch_fwd<21>(Q, K, V, kpm, O, LSE, B, H, Tq, Sk, ldq, ldk, ldv, ldo, scale, st);
+  if (Sk <= 32) return launch_fwd<1>(Q, K, V, kpm, O, LSE, B, H, Tq, Sk, ldq, ldk, ldv, ldo, scale, dk, st);
+  if (Sk <= 128) return launch_fwd<4>(Q, K, V, kpm, O, LSE, B, H, Tq, Sk, ldq, ldk, ldv, ldo, scale, dk, st);
+  if (Sk <= 448) return launch_fwd<14>(Q, K, V, kpm, O, LSE, B, H, Tq, Sk, ldq, ldk, ldv, ldo, scale, dk, st);
+  if (Sk <= 672) return launch_fwd<21>(Q, K, V, kpm, O, LSE, B, H, Tq, Sk, ldq, ldk, ldv, ldo, scale, dk, st);
   return rb_fail("rb_attn_fwd: Sk = %d > 672 keys is not built yet", Sk);
 }
 
 int rb::attn_bwd_simt(const void* Q, const void* K, const void* V, const void* kpm, const void* O, const void* dO, const float* LSE, void* dQ, void* dK,
                            void* dV, float* Dbuf, int B, int H, int dh, int Tq, int Sk, long long ldq, long long ldk, long long ldv, long long ldo,
-                           long long lddo, long long lddq, long long lddk, long long lddv, float scale, void* stream) {
+                           long long lddo, long long lddq, long long lddk, long long lddv, float scale, const rb_dropout* drop, void* stream) {
   RB_ATTN_CHECK("rb_attn_bwd");
+  const DropK dk = make_dropk(drop);
   if ((ldk % 8) || (ldv % 8) || (ldq % 8) || (lddo % 8)) return rb_fail("rb_attn_bwd: pitches must be multiples of 8 elements");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int rc;
-  if (Sk <= 32) rc = launch_dq<1>(Q, K, V, kpm, O, dO, LSE, dQ, Dbuf, B, H, Tq, Sk, ldq, ldk, ldv, ldo, lddo, lddq, scale, st);
-  else if (Sk <= 128) rc = launch_dq<4>(Q, K, V, kpm, O, dO, LSE, dQ, Dbuf, B, H, Tq, Sk, ldq, ldk, ldv, ldo, lddo, lddq, scale, st);
-  else if (Sk <= 448) rc = launch_dq<14>(Q, K, V, kpm, O, dO, LSE, dQ, Dbuf, B, H, Tq, Sk, ldq, ldk, ldv, ldo, lddo, lddq, scale, st);
-  else if (Sk <= 672) rc = launch_dq<21>(Q, K, V, kpm, O, dO, LSE, dQ, Dbuf, B, H, Tq, Sk, ldq, ldk, ldv, ldo, lddo, lddq, scale, st);
+  if (Sk <= 32) rc = launch_dq<1>(Q, K, V, kpm, O, dO, LSE, dQ, Dbuf, B, H, Tq, Sk, ldq, ldk, ldv, ldo, lddo, lddq, scale, dk, st);
+  else if (Sk <= 128) rc = launch_dq<4>(Q, K, V, kpm, O, dO, LSE, dQ, Dbuf, B, H, Tq, Sk, ldq, ldk, ldv, ldo, lddo, lddq, scale, dk, st);
+  else if (Sk <= 448) rc = launch_dq<14>(Q, K, V, kpm, O, dO, LSE, dQ, Dbuf, B, H, Tq, Sk, ldq, ldk, ldv, ldo, lddo, lddq, scale, dk, st);
+  else if (Sk <= 672) rc = launch_dq<21>(Q, K, V, kpm, O, dO, LSE, dQ, Dbuf, B, H, Tq, Sk, ldq, ldk, ldv, ldo, lddo, lddq, scale, dk, st);
   else return rb_fail("rb_attn_bwd: Sk = %d > 672 keys is not built yet", Sk);
   if (rc) return rc;
-  if (Tq <= 32) return launch_dkv<1, 8>(Q, K, V, kpm, dO, LSE, Dbuf, dK, dV, B, H, Tq, Sk, ldq, ldk, ldv, lddo, lddk, lddv, scale, st);
-  if (Tq <= 128) return launch_dkv<4, 8>(Q, K, V, kpm, dO, LSE, Dbuf, dK, dV, B, H, Tq, Sk, ldq, ldk, ldv, lddo, lddk, lddv, scale, st);
-  if (Tq <= 448) return launch_dkv<14, 8>(Q, K, V, kpm, dO, LSE, Dbuf, dK, dV, B, H, Tq, Sk, ldq, ldk, ldv, lddo, lddk, lddv, scale, st);
-  if (Tq <= 672) return launch_dkv<21, 4>(Q, K, V, kpm, dO, LSE, Dbuf, dK, dV, B, H, Tq, Sk, ldq, ldk, ldv, lddo, lddk, lddv, scale, st);
+  if (Tq <= 32) return launch_dkv<1, 8>(Q, K, V, kpm, dO, LSE, Dbuf, dK, dV, B, H, Tq, Sk, ldq, ldk, ldv, lddo, lddk, lddv, scale, dk, st);
+  if (Tq <= 128) return launch_dkv<4, 8>(Q, K, V, kpm, dO, LSE, Dbuf, dK, dV, B, H, Tq, Sk, ldq, ldk, ldv, lddo, lddk, lddv, scale, dk, st);
+  if (Tq <= 448) return launch_dkv<14, 8>(Q, K, V, kpm, dO, LSE, Dbuf, dK, dV, B, H, Tq, Sk, ldq, ldk, ldv, lddo, lddk, lddv, scale, dk, st);
+  if (Tq <= 672) return launch_dkv<21, 4>(Q, K, V, kpm, dO, LSE, Dbuf, dK, dV, B, H, Tq, Sk, ldq, ldk, ldv, lddo, lddk, lddv, scale, dk, st);
   return rb_fail("rb_attn_bwd: Tq = %d > 672 queries is not built yet", Tq);
 }
 

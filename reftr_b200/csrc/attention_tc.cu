@@ -121,7 +121,7 @@ __device__ __forceinline__ void atc_init(const AtcSmem& s, int warp, int tmem_co
 __global__ void __launch_bounds__(ATC_THREADS)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                    const uint8_t* __restrict__ kpm, __nv_bfloat16* __restrict__ O, float* __restrict__ LSE, int H, int Tq, int Sk, long long ldo,
-                   float scale) {
+                   float scale, DropK drop) {
   extern __shared__ uint8_t smem_raw[];
   const AtcSmem s = carve(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -173,6 +173,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
     const float c = scale * 1.4426950408889634f;
     float m = -INFINITY, l = 0.f;
+    const bool use_drop = drop.seed != nullptr;
+    const uint32_t dkey = use_drop ? drop_key(drop) : 0u;
+    const uint32_t wrow = (static_cast<uint32_t>(bh) * Tq + (q0 + r)) * static_cast<uint32_t>((Sk + 1) >> 1);
     for (int j = 0; j < nb; ++j) {
       mbar_wait(&s.bars[BAR_ACC], j & 1);
       tc_fence_after();
@@ -201,6 +204,17 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
       l = l * alpha + sum;
       m = m_new;
+      if (use_drop) {  // dropout on the probabilities (l stays the undropped row sum; 1/(1-p) is applied with 1/l at the end)
+        const uint32_t cb = wrow + j * (ATC_BLK / 2);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const uint32_t w0 = drop_word(dkey, cb + i), w1 = drop_word(dkey, cb + 16 + i);
+          if (!drop_keep(w0, 0, drop.thr)) p0[2 * i] = 0.f;
+          if (!drop_keep(w0, 1, drop.thr)) p0[2 * i + 1] = 0.f;
+          if (!drop_keep(w1, 0, drop.thr)) p1[2 * i] = 0.f;
+          if (!drop_keep(w1, 1, drop.thr)) p1[2 * i + 1] = 0.f;
+        }
+      }
       if (j > 0) {
         // the previous block's P V must have completed before P is overwritten and O is rescaled
         mbar_wait(&s.bars[BAR_FREE + ((j - 1) & 1)], ((j - 1) >> 1) & 1);
@@ -228,7 +242,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     tmem_ld_wait();
     const int q = q0 + r;
     if (q < Tq) {
-      const float inv = l > 0.f ? 1.f / l : 0.f;
+      const float inv = l > 0.f ? drop.scale / l : 0.f;
       uint4* dst = reinterpret_cast<uint4*>(O + (static_cast<long long>(b) * Tq + q) * ldo + h * ATC_DH);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -255,7 +269,7 @@ __global__ void __launch_bounds__(ATC_THREADS)
 attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                       const __grid_constant__ CUtensorMap tmdO, const uint8_t* __restrict__ kpm, const __nv_bfloat16* __restrict__ O,
                       const __nv_bfloat16* __restrict__ dO, const float* __restrict__ LSE, __nv_bfloat16* __restrict__ dQ, float* __restrict__ Dbuf, int H,
-                      int Tq, int Sk, long long ldo, long long lddo, long long lddq, float scale) {
+                      int Tq, int Sk, long long ldo, long long lddo, long long lddq, float scale, DropK drop) {
   extern __shared__ uint8_t smem_raw[];
   const AtcSmem s = carve(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -312,6 +326,9 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     const int q = q0 + r;
     const bool q_ok = q < Tq;
     float lse2 = INFINITY, D = 0.f;
+    const bool use_drop = drop.seed != nullptr;
+    const uint32_t dkey = use_drop ? drop_key(drop) : 0u;
+    const uint32_t wrow = (static_cast<uint32_t>(bh) * Tq + q) * static_cast<uint32_t>((Sk + 1) >> 1);
     if (q_ok) {
       lse2 = LSE[static_cast<long long>(bh) * Tq + q] * 1.4426950408889634f;
       const uint4* po = reinterpret_cast<const uint4*>(O + (static_cast<long long>(b) * Tq + q) * ldo + h * ATC_DH);
@@ -339,6 +356,15 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         tmem_ld_wait();
         const uint32_t mb = s.maskbits[2 * j + half];
         float ds[32];
+        if (use_drop) {  // dv is the gradient w.r.t. the DROPPED probabilities
+          const uint32_t cb = wrow + j * (ATC_BLK / 2) + half * 16;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const uint32_t w = drop_word(dkey, cb + i);
+            dv[2 * i] = drop_keep(w, 0, drop.thr) ? __float_as_uint(__uint_as_float(dv[2 * i]) * drop.scale) : 0u;
+            dv[2 * i + 1] = drop_keep(w, 1, drop.thr) ? __float_as_uint(__uint_as_float(dv[2 * i + 1]) * drop.scale) : 0u;
+          }
+        }
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           const float p = ((mb >> i) & 1u) ? 0.f : ex2(__uint_as_float(sv[i]) * c - lse2);
@@ -380,7 +406,7 @@ __global__ void __launch_bounds__(ATC_THREADS)
 attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                        const __grid_constant__ CUtensorMap tmdO, const uint8_t* __restrict__ kpm, const float* __restrict__ LSE,
                        const float* __restrict__ Dbuf, __nv_bfloat16* __restrict__ dK, __nv_bfloat16* __restrict__ dV, int H, int Tq, int Sk, long long lddk,
-                       long long lddv, float scale) {
+                       long long lddv, float scale, DropK drop) {
   extern __shared__ uint8_t smem_raw[];
   const AtcSmem s = carve(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -448,6 +474,9 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     const float c = scale * 1.4426950408889634f;
     const int key = k0 + r;
     const bool key_ok = key < Sk && !(kpm && kpm[static_cast<long long>(b) * Sk + key]);
+    const bool use_drop = drop.seed != nullptr;
+    const uint32_t dkey = use_drop ? drop_key(drop) : 0u;
+    const uint32_t wpr = static_cast<uint32_t>((Sk + 1) >> 1);
     for (int i = 0; i < nb; ++i) {
       const int st = i & 1;
       mbar_wait(&s.bars[BAR_FULL + st], (i >> 1) & 1);  // colL / colD of this block are visible
@@ -466,11 +495,15 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         tmem_ld_32x32(T_dP + lane_addr + half * 32, dv);
         tmem_ld_wait();
         float p[32], ds[32];
+        // element (query i*64 + half*32 + t, key): this thread owns one key, so one random word per element
+        uint32_t ctr = (static_cast<uint32_t>(bh) * Tq + i * ATC_BLK + half * 32) * wpr + static_cast<uint32_t>(key >> 1);
 #pragma unroll
         for (int t = 0; t < 32; ++t) {
           const float pv = key_ok ? ex2(__uint_as_float(sv[t]) * c - cl[half * 32 + t]) : 0.f;
-          p[t] = pv;
-          ds[t] = pv * (__uint_as_float(dv[t]) - cd[half * 32 + t]) * scale;
+          float mk = 1.f;
+          if (use_drop) { mk = drop_keep(drop_word(dkey, ctr), key & 1, drop.thr) ? drop.scale : 0.f; ctr += wpr; }
+          p[t] = pv * mk;  // dV uses the dropped probabilities
+          ds[t] = pv * (__uint_as_float(dv[t]) * mk - cd[half * 32 + t]) * scale;
         }
         store_row_half_sw128(s.tileA, r, half, p);
         store_row_half_sw128(s.tileB, r, half, ds);
@@ -530,9 +563,10 @@ static int set_smem(K kern, int bytes) {
 using namespace rb;
 
 extern "C" int rb_attn_fwd(const void* Q, const void* K, const void* V, const void* kpm, void* O, float* LSE, int B, int H, int dh, int Tq, int Sk,
-                           long long ldq, long long ldk, long long ldv, long long ldo, float scale, void* stream) {
+                           long long ldq, long long ldk, long long ldv, long long ldo, float scale, const rb_dropout* drop, void* stream) {
+  if (static_cast<long long>(B) * H * Tq * ((Sk + 1) / 2) >= (1LL << 32)) return rb_fail("rb_attn_fwd: dropout counter overflow");
   if (!tc_eligible(dh, Tq, Sk, {Q, K, V, O}, {ldq, ldk, ldv, ldo}))
-    return attn_fwd_simt(Q, K, V, kpm, O, LSE, B, H, dh, Tq, Sk, ldq, ldk, ldv, ldo, scale, stream);
+    return attn_fwd_simt(Q, K, V, kpm, O, LSE, B, H, dh, Tq, Sk, ldq, ldk, ldv, ldo, scale, drop, stream);
   CUtensorMap tmQ, tmK, tmV;
   if (make_tmap_2d(&tmQ, Q, static_cast<uint64_t>(H) * dh, static_cast<uint64_t>(B) * Tq, ldq * 2, ATC_DH, ATC_ROWS)) return 1;
   if (make_tmap_2d(&tmK, K, static_cast<uint64_t>(H) * dh, static_cast<uint64_t>(B) * Sk, ldk * 2, ATC_DH, ATC_BLK)) return 1;
@@ -541,16 +575,17 @@ extern "C" int rb_attn_fwd(const void* Q, const void* K, const void* V, const vo
   if (!cfg) { if (set_smem(attn_fwd_tc_kernel, ATC_SMEM_FWD)) return 1; cfg = true; }
   dim3 grid((Tq + ATC_ROWS - 1) / ATC_ROWS, B * H);
   attn_fwd_tc_kernel<<<grid, ATC_THREADS, ATC_SMEM_FWD, static_cast<cudaStream_t>(stream)>>>(
-      tmQ, tmK, tmV, static_cast<const uint8_t*>(kpm), static_cast<__nv_bfloat16*>(O), LSE, H, Tq, Sk, ldo, scale);
+      tmQ, tmK, tmV, static_cast<const uint8_t*>(kpm), static_cast<__nv_bfloat16*>(O), LSE, H, Tq, Sk, ldo, scale, make_dropk(drop));
   RB_CUDA(cudaGetLastError());
   return 0;
 }
 
 extern "C" int rb_attn_bwd(const void* Q, const void* K, const void* V, const void* kpm, const void* O, const void* dO, const float* LSE, void* dQ, void* dK,
                            void* dV, float* Dbuf, int B, int H, int dh, int Tq, int Sk, long long ldq, long long ldk, long long ldv, long long ldo,
-                           long long lddo, long long lddq, long long lddk, long long lddv, float scale, void* stream) {
+                           long long lddo, long long lddq, long long lddk, long long lddv, float scale, const rb_dropout* drop, void* stream) {
   if (!tc_eligible(dh, Tq, Sk, {Q, K, V, O, dO, dQ, dK, dV}, {ldq, ldk, ldv, ldo, lddo, lddq, lddk, lddv}))
-    return attn_bwd_simt(Q, K, V, kpm, O, dO, LSE, dQ, dK, dV, Dbuf, B, H, dh, Tq, Sk, ldq, ldk, ldv, ldo, lddo, lddq, lddk, lddv, scale, stream);
+    return attn_bwd_simt(Q, K, V, kpm, O, dO, LSE, dQ, dK, dV, Dbuf, B, H, dh, Tq, Sk, ldq, ldk, ldv, ldo, lddo, lddq, lddk, lddv, scale, drop, stream);
+  const DropK dk = make_dropk(drop);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   static bool cfg = false;
   if (!cfg) { if (set_smem(attn_bwd_dq_tc_kernel, ATC_SMEM_DQ) || set_smem(attn_bwd_dkv_tc_kernel, ATC_SMEM_DKV)) return 1; cfg = true; }
@@ -563,7 +598,7 @@ extern "C" int rb_attn_bwd(const void* Q, const void* K, const void* V, const vo
     dim3 grid((Tq + ATC_ROWS - 1) / ATC_ROWS, B * H);
     attn_bwd_dq_tc_kernel<<<grid, ATC_THREADS, ATC_SMEM_DQ, st>>>(tmQ, tmK, tmV, tmdO, static_cast<const uint8_t*>(kpm),
                                                                     static_cast<const __nv_bfloat16*>(O), static_cast<const __nv_bfloat16*>(dO), LSE,
-                                                                    static_cast<__nv_bfloat16*>(dQ), Dbuf, H, Tq, Sk, ldo, lddo, lddq, scale);
+                                                                    static_cast<__nv_bfloat16*>(dQ), Dbuf, H, Tq, Sk, ldo, lddo, lddq, scale, dk);
     RB_CUDA(cudaGetLastError());
   }
   {
@@ -575,7 +610,7 @@ extern "C" int rb_attn_bwd(const void* Q, const void* K, const void* V, const vo
     dim3 grid((Sk + ATC_ROWS - 1) / ATC_ROWS, B * H);
     attn_bwd_dkv_tc_kernel<<<grid, ATC_THREADS, ATC_SMEM_DKV, st>>>(tmQ, tmK, tmV, tmdO, static_cast<const uint8_t*>(kpm), LSE, Dbuf,
                                                                      static_cast<__nv_bfloat16*>(dK), static_cast<__nv_bfloat16*>(dV), H, Tq, Sk, lddk, lddv,
-                                                                     scale);
+                                                                     scale, dk);
     RB_CUDA(cudaGetLastError());
   }
   return 0;

@@ -37,11 +37,20 @@ __global__ void bert_embed_bwd_kernel(const float* __restrict__ d, const long lo
   }
 }
 
+// dropout on 4 consecutive elements starting at an even column: word counters c0, c0 + 1
+__device__ __forceinline__ void drop4(float4& o, uint32_t key, const DropK& d, uint32_t c0) {
+  const uint32_t w0 = drop_word(key, c0), w1 = drop_word(key, c0 + 1);
+  o.x = drop_keep(w0, 0, d.thr) ? o.x * d.scale : 0.f;
+  o.y = drop_keep(w0, 1, d.thr) ? o.y * d.scale : 0.f;
+  o.z = drop_keep(w1, 0, d.thr) ? o.z * d.scale : 0.f;
+  o.w = drop_keep(w1, 1, d.thr) ? o.w * d.scale : 0.f;
+}
+
 // ------------------------------------------------------------------------------------------------ LayerNorm, D = 32*4*NV
 template <int NV>
 __global__ void __launch_bounds__(256)
 ln_wide_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, long long rows, float eps,
-                   float* __restrict__ y32, __nv_bfloat16* __restrict__ yb, float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+                   float* __restrict__ y32, __nv_bfloat16* __restrict__ yb, float* __restrict__ mean_out, float* __restrict__ rstd_out, DropK drop) {
   constexpr int D = NV * 128;
   const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -65,11 +74,13 @@ ln_wide_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
     if (mean_out) mean_out[row] = mean;
     if (rstd_out) rstd_out[row] = rstd;
   }
+  const uint32_t dkey = drop.seed ? drop_key(drop) : 0u;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const float4 g = *reinterpret_cast<const float4*>(gamma + i * 128 + lane * 4);
     const float4 b = *reinterpret_cast<const float4*>(beta + i * 128 + lane * 4);
-    const float4 o = make_float4(v[i].x * rstd * g.x + b.x, v[i].y * rstd * g.y + b.y, v[i].z * rstd * g.z + b.z, v[i].w * rstd * g.w + b.w);
+    float4 o = make_float4(v[i].x * rstd * g.x + b.x, v[i].y * rstd * g.y + b.y, v[i].z * rstd * g.z + b.z, v[i].w * rstd * g.w + b.w);
+    if (drop.seed) drop4(o, dkey, drop, static_cast<uint32_t>(row) * (D / 2) + i * 64 + lane * 2);
     if (y32) *reinterpret_cast<float4*>(y32 + row * D + i * 128 + lane * 4) = o;
     if (yb) {
       uint2 p;
@@ -84,9 +95,10 @@ template <int NV>
 __global__ void __launch_bounds__(256)
 ln_wide_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ dy2, const float* __restrict__ x, const float* __restrict__ gamma,
                    const float* __restrict__ mean, const float* __restrict__ rstd, long long rows, float* __restrict__ dx32, __nv_bfloat16* __restrict__ dxb,
-                   float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                   float* __restrict__ dgamma, float* __restrict__ dbeta, DropK idrop, DropK odrop) {
   constexpr int D = NV * 128;
   __shared__ float red[2][D];
+  const uint32_t ikey = idrop.seed ? drop_key(idrop) : 0u, okey = odrop.seed ? drop_key(odrop) : 0u;
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   const long long warp_global = static_cast<long long>(blockIdx.x) * warps_per_block + (threadIdx.x >> 5);
@@ -107,6 +119,7 @@ ln_wide_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ dy2, 
         const float4 e = *reinterpret_cast<const float4*>(dy2 + row * D + i * 128 + lane * 4);
         d[i].x += e.x; d[i].y += e.y; d[i].z += e.z; d[i].w += e.w;
       }
+      if (idrop.seed) drop4(d[i], ikey, idrop, static_cast<uint32_t>(row) * (D / 2) + i * 64 + lane * 2);
       const float4 xv = *reinterpret_cast<const float4*>(x + row * D + i * 128 + lane * 4);
       xh[i] = make_float4((xv.x - m) * rs, (xv.y - m) * rs, (xv.z - m) * rs, (xv.w - m) * rs);
       dg[i].x += d[i].x * xh[i].x; dg[i].y += d[i].y * xh[i].y; dg[i].z += d[i].z * xh[i].z; dg[i].w += d[i].w * xh[i].w;
@@ -120,10 +133,11 @@ ln_wide_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ dy2, 
     s2 = warp_sum(s2) * (1.f / D);
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      const float4 o = make_float4(rs * (d[i].x - s1 - xh[i].x * s2), rs * (d[i].y - s1 - xh[i].y * s2), rs * (d[i].z - s1 - xh[i].z * s2),
-                                   rs * (d[i].w - s1 - xh[i].w * s2));
+      float4 o = make_float4(rs * (d[i].x - s1 - xh[i].x * s2), rs * (d[i].y - s1 - xh[i].y * s2), rs * (d[i].z - s1 - xh[i].z * s2),
+                             rs * (d[i].w - s1 - xh[i].w * s2));
       if (dx32) *reinterpret_cast<float4*>(dx32 + row * D + i * 128 + lane * 4) = o;
       if (dxb) {
+        if (odrop.seed) drop4(o, okey, odrop, static_cast<uint32_t>(row) * (D / 2) + i * 64 + lane * 2);
         uint2 p;
         p.x = pack_bf16x2(o.x, o.y);
         p.y = pack_bf16x2(o.z, o.w);
@@ -195,7 +209,7 @@ constexpr int AS_PAD = 65;
 __global__ void __launch_bounds__(128)
 attn_small_fwd_kernel(const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16* __restrict__ K, const __nv_bfloat16* __restrict__ V,
                       const uint8_t* __restrict__ mask, __nv_bfloat16* __restrict__ O, float* __restrict__ P, int H, int S, long long ldq, long long ldk,
-                      long long ldv, long long ldo, float scale) {
+                      long long ldv, long long ldo, float scale, DropK drop) {
   extern __shared__ float sm[];
   float* q = sm;
   float* k = q + S * AS_PAD;
@@ -219,6 +233,7 @@ attn_small_fwd_kernel(const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16* 
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t dkey = drop.seed ? drop_key(drop) : 0u;
   for (int r = warp; r < S; r += blockDim.x >> 5) {
     float mx = -INFINITY;
     for (int c = lane; c < S; c += 32) mx = fmaxf(mx, p[r * S + c]);
@@ -232,10 +247,11 @@ attn_small_fwd_kernel(const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16* 
     }
     sum = warp_sum(sum);
     const float inv = sum > 0.f ? 1.f / sum : 0.f;
+    const uint32_t wrow = (static_cast<uint32_t>(blockIdx.x) * S + r) * ((S + 1) >> 1);
     for (int c = lane; c < S; c += 32) {
       const float a = p[r * S + c] * inv;
-      p[r * S + c] = a;
-      P[(static_cast<long long>(blockIdx.x) * S + r) * S + c] = a;
+      P[(static_cast<long long>(blockIdx.x) * S + r) * S + c] = a;  // the UNDROPPED softmax is saved; the backward recomputes the mask
+      p[r * S + c] = (!drop.seed) ? a : (drop_keep(drop_word(dkey, wrow + (c >> 1)), c & 1, drop.thr) ? a * drop.scale : 0.f);
     }
   }
   __syncthreads();
@@ -251,7 +267,7 @@ __global__ void __launch_bounds__(128)
 attn_small_bwd_kernel(const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16* __restrict__ K, const __nv_bfloat16* __restrict__ V,
                       const __nv_bfloat16* __restrict__ dO, const float* __restrict__ P, __nv_bfloat16* __restrict__ dQ, __nv_bfloat16* __restrict__ dK,
                       __nv_bfloat16* __restrict__ dV, int H, int S, long long ldq, long long ldk, long long ldv, long long lddo, long long lddq,
-                      long long lddk, long long lddv, float scale) {
+                      long long lddk, long long lddv, float scale, DropK drop) {
   extern __shared__ float sm[];
   float* q = sm;
   float* k = q + S * AS_PAD;
@@ -259,6 +275,7 @@ attn_small_bwd_kernel(const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16* 
   float* go = v + S * AS_PAD;
   float* p = go + S * AS_PAD;  // [S][S] probabilities
   float* ds = p + S * S;       // [S][S] d(scores)
+  float* pm = drop.seed ? ds + S * S : p;  // [S][S] dropped probabilities (aliases p without dropout: same thread, read before write)
   const int b = blockIdx.x / H, h = blockIdx.x - b * H;
   for (int i = threadIdx.x; i < S * AS_DH; i += blockDim.x) {
     const int r = i / AS_DH, c = i - r * AS_DH;
@@ -280,9 +297,19 @@ attn_small_bwd_kernel(const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16* 
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t dkey = drop.seed ? drop_key(drop) : 0u;
   for (int r = warp; r < S; r += blockDim.x >> 5) {
+    // with dropout: O = (P .* M) V, M = keep * scale.  dP = (dO V^T) .* M, dS = P .* (dP - rowsum(P .* dP)); dV uses P .* M
+    const uint32_t wrow = (static_cast<uint32_t>(blockIdx.x) * S + r) * ((S + 1) >> 1);
     float dot = 0.f;
-    for (int c = lane; c < S; c += 32) dot += ds[r * S + c] * p[r * S + c];
+    for (int c = lane; c < S; c += 32) {
+      float mk = 1.f;
+      if (drop.seed) mk = drop_keep(drop_word(dkey, wrow + (c >> 1)), c & 1, drop.thr) ? drop.scale : 0.f;
+      const float dp = ds[r * S + c] * mk;
+      ds[r * S + c] = dp;
+      dot += dp * p[r * S + c];
+      pm[r * S + c] = p[r * S + c] * mk;
+    }
     dot = warp_sum(dot);
     for (int c = lane; c < S; c += 32) ds[r * S + c] = p[r * S + c] * (ds[r * S + c] - dot) * scale;
   }
@@ -293,7 +320,7 @@ attn_small_bwd_kernel(const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16* 
     for (int j = 0; j < S; ++j) {
       aq = fmaf(ds[r * S + j], k[j * AS_PAD + c], aq);   // dQ[r] = sum_j dS[r,j] K[j]
       ak = fmaf(ds[j * S + r], q[j * AS_PAD + c], ak);   // dK[r] = sum_j dS[j,r] Q[j]
-      av = fmaf(p[j * S + r], go[j * AS_PAD + c], av);   // dV[r] = sum_j P[j,r] dO[j]
+      av = fmaf(pm[j * S + r], go[j * AS_PAD + c], av);  // dV[r] = sum_j (P .* M)[j,r] dO[j]
     }
     const long long row = static_cast<long long>(b) * S + r;
     dQ[row * lddq + h * AS_DH + c] = __float2bfloat16(aq);
@@ -325,26 +352,28 @@ extern "C" int rb_bert_embed_bwd(const float* d, const long long* ids, long long
 }
 
 extern "C" int rb_ln_wide_fwd(const float* x, const float* gamma, const float* beta, long long rows, int D, float eps, float* y32, void* yb, float* mean,
-                              float* rstd, void* stream) {
+                              float* rstd, const rb_dropout* drop, void* stream) {
   if (rows <= 0) return 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
-  if (D == 768) ln_wide_fwd_kernel<6><<<grid, 256, 0, st>>>(x, gamma, beta, rows, eps, y32, static_cast<__nv_bfloat16*>(yb), mean, rstd);
-  else if (D == 1024) ln_wide_fwd_kernel<8><<<grid, 256, 0, st>>>(x, gamma, beta, rows, eps, y32, static_cast<__nv_bfloat16*>(yb), mean, rstd);
+  if (D == 768) ln_wide_fwd_kernel<6><<<grid, 256, 0, st>>>(x, gamma, beta, rows, eps, y32, static_cast<__nv_bfloat16*>(yb), mean, rstd, make_dropk(drop));
+  else if (D == 1024) ln_wide_fwd_kernel<8><<<grid, 256, 0, st>>>(x, gamma, beta, rows, eps, y32, static_cast<__nv_bfloat16*>(yb), mean, rstd, make_dropk(drop));
   else return rb_fail("rb_ln_wide_fwd: D must be 768 or 1024 (got %d)", D);
   RB_CUDA(cudaGetLastError());
   return 0;
 }
 
 extern "C" int rb_ln_wide_bwd(const float* dy, const float* dy2, const float* x, const float* gamma, const float* mean, const float* rstd, long long rows,
-                              int D, float* dx32, void* dxb, float* dgamma, float* dbeta, void* stream) {
+                              int D, float* dx32, void* dxb, float* dgamma, float* dbeta, const rb_dropout* dy_drop, const rb_dropout* dxb_drop, void* stream) {
   if (rows <= 0) return 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   long long blocks = (rows + 7) / 8;
   if (blocks > 148) blocks = 148;
   const unsigned grid = static_cast<unsigned>(blocks);
-  if (D == 768) ln_wide_bwd_kernel<6><<<grid, 256, 0, st>>>(dy, dy2, x, gamma, mean, rstd, rows, dx32, static_cast<__nv_bfloat16*>(dxb), dgamma, dbeta);
-  else if (D == 1024) ln_wide_bwd_kernel<8><<<grid, 256, 0, st>>>(dy, dy2, x, gamma, mean, rstd, rows, dx32, static_cast<__nv_bfloat16*>(dxb), dgamma, dbeta);
+  if (D == 768) ln_wide_bwd_kernel<6><<<grid, 256, 0, st>>>(dy, dy2, x, gamma, mean, rstd, rows, dx32, static_cast<__nv_bfloat16*>(dxb), dgamma, dbeta,
+                                                                  make_dropk(dy_drop), make_dropk(dxb_drop));
+  else if (D == 1024) ln_wide_bwd_kernel<8><<<grid, 256, 0, st>>>(dy, dy2, x, gamma, mean, rstd, rows, dx32, static_cast<__nv_bfloat16*>(dxb), dgamma, dbeta,
+                                                                   make_dropk(dy_drop), make_dropk(dxb_drop));
   else return rb_fail("rb_ln_wide_bwd: D must be 768 or 1024 (got %d)", D);
   RB_CUDA(cudaGetLastError());
   return 0;
@@ -382,7 +411,7 @@ extern "C" int rb_tanh_bwd(const float* dy, const float* y, float* dx, void* dxb
 }
 
 extern "C" int rb_attn_small_fwd(const void* Q, const void* K, const void* V, const void* mask, void* O, float* P, int B, int H, int dh, int S, long long ldq,
-                                 long long ldk, long long ldv, long long ldo, float scale, void* stream) {
+                                 long long ldk, long long ldv, long long ldo, float scale, const rb_dropout* drop, void* stream) {
   if (dh != AS_DH) return rb_fail("rb_attn_small_fwd: head_dim must be 64 (got %d)", dh);
   if (S < 1 || S > 128) return rb_fail("rb_attn_small_fwd: 1 <= S <= 128 tokens (got %d)", S);
   const size_t smem = (static_cast<size_t>(3) * S * AS_PAD + static_cast<size_t>(S) * S) * sizeof(float);
@@ -390,23 +419,24 @@ extern "C" int rb_attn_small_fwd(const void* Q, const void* K, const void* V, co
   if (!cfg) { RB_CUDA(cudaFuncSetAttribute(attn_small_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); cfg = true; }
   attn_small_fwd_kernel<<<B * H, 128, smem, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(Q), static_cast<const __nv_bfloat16*>(K), static_cast<const __nv_bfloat16*>(V), static_cast<const uint8_t*>(mask),
-      static_cast<__nv_bfloat16*>(O), P, H, S, ldq, ldk, ldv, ldo, scale);
+      static_cast<__nv_bfloat16*>(O), P, H, S, ldq, ldk, ldv, ldo, scale, make_dropk(drop));
   RB_CUDA(cudaGetLastError());
   return 0;
 }
 
 extern "C" int rb_attn_small_bwd(const void* Q, const void* K, const void* V, const void* dO, const float* P, void* dQ, void* dK, void* dV, int B, int H,
                                  int dh, int S, long long ldq, long long ldk, long long ldv, long long lddo, long long lddq, long long lddk, long long lddv,
-                                 float scale, void* stream) {
+                                 float scale, const rb_dropout* drop, void* stream) {
   if (dh != AS_DH) return rb_fail("rb_attn_small_bwd: head_dim must be 64 (got %d)", dh);
   if (S < 1 || S > 128) return rb_fail("rb_attn_small_bwd: 1 <= S <= 128 tokens (got %d)", S);
-  const size_t smem = (static_cast<size_t>(4) * S * AS_PAD + static_cast<size_t>(2) * S * S) * sizeof(float);
+  const DropK dk = make_dropk(drop);
+  const size_t smem = (static_cast<size_t>(4) * S * AS_PAD + static_cast<size_t>(dk.seed ? 3 : 2) * S * S) * sizeof(float);
   if (smem > 220 * 1024) return rb_fail("rb_attn_small_bwd: S = %d exceeds the shared-memory plan", S);
   static bool cfg = false;
   if (!cfg) { RB_CUDA(cudaFuncSetAttribute(attn_small_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); cfg = true; }
   attn_small_bwd_kernel<<<B * H, 128, smem, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(Q), static_cast<const __nv_bfloat16*>(K), static_cast<const __nv_bfloat16*>(V), static_cast<const __nv_bfloat16*>(dO), P,
-      static_cast<__nv_bfloat16*>(dQ), static_cast<__nv_bfloat16*>(dK), static_cast<__nv_bfloat16*>(dV), H, S, ldq, ldk, ldv, lddo, lddq, lddk, lddv, scale);
+      static_cast<__nv_bfloat16*>(dQ), static_cast<__nv_bfloat16*>(dK), static_cast<__nv_bfloat16*>(dV), H, S, ldq, ldk, ldv, lddo, lddq, lddk, lddv, scale, dk);
   RB_CUDA(cudaGetLastError());
   return 0;
 }

@@ -170,6 +170,24 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
 
+// ----------------------------------------------------------------------------- counter-based dropout (rb_dropout)
+struct DropK {  // device-side form of rb_dropout; seed == nullptr: off
+  const unsigned long long* seed;
+  uint32_t site, thr;
+  float scale;
+};
+__host__ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x21f0aaadu; x ^= x >> 15; x *= 0x735a2d97u; x ^= x >> 15;
+  return x;
+}
+__device__ __forceinline__ uint32_t drop_key(const DropK& d) {
+  const unsigned long long s = *d.seed;
+  return mix32(static_cast<uint32_t>(s) ^ mix32(static_cast<uint32_t>(s >> 32) + d.site * 0x9E3779B9u));
+}
+// word `ctr` of a site covers the two elements (row, 2c) and (row, 2c + 1), ctr = row * ((cols + 1) / 2) + c
+__device__ __forceinline__ uint32_t drop_word(uint32_t key, uint32_t ctr) { return mix32(ctr * 0x9E3779B1u + key); }
+__device__ __forceinline__ bool drop_keep(uint32_t word, int lane, uint32_t thr) { return ((word >> (lane * 16)) & 0xFFFFu) >= thr; }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

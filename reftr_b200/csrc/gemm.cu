@@ -56,6 +56,10 @@ struct GemmKParams {
   uint32_t off_out, out_slot_bytes, out_off_f32;         // out_slots per team, 2 teams
   uint32_t off_bars;
   rb_geom geom;
+  DropK drop;          // dropout on relu?(acc + bias), before the residuals
+  int drop_gshift;     // the site's element of output column n is n >> drop_gshift
+  uint32_t drop_wpr;   // 32-bit random words per row of the site
+  float mask_scale;    // multiplies what mask_src keeps
 };
 
 __device__ __forceinline__ bool row_is_interior(const rb_geom& g, long long row) {
@@ -253,6 +257,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const bool store_thread = (threadIdx.x == 64 + team * 128);
     const int sw128 = r & 7;
     const bool use_ein = has_ein && !p.atomic;
+    const bool use_drop = p.drop.seed != nullptr;
+    const uint32_t dkey = use_drop ? drop_key(p.drop) : 0u;
     int tcount = 0, g = 0, o = 0;
     for (int t = blockIdx.x; t < p.tiles_total; t += gridDim.x) {
       const TileCoord c = tile_coord(p, t);
@@ -323,6 +329,28 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 if (hc0 + j < p.N) f[j] += __ldg(p.bias + hc0 + j);
             }
           }
+          if (use_drop) {
+            if (p.relu) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+            }
+            const uint32_t wbase = static_cast<uint32_t>(orow) * p.drop_wpr;
+            if (p.drop_gshift == 0) {
+              const uint32_t c0 = wbase + static_cast<uint32_t>(hc0 >> 1);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const uint32_t w = drop_word(dkey, c0 + j);
+                f[2 * j] = drop_keep(w, 0, p.drop.thr) ? f[2 * j] * p.drop.scale : 0.f;
+                f[2 * j + 1] = drop_keep(w, 1, p.drop.thr) ? f[2 * j + 1] * p.drop.scale : 0.f;
+              }
+            } else {  // groups of >= 32 columns (whole heads): one decision for this 32-column half
+              const int e = hc0 >> p.drop_gshift;
+              const uint32_t w = drop_word(dkey, wbase + static_cast<uint32_t>(e >> 1));
+              const float ks = drop_keep(w, e & 1, p.drop.thr) ? p.drop.scale : 0.f;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] *= ks;
+            }
+          }
           if (p.has_res) {
             const uint8_t* row = ein + r * 128;
 #pragma unroll
@@ -340,7 +368,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               f[4 * j] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
             }
           }
-          if (p.relu) {
+          if (p.relu && !use_drop) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
           }
@@ -352,8 +380,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               const uint32_t w[4] = {tt.x, tt.y, tt.z, tt.w};
 #pragma unroll
               for (int ee = 0; ee < 4; ++ee) {
-                if (!(bf16_lo(w[ee]) > 0.f)) f[8 * j + 2 * ee] = 0.f;
-                if (!(bf16_hi(w[ee]) > 0.f)) f[8 * j + 2 * ee + 1] = 0.f;
+                f[8 * j + 2 * ee] = (bf16_lo(w[ee]) > 0.f) ? f[8 * j + 2 * ee] * p.mask_scale : 0.f;
+                f[8 * j + 2 * ee + 1] = (bf16_hi(w[ee]) > 0.f) ? f[8 * j + 2 * ee + 1] * p.mask_scale : 0.f;
               }
             }
           }
@@ -458,6 +486,17 @@ extern "C" int rb_gemm(const rb_gemm_args* a, void* stream) {
   kp.bias = a->bias;
   kp.relu = a->relu; kp.atomic = a->atomic; kp.geom = a->geom;
   kp.kblocks = (a->K + BK - 1) / BK;
+  kp.drop = make_dropk(a->drop);
+  kp.drop_gshift = a->drop_gshift;
+  kp.mask_scale = a->mask_scale == 0.f ? 1.f : a->mask_scale;
+  if (kp.drop.seed) {
+    if (a->atomic) return rb_fail("rb_gemm: dropout is not available in atomic mode");
+    if (a->relu && (a->res || a->res32)) return rb_fail("rb_gemm: dropout with ReLU after a residual is not defined");
+    if ((a->drop_gshift != 0 && (a->drop_gshift < 5 || a->drop_gshift > 16)) || (a->drop_gshift == 0 && (a->N & 1))) return rb_fail("rb_gemm: dropout needs an even N (gshift 0) or gshift >= 5");
+    const long long cols = (static_cast<long long>(a->N) + (1LL << a->drop_gshift) - 1) >> a->drop_gshift;
+    kp.drop_wpr = static_cast<uint32_t>((cols + 1) >> 1);
+    if ((static_cast<long long>(a->M) + a->out_row_off) * kp.drop_wpr >= (1LL << 32)) return rb_fail("rb_gemm: dropout site too large for a 32-bit counter");
+  }
   const int nsm = sm_count();
   const long long tiles_m = (a->M + BM - 1) / BM;
   const long long k_iters = a->mode == 0 ? static_cast<long long>(a->taps) * kp.kblocks : (kp.kblocks + kp.splits - 1) / kp.splits;

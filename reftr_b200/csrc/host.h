@@ -5,6 +5,7 @@
 #include <stdint.h>
 
 #include "../../include/reftr_b200.h"
+#include "common.cuh"
 
 namespace rb {
 int rb_fail(const char* fmt, ...);
@@ -16,12 +17,26 @@ int make_tmap_2d(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t row
 int make_tmap_2d_f32(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t rows, uint64_t pitch_bytes, uint32_t box_inner,
                      uint32_t box_rows);
 int sm_count();
+// host rb_dropout (nullable) -> kernel parameter; off when NULL / seed == NULL / p <= 0
+inline DropK make_dropk(const rb_dropout* d) {
+  DropK k;
+  k.seed = nullptr; k.site = 0; k.thr = 0; k.scale = 1.f;
+  if (d && d->seed && d->p > 0.f) {
+    uint32_t thr = static_cast<uint32_t>(d->p * 65536.f + 0.5f);
+    if (thr > 65535u) thr = 65535u;
+    k.seed = static_cast<const unsigned long long*>(d->seed);
+    k.site = static_cast<uint32_t>(d->site);
+    k.thr = thr;
+    k.scale = 65536.f / static_cast<float>(65536u - thr);
+  }
+  return k;
+}
 // SIMT attention (attention.cu); the C-ABI entry points in attention_tc.cu fall back to these for short query counts
 int attn_fwd_simt(const void* Q, const void* K, const void* V, const void* kpm, void* O, float* LSE, int B, int H, int dh, int Tq, int Sk, long long ldq,
-                  long long ldk, long long ldv, long long ldo, float scale, void* stream);
+                  long long ldk, long long ldv, long long ldo, float scale, const rb_dropout* drop, void* stream);
 int attn_bwd_simt(const void* Q, const void* K, const void* V, const void* kpm, const void* O, const void* dO, const float* LSE, void* dQ, void* dK,
                   void* dV, float* Dbuf, int B, int H, int dh, int Tq, int Sk, long long ldq, long long ldk, long long ldv, long long ldo,
-                  long long lddo, long long lddq, long long lddk, long long lddv, float scale, void* stream);
+                  long long lddo, long long lddq, long long lddk, long long lddv, float scale, const rb_dropout* drop, void* stream);
 }  // namespace rb
 
 #define RB_CUDA(expr)                                                                         \

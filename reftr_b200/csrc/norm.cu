@@ -19,7 +19,8 @@ constexpr int LN_D = 256;
 // Replaces nn.LayerNorm at transformer.py:176/:181/:242/:248/:252, reftr_transformer.py:17/:21/:38.
 __global__ void layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, long long rows,
                                      float eps, float* __restrict__ y32, __nv_bfloat16* __restrict__ yb, const float* __restrict__ pos32,
-                                     __nv_bfloat16* __restrict__ ypb, int relu, float* __restrict__ mean_out, float* __restrict__ rstd_out, RowMap map) {
+                                     __nv_bfloat16* __restrict__ ypb, int relu, float* __restrict__ mean_out, float* __restrict__ rstd_out, RowMap map,
+                                     DropK drop) {
   const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -47,6 +48,16 @@ __global__ void layernorm_fwd_kernel(const float* __restrict__ x, const float* _
     v[i] = v[i] * rstd * g[i] + bb[i];
     if (relu) v[i] = fmaxf(v[i], 0.f);
   }
+  if (drop.seed) {  // nn.Dropout after the ReLU of mlp_mapping (reftr_transformer.py:19); site tensor = the compact [rows, 256]
+    const uint32_t key = drop_key(drop);
+    const uint32_t c0 = static_cast<uint32_t>(row) * (LN_D / 2) + lane * 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t w = drop_word(key, c0 + i);
+      v[2 * i] = drop_keep(w, 0, drop.thr) ? v[2 * i] * drop.scale : 0.f;
+      v[2 * i + 1] = drop_keep(w, 1, drop.thr) ? v[2 * i + 1] * drop.scale : 0.f;
+    }
+  }
   const long long orow = map(row);
   if (y32) {
     float4* o = reinterpret_cast<float4*>(y32 + orow * LN_D + lane * 8);
@@ -70,11 +81,12 @@ __global__ void layernorm_fwd_kernel(const float* __restrict__ x, const float* _
 // ------------------------------------------------------------------------------------------------ LayerNorm bwd
 // dy is read at mapped rows (+ optional second addend dy2 at the same rows); y (mapped rows) gives the ReLU mask.
 // dx = rstd*(g - mean(g) - xhat*mean(g*xhat)), g = dy*gamma; dgamma += dy*xhat, dbeta += dy (atomics, once per warp).
-__global__ void layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ dy2, const float* __restrict__ y_relu,
+__global__ void layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ dy2, const float* __restrict__ y_relu, float relu_scale,
                                      const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ mean,
                                      const float* __restrict__ rstd, long long rows, float* __restrict__ dx32, __nv_bfloat16* __restrict__ dxb,
-                                     float* __restrict__ dgamma, float* __restrict__ dbeta, RowMap map) {
+                                     float* __restrict__ dgamma, float* __restrict__ dbeta, RowMap map, DropK odrop) {
   const int lane = threadIdx.x & 31;
+  const uint32_t okey = odrop.seed ? drop_key(odrop) : 0u;
   const int warps_per_block = blockDim.x >> 5;
   const long long warp_global = static_cast<long long>(blockIdx.x) * warps_per_block + (threadIdx.x >> 5);
   const long long n_warps = static_cast<long long>(gridDim.x) * warps_per_block;
@@ -96,8 +108,7 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ dy, const float* 
       a = yr[0]; b = yr[1];
       const float yy[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        if (!(yy[i] > 0.f)) d[i] = 0.f;
+      for (int i = 0; i < 8; ++i) d[i] = (yy[i] > 0.f) ? d[i] * relu_scale : 0.f;
     }
     const float4* xr = reinterpret_cast<const float4*>(x + row * LN_D + lane * 8);
     a = xr[0]; b = xr[1];
@@ -123,6 +134,15 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ dy, const float* 
       p[1] = make_float4(o[4], o[5], o[6], o[7]);
     }
     if (dxb) {
+      if (odrop.seed) {  // the bf16 copy feeds the backward of the layer whose output was dropped before this LN's residual sum
+        const uint32_t c0 = static_cast<uint32_t>(row) * (LN_D / 2) + lane * 4;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t w = drop_word(okey, c0 + i);
+          o[2 * i] = drop_keep(w, 0, odrop.thr) ? o[2 * i] * odrop.scale : 0.f;
+          o[2 * i + 1] = drop_keep(w, 1, odrop.thr) ? o[2 * i + 1] * odrop.scale : 0.f;
+        }
+      }
       uint4 p;
       p.x = pack_bf16x2(o[0], o[1]); p.y = pack_bf16x2(o[2], o[3]); p.z = pack_bf16x2(o[4], o[5]); p.w = pack_bf16x2(o[6], o[7]);
       *reinterpret_cast<uint4*>(dxb + row * LN_D + lane * 8) = p;
@@ -389,27 +409,28 @@ using namespace rb;
 
 extern "C" int rb_layernorm_fwd(const float* x, const float* gamma, const float* beta, long long rows, int D, float eps, float* y32, void* yb,
                                 const float* pos32, void* ypb, int relu, float* mean, float* rstd, int map_group, int map_stride, int map_offset,
-                                void* stream) {
+                                const rb_dropout* drop, void* stream) {
   if (D != LN_D) return rb_fail("rb_layernorm_fwd: only D == 256 is built (got %d)", D);
   if (rows <= 0) return 0;
   if (ypb && !pos32) return rb_fail("rb_layernorm_fwd: ypb needs pos32");
   RowMap m{map_group, map_stride, map_offset};
   layernorm_fwd_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, gamma, beta, rows, eps, y32, static_cast<__nv_bfloat16*>(yb), pos32, static_cast<__nv_bfloat16*>(ypb), relu, mean, rstd, m);
+      x, gamma, beta, rows, eps, y32, static_cast<__nv_bfloat16*>(yb), pos32, static_cast<__nv_bfloat16*>(ypb), relu, mean, rstd, m, make_dropk(drop));
   RB_CUDA(cudaGetLastError());
   return 0;
 }
 
-extern "C" int rb_layernorm_bwd(const float* dy, const float* dy2, const float* y_relu, const float* x, const float* gamma, const float* mean,
-                                const float* rstd, long long rows, int D, float* dx32, void* dxb, float* dgamma, float* dbeta, int map_group,
-                                int map_stride, int map_offset, void* stream) {
+extern "C" int rb_layernorm_bwd(const float* dy, const float* dy2, const float* y_relu, float relu_scale, const float* x, const float* gamma,
+                                const float* mean, const float* rstd, long long rows, int D, float* dx32, void* dxb, float* dgamma, float* dbeta,
+                                int map_group, int map_stride, int map_offset, const rb_dropout* dxb_drop, void* stream) {
   if (D != LN_D) return rb_fail("rb_layernorm_bwd: only D == 256 is built (got %d)", D);
   if (rows <= 0) return 0;
   RowMap m{map_group, map_stride, map_offset};
   long long blocks = (rows + 7) / 8;
   if (blocks > 148) blocks = 148;  // one per SM; warps stride over rows, dgamma/dbeta cost one atomic per column per block
   layernorm_bwd_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      dy, dy2, y_relu, x, gamma, mean, rstd, rows, dx32, static_cast<__nv_bfloat16*>(dxb), dgamma, dbeta, m);
+      dy, dy2, y_relu, relu_scale == 0.f ? 1.f : relu_scale, x, gamma, mean, rstd, rows, dx32, static_cast<__nv_bfloat16*>(dxb), dgamma, dbeta, m,
+      make_dropk(dxb_drop));
   RB_CUDA(cudaGetLastError());
   return 0;
 }

@@ -205,10 +205,38 @@ class RefTREngine:
         self._vsig, self._pack_dev = None, None
         self.force_eager = False  # bench.py: run the next steps launch by launch on the graphed workspace (profiling)
         self.launches = 0
+        # ---- dropout (train mode): counter-based, nothing stored; ONE device seed rewritten before every forward --------
+        self.p_drop = float(vt.dropout)
+        self.train_mode = False
+        self.seed_dev = None
+        self.next_seed = None  # tests: force the seed of the next forward
+        self.last_seed = None
+        self._drops = {}
 
     # ------------------------------------------------------------------------------------------------------------
     def param_list(self):
         return [p for _, p in self.named]
+
+    def drop(self, name, p=None):
+        """Handle of the dropout site `name` (rb_dropout), or None when dropout is inactive (eval mode / p == 0)."""
+        p = self.p_drop if p is None else float(p)
+        if not self.train_mode or p <= 0.0:
+            return None
+        d = self._drops.get(name)
+        if d is None or d.p != p or d.seed is not self.seed_dev:
+            d = self._drops[name] = ops.Drop(self.seed_dev, name, p)
+        return d
+
+    def _new_seed(self):
+        """One 63-bit seed per forward from torch's CPU generator (so torch.manual_seed governs the masks; ranks differ when
+        their torch seeds differ, main_vg.py:173-177).  Written to the device by a stream-ordered fill: no host sync, and a
+        replayed CUDA graph reads the new value."""
+        if self.next_seed is not None:
+            seed, self.next_seed = int(self.next_seed), None
+        else:
+            seed = int(torch.empty((), dtype=torch.int64).random_().item()) & 0x7FFFFFFFFFFFFFFF
+        self.last_seed = seed
+        self.seed_dev.fill_(seed)
 
     def _prepare(self, device):
         """Re-packs weights whose master copy changed (optimizer step / load_state_dict) and drops captured graphs when
@@ -219,6 +247,8 @@ class RefTREngine:
             self._vsig = None
             self._states = {}
             self.gflat = torch.zeros(self.n_flat, dtype=torch.float32, device=device)
+            self.seed_dev = torch.zeros(1, dtype=torch.int64, device=device)
+            self._drops = {}
         # cheap change detection first (one tuple compare); the per-pack refresh walk only runs when something moved
         vsig = tuple(t._version for t in self._tracked)
         if vsig != self._vsig or device != self._pack_dev:
@@ -258,7 +288,10 @@ class RefTREngine:
         B, L = sent_mask.shape[:2]
         T = n_ph * self.model.num_queries_per_phrase
         Lp = ph_ids.shape[-1] if (native and ph_ids is not None) else 0
-        key = (tuple(img.shape), L, n_ph, bool(want_seg), native, Lp)
+        self.train_mode = bool(self.model.training)
+        if self.train_mode:
+            self._new_seed()
+        key = (tuple(img.shape), L, n_ph, bool(want_seg), native, Lp, self.train_mode)
         st = self._state(key)
         self._cur = st
         self.ws = ws = st["ws"]
@@ -572,7 +605,8 @@ class RefTREngine:
         a1 = ws.get(key + ".a1", [rows, D], torch.float32)
         a1b = ws.get(key + ".a1b", [rows, D])
         m0, r0 = ws.get(key + ".m0", [rows], torch.float32), ws.get(key + ".r0", [rows], torch.float32)
-        ops.layernorm_fwd(y0, seq[1].weight, seq[1].bias, rows, y32=a1, yb=a1b, relu=True, mean=m0, rstd=r0, eps=seq[1].eps)
+        dr = self.drop(key + ".drop", seq[3].p)  # nn.Dropout(0.1) after the first ReLU (reftr_transformer.py:19)
+        ops.layernorm_fwd(y0, seq[1].weight, seq[1].bias, rows, y32=a1, yb=a1b, relu=True, mean=m0, rstd=r0, eps=seq[1].eps, drop=dr)
         y1 = ws.get(key + ".y1", [rows, D], torch.float32)
         ops.gemm(a1b, packs[1].wb, rows, D, D, bias=packs[1].bias, out32=y1)
         m1, r1 = ws.get(key + ".m1", [rows], torch.float32), ws.get(key + ".r1", [rows], torch.float32)
@@ -594,8 +628,9 @@ class RefTREngine:
         ops.gemm(d1b, packs[1].wt, rows, D, D, out32=da1)
         d0 = ws.get(key + ".d0", [rows, D], torch.float32)
         d0b = ws.get(key + ".d0b", [rows, D])
-        ops.layernorm_bwd(da1, y0, seq[1].weight, m0, r0, rows, y_relu=a1, dx32=d0, dxb=d0b, dgamma=self.G(seq[1].weight),
-                          dbeta=self.G(seq[1].bias))
+        dr = self.drop(key + ".drop", seq[3].p)  # a1 > 0 <=> ReLU passed AND kept; kept gradients are scaled by 1/(1-p)
+        ops.layernorm_bwd(da1, y0, seq[1].weight, m0, r0, rows, y_relu=a1, relu_scale=dr.scale if dr else 1.0, dx32=d0, dxb=d0b,
+                          dgamma=self.G(seq[1].weight), dbeta=self.G(seq[1].bias))
         self.colsum(d0, self.G(seq[0].bias))
         self.wgrad_linear(d0b, A, self.G(seq[0].weight), D, K, rows)
         if not need_dA:
@@ -617,18 +652,18 @@ class RefTREngine:
         ops.gemm(xb, e.inp.wb[2 * D:], rows, D, D, bias=e.inp.bias[2 * D:], out=qkv[:, 2 * D:])
         o = ws.get(k + ".o", [rows, D])
         lse = ws.get(k + ".lse", [B, NH, S], torch.float32)
-        ops.attn_fwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], kpm, o, lse, B, NH, S, S, DH ** -0.5)
+        ops.attn_fwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], kpm, o, lse, B, NH, S, S, DH ** -0.5, drop=self.drop(k + ".attn"))
         y1 = ws.get(k + ".y1", [rows, D], torch.float32)
-        ops.gemm(o, e.out.wb, rows, D, D, bias=e.out.bias, res32=x32, out32=y1)
+        ops.gemm(o, e.out.wb, rows, D, D, bias=e.out.bias, res32=x32, out32=y1, drop=self.drop(k + ".drop1"))
         x1 = ws.get(k + ".x1", [rows, D], torch.float32)
         x1b = ws.get(k + ".x1b", [rows, D])
         m1, r1 = ws.get(k + ".m1", [rows], torch.float32), ws.get(k + ".r1", [rows], torch.float32)
         ops.layernorm_fwd(y1, lay.norm1.weight, lay.norm1.bias, rows, y32=x1, yb=x1b, mean=m1, rstd=r1, eps=lay.norm1.eps)
         dff = e.l1.N
         h = ws.get(k + ".h", [rows, dff])
-        ops.gemm(x1b, e.l1.wb, rows, dff, D, bias=e.l1.bias, relu=True, out=h)
+        ops.gemm(x1b, e.l1.wb, rows, dff, D, bias=e.l1.bias, relu=True, out=h, drop=self.drop(k + ".ffn"))
         y2 = ws.get(k + ".y2", [rows, D], torch.float32)
-        ops.gemm(h, e.l2.wb, rows, D, dff, bias=e.l2.bias, res32=x1, out32=y2)
+        ops.gemm(h, e.l2.wb, rows, D, dff, bias=e.l2.bias, res32=x1, out32=y2, drop=self.drop(k + ".drop2"))
         xo = ws.get(k + ".xo", [rows, D], torch.float32)
         xob = ws.get(k + ".xob", [rows, D])
         xopb = ws.get(k + ".xopb", [rows, D])
@@ -638,15 +673,17 @@ class RefTREngine:
         self.saved[k] = (xb, xpb, qkv, o, lse, y1, m1, r1, x1b, h, y2, m2, r2)
         return xo, xob, xopb
 
-    def _ffn_bwd(self, key, lin1, lin2, mod, dy32, dyb, x_in_b, h, rows, out32):
+    def _ffn_bwd(self, key, lin1, lin2, mod, dy32, dyb, x_in_b, h, rows, out32, drop_out=None, drop_h=None):
         """Shared by encoder and decoder: given dy (= gradient at the FFN's residual sum, fp32 + bf16), accumulates the
-        weight/bias gradients of linear1/linear2 and writes out32 = dy + d(FFN input)."""
+        weight/bias gradients of linear1/linear2 and writes out32 = dy + d(FFN input).  In train mode ``dyb`` already carries the
+        mask of the dropout on linear2's output (``drop_out``; dy32 stays the undropped residual gradient) and ``h`` is the
+        dropped hidden activation, so h > 0 <=> ReLU passed and kept (``drop_h`` gives the 1/(1-p) scale)."""
         ws = self.ws
         dff = lin1.N
-        self.colsum(dy32, self.G(mod.linear2.bias))
+        self.colsum(dyb if drop_out is not None else dy32, self.G(mod.linear2.bias))
         self.wgrad_linear(dyb, h, self.G(mod.linear2.weight), D, dff, rows)
         dh = ws.get(key + ".dh", [rows, dff])
-        ops.gemm(dyb, lin2.wt, rows, dff, D, mask_src=h, out=dh)
+        ops.gemm(dyb, lin2.wt, rows, dff, D, mask_src=h, out=dh, mask_scale=drop_h.scale if drop_h is not None else 1.0)
         self.colsum(dh, self.G(mod.linear1.bias))
         self.wgrad_linear(dh, x_in_b, self.G(mod.linear1.weight), dff, D, rows)
         ops.gemm(dh, lin1.wt, rows, D, dff, res32=dy32, out32=out32)
@@ -660,22 +697,23 @@ class RefTREngine:
         xb, xpb, qkv, o, lse, y1, m1, r1, x1b, h, y2, m2, r2 = self.saved[k]
         dy2 = ws.get(f"encb{l}.dy2", [rows, D], torch.float32)
         dy2b = ws.get(f"encb{l}.dy2b", [rows, D])
+        dr1, dr2 = self.drop(k + ".drop1"), self.drop(k + ".drop2")
         ops.layernorm_bwd(g, y2, lay.norm2.weight, m2, r2, rows, dx32=dy2, dxb=dy2b, dgamma=self.G(lay.norm2.weight),
-                          dbeta=self.G(lay.norm2.bias))
+                          dbeta=self.G(lay.norm2.bias), dxb_drop=dr2)
         g1 = ws.get(f"encb{l}.g1", [rows, D], torch.float32)
-        self._ffn_bwd(f"encb{l}", e.l1, e.l2, lay, dy2, dy2b, x1b, h, rows, g1)
+        self._ffn_bwd(f"encb{l}", e.l1, e.l2, lay, dy2, dy2b, x1b, h, rows, g1, drop_out=dr2, drop_h=self.drop(k + ".ffn"))
         dy1 = ws.get(f"encb{l}.dy1", [rows, D], torch.float32)
         dy1b = ws.get(f"encb{l}.dy1b", [rows, D])
         ops.layernorm_bwd(g1, y1, lay.norm1.weight, m1, r1, rows, dx32=dy1, dxb=dy1b, dgamma=self.G(lay.norm1.weight),
-                          dbeta=self.G(lay.norm1.bias))
-        self.colsum(dy1, self.G(lay.self_attn.out_proj.bias))
+                          dbeta=self.G(lay.norm1.bias), dxb_drop=dr1)
+        self.colsum(dy1b if dr1 is not None else dy1, self.G(lay.self_attn.out_proj.bias))
         self.wgrad_linear(dy1b, o, self.G(lay.self_attn.out_proj.weight), D, D, rows)
         do = ws.get(f"encb{l}.do", [rows, D])
         ops.gemm(dy1b, e.out.wt, rows, D, D, out=do)
         dqkv = ws.get(f"encb{l}.dqkv", [rows, 3 * D])
         dbuf = ws.get(f"encb{l}.dbuf", [B, NH, S], torch.float32)
         ops.attn_bwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], kpm, o, do, lse, dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:], dbuf,
-                     B, NH, S, S, DH ** -0.5)
+                     B, NH, S, S, DH ** -0.5, drop=self.drop(k + ".attn"))
         self.colsum(dqkv, self.G(lay.self_attn.in_proj_bias))
         gw = self.G(lay.self_attn.in_proj_weight)
         self.wgrad_linear(dqkv[:, :2 * D], xpb, gw[:2 * D], 2 * D, D, rows)
@@ -803,15 +841,16 @@ class RefTREngine:
             if T == 1:
                 # one query per sample (every RES/REC config): the self-attention softmax runs over a single key, so its output is
                 # exactly the value projection; q / k projections, the attention kernel and their (exactly zero) gradients are skipped
+                # (train mode: the dropout on that single attention probability zeroes whole heads -- epilogue dropout over [rt, 8])
                 o_s = qkv[:, 2 * D:]
-                ops.gemm(tgtb, d.sa.wb[2 * D:], rt, D, D, bias=d.sa.bias[2 * D:], out=o_s)
+                ops.gemm(tgtb, d.sa.wb[2 * D:], rt, D, D, bias=d.sa.bias[2 * D:], out=o_s, drop=self.drop(k + ".sa"), drop_gshift=5)
             else:
                 ops.gemm(tqb, d.sa.wb[:2 * D], rt, 2 * D, D, bias=d.sa.bias[:2 * D], out=qkv[:, :2 * D])
                 ops.gemm(tgtb, d.sa.wb[2 * D:], rt, D, D, bias=d.sa.bias[2 * D:], out=qkv[:, 2 * D:])
                 o_s = ws.get(k + ".o_s", [rt, D])
-                ops.attn_fwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], qmask, o_s, lse_s, B, NH, T, T, scale)
+                ops.attn_fwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], qmask, o_s, lse_s, B, NH, T, T, scale, drop=self.drop(k + ".sa"))
             y1 = ws.get(k + ".y1", [rt, D], torch.float32)
-            ops.gemm(o_s, d.sa_out.wb, rt, D, D, bias=d.sa_out.bias, res32=tgt32, out32=y1)
+            ops.gemm(o_s, d.sa_out.wb, rt, D, D, bias=d.sa_out.bias, res32=tgt32, out32=y1, drop=self.drop(k + ".drop1"))
             t1 = ws.get(k + ".t1", [rt, D], torch.float32)
             t1qb = ws.get(k + ".t1qb", [rt, D])
             m1, r1 = ws.get(k + ".m1", [rt], torch.float32), ws.get(k + ".r1", [rt], torch.float32)
@@ -822,18 +861,18 @@ class RefTREngine:
             kl, vl = kall[:, l * D:(l + 1) * D], vall[:, l * D:(l + 1) * D]
             o_c = ws.get(k + ".o_c", [rt, D])
             lse_c = ws.get(k + ".lse_c", [B, NH, T], torch.float32)
-            ops.attn_fwd(qc, kl, vl, kpm, o_c, lse_c, B, NH, T, S, scale)
+            ops.attn_fwd(qc, kl, vl, kpm, o_c, lse_c, B, NH, T, S, scale, drop=self.drop(k + ".ca"))
             y2 = ws.get(k + ".y2", [rt, D], torch.float32)
-            ops.gemm(o_c, d.ca_out.wb, rt, D, D, bias=d.ca_out.bias, res32=t1, out32=y2)
+            ops.gemm(o_c, d.ca_out.wb, rt, D, D, bias=d.ca_out.bias, res32=t1, out32=y2, drop=self.drop(k + ".drop2"))
             t2 = ws.get(k + ".t2", [rt, D], torch.float32)
             t2b = ws.get(k + ".t2b", [rt, D])
             m2, r2 = ws.get(k + ".m2", [rt], torch.float32), ws.get(k + ".r2", [rt], torch.float32)
             ops.layernorm_fwd(y2, lay.norm2.weight, lay.norm2.bias, rt, y32=t2, yb=t2b, mean=m2, rstd=r2, eps=lay.norm2.eps)
             dff = d.l1.N
             h = ws.get(k + ".h", [rt, dff])
-            ops.gemm(t2b, d.l1.wb, rt, dff, D, bias=d.l1.bias, relu=True, out=h)
+            ops.gemm(t2b, d.l1.wb, rt, dff, D, bias=d.l1.bias, relu=True, out=h, drop=self.drop(k + ".ffn"))
             y3 = ws.get(k + ".y3", [rt, D], torch.float32)
-            ops.gemm(h, d.l2.wb, rt, D, dff, bias=d.l2.bias, res32=t2, out32=y3)
+            ops.gemm(h, d.l2.wb, rt, D, dff, bias=d.l2.bias, res32=t2, out32=y3, drop=self.drop(k + ".drop3"))
             t3 = ws.get(k + ".t3", [rt, D], torch.float32)
             t3b = ws.get(k + ".t3b", [rt, D])
             t3qb = ws.get(k + ".t3qb", [rt, D])
@@ -875,23 +914,25 @@ class RefTREngine:
                               dbeta=self.G(vt.decoder.norm.bias))
             dy3 = ws.get(f"decb{l}.dy3", [rt, D], torch.float32)
             dy3b = ws.get(f"decb{l}.dy3b", [rt, D])
+            dr1, dr2, dr3 = self.drop(k + ".drop1"), self.drop(k + ".drop2"), self.drop(k + ".drop3")
             ops.layernorm_bwd(gh, y3, lay.norm3.weight, m3, r3, rt, dy2=g_next, dx32=dy3, dxb=dy3b, dgamma=self.G(lay.norm3.weight),
-                              dbeta=self.G(lay.norm3.bias))
+                              dbeta=self.G(lay.norm3.bias), dxb_drop=dr3)
             g2 = ws.get(f"decb{l}.g2", [rt, D], torch.float32)
-            self._ffn_bwd(f"decb{l}", d.l1, d.l2, lay, dy3, dy3b, t2b, h, rt, g2)
+            self._ffn_bwd(f"decb{l}", d.l1, d.l2, lay, dy3, dy3b, t2b, h, rt, g2, drop_out=dr3, drop_h=self.drop(k + ".ffn"))
             dy2 = ws.get(f"decb{l}.dy2", [rt, D], torch.float32)
             dy2b = ws.get(f"decb{l}.dy2b", [rt, D])
             ops.layernorm_bwd(g2, y2, lay.norm2.weight, m2, r2, rt, dx32=dy2, dxb=dy2b, dgamma=self.G(lay.norm2.weight),
-                              dbeta=self.G(lay.norm2.bias))
+                              dbeta=self.G(lay.norm2.bias), dxb_drop=dr2)
             # cross attention
-            self.colsum(dy2, self.G(lay.multihead_attn.out_proj.bias))
+            self.colsum(dy2b if dr2 is not None else dy2, self.G(lay.multihead_attn.out_proj.bias))
             self.wgrad_linear(dy2b, o_c, self.G(lay.multihead_attn.out_proj.weight), D, D, rt)
             do_c = ws.get(f"decb{l}.do_c", [rt, D])
             ops.gemm(dy2b, d.ca_out.wt, rt, D, D, out=do_c)
             dqc = ws.get(f"decb{l}.dqc", [rt, D])
             dbuf = ws.get(f"decb{l}.dbuf", [B, NH, T], torch.float32)
             cs = slice(l * D, (l + 1) * D)
-            ops.attn_bwd(qc, kall[:, cs], vall[:, cs], kpm, o_c, do_c, lse_c, dqc, dkall[:, cs], dvall[:, cs], dbuf, B, NH, T, S, scale)
+            ops.attn_bwd(qc, kall[:, cs], vall[:, cs], kpm, o_c, do_c, lse_c, dqc, dkall[:, cs], dvall[:, cs], dbuf, B, NH, T, S, scale,
+                         drop=self.drop(k + ".ca"))
             gw = self.G(lay.multihead_attn.in_proj_weight)
             gb = self.G(lay.multihead_attn.in_proj_bias)
             self.colsum(dqc, gb[:D])
@@ -906,12 +947,15 @@ class RefTREngine:
             dy1 = ws.get(f"decb{l}.dy1", [rt, D], torch.float32)
             dy1b = ws.get(f"decb{l}.dy1b", [rt, D])
             ops.layernorm_bwd(g1, y1, lay.norm1.weight, m1, r1, rt, dx32=dy1, dxb=dy1b, dgamma=self.G(lay.norm1.weight),
-                              dbeta=self.G(lay.norm1.bias))
+                              dbeta=self.G(lay.norm1.bias), dxb_drop=dr1)
             # self attention
-            self.colsum(dy1, self.G(lay.self_attn.out_proj.bias))
+            self.colsum(dy1b if dr1 is not None else dy1, self.G(lay.self_attn.out_proj.bias))
             self.wgrad_linear(dy1b, o_s, self.G(lay.self_attn.out_proj.weight), D, D, rt)
             do_s = ws.get(f"decb{l}.do_s", [rt, D])
-            ops.gemm(dy1b, d.sa_out.wt, rt, D, D, out=do_s)
+            if T == 1:  # the head dropout of the forward shortcut, applied to d(attention output) = d(value projection)
+                ops.gemm(dy1b, d.sa_out.wt, rt, D, D, out=do_s, drop=self.drop(k + ".sa"), drop_gshift=5)
+            else:
+                ops.gemm(dy1b, d.sa_out.wt, rt, D, D, out=do_s)
             g_prev = gbuf[l & 1]
             gws = self.G(lay.self_attn.in_proj_weight)
             if T == 1:  # d(value projection) = d(attention output); q / k receive no gradient
@@ -921,7 +965,7 @@ class RefTREngine:
             else:
                 dqkv = ws.get(f"decb{l}.dqkv", [rt, 3 * D])
                 ops.attn_bwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], qmask, o_s, do_s, lse_s, dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:],
-                             dbuf, B, NH, T, T, scale)
+                             dbuf, B, NH, T, T, scale, drop=self.drop(k + ".sa"))
                 self.colsum(dqkv, self.G(lay.self_attn.in_proj_bias))
                 self.wgrad_linear(dqkv[:, :2 * D], tqb, gws[:2 * D], 2 * D, D, rt)
                 self.wgrad_linear(dqkv[:, 2 * D:], tgtb, gws[2 * D:], D, D, rt)

@@ -5,7 +5,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import GemmArgs, Geom
+from ._lib import Dropout, GemmArgs, Geom
 
 
 PROFILE = None  # bench.py sets this to a list: every rb_gemm launch descriptor is then recorded -> (args, flops, signature)
@@ -30,6 +30,32 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
 
+def site_id(name):
+    """Stable 31-bit id of a named dropout site (rb_dropout.site)."""
+    import zlib
+    return zlib.crc32(name.encode()) & 0x7FFFFFFF
+
+
+class Drop:
+    """Host handle of one dropout site: ``seed`` is a 1-element int64 device tensor the engine rewrites every step."""
+
+    def __init__(self, seed, name, p):
+        assert seed.dtype == torch.int64 and seed.numel() == 1
+        self.seed, self.name, self.p = seed, name, float(p)
+        self.site = site_id(name)
+        thr = min(int(self.p * 65536.0 + 0.5), 65535)
+        self.thr = thr
+        self.scale = 65536.0 / (65536 - thr)   # what kept values are multiplied by (1 / (1 - p) with p rounded to 1/65536)
+        self.c = Dropout(seed.data_ptr(), self.site, self.p)
+
+    def ptr(self):
+        return C.addressof(self.c)
+
+
+def _dp(drop):
+    return None if drop is None else drop.ptr()
+
+
 def make_geom(mode=0, Wp=0, HpWp=0, H=0, W=0, Rs=0):
     return Geom(mode, Wp, HpWp, H, W, Rs)
 
@@ -39,7 +65,8 @@ def _check_2d(t, dtype, name):
 
 
 def gemm(A, B, M, N, K, *, mode=0, taps=((0, 0),), bias=None, res=None, res32=None, mask_src=None, relu=False,
-         out=None, out32=None, atomic=False, splits=1, geom=None, out_row_off=0, out32_z_stride=0, block_n=0):
+         out=None, out32=None, atomic=False, splits=1, geom=None, out_row_off=0, out32_z_stride=0, block_n=0, drop=None, drop_gshift=0,
+         mask_scale=1.0):
     """See rb_gemm in include/reftr_b200.h.  ``taps`` is a sequence of (a_rowoff, b_koff) pairs."""
     _check_2d(A, torch.bfloat16, "A")
     _check_2d(B, torch.bfloat16, "B")
@@ -78,6 +105,9 @@ def gemm(A, B, M, N, K, *, mode=0, taps=((0, 0),), bias=None, res=None, res32=No
     a.atomic = int(atomic)
     if geom is not None:
         a.geom = geom
+    if drop is not None:
+        a.drop, a.drop_gshift = drop.ptr(), drop_gshift
+    a.mask_scale = mask_scale
     if PROFILE is not None:  # bench.py: keep the launch descriptor so the launch can be re-issued and timed in isolation
         PROFILE.append((a, 2.0 * M * N * K * len(taps), (mode, M, N, K, len(taps), bool(atomic), res is not None, res32 is not None,
                                                        mask_src is not None, out32 is not None)))
@@ -166,14 +196,15 @@ def add(a, b, y=None, yb=None):
 
 
 def layernorm_fwd(x, gamma, beta, rows, *, y32=None, yb=None, pos32=None, ypb=None, relu=False, mean=None, rstd=None, rowmap=(0, 0, 0),
-                  eps=1e-5):
+                  eps=1e-5, drop=None):
     _lib.call("rb_layernorm_fwd", _p(x), _p(gamma), _p(beta), rows, x.shape[-1], eps, _p(y32), _p(yb), _p(pos32), _p(ypb), int(relu),
-              _p(mean), _p(rstd), rowmap[0], rowmap[1], rowmap[2], _s())
+              _p(mean), _p(rstd), rowmap[0], rowmap[1], rowmap[2], _dp(drop), _s())
 
 
-def layernorm_bwd(dy, x, gamma, mean, rstd, rows, *, dy2=None, y_relu=None, dx32=None, dxb=None, dgamma=None, dbeta=None, rowmap=(0, 0, 0)):
-    _lib.call("rb_layernorm_bwd", _p(dy), _p(dy2), _p(y_relu), _p(x), _p(gamma), _p(mean), _p(rstd), rows, x.shape[-1], _p(dx32), _p(dxb),
-              _p(dgamma), _p(dbeta), rowmap[0], rowmap[1], rowmap[2], _s())
+def layernorm_bwd(dy, x, gamma, mean, rstd, rows, *, dy2=None, y_relu=None, relu_scale=1.0, dx32=None, dxb=None, dgamma=None, dbeta=None,
+                  rowmap=(0, 0, 0), dxb_drop=None):
+    _lib.call("rb_layernorm_bwd", _p(dy), _p(dy2), _p(y_relu), relu_scale, _p(x), _p(gamma), _p(mean), _p(rstd), rows, x.shape[-1], _p(dx32),
+              _p(dxb), _p(dgamma), _p(dbeta), rowmap[0], rowmap[1], rowmap[2], _dp(dxb_drop), _s())
 
 
 def groupnorm_tokens_fwd(x, gamma, beta, B, h, w, S, L, y32, yb, pos32, ypb, mean, rstd, eps=1e-5):
@@ -196,14 +227,14 @@ def embed_grad(dpos, B, S, L, d_lang_pos, d_token_type, d_level):
     _lib.call("rb_embed_grad", _p(dpos), B, S, L, _p(d_lang_pos), _p(d_token_type), _p(d_level), _s())
 
 
-def attn_fwd(Q, K, V, kpm, O, LSE, B, H, Tq, Sk, scale):
+def attn_fwd(Q, K, V, kpm, O, LSE, B, H, Tq, Sk, scale, drop=None):
     _lib.call("rb_attn_fwd", _p(Q), _p(K), _p(V), _p(kpm), _p(O), _p(LSE), B, H, 32, Tq, Sk, Q.stride(0), K.stride(0), V.stride(0),
-              O.stride(0), scale, _s())
+              O.stride(0), scale, _dp(drop), _s())
 
 
-def attn_bwd(Q, K, V, kpm, O, dO, LSE, dQ, dK, dV, Dbuf, B, H, Tq, Sk, scale):
+def attn_bwd(Q, K, V, kpm, O, dO, LSE, dQ, dK, dV, Dbuf, B, H, Tq, Sk, scale, drop=None):
     _lib.call("rb_attn_bwd", _p(Q), _p(K), _p(V), _p(kpm), _p(O), _p(dO), _p(LSE), _p(dQ), _p(dK), _p(dV), _p(Dbuf), B, H, 32, Tq, Sk,
-              Q.stride(0), K.stride(0), V.stride(0), O.stride(0), dO.stride(0), dQ.stride(0), dK.stride(0), dV.stride(0), scale, _s())
+              Q.stride(0), K.stride(0), V.stride(0), O.stride(0), dO.stride(0), dQ.stride(0), dK.stride(0), dV.stride(0), scale, _dp(drop), _s())
 
 
 def qenc_pool_fwd(k, q, v, mask, B, L, n_ph, att, c):
@@ -284,12 +315,13 @@ def bert_embed_bwd(d, ids, L, dword, dpos, dtype0):
     _lib.call("rb_bert_embed_bwd", _p(d), _p(ids), ids.numel(), L, d.shape[1], _p(dword), _p(dpos), _p(dtype0), _s())
 
 
-def ln_wide_fwd(x, gamma, beta, rows, *, y32=None, yb=None, mean=None, rstd=None, eps=1e-12):
-    _lib.call("rb_ln_wide_fwd", _p(x), _p(gamma), _p(beta), rows, x.shape[-1], eps, _p(y32), _p(yb), _p(mean), _p(rstd), _s())
+def ln_wide_fwd(x, gamma, beta, rows, *, y32=None, yb=None, mean=None, rstd=None, eps=1e-12, drop=None):
+    _lib.call("rb_ln_wide_fwd", _p(x), _p(gamma), _p(beta), rows, x.shape[-1], eps, _p(y32), _p(yb), _p(mean), _p(rstd), _dp(drop), _s())
 
 
-def ln_wide_bwd(dy, x, gamma, mean, rstd, rows, *, dy2=None, dx32=None, dxb=None, dgamma=None, dbeta=None):
-    _lib.call("rb_ln_wide_bwd", _p(dy), _p(dy2), _p(x), _p(gamma), _p(mean), _p(rstd), rows, x.shape[-1], _p(dx32), _p(dxb), _p(dgamma), _p(dbeta), _s())
+def ln_wide_bwd(dy, x, gamma, mean, rstd, rows, *, dy2=None, dx32=None, dxb=None, dgamma=None, dbeta=None, dy_drop=None, dxb_drop=None):
+    _lib.call("rb_ln_wide_bwd", _p(dy), _p(dy2), _p(x), _p(gamma), _p(mean), _p(rstd), rows, x.shape[-1], _p(dx32), _p(dxb), _p(dgamma), _p(dbeta),
+              _dp(dy_drop), _dp(dxb_drop), _s())
 
 
 def gelu_fwd(x, y):
@@ -308,13 +340,14 @@ def tanh_bwd(dy, y, dx=None, dxb=None):
     _lib.call("rb_tanh_bwd", _p(dy), _p(y), _p(dx), _p(dxb), y.numel(), _s())
 
 
-def attn_small_fwd(Q, K, V, mask, O, P, B, H, S, scale):
-    _lib.call("rb_attn_small_fwd", _p(Q), _p(K), _p(V), _p(mask), _p(O), _p(P), B, H, 64, S, Q.stride(0), K.stride(0), V.stride(0), O.stride(0), scale, _s())
+def attn_small_fwd(Q, K, V, mask, O, P, B, H, S, scale, drop=None):
+    _lib.call("rb_attn_small_fwd", _p(Q), _p(K), _p(V), _p(mask), _p(O), _p(P), B, H, 64, S, Q.stride(0), K.stride(0), V.stride(0), O.stride(0), scale,
+              _dp(drop), _s())
 
 
-def attn_small_bwd(Q, K, V, dO, P, dQ, dK, dV, B, H, S, scale):
+def attn_small_bwd(Q, K, V, dO, P, dQ, dK, dV, B, H, S, scale, drop=None):
     _lib.call("rb_attn_small_bwd", _p(Q), _p(K), _p(V), _p(dO), _p(P), _p(dQ), _p(dK), _p(dV), B, H, 64, S, Q.stride(0), K.stride(0), V.stride(0),
-              dO.stride(0), dQ.stride(0), dK.stride(0), dV.stride(0), scale, _s())
+              dO.stride(0), dQ.stride(0), dK.stride(0), dV.stride(0), scale, _dp(drop), _s())
 
 
 def box_loss(boxes, tgt, valid, inv_norm, inv_norm_dev, losses, dl1, dgiou):

@@ -25,6 +25,21 @@ def launch_count():
     return _LAUNCHES[0]
 
 
+class Drop:
+    """Emulation of reftr_b200.ops.Drop (one dropout site; the seed tensor lives on the CPU here)."""
+
+    def __init__(self, seed, name, p):
+        import dropout_ref
+        self.seed, self.name, self.p = seed, name, float(p)
+        self.site = dropout_ref.site_id(name)
+        self.thr, self.scale = dropout_ref.thr_scale(self.p)
+
+    def mask(self, rows, cols):
+        """fp32 [rows, cols]: 0 where dropped, scale where kept."""
+        import dropout_ref
+        return dropout_ref.mask_scale(int(self.seed.item()), self.name, rows, cols, self.p)
+
+
 def make_geom(mode=0, Wp=0, HpWp=0, H=0, W=0, Rs=0):
     return Geom(mode, Wp, HpWp, H, W, Rs)
 
@@ -58,7 +73,7 @@ def _cols(Bm, n, k0, K):
 
 
 def gemm(A, B, M, N, K, *, mode=0, taps=((0, 0),), bias=None, res=None, res32=None, mask_src=None, relu=False, out=None, out32=None,
-         atomic=False, splits=1, geom=None, out_row_off=0, out32_z_stride=0, block_n=0):
+         atomic=False, splits=1, geom=None, out_row_off=0, out32_z_stride=0, block_n=0, drop=None, drop_gshift=0, mask_scale=1.0):
     _LAUNCHES[0] += 1
     assert A.dtype == _lp() and B.dtype == _lp() and A.stride(1) == 1 and B.stride(1) == 1
     assert A.stride(0) % 8 == 0 and B.stride(0) % 8 == 0, "TMA pitch"
@@ -74,14 +89,21 @@ def gemm(A, B, M, N, K, *, mode=0, taps=((0, 0),), bias=None, res=None, res32=No
         v = acc
         if bias is not None:
             v = v + bias[:N].float()
+        if drop is not None:  # v = res + dropout(relu?(acc + bias))
+            assert not (relu and (res is not None or res32 is not None)) and out_row_off == 0
+            if relu:
+                v = v.clamp_min(0)
+            g = 1 << drop_gshift
+            mk = drop.mask(M, (N + g - 1) // g)
+            v = v * mk.repeat_interleave(g, dim=1)[:, :N]
         if res is not None:
             v = v + res[rows, :N].float()
         if res32 is not None:
             v = v + res32[rows, :N]
-        if relu:
+        if relu and drop is None:
             v = v.clamp_min(0)
         if mask_src is not None:
-            v = torch.where(mask_src[rows, :N].float() > 0, v, torch.zeros(()))
+            v = torch.where(mask_src[rows, :N].float() > 0, v * mask_scale, torch.zeros(()))
         v = torch.where(_interior(geom, rows)[:, None], v, torch.zeros(()))
         if out is not None:
             out[rows, :N] = v.to(_lp())
@@ -238,7 +260,7 @@ def _map3(rowmap, r):
 
 # ------------------------------------------------------------------------------------------------ normalisation
 def layernorm_fwd(x, gamma, beta, rows, *, y32=None, yb=None, pos32=None, ypb=None, relu=False, mean=None, rstd=None, rowmap=(0, 0, 0),
-                  eps=1e-5):
+                  eps=1e-5, drop=None):
     _LAUNCHES[0] += 1
     xr = x[:rows].float()
     mu = xr.mean(-1, keepdim=True)
@@ -247,6 +269,8 @@ def layernorm_fwd(x, gamma, beta, rows, *, y32=None, yb=None, pos32=None, ypb=No
     y = (xr - mu) * rs * gamma.detach() + beta.detach()
     if relu:
         y = y.clamp_min(0)
+    if drop is not None:
+        y = y * drop.mask(rows, y.shape[1])
     if mean is not None:
         mean[:rows] = mu[:, 0]
     if rstd is not None:
@@ -260,14 +284,15 @@ def layernorm_fwd(x, gamma, beta, rows, *, y32=None, yb=None, pos32=None, ypb=No
         ypb[o] = (y + pos32[o]).to(_lp())
 
 
-def layernorm_bwd(dy, x, gamma, mean, rstd, rows, *, dy2=None, y_relu=None, dx32=None, dxb=None, dgamma=None, dbeta=None, rowmap=(0, 0, 0)):
+def layernorm_bwd(dy, x, gamma, mean, rstd, rows, *, dy2=None, y_relu=None, relu_scale=1.0, dx32=None, dxb=None, dgamma=None, dbeta=None,
+                  rowmap=(0, 0, 0), dxb_drop=None):
     _LAUNCHES[0] += 1
     i = _map3(rowmap, torch.arange(rows))
     d = dy[i].float()
     if dy2 is not None:
         d = d + dy2[i]
     if y_relu is not None:
-        d = torch.where(y_relu[i] > 0, d, torch.zeros(()))
+        d = torch.where(y_relu[i] > 0, d * relu_scale, torch.zeros(()))
     xh = (x[:rows] - mean[:rows, None]) * rstd[:rows, None]
     if dgamma is not None:
         dgamma += (d * xh).sum(0)
@@ -278,6 +303,8 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, rows, *, dy2=None, y_relu=None, dx32
     if dx32 is not None:
         dx32[:rows] = dx
     if dxb is not None:
+        if dxb_drop is not None:
+            dx = dx * dxb_drop.mask(rows, dx.shape[1])
         dxb[:rows] = dx.to(_lp())
 
 
@@ -365,22 +392,26 @@ def _attn(Q, K, V, kpm, B, H, Tq, Sk, scale):
     return s, v
 
 
-def attn_fwd(Q, K, V, kpm, O, LSE, B, H, Tq, Sk, scale):
+def _pdrop(p, drop, B, H, Tq, Sk):
+    return p if drop is None else p * drop.mask(B * H * Tq, Sk).view(B, H, Tq, Sk)
+
+
+def attn_fwd(Q, K, V, kpm, O, LSE, B, H, Tq, Sk, scale, drop=None):
     _LAUNCHES[0] += 1
     s, v = _attn(Q, K, V, kpm, B, H, Tq, Sk, scale)
     LSE.view(B, H, Tq).copy_(torch.logsumexp(s, -1))
-    o = (s.softmax(-1) @ v).transpose(1, 2).reshape(B * Tq, H * 32)
+    o = (_pdrop(s.softmax(-1), drop, B, H, Tq, Sk) @ v).transpose(1, 2).reshape(B * Tq, H * 32)
     O[:, :H * 32] = o.to(_lp())
 
 
-def attn_bwd(Q, K, V, kpm, O, dO, LSE, dQ, dK, dV, Dbuf, B, H, Tq, Sk, scale):
+def attn_bwd(Q, K, V, kpm, O, dO, LSE, dQ, dK, dV, Dbuf, B, H, Tq, Sk, scale, drop=None):
     _LAUNCHES[0] += 1
     with torch.enable_grad():
         q = Q[:, :H * 32].float().requires_grad_()
         k = K[:, :H * 32].float().requires_grad_()
         v = V[:, :H * 32].float().requires_grad_()
         s, vh = _attn(q, k, v, kpm, B, H, Tq, Sk, scale)
-        o = (s.softmax(-1) @ vh).transpose(1, 2).reshape(B * Tq, H * 32)
+        o = (_pdrop(s.softmax(-1), drop, B, H, Tq, Sk) @ vh).transpose(1, 2).reshape(B * Tq, H * 32)
         o.backward(dO[:, :H * 32].float())
     dQ[:, :H * 32] = q.grad.to(_lp())
     dK[:, :H * 32] = k.grad.to(_lp())
@@ -558,13 +589,15 @@ def bert_embed_bwd(d, ids, L, dword, dpos, dtype0):
         dtype0 += d.sum(0).reshape(dtype0.shape)
 
 
-def ln_wide_fwd(x, gamma, beta, rows, *, y32=None, yb=None, mean=None, rstd=None, eps=1e-12):
+def ln_wide_fwd(x, gamma, beta, rows, *, y32=None, yb=None, mean=None, rstd=None, eps=1e-12, drop=None):
     _LAUNCHES[0] += 1
     xx = x[:rows]
     mu = xx.mean(-1, keepdim=True)
     var = ((xx - mu) ** 2).mean(-1, keepdim=True)
     rs = torch.rsqrt(var + eps)
     y = (xx - mu) * rs * gamma.detach() + beta.detach()
+    if drop is not None:
+        y = y * drop.mask(rows, y.shape[1])
     if mean is not None:
         mean[:rows] = mu.flatten()
         rstd[:rows] = rs.flatten()
@@ -574,9 +607,11 @@ def ln_wide_fwd(x, gamma, beta, rows, *, y32=None, yb=None, mean=None, rstd=None
         yb[:rows] = y.to(_lp())
 
 
-def ln_wide_bwd(dy, x, gamma, mean, rstd, rows, *, dy2=None, dx32=None, dxb=None, dgamma=None, dbeta=None):
+def ln_wide_bwd(dy, x, gamma, mean, rstd, rows, *, dy2=None, dx32=None, dxb=None, dgamma=None, dbeta=None, dy_drop=None, dxb_drop=None):
     _LAUNCHES[0] += 1
     d = dy[:rows] if dy2 is None else dy[:rows] + dy2[:rows]
+    if dy_drop is not None:
+        d = d * dy_drop.mask(rows, d.shape[1])
     xh = (x[:rows] - mean[:rows, None]) * rstd[:rows, None]
     if dgamma is not None:
         dgamma += (d * xh).sum(0)
@@ -589,6 +624,8 @@ def ln_wide_bwd(dy, x, gamma, mean, rstd, rows, *, dy2=None, dx32=None, dxb=None
     if dx32 is not None:
         dx32[:rows] = dx
     if dxb is not None:
+        if dxb_drop is not None:
+            dx = dx * dxb_drop.mask(rows, dx.shape[1])
         dxb[:rows] = dx.to(_lp())
 
 
@@ -618,7 +655,7 @@ def tanh_bwd(dy, y, dx=None, dxb=None):
         dxb.copy_(v.to(_lp()))
 
 
-def attn_small_fwd(Q, K, V, mask, O, P, B, H, S, scale):
+def attn_small_fwd(Q, K, V, mask, O, P, B, H, S, scale, drop=None):
     _LAUNCHES[0] += 1
     q = Q.float().reshape(B, S, H, 64).transpose(1, 2) * scale
     k = K.float().reshape(B, S, H, 64).transpose(1, 2)
@@ -628,18 +665,18 @@ def attn_small_fwd(Q, K, V, mask, O, P, B, H, S, scale):
         s = s.masked_fill(mask.view(B, 1, 1, S).bool(), float("-inf"))
     p = torch.softmax(s, -1)
     P.view(B, H, S, S).copy_(p)
-    O.copy_((p @ v).transpose(1, 2).reshape(B * S, H * 64).to(_lp()))
+    O.copy_((_pdrop(p, drop, B, H, S, S) @ v).transpose(1, 2).reshape(B * S, H * 64).to(_lp()))
 
 
-def attn_small_bwd(Q, K, V, dO, P, dQ, dK, dV, B, H, S, scale):
+def attn_small_bwd(Q, K, V, dO, P, dQ, dK, dV, B, H, S, scale, drop=None):
     _LAUNCHES[0] += 1
     q = Q.float().reshape(B, S, H, 64).transpose(1, 2)
     k = K.float().reshape(B, S, H, 64).transpose(1, 2)
     v = V.float().reshape(B, S, H, 64).transpose(1, 2)
     do = dO.float().reshape(B, S, H, 64).transpose(1, 2)
     p = P.view(B, H, S, S)
-    dv = p.transpose(-1, -2) @ do
-    dp = do @ v.transpose(-1, -2)
+    dv = _pdrop(p, drop, B, H, S, S).transpose(-1, -2) @ do
+    dp = _pdrop(do @ v.transpose(-1, -2), drop, B, H, S, S)
     ds = p * (dp - (dp * p).sum(-1, keepdim=True)) * scale
     dq = ds @ k
     dk = ds.transpose(-1, -2) @ q

@@ -142,3 +142,66 @@ def test_engine_wiring_exact(name, emulated_exact):
     bad = {n: e for n, e in errs.items() if e > 1e-2 and norms[n] > 1e-6 * big}  # exclude mathematically-zero gradients (key biases)
     print(name, sorted(errs.items(), key=lambda kv: -kv[1])[:6])
     assert not bad, bad
+
+
+def _train_case(name):
+    case = dict(CASES[name])
+    case["oracle_kw"] = dict(case["oracle_kw"], dropout=0.1)
+    return case
+
+
+@pytest.mark.parametrize("name", ["cfg1_box", "multi_phrase", "pad_box"])
+def test_engine_train_mode_dropout_exact(name, emulated_exact):
+    """Train mode (transformer.py:151-160, :211-223 dropouts, mlp_mapping's nn.Dropout, HF BERT's dropouts): with the oracle
+    drawing the SAME counter-based masks (tests/dropout_ref.py), outputs and every gradient must agree to fp32 accuracy --
+    this pins where each mask is applied in the forward and how it re-enters the backward."""
+    import oracle.reftr_oracle as orc
+    import dropout_ref
+    case = _train_case(name)
+    torch.set_num_threads(os.cpu_count())
+    oracle = build_oracle(case).train()
+    cand = build_candidate(case).train()
+    seed = 0x1234ABCD5678EF01 & 0x7FFFFFFFFFFFFFFF
+    hook = dropout_ref.OracleDropoutHook(seed)
+    undo = dropout_ref.hook_hf_bert(oracle.lang_backbone, hook, orc.DROP_CTX)
+    orc.DROPOUT_HOOK = hook
+    try:
+        s = synthetic_samples(**case["inputs"])
+        out_o = oracle(s)
+        _linear_loss(out_o).backward()
+    finally:
+        orc.DROPOUT_HOOK = None
+        undo()
+    eng = cand.engine()
+    eng.next_seed = seed
+    out_c = cand(s)
+    assert eng.last_seed == seed and eng.train_mode
+    _linear_loss(out_c).backward()
+    # every site the oracle visited exists in the engine under the same name, and dropout really happened
+    assert set(hook.seen) == set(eng._drops), (set(hook.seen) ^ set(eng._drops))
+    assert len(hook.seen) > 10
+    eval_out = build_oracle(case)(s)["pred_boxes"]
+    assert (out_o["pred_boxes"] - eval_out).abs().max().item() > 1e-4  # train output differs from the eval output
+    assert (out_c["pred_boxes"] - out_o["pred_boxes"]).abs().max().item() < 2e-5
+    errs = compare_grads(cand, oracle)
+    norms = {n: p.grad.norm().item() for n, p in oracle.named_parameters() if p.grad is not None}
+    big = max(norms.values())
+    bad = {n: e for n, e in errs.items() if e > 1e-2 and norms[n] > 1e-6 * big}
+    print(name, sorted(errs.items(), key=lambda kv: -kv[1])[:6])
+    assert not bad, bad
+
+
+def test_dropout_generator_statistics():
+    """The counter-based generator: keep rate = 1 - p to sampling accuracy, different sites / seeds decorrelate, and the
+    two 16-bit lanes of a word are independent."""
+    import dropout_ref
+    p = 0.1
+    m1 = dropout_ref.keep_mask(12345, dropout_ref.site_id("enc0.attn"), 2048, 420, p)
+    m2 = dropout_ref.keep_mask(12345, dropout_ref.site_id("enc1.attn"), 2048, 420, p)
+    m3 = dropout_ref.keep_mask(12346, dropout_ref.site_id("enc0.attn"), 2048, 420, p)
+    n = m1.numel()
+    for m in (m1, m2, m3):
+        assert abs(m.float().mean().item() - (1 - p)) < 4 * (p * (1 - p) / n) ** 0.5 + 1e-5
+    for a, b in ((m1, m2), (m1, m3), (m1[:, 0::2], m1[:, 1::2]), (m1[:-1], m1[1:])):
+        both = (~a & ~b).float().mean().item()  # P(both dropped) = p^2 when independent
+        assert abs(both - p * p) < 1.5e-3, both
