@@ -44,7 +44,8 @@ METRIC = "samples/sec fwd+bwd (640x640, 20-tok phrase, bs16/GPU)"
 
 
 CONFIG = {"workload": "cfg2: ResNet-50 + 6+6-layer RefTR box model, 640x640, 20-token phrase, bs16 per GPU, aux_loss",
-          "mode": "eval+grad (dropout inactive), fwd+criterion+bwd, no optimizer"}
+          "mode": "model.train(): dropout 0.1 active at every site of the reference (MHA probabilities, residual / FFN dropouts, "
+                  "mlp_mapping, BERT), fwd+criterion+bwd, no optimizer"}
 
 
 def peaks():
@@ -165,7 +166,7 @@ def oracle_cpu_rate(B_sample, steps, warmup):
     from reftr_b200.synthetic import synthetic_samples, synthetic_targets
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
-    model = build_oracle_model("cpu").eval()  # eval + grad: dropout inactive, as in our arm (see config.mode)
+    model = build_oracle_model("cpu").train()  # train mode: dropout active, as in our arm (see config.mode)
     times = []
     for i in range(warmup + steps):
         s = synthetic_samples(B_sample, WORKLOAD["H"], WORKLOAD["W"], WORKLOAD["L"], seed=1 + i)
@@ -220,11 +221,11 @@ def main():
 
     if a.impl == "stock-gpu":
         from oracle.reftr_oracle import total_box_loss
-        model = build_oracle_model(device).eval()
+        model = build_oracle_model(device).train()
         crit = None
     else:
         model, crit, _ = build_ours(device, a.workload)
-        model.eval()  # dropout inactive (parity mode); gradients flow.  Stated in config.mode.
+        model.train() if os.environ.get("REFTR_B200_BENCH_EVAL") != "1" else model.eval()  # train mode: every dropout of the reference active
     net = model
     if a.diag == "replicas":
         model.engine_allreduce = False
@@ -324,7 +325,7 @@ def main():
     value = world * B * a.steps / ms * 1e3
     e2e = world * B * a.steps / ms_e2e * 1e3
     out = dict(base, value=value, ms_per_step=ms / a.steps, dtype="bf16",
-               config={"workload": CONFIG["workload"] if a.workload == "cfg2" else f"{a.workload} (NOT the metric's configuration): {wl_shape}", "global_batch": world * B, "parallelism": f"dp{world}", "mode": CONFIG["mode"],
+               config={"workload": CONFIG["workload"] if a.workload == "cfg2" else f"{a.workload} (NOT the metric's configuration): {wl_shape}", "global_batch": world * B, "parallelism": f"dp{world}", "mode": CONFIG["mode"] if model.training else "eval+grad (dropout inactive; diagnostic)",
                        "bert": "BERT-base on the same C-ABI kernels (bf16 operands, fp32 residual/LN), inside the step graphs",
                        "l2": "per-step working set (saved activations, several GB) far exceeds the 126 MB L2; no explicit flush"},
                e2e={"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": nbytes(s_host, t_host), "d2h_bytes_per_step": 4,
