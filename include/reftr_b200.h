@@ -23,6 +23,9 @@ extern "C" {
 
 const char* rb_last_error(void);
 int rb_version(void);
+/* the 16-bit type "t16" of tensor-core operands, saved activations and activation gradients this library was built for:
+ * 0 = IEEE half (default), 1 = bfloat16 (-DRB_ACT_BF16).  Everything called "bf16" below is this type. */
+int rb_act_dtype(void);
 
 /* Row geometry for border masking in GEMM epilogues (rows that are padding must be written as zero). */
 typedef struct {

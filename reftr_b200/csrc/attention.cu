@@ -30,7 +30,7 @@ __device__ __forceinline__ void dot_phase(const float* __restrict__ vec, const u
 #pragma unroll
     for (int c = 0; c < SCH; ++c) {
       const uint32_t kk = row[32 * c];
-      const float k0 = bf16_lo(kk), k1 = bf16_hi(kk);
+      const float k0 = t_lo(kk), k1 = t_hi(kk);
 #pragma unroll
       for (int q = 0; q < NQ; ++q) s[q][c] = fmaf(qv[q].x, k0, fmaf(qv[q].y, k1, s[q][c]));
     }
@@ -38,15 +38,15 @@ __device__ __forceinline__ void dot_phase(const float* __restrict__ vec, const u
 }
 
 // acc[q] = sum_j w[q][j] * M[j][lane]   (M row-major bf16 [n][32], w fp32 in shared memory, n multiple of 4)
-__device__ __forceinline__ void mix_phase(const float* __restrict__ w, int SP, const __nv_bfloat16* __restrict__ M, int n, int lane, float (&acc)[NQ]) {
+__device__ __forceinline__ void mix_phase(const float* __restrict__ w, int SP, const rb_t* __restrict__ M, int n, int lane, float (&acc)[NQ]) {
 #pragma unroll
   for (int q = 0; q < NQ; ++q) acc[q] = 0.f;
   for (int j = 0; j < n; j += 4) {
     float4 p[NQ];
 #pragma unroll
     for (int q = 0; q < NQ; ++q) p[q] = *reinterpret_cast<const float4*>(w + q * SP + j);
-    const float v0 = __bfloat162float(M[(j + 0) * DH + lane]), v1 = __bfloat162float(M[(j + 1) * DH + lane]);
-    const float v2 = __bfloat162float(M[(j + 2) * DH + lane]), v3 = __bfloat162float(M[(j + 3) * DH + lane]);
+    const float v0 = t2f(M[(j + 0) * DH + lane]), v1 = t2f(M[(j + 1) * DH + lane]);
+    const float v2 = t2f(M[(j + 2) * DH + lane]), v3 = t2f(M[(j + 3) * DH + lane]);
 #pragma unroll
     for (int q = 0; q < NQ; ++q) acc[q] = fmaf(p[q].x, v0, fmaf(p[q].y, v1, fmaf(p[q].z, v2, fmaf(p[q].w, v3, acc[q]))));
   }
@@ -54,7 +54,7 @@ __device__ __forceinline__ void mix_phase(const float* __restrict__ w, int SP, c
 
 // Stage rows [0,n) of a [*, ld] bf16 matrix (columns col0..col0+31) into shared memory: row-major copy `rm` ([SP][32] bf16)
 // and/or transposed-packed copy `t2` ([16][SP] uint32).  Rows >= n are zero-filled up to SP.
-__device__ __forceinline__ void stage_rows(const __nv_bfloat16* __restrict__ g, long long ld, int n, int SP, __nv_bfloat16* rm, uint32_t* t2) {
+__device__ __forceinline__ void stage_rows(const rb_t* __restrict__ g, long long ld, int n, int SP, rb_t* rm, uint32_t* t2) {
   for (int idx = threadIdx.x; idx < SP * 4; idx += blockDim.x) {
     const int j = idx >> 2, part = idx & 3;  // 4 x 16B per row
     uint4 v = make_uint4(0, 0, 0, 0);
@@ -69,15 +69,15 @@ __device__ __forceinline__ void stage_rows(const __nv_bfloat16* __restrict__ g, 
 
 template <int SCH, int NWARPS>
 __global__ void __launch_bounds__(NWARPS * 32)
-attn_fwd_kernel(const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16* __restrict__ K, const __nv_bfloat16* __restrict__ V,
-                const uint8_t* __restrict__ kpm, __nv_bfloat16* __restrict__ O, float* __restrict__ LSE, int H, int Tq, int Sk, long long ldq,
+attn_fwd_kernel(const rb_t* __restrict__ Q, const rb_t* __restrict__ K, const rb_t* __restrict__ V,
+                const uint8_t* __restrict__ kpm, rb_t* __restrict__ O, float* __restrict__ LSE, int H, int Tq, int Sk, long long ldq,
                 long long ldk, long long ldv, long long ldo, float scale, int q_per_block, DropK drop) {
   constexpr int SP = SCH * 32;
   const uint32_t dkey = drop.seed ? drop_key(drop) : 0u;
   const uint32_t wpr = static_cast<uint32_t>((Sk + 1) >> 1);
   extern __shared__ __align__(16) uint8_t smem[];
   uint32_t* Kt2 = reinterpret_cast<uint32_t*>(smem);                          // [16][SP]
-  __nv_bfloat16* Vs = reinterpret_cast<__nv_bfloat16*>(Kt2 + 16 * SP);        // [SP][32]
+  rb_t* Vs = reinterpret_cast<rb_t*>(Kt2 + 16 * SP);        // [SP][32]
   float* ps = reinterpret_cast<float*>(Vs + SP * DH);                         // [NWARPS][NQ][SP]
   float* qs = ps + NWARPS * NQ * SP;                                          // [NWARPS][NQ][32]
   uint8_t* msk = reinterpret_cast<uint8_t*>(qs + NWARPS * NQ * DH);           // [SP]
@@ -95,7 +95,7 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16* __rest
 #pragma unroll
     for (int q = 0; q < NQ; ++q) {
       const int t = t0 + q;
-      myq[q * DH + lane] = t < q_end ? __bfloat162float(Q[(static_cast<long long>(b) * Tq + t) * ldq + h * DH + lane]) * scale : 0.f;
+      myq[q * DH + lane] = t < q_end ? t2f(Q[(static_cast<long long>(b) * Tq + t) * ldq + h * DH + lane]) * scale : 0.f;
     }
     __syncwarp();
     float s[NQ][SCH];
@@ -132,7 +132,7 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16* __rest
       const int t = t0 + q;
       if (t < q_end) {
         const float inv = sum[q] > 0.f ? drop.scale / sum[q] : 0.f;
-        O[(static_cast<long long>(b) * Tq + t) * ldo + h * DH + lane] = __float2bfloat16(acc[q] * inv);
+        O[(static_cast<long long>(b) * Tq + t) * ldo + h * DH + lane] = f2t(acc[q] * inv);
         if (lane == 0 && LSE) LSE[(static_cast<long long>(b) * H + h) * Tq + t] = mx[q] + __logf(fmaxf(sum[q], 1e-30f));
       }
     }
@@ -143,9 +143,9 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16* __rest
 // dQ (and D = rowsum(dO*O)) -- same loop structure as the forward pass.
 template <int SCH, int NWARPS>
 __global__ void __launch_bounds__(NWARPS * 32)
-attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16* __restrict__ K, const __nv_bfloat16* __restrict__ V,
-                   const uint8_t* __restrict__ kpm, const __nv_bfloat16* __restrict__ O, const __nv_bfloat16* __restrict__ dO,
-                   const float* __restrict__ LSE, __nv_bfloat16* __restrict__ dQ, float* __restrict__ Dbuf, int H, int Tq, int Sk, long long ldq,
+attn_bwd_dq_kernel(const rb_t* __restrict__ Q, const rb_t* __restrict__ K, const rb_t* __restrict__ V,
+                   const uint8_t* __restrict__ kpm, const rb_t* __restrict__ O, const rb_t* __restrict__ dO,
+                   const float* __restrict__ LSE, rb_t* __restrict__ dQ, float* __restrict__ Dbuf, int H, int Tq, int Sk, long long ldq,
                    long long ldk, long long ldv, long long ldo, long long lddo, long long lddq, float scale, int q_per_block, DropK drop) {
   constexpr int SP = SCH * 32;
   const uint32_t dkey = drop.seed ? drop_key(drop) : 0u;
@@ -153,7 +153,7 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16* __r
   extern __shared__ __align__(16) uint8_t smem[];
   uint32_t* Kt2 = reinterpret_cast<uint32_t*>(smem);
   uint32_t* Vt2 = Kt2 + 16 * SP;
-  __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(Vt2 + 16 * SP);
+  rb_t* Ks = reinterpret_cast<rb_t*>(Vt2 + 16 * SP);
   float* ps = reinterpret_cast<float*>(Ks + SP * DH);
   float* qs = ps + NWARPS * NQ * SP;        // [NWARPS][2][NQ][32]: q then dO
   uint8_t* msk = reinterpret_cast<uint8_t*>(qs + NWARPS * 2 * NQ * DH);
@@ -176,9 +176,9 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16* __r
       float qv = 0.f, dov = 0.f, ov = 0.f;
       if (t < q_end) {
         const long long r = static_cast<long long>(b) * Tq + t;
-        qv = __bfloat162float(Q[r * ldq + h * DH + lane]) * scale;
-        dov = __bfloat162float(dO[r * lddo + h * DH + lane]);
-        ov = __bfloat162float(O[r * ldo + h * DH + lane]);
+        qv = t2f(Q[r * ldq + h * DH + lane]) * scale;
+        dov = t2f(dO[r * lddo + h * DH + lane]);
+        ov = t2f(O[r * ldo + h * DH + lane]);
         lse[q] = LSE[(static_cast<long long>(b) * H + h) * Tq + t];
       } else {
         lse[q] = 0.f;
@@ -210,7 +210,7 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16* __r
 #pragma unroll
     for (int q = 0; q < NQ; ++q) {
       const int t = t0 + q;
-      if (t < q_end) dQ[(static_cast<long long>(b) * Tq + t) * lddq + h * DH + lane] = __float2bfloat16(acc[q]);
+      if (t < q_end) dQ[(static_cast<long long>(b) * Tq + t) * lddq + h * DH + lane] = f2t(acc[q]);
     }
     __syncwarp();
   }
@@ -219,9 +219,9 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16* __r
 // dK, dV: roles swapped -- each warp owns 2 keys, loops over all queries of (b, h) staged in shared memory.
 template <int TCH, int NWARPS>
 __global__ void __launch_bounds__(NWARPS * 32)
-attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16* __restrict__ K, const __nv_bfloat16* __restrict__ V,
-                    const uint8_t* __restrict__ kpm, const __nv_bfloat16* __restrict__ dO, const float* __restrict__ LSE, const float* __restrict__ Dbuf,
-                    __nv_bfloat16* __restrict__ dK, __nv_bfloat16* __restrict__ dV, int H, int Tq, int Sk, long long ldq, long long ldk, long long ldv,
+attn_bwd_dkv_kernel(const rb_t* __restrict__ Q, const rb_t* __restrict__ K, const rb_t* __restrict__ V,
+                    const uint8_t* __restrict__ kpm, const rb_t* __restrict__ dO, const float* __restrict__ LSE, const float* __restrict__ Dbuf,
+                    rb_t* __restrict__ dK, rb_t* __restrict__ dV, int H, int Tq, int Sk, long long ldq, long long ldk, long long ldv,
                     long long lddo, long long lddk, long long lddv, float scale, int k_per_block, DropK drop) {
   constexpr int TP = TCH * 32;
   const uint32_t dkey = drop.seed ? drop_key(drop) : 0u;
@@ -229,8 +229,8 @@ attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16* __
   extern __shared__ __align__(16) uint8_t smem[];
   uint32_t* Qt2 = reinterpret_cast<uint32_t*>(smem);
   uint32_t* dOt2 = Qt2 + 16 * TP;
-  __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(dOt2 + 16 * TP);
-  __nv_bfloat16* dOs = Qs + TP * DH;
+  rb_t* Qs = reinterpret_cast<rb_t*>(dOt2 + 16 * TP);
+  rb_t* dOs = Qs + TP * DH;
   float* ps = reinterpret_cast<float*>(dOs + TP * DH);  // [NWARPS][2][NQ][TP]
   float* ks = ps + NWARPS * 2 * NQ * TP;                // [NWARPS][2][NQ][32]
   float* lse_s = ks + NWARPS * 2 * NQ * DH;             // [TP]
@@ -258,8 +258,8 @@ attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16* __
       dead[q] = (j >= k_end) || (kpm && kpm[static_cast<long long>(b) * Sk + j]);
       float kv = 0.f, vv = 0.f;
       if (j < k_end) {
-        kv = __bfloat162float(K[(static_cast<long long>(b) * Sk + j) * ldk + h * DH + lane]) * scale;
-        vv = __bfloat162float(V[(static_cast<long long>(b) * Sk + j) * ldv + h * DH + lane]);
+        kv = t2f(K[(static_cast<long long>(b) * Sk + j) * ldk + h * DH + lane]) * scale;
+        vv = t2f(V[(static_cast<long long>(b) * Sk + j) * ldv + h * DH + lane]);
       }
       myk[q * DH + lane] = kv;
       myv[q * DH + lane] = vv;
@@ -290,8 +290,8 @@ attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16* __
     for (int q = 0; q < NQ; ++q) {
       const int j = j0 + q;
       if (j < k_end) {
-        dV[(static_cast<long long>(b) * Sk + j) * lddv + h * DH + lane] = __float2bfloat16(accv[q]);
-        dK[(static_cast<long long>(b) * Sk + j) * lddk + h * DH + lane] = __float2bfloat16(acck[q]);
+        dV[(static_cast<long long>(b) * Sk + j) * lddv + h * DH + lane] = f2t(accv[q]);
+        dK[(static_cast<long long>(b) * Sk + j) * lddk + h * DH + lane] = f2t(acck[q]);
       }
     }
     __syncwarp();
@@ -385,9 +385,9 @@ static int launch_fwd(const void* Q, const void* K, const void* V, const void* k
   static bool cfg = false;
   if (!cfg) { RB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM)); cfg = true; }
   const int qpb = 64;
-  kern<<<dim3((Tq + qpb - 1) / qpb, B * H), NW * 32, SMEM, st>>>(static_cast<const __nv_bfloat16*>(Q), static_cast<const __nv_bfloat16*>(K),
-                                                              static_cast<const __nv_bfloat16*>(V), static_cast<const uint8_t*>(kpm),
-                                                              static_cast<__nv_bfloat16*>(O), LSE, H, Tq, Sk, ldq, ldk, ldv, ldo, scale, qpb, drop);
+  kern<<<dim3((Tq + qpb - 1) / qpb, B * H), NW * 32, SMEM, st>>>(static_cast<const rb_t*>(Q), static_cast<const rb_t*>(K),
+                                                              static_cast<const rb_t*>(V), static_cast<const uint8_t*>(kpm),
+                                                              static_cast<rb_t*>(O), LSE, H, Tq, Sk, ldq, ldk, ldv, ldo, scale, qpb, drop);
   RB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -403,8 +403,8 @@ static int launch_dq(const void* Q, const void* K, const void* V, const void* kp
   if (!cfg) { RB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM)); cfg = true; }
   const int qpb = 64;
   kern<<<dim3((Tq + qpb - 1) / qpb, B * H), NW * 32, SMEM, st>>>(
-      static_cast<const __nv_bfloat16*>(Q), static_cast<const __nv_bfloat16*>(K), static_cast<const __nv_bfloat16*>(V), static_cast<const uint8_t*>(kpm),
-      static_cast<const __nv_bfloat16*>(O), static_cast<const __nv_bfloat16*>(dO), LSE, static_cast<__nv_bfloat16*>(dQ), Dbuf, H, Tq, Sk, ldq, ldk, ldv,
+      static_cast<const rb_t*>(Q), static_cast<const rb_t*>(K), static_cast<const rb_t*>(V), static_cast<const uint8_t*>(kpm),
+      static_cast<const rb_t*>(O), static_cast<const rb_t*>(dO), LSE, static_cast<rb_t*>(dQ), Dbuf, H, Tq, Sk, ldq, ldk, ldv,
       ldo, lddo, lddq, scale, qpb, drop);
   RB_CUDA(cudaGetLastError());
   return 0;
@@ -421,8 +421,8 @@ static int launch_dkv(const void* Q, const void* K, const void* V, const void* k
   if (!cfg) { RB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM)); cfg = true; }
   const int kpb = 64;
   kern<<<dim3((Sk + kpb - 1) / kpb, B * H), NW * 32, SMEM, st>>>(
-      static_cast<const __nv_bfloat16*>(Q), static_cast<const __nv_bfloat16*>(K), static_cast<const __nv_bfloat16*>(V), static_cast<const uint8_t*>(kpm),
-      static_cast<const __nv_bfloat16*>(dO), LSE, Dbuf, static_cast<__nv_bfloat16*>(dK), static_cast<__nv_bfloat16*>(dV), H, Tq, Sk, ldq, ldk, ldv, lddo,
+      static_cast<const rb_t*>(Q), static_cast<const rb_t*>(K), static_cast<const rb_t*>(V), static_cast<const uint8_t*>(kpm),
+      static_cast<const rb_t*>(dO), LSE, Dbuf, static_cast<rb_t*>(dK), static_cast<rb_t*>(dV), H, Tq, Sk, ldq, ldk, ldv, lddo,
       lddk, lddv, scale, kpb, drop);
   RB_CUDA(cudaGetLastError());
   return 0;

@@ -44,8 +44,8 @@ __device__ __forceinline__ void store_row_half_sw128(uint8_t* tile, int r, int h
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     uint4 t;
-    t.x = pack_bf16x2(v[8 * c], v[8 * c + 1]); t.y = pack_bf16x2(v[8 * c + 2], v[8 * c + 3]);
-    t.z = pack_bf16x2(v[8 * c + 4], v[8 * c + 5]); t.w = pack_bf16x2(v[8 * c + 6], v[8 * c + 7]);
+    t.x = pack_t2(v[8 * c], v[8 * c + 1]); t.y = pack_t2(v[8 * c + 2], v[8 * c + 3]);
+    t.z = pack_t2(v[8 * c + 4], v[8 * c + 5]); t.w = pack_t2(v[8 * c + 6], v[8 * c + 7]);
     const int chunk = half * 4 + c;
     *reinterpret_cast<uint4*>(row + ((chunk ^ (r & 7)) << 4)) = t;
   }
@@ -120,7 +120,7 @@ __device__ __forceinline__ void atc_init(const AtcSmem& s, int warp, int tmem_co
 // =====================================================================================================================
 __global__ void __launch_bounds__(ATC_THREADS)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
-                   const uint8_t* __restrict__ kpm, __nv_bfloat16* __restrict__ O, float* __restrict__ LSE, int H, int Tq, int Sk, long long ldo,
+                   const uint8_t* __restrict__ kpm, rb_t* __restrict__ O, float* __restrict__ LSE, int H, int Tq, int Sk, long long ldo,
                    float scale, DropK drop) {
   extern __shared__ uint8_t smem_raw[];
   const AtcSmem s = carve(smem_raw);
@@ -148,8 +148,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     __syncwarp();
   } else if (warp == 5) {
     if (lane == 0) {
-      constexpr uint32_t idS = umma_idesc_bf16(128, 64, 0, 0);
-      constexpr uint32_t idO = umma_idesc_bf16(128, 32, 0, 1);
+      constexpr uint32_t idS = umma_idesc_t(128, 64, 0, 0);
+      constexpr uint32_t idO = umma_idesc_t(128, 32, 0, 1);
       const uint32_t aQ = smem_u32(s.rowA), aP = smem_u32(s.tileA);
       mbar_wait(&s.bars[BAR_ROWS], 0);
       for (int j = 0; j < nb; ++j) {
@@ -158,12 +158,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tc_fence_after();
         const uint32_t aK = smem_u32(s.blk0 + st * 4096), aV = smem_u32(s.blk1 + st * 4096);
 #pragma unroll
-        for (int k = 0; k < 2; ++k) umma_bf16_ss(T_S, desc_k64(aQ, k), desc_k64(aK, k), idS, k);
+        for (int k = 0; k < 2; ++k) umma_f16_ss(T_S, desc_k64(aQ, k), desc_k64(aK, k), idS, k);
         umma_commit(&s.bars[BAR_ACC]);
         mbar_wait(&s.bars[BAR_EW], j & 1);
         tc_fence_after();
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16_ss(T_O, desc_k128(aP, k), desc_mn64(aV, k), idO, (j | k) != 0);
+        for (int k = 0; k < 4; ++k) umma_f16_ss(T_O, desc_k128(aP, k), desc_mn64(aV, k), idO, (j | k) != 0);
         umma_commit(&s.bars[BAR_FREE + st]);
       }
     }
@@ -247,10 +247,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         uint4 t;
-        t.x = pack_bf16x2(__uint_as_float(o[8 * i]) * inv, __uint_as_float(o[8 * i + 1]) * inv);
-        t.y = pack_bf16x2(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv);
-        t.z = pack_bf16x2(__uint_as_float(o[8 * i + 4]) * inv, __uint_as_float(o[8 * i + 5]) * inv);
-        t.w = pack_bf16x2(__uint_as_float(o[8 * i + 6]) * inv, __uint_as_float(o[8 * i + 7]) * inv);
+        t.x = pack_t2(__uint_as_float(o[8 * i]) * inv, __uint_as_float(o[8 * i + 1]) * inv);
+        t.y = pack_t2(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv);
+        t.z = pack_t2(__uint_as_float(o[8 * i + 4]) * inv, __uint_as_float(o[8 * i + 5]) * inv);
+        t.w = pack_t2(__uint_as_float(o[8 * i + 6]) * inv, __uint_as_float(o[8 * i + 7]) * inv);
         dst[i] = t;
       }
       if (LSE) LSE[static_cast<long long>(bh) * Tq + q] = (m == -INFINITY) ? -69.07755279f /* log(1e-30), as the SIMT kernel */
@@ -267,8 +267,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 // =====================================================================================================================
 __global__ void __launch_bounds__(ATC_THREADS)
 attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
-                      const __grid_constant__ CUtensorMap tmdO, const uint8_t* __restrict__ kpm, const __nv_bfloat16* __restrict__ O,
-                      const __nv_bfloat16* __restrict__ dO, const float* __restrict__ LSE, __nv_bfloat16* __restrict__ dQ, float* __restrict__ Dbuf, int H,
+                      const __grid_constant__ CUtensorMap tmdO, const uint8_t* __restrict__ kpm, const rb_t* __restrict__ O,
+                      const rb_t* __restrict__ dO, const float* __restrict__ LSE, rb_t* __restrict__ dQ, float* __restrict__ Dbuf, int H,
                       int Tq, int Sk, long long ldo, long long lddo, long long lddq, float scale, DropK drop) {
   extern __shared__ uint8_t smem_raw[];
   const AtcSmem s = carve(smem_raw);
@@ -297,8 +297,8 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     __syncwarp();
   } else if (warp == 5) {
     if (lane == 0) {
-      constexpr uint32_t idS = umma_idesc_bf16(128, 64, 0, 0);
-      constexpr uint32_t idQ = umma_idesc_bf16(128, 32, 0, 1);
+      constexpr uint32_t idS = umma_idesc_t(128, 64, 0, 0);
+      constexpr uint32_t idQ = umma_idesc_t(128, 32, 0, 1);
       const uint32_t aQ = smem_u32(s.rowA), adO = smem_u32(s.rowB), aDS = smem_u32(s.tileA);
       mbar_wait(&s.bars[BAR_ROWS], 0);
       for (int j = 0; j < nb; ++j) {
@@ -307,14 +307,14 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         tc_fence_after();
         const uint32_t aK = smem_u32(s.blk0 + st * 4096), aV = smem_u32(s.blk1 + st * 4096);
 #pragma unroll
-        for (int k = 0; k < 2; ++k) umma_bf16_ss(T_S, desc_k64(aQ, k), desc_k64(aK, k), idS, k);
+        for (int k = 0; k < 2; ++k) umma_f16_ss(T_S, desc_k64(aQ, k), desc_k64(aK, k), idS, k);
 #pragma unroll
-        for (int k = 0; k < 2; ++k) umma_bf16_ss(T_dP, desc_k64(adO, k), desc_k64(aV, k), idS, k);
+        for (int k = 0; k < 2; ++k) umma_f16_ss(T_dP, desc_k64(adO, k), desc_k64(aV, k), idS, k);
         umma_commit(&s.bars[BAR_ACC]);
         mbar_wait(&s.bars[BAR_EW], j & 1);
         tc_fence_after();
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16_ss(T_dQ, desc_k128(aDS, k), desc_mn64(aK, k), idQ, (j | k) != 0);
+        for (int k = 0; k < 4; ++k) umma_f16_ss(T_dQ, desc_k128(aDS, k), desc_mn64(aK, k), idQ, (j | k) != 0);
         umma_commit(&s.bars[BAR_FREE + st]);
       }
     }
@@ -336,8 +336,8 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const uint4 a = po[i], d = pd[i];
-        D += bf16_lo(a.x) * bf16_lo(d.x) + bf16_hi(a.x) * bf16_hi(d.x) + bf16_lo(a.y) * bf16_lo(d.y) + bf16_hi(a.y) * bf16_hi(d.y) +
-             bf16_lo(a.z) * bf16_lo(d.z) + bf16_hi(a.z) * bf16_hi(d.z) + bf16_lo(a.w) * bf16_lo(d.w) + bf16_hi(a.w) * bf16_hi(d.w);
+        D += t_lo(a.x) * t_lo(d.x) + t_hi(a.x) * t_hi(d.x) + t_lo(a.y) * t_lo(d.y) + t_hi(a.y) * t_hi(d.y) +
+             t_lo(a.z) * t_lo(d.z) + t_hi(a.z) * t_hi(d.z) + t_lo(a.w) * t_lo(d.w) + t_hi(a.w) * t_hi(d.w);
       }
       Dbuf[static_cast<long long>(bh) * Tq + q] = D;
     }
@@ -386,10 +386,10 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         uint4 t;
-        t.x = pack_bf16x2(__uint_as_float(o[8 * i]), __uint_as_float(o[8 * i + 1]));
-        t.y = pack_bf16x2(__uint_as_float(o[8 * i + 2]), __uint_as_float(o[8 * i + 3]));
-        t.z = pack_bf16x2(__uint_as_float(o[8 * i + 4]), __uint_as_float(o[8 * i + 5]));
-        t.w = pack_bf16x2(__uint_as_float(o[8 * i + 6]), __uint_as_float(o[8 * i + 7]));
+        t.x = pack_t2(__uint_as_float(o[8 * i]), __uint_as_float(o[8 * i + 1]));
+        t.y = pack_t2(__uint_as_float(o[8 * i + 2]), __uint_as_float(o[8 * i + 3]));
+        t.z = pack_t2(__uint_as_float(o[8 * i + 4]), __uint_as_float(o[8 * i + 5]));
+        t.w = pack_t2(__uint_as_float(o[8 * i + 6]), __uint_as_float(o[8 * i + 7]));
         dst[i] = t;
       }
     }
@@ -405,7 +405,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 __global__ void __launch_bounds__(ATC_THREADS)
 attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                        const __grid_constant__ CUtensorMap tmdO, const uint8_t* __restrict__ kpm, const float* __restrict__ LSE,
-                       const float* __restrict__ Dbuf, __nv_bfloat16* __restrict__ dK, __nv_bfloat16* __restrict__ dV, int H, int Tq, int Sk, long long lddk,
+                       const float* __restrict__ Dbuf, rb_t* __restrict__ dK, rb_t* __restrict__ dV, int H, int Tq, int Sk, long long lddk,
                        long long lddv, float scale, DropK drop) {
   extern __shared__ uint8_t smem_raw[];
   const AtcSmem s = carve(smem_raw);
@@ -444,8 +444,8 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     }
   } else if (warp == 5) {
     if (lane == 0) {
-      constexpr uint32_t idS = umma_idesc_bf16(128, 64, 0, 0);
-      constexpr uint32_t idG = umma_idesc_bf16(128, 32, 0, 1);
+      constexpr uint32_t idS = umma_idesc_t(128, 64, 0, 0);
+      constexpr uint32_t idG = umma_idesc_t(128, 32, 0, 1);
       const uint32_t aK = smem_u32(s.rowA), aV = smem_u32(s.rowB), aPT = smem_u32(s.tileA), aDST = smem_u32(s.tileB);
       mbar_wait(&s.bars[BAR_ROWS], 0);
       for (int i = 0; i < nb; ++i) {
@@ -454,16 +454,16 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         tc_fence_after();
         const uint32_t aQ = smem_u32(s.blk0 + st * 4096), adO = smem_u32(s.blk1 + st * 4096);
 #pragma unroll
-        for (int k = 0; k < 2; ++k) umma_bf16_ss(T_S, desc_k64(aK, k), desc_k64(aQ, k), idS, k);
+        for (int k = 0; k < 2; ++k) umma_f16_ss(T_S, desc_k64(aK, k), desc_k64(aQ, k), idS, k);
 #pragma unroll
-        for (int k = 0; k < 2; ++k) umma_bf16_ss(T_dP, desc_k64(aV, k), desc_k64(adO, k), idS, k);
+        for (int k = 0; k < 2; ++k) umma_f16_ss(T_dP, desc_k64(aV, k), desc_k64(adO, k), idS, k);
         umma_commit(&s.bars[BAR_ACC]);
         mbar_wait(&s.bars[BAR_EW], i & 1);
         tc_fence_after();
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16_ss(T_dV, desc_k128(aPT, k), desc_mn64(adO, k), idG, (i | k) != 0);
+        for (int k = 0; k < 4; ++k) umma_f16_ss(T_dV, desc_k128(aPT, k), desc_mn64(adO, k), idG, (i | k) != 0);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16_ss(T_dK, desc_k128(aDST, k), desc_mn64(aQ, k), idG, (i | k) != 0);
+        for (int k = 0; k < 4; ++k) umma_f16_ss(T_dK, desc_k128(aDST, k), desc_mn64(aQ, k), idG, (i | k) != 0);
         umma_commit(&s.bars[BAR_FREE + st]);
       }
     }
@@ -524,15 +524,15 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         uint4 t;
-        t.x = pack_bf16x2(__uint_as_float(gv[8 * i]), __uint_as_float(gv[8 * i + 1]));
-        t.y = pack_bf16x2(__uint_as_float(gv[8 * i + 2]), __uint_as_float(gv[8 * i + 3]));
-        t.z = pack_bf16x2(__uint_as_float(gv[8 * i + 4]), __uint_as_float(gv[8 * i + 5]));
-        t.w = pack_bf16x2(__uint_as_float(gv[8 * i + 6]), __uint_as_float(gv[8 * i + 7]));
+        t.x = pack_t2(__uint_as_float(gv[8 * i]), __uint_as_float(gv[8 * i + 1]));
+        t.y = pack_t2(__uint_as_float(gv[8 * i + 2]), __uint_as_float(gv[8 * i + 3]));
+        t.z = pack_t2(__uint_as_float(gv[8 * i + 4]), __uint_as_float(gv[8 * i + 5]));
+        t.w = pack_t2(__uint_as_float(gv[8 * i + 6]), __uint_as_float(gv[8 * i + 7]));
         pv[i] = t;
-        t.x = pack_bf16x2(__uint_as_float(gk[8 * i]), __uint_as_float(gk[8 * i + 1]));
-        t.y = pack_bf16x2(__uint_as_float(gk[8 * i + 2]), __uint_as_float(gk[8 * i + 3]));
-        t.z = pack_bf16x2(__uint_as_float(gk[8 * i + 4]), __uint_as_float(gk[8 * i + 5]));
-        t.w = pack_bf16x2(__uint_as_float(gk[8 * i + 6]), __uint_as_float(gk[8 * i + 7]));
+        t.x = pack_t2(__uint_as_float(gk[8 * i]), __uint_as_float(gk[8 * i + 1]));
+        t.y = pack_t2(__uint_as_float(gk[8 * i + 2]), __uint_as_float(gk[8 * i + 3]));
+        t.z = pack_t2(__uint_as_float(gk[8 * i + 4]), __uint_as_float(gk[8 * i + 5]));
+        t.w = pack_t2(__uint_as_float(gk[8 * i + 6]), __uint_as_float(gk[8 * i + 7]));
         pk[i] = t;
       }
     }
@@ -575,7 +575,7 @@ extern "C" int rb_attn_fwd(const void* Q, const void* K, const void* V, const vo
   if (!cfg) { if (set_smem(attn_fwd_tc_kernel, ATC_SMEM_FWD)) return 1; cfg = true; }
   dim3 grid((Tq + ATC_ROWS - 1) / ATC_ROWS, B * H);
   attn_fwd_tc_kernel<<<grid, ATC_THREADS, ATC_SMEM_FWD, static_cast<cudaStream_t>(stream)>>>(
-      tmQ, tmK, tmV, static_cast<const uint8_t*>(kpm), static_cast<__nv_bfloat16*>(O), LSE, H, Tq, Sk, ldo, scale, make_dropk(drop));
+      tmQ, tmK, tmV, static_cast<const uint8_t*>(kpm), static_cast<rb_t*>(O), LSE, H, Tq, Sk, ldo, scale, make_dropk(drop));
   RB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -597,8 +597,8 @@ extern "C" int rb_attn_bwd(const void* Q, const void* K, const void* V, const vo
     if (make_tmap_2d(&tmV, V, static_cast<uint64_t>(H) * dh, static_cast<uint64_t>(B) * Sk, ldv * 2, ATC_DH, ATC_BLK)) return 1;
     dim3 grid((Tq + ATC_ROWS - 1) / ATC_ROWS, B * H);
     attn_bwd_dq_tc_kernel<<<grid, ATC_THREADS, ATC_SMEM_DQ, st>>>(tmQ, tmK, tmV, tmdO, static_cast<const uint8_t*>(kpm),
-                                                                    static_cast<const __nv_bfloat16*>(O), static_cast<const __nv_bfloat16*>(dO), LSE,
-                                                                    static_cast<__nv_bfloat16*>(dQ), Dbuf, H, Tq, Sk, ldo, lddo, lddq, scale, dk);
+                                                                    static_cast<const rb_t*>(O), static_cast<const rb_t*>(dO), LSE,
+                                                                    static_cast<rb_t*>(dQ), Dbuf, H, Tq, Sk, ldo, lddo, lddq, scale, dk);
     RB_CUDA(cudaGetLastError());
   }
   {
@@ -609,7 +609,7 @@ extern "C" int rb_attn_bwd(const void* Q, const void* K, const void* V, const vo
     if (make_tmap_2d(&tmV, V, static_cast<uint64_t>(H) * dh, static_cast<uint64_t>(B) * Sk, ldv * 2, ATC_DH, ATC_ROWS)) return 1;
     dim3 grid((Sk + ATC_ROWS - 1) / ATC_ROWS, B * H);
     attn_bwd_dkv_tc_kernel<<<grid, ATC_THREADS, ATC_SMEM_DKV, st>>>(tmQ, tmK, tmV, tmdO, static_cast<const uint8_t*>(kpm), LSE, Dbuf,
-                                                                     static_cast<__nv_bfloat16*>(dK), static_cast<__nv_bfloat16*>(dV), H, Tq, Sk, lddk, lddv,
+                                                                     static_cast<rb_t*>(dK), static_cast<rb_t*>(dV), H, Tq, Sk, lddk, lddv,
                                                                      scale, dk);
     RB_CUDA(cudaGetLastError());
   }

@@ -50,7 +50,7 @@ __device__ __forceinline__ void drop4(float4& o, uint32_t key, const DropK& d, u
 template <int NV>
 __global__ void __launch_bounds__(256)
 ln_wide_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, long long rows, float eps,
-                   float* __restrict__ y32, __nv_bfloat16* __restrict__ yb, float* __restrict__ mean_out, float* __restrict__ rstd_out, DropK drop) {
+                   float* __restrict__ y32, rb_t* __restrict__ yb, float* __restrict__ mean_out, float* __restrict__ rstd_out, DropK drop) {
   constexpr int D = NV * 128;
   const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -84,8 +84,8 @@ ln_wide_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
     if (y32) *reinterpret_cast<float4*>(y32 + row * D + i * 128 + lane * 4) = o;
     if (yb) {
       uint2 p;
-      p.x = pack_bf16x2(o.x, o.y);
-      p.y = pack_bf16x2(o.z, o.w);
+      p.x = pack_t2(o.x, o.y);
+      p.y = pack_t2(o.z, o.w);
       *reinterpret_cast<uint2*>(yb + row * D + i * 128 + lane * 4) = p;
     }
   }
@@ -94,7 +94,7 @@ ln_wide_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
 template <int NV>
 __global__ void __launch_bounds__(256)
 ln_wide_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ dy2, const float* __restrict__ x, const float* __restrict__ gamma,
-                   const float* __restrict__ mean, const float* __restrict__ rstd, long long rows, float* __restrict__ dx32, __nv_bfloat16* __restrict__ dxb,
+                   const float* __restrict__ mean, const float* __restrict__ rstd, long long rows, float* __restrict__ dx32, rb_t* __restrict__ dxb,
                    float* __restrict__ dgamma, float* __restrict__ dbeta, DropK idrop, DropK odrop) {
   constexpr int D = NV * 128;
   __shared__ float red[2][D];
@@ -139,8 +139,8 @@ ln_wide_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ dy2, 
       if (dxb) {
         if (odrop.seed) drop4(o, okey, odrop, static_cast<uint32_t>(row) * (D / 2) + i * 64 + lane * 2);
         uint2 p;
-        p.x = pack_bf16x2(o.x, o.y);
-        p.y = pack_bf16x2(o.z, o.w);
+        p.x = pack_t2(o.x, o.y);
+        p.y = pack_t2(o.z, o.w);
         *reinterpret_cast<uint2*>(dxb + row * D + i * 128 + lane * 4) = p;
       }
     }
@@ -169,10 +169,10 @@ __global__ void gelu_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__
   if (i >= n8) return;
   const uint4 v = x[i];
   uint4 o;
-  o.x = pack_bf16x2(gelu_f(bf16_lo(v.x)), gelu_f(bf16_hi(v.x)));
-  o.y = pack_bf16x2(gelu_f(bf16_lo(v.y)), gelu_f(bf16_hi(v.y)));
-  o.z = pack_bf16x2(gelu_f(bf16_lo(v.z)), gelu_f(bf16_hi(v.z)));
-  o.w = pack_bf16x2(gelu_f(bf16_lo(v.w)), gelu_f(bf16_hi(v.w)));
+  o.x = pack_t2(gelu_f(t_lo(v.x)), gelu_f(t_hi(v.x)));
+  o.y = pack_t2(gelu_f(t_lo(v.y)), gelu_f(t_hi(v.y)));
+  o.z = pack_t2(gelu_f(t_lo(v.z)), gelu_f(t_hi(v.z)));
+  o.w = pack_t2(gelu_f(t_lo(v.w)), gelu_f(t_hi(v.w)));
   y[i] = o;
 }
 
@@ -181,10 +181,10 @@ __global__ void gelu_bwd_kernel(const uint4* __restrict__ dy, const uint4* __res
   if (i >= n8) return;
   const uint4 v = x[i], d = dy[i];
   uint4 o;
-  o.x = pack_bf16x2(bf16_lo(d.x) * gelu_grad_f(bf16_lo(v.x)), bf16_hi(d.x) * gelu_grad_f(bf16_hi(v.x)));
-  o.y = pack_bf16x2(bf16_lo(d.y) * gelu_grad_f(bf16_lo(v.y)), bf16_hi(d.y) * gelu_grad_f(bf16_hi(v.y)));
-  o.z = pack_bf16x2(bf16_lo(d.z) * gelu_grad_f(bf16_lo(v.z)), bf16_hi(d.z) * gelu_grad_f(bf16_hi(v.z)));
-  o.w = pack_bf16x2(bf16_lo(d.w) * gelu_grad_f(bf16_lo(v.w)), bf16_hi(d.w) * gelu_grad_f(bf16_hi(v.w)));
+  o.x = pack_t2(t_lo(d.x) * gelu_grad_f(t_lo(v.x)), t_hi(d.x) * gelu_grad_f(t_hi(v.x)));
+  o.y = pack_t2(t_lo(d.y) * gelu_grad_f(t_lo(v.y)), t_hi(d.y) * gelu_grad_f(t_hi(v.y)));
+  o.z = pack_t2(t_lo(d.z) * gelu_grad_f(t_lo(v.z)), t_hi(d.z) * gelu_grad_f(t_hi(v.z)));
+  o.w = pack_t2(t_lo(d.w) * gelu_grad_f(t_lo(v.w)), t_hi(d.w) * gelu_grad_f(t_hi(v.w)));
   dx[i] = o;
 }
 
@@ -193,12 +193,12 @@ __global__ void tanh_fwd_kernel(const float* __restrict__ x, float* __restrict__
   if (i < n) y[i] = tanhf(x[i]);
 }
 
-__global__ void tanh_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, float* __restrict__ dx, __nv_bfloat16* __restrict__ dxb, long long n) {
+__global__ void tanh_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, float* __restrict__ dx, rb_t* __restrict__ dxb, long long n) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float v = dy[i] * (1.f - y[i] * y[i]);
   if (dx) dx[i] = v;
-  if (dxb) dxb[i] = __float2bfloat16(v);
+  if (dxb) dxb[i] = f2t(v);
 }
 
 // ------------------------------------------------------------------------------------------------ attention, head_dim 64, S <= 128
@@ -207,8 +207,8 @@ constexpr int AS_DH = 64;
 constexpr int AS_PAD = 65;
 
 __global__ void __launch_bounds__(128)
-attn_small_fwd_kernel(const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16* __restrict__ K, const __nv_bfloat16* __restrict__ V,
-                      const uint8_t* __restrict__ mask, __nv_bfloat16* __restrict__ O, float* __restrict__ P, int H, int S, long long ldq, long long ldk,
+attn_small_fwd_kernel(const rb_t* __restrict__ Q, const rb_t* __restrict__ K, const rb_t* __restrict__ V,
+                      const uint8_t* __restrict__ mask, rb_t* __restrict__ O, float* __restrict__ P, int H, int S, long long ldq, long long ldk,
                       long long ldv, long long ldo, float scale, DropK drop) {
   extern __shared__ float sm[];
   float* q = sm;
@@ -219,9 +219,9 @@ attn_small_fwd_kernel(const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16* 
   for (int i = threadIdx.x; i < S * AS_DH; i += blockDim.x) {
     const int r = i / AS_DH, c = i - r * AS_DH;
     const long long row = static_cast<long long>(b) * S + r;
-    q[r * AS_PAD + c] = __bfloat162float(Q[row * ldq + h * AS_DH + c]) * scale;
-    k[r * AS_PAD + c] = __bfloat162float(K[row * ldk + h * AS_DH + c]);
-    v[r * AS_PAD + c] = __bfloat162float(V[row * ldv + h * AS_DH + c]);
+    q[r * AS_PAD + c] = t2f(Q[row * ldq + h * AS_DH + c]) * scale;
+    k[r * AS_PAD + c] = t2f(K[row * ldk + h * AS_DH + c]);
+    v[r * AS_PAD + c] = t2f(V[row * ldv + h * AS_DH + c]);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < S * S; i += blockDim.x) {
@@ -259,14 +259,14 @@ attn_small_fwd_kernel(const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16* 
     const int r = i / AS_DH, c = i - r * AS_DH;
     float acc = 0.f;
     for (int j = 0; j < S; ++j) acc = fmaf(p[r * S + j], v[j * AS_PAD + c], acc);
-    O[(static_cast<long long>(b) * S + r) * ldo + h * AS_DH + c] = __float2bfloat16(acc);
+    O[(static_cast<long long>(b) * S + r) * ldo + h * AS_DH + c] = f2t(acc);
   }
 }
 
 __global__ void __launch_bounds__(128)
-attn_small_bwd_kernel(const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16* __restrict__ K, const __nv_bfloat16* __restrict__ V,
-                      const __nv_bfloat16* __restrict__ dO, const float* __restrict__ P, __nv_bfloat16* __restrict__ dQ, __nv_bfloat16* __restrict__ dK,
-                      __nv_bfloat16* __restrict__ dV, int H, int S, long long ldq, long long ldk, long long ldv, long long lddo, long long lddq,
+attn_small_bwd_kernel(const rb_t* __restrict__ Q, const rb_t* __restrict__ K, const rb_t* __restrict__ V,
+                      const rb_t* __restrict__ dO, const float* __restrict__ P, rb_t* __restrict__ dQ, rb_t* __restrict__ dK,
+                      rb_t* __restrict__ dV, int H, int S, long long ldq, long long ldk, long long ldv, long long lddo, long long lddq,
                       long long lddk, long long lddv, float scale, DropK drop) {
   extern __shared__ float sm[];
   float* q = sm;
@@ -280,10 +280,10 @@ attn_small_bwd_kernel(const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16* 
   for (int i = threadIdx.x; i < S * AS_DH; i += blockDim.x) {
     const int r = i / AS_DH, c = i - r * AS_DH;
     const long long row = static_cast<long long>(b) * S + r;
-    q[r * AS_PAD + c] = __bfloat162float(Q[row * ldq + h * AS_DH + c]);
-    k[r * AS_PAD + c] = __bfloat162float(K[row * ldk + h * AS_DH + c]);
-    v[r * AS_PAD + c] = __bfloat162float(V[row * ldv + h * AS_DH + c]);
-    go[r * AS_PAD + c] = __bfloat162float(dO[row * lddo + h * AS_DH + c]);
+    q[r * AS_PAD + c] = t2f(Q[row * ldq + h * AS_DH + c]);
+    k[r * AS_PAD + c] = t2f(K[row * ldk + h * AS_DH + c]);
+    v[r * AS_PAD + c] = t2f(V[row * ldv + h * AS_DH + c]);
+    go[r * AS_PAD + c] = t2f(dO[row * lddo + h * AS_DH + c]);
   }
   for (int i = threadIdx.x; i < S * S; i += blockDim.x) p[i] = P[static_cast<long long>(blockIdx.x) * S * S + i];
   __syncthreads();
@@ -323,9 +323,9 @@ attn_small_bwd_kernel(const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16* 
       av = fmaf(pm[j * S + r], go[j * AS_PAD + c], av);  // dV[r] = sum_j (P .* M)[j,r] dO[j]
     }
     const long long row = static_cast<long long>(b) * S + r;
-    dQ[row * lddq + h * AS_DH + c] = __float2bfloat16(aq);
-    dK[row * lddk + h * AS_DH + c] = __float2bfloat16(ak);
-    dV[row * lddv + h * AS_DH + c] = __float2bfloat16(av);
+    dQ[row * lddq + h * AS_DH + c] = f2t(aq);
+    dK[row * lddk + h * AS_DH + c] = f2t(ak);
+    dV[row * lddv + h * AS_DH + c] = f2t(av);
   }
 }
 
@@ -356,8 +356,8 @@ extern "C" int rb_ln_wide_fwd(const float* x, const float* gamma, const float* b
   if (rows <= 0) return 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
-  if (D == 768) ln_wide_fwd_kernel<6><<<grid, 256, 0, st>>>(x, gamma, beta, rows, eps, y32, static_cast<__nv_bfloat16*>(yb), mean, rstd, make_dropk(drop));
-  else if (D == 1024) ln_wide_fwd_kernel<8><<<grid, 256, 0, st>>>(x, gamma, beta, rows, eps, y32, static_cast<__nv_bfloat16*>(yb), mean, rstd, make_dropk(drop));
+  if (D == 768) ln_wide_fwd_kernel<6><<<grid, 256, 0, st>>>(x, gamma, beta, rows, eps, y32, static_cast<rb_t*>(yb), mean, rstd, make_dropk(drop));
+  else if (D == 1024) ln_wide_fwd_kernel<8><<<grid, 256, 0, st>>>(x, gamma, beta, rows, eps, y32, static_cast<rb_t*>(yb), mean, rstd, make_dropk(drop));
   else return rb_fail("rb_ln_wide_fwd: D must be 768 or 1024 (got %d)", D);
   RB_CUDA(cudaGetLastError());
   return 0;
@@ -370,9 +370,9 @@ extern "C" int rb_ln_wide_bwd(const float* dy, const float* dy2, const float* x,
   long long blocks = (rows + 7) / 8;
   if (blocks > 148) blocks = 148;
   const unsigned grid = static_cast<unsigned>(blocks);
-  if (D == 768) ln_wide_bwd_kernel<6><<<grid, 256, 0, st>>>(dy, dy2, x, gamma, mean, rstd, rows, dx32, static_cast<__nv_bfloat16*>(dxb), dgamma, dbeta,
+  if (D == 768) ln_wide_bwd_kernel<6><<<grid, 256, 0, st>>>(dy, dy2, x, gamma, mean, rstd, rows, dx32, static_cast<rb_t*>(dxb), dgamma, dbeta,
                                                                   make_dropk(dy_drop), make_dropk(dxb_drop));
-  else if (D == 1024) ln_wide_bwd_kernel<8><<<grid, 256, 0, st>>>(dy, dy2, x, gamma, mean, rstd, rows, dx32, static_cast<__nv_bfloat16*>(dxb), dgamma, dbeta,
+  else if (D == 1024) ln_wide_bwd_kernel<8><<<grid, 256, 0, st>>>(dy, dy2, x, gamma, mean, rstd, rows, dx32, static_cast<rb_t*>(dxb), dgamma, dbeta,
                                                                    make_dropk(dy_drop), make_dropk(dxb_drop));
   else return rb_fail("rb_ln_wide_bwd: D must be 768 or 1024 (got %d)", D);
   RB_CUDA(cudaGetLastError());
@@ -405,7 +405,7 @@ extern "C" int rb_tanh_fwd(const float* x, float* y, long long n, void* stream) 
 
 extern "C" int rb_tanh_bwd(const float* dy, const float* y, float* dx, void* dxb, long long n, void* stream) {
   if (n <= 0) return 0;
-  tanh_bwd_kernel<<<nblk(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(dy, y, dx, static_cast<__nv_bfloat16*>(dxb), n);
+  tanh_bwd_kernel<<<nblk(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(dy, y, dx, static_cast<rb_t*>(dxb), n);
   RB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -418,8 +418,8 @@ extern "C" int rb_attn_small_fwd(const void* Q, const void* K, const void* V, co
   static bool cfg = false;
   if (!cfg) { RB_CUDA(cudaFuncSetAttribute(attn_small_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); cfg = true; }
   attn_small_fwd_kernel<<<B * H, 128, smem, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(Q), static_cast<const __nv_bfloat16*>(K), static_cast<const __nv_bfloat16*>(V), static_cast<const uint8_t*>(mask),
-      static_cast<__nv_bfloat16*>(O), P, H, S, ldq, ldk, ldv, ldo, scale, make_dropk(drop));
+      static_cast<const rb_t*>(Q), static_cast<const rb_t*>(K), static_cast<const rb_t*>(V), static_cast<const uint8_t*>(mask),
+      static_cast<rb_t*>(O), P, H, S, ldq, ldk, ldv, ldo, scale, make_dropk(drop));
   RB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -435,8 +435,8 @@ extern "C" int rb_attn_small_bwd(const void* Q, const void* K, const void* V, co
   static bool cfg = false;
   if (!cfg) { RB_CUDA(cudaFuncSetAttribute(attn_small_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); cfg = true; }
   attn_small_bwd_kernel<<<B * H, 128, smem, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(Q), static_cast<const __nv_bfloat16*>(K), static_cast<const __nv_bfloat16*>(V), static_cast<const __nv_bfloat16*>(dO), P,
-      static_cast<__nv_bfloat16*>(dQ), static_cast<__nv_bfloat16*>(dK), static_cast<__nv_bfloat16*>(dV), H, S, ldq, ldk, ldv, lddo, lddq, lddk, lddv, scale, dk);
+      static_cast<const rb_t*>(Q), static_cast<const rb_t*>(K), static_cast<const rb_t*>(V), static_cast<const rb_t*>(dO), P,
+      static_cast<rb_t*>(dQ), static_cast<rb_t*>(dK), static_cast<rb_t*>(dV), H, S, ldq, ldk, ldv, lddo, lddq, lddk, lddv, scale, dk);
   RB_CUDA(cudaGetLastError());
   return 0;
 }

@@ -3,10 +3,27 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 namespace rb {
+
+// The 16-bit type of tensor-core operands and saved activations / activation gradients.  IEEE half (10 mantissa bits) by
+// default: the reference runs fp32 / TF32 (10 bits), and the north star's 1e-3 parity needs more than bf16's 7 bits
+// (DESIGN.md section 2).  -DRB_ACT_BF16 builds the bf16 variant (wider range, 8x coarser).  Accumulation, the residual
+// stream, normalisation statistics and softmax are fp32 in both.
+#ifdef RB_ACT_BF16
+using rb_t = __nv_bfloat16;
+constexpr int RB_ACT_DTYPE = 1;
+__device__ __forceinline__ rb_t f2t(float v) { return __float2bfloat16(v); }
+__device__ __forceinline__ float t2f(rb_t v) { return __bfloat162float(v); }
+#else
+using rb_t = __half;
+constexpr int RB_ACT_DTYPE = 0;
+__device__ __forceinline__ rb_t f2t(float v) { return __float2half(v); }
+__device__ __forceinline__ float t2f(rb_t v) { return __half2float(v); }
+#endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
@@ -133,15 +150,15 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t lbo_
   d |= layout << 61;
   return d;
 }
-// Instruction descriptor for kind::f16 with bf16 inputs and fp32 accumulation.
-// c_format=1 [4,6) | a_format=1 (bf16) [7,10) | b_format=1 [10,13) | a_major [15] | b_major [16] | N>>3 [17,23) | M>>4 [24,29)
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(a_mn_major) << 15) |
+// Instruction descriptor for kind::f16 with rb_t inputs and fp32 accumulation.
+// c_format=1 (f32) [4,6) | a_format (0 = f16, 1 = bf16) [7,10) | b_format [10,13) | a_major [15] | b_major [16] | N>>3 [17,23) | M>>4 [24,29)
+__host__ __device__ constexpr uint32_t umma_idesc_t(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (static_cast<uint32_t>(RB_ACT_DTYPE) << 7) | (static_cast<uint32_t>(RB_ACT_DTYPE) << 10) | (static_cast<uint32_t>(a_mn_major) << 15) |
          (static_cast<uint32_t>(b_mn_major) << 16) | (static_cast<uint32_t>(N >> 3) << 17) |
          (static_cast<uint32_t>(M >> 4) << 24);
 }
 // D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread.
-__device__ __forceinline__ void umma_bf16_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_f16_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
@@ -149,7 +166,7 @@ __device__ __forceinline__ void umma_bf16_ss(uint32_t d_tmem, uint64_t adesc, ui
       : "memory");
 }
 // A operand from TMEM (e.g. softmax probabilities), B from smem.
-__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem),
@@ -163,12 +180,25 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 }
 
 // ----------------------------------------------------------------------------- small helpers
-__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+#ifdef RB_ACT_BF16
+__device__ __forceinline__ uint32_t pack_t2(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
 }
-__device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
-__device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
+__device__ __forceinline__ float t_lo(uint32_t v) { return __uint_as_float(v << 16); }
+__device__ __forceinline__ float t_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
+#else
+__device__ __forceinline__ uint32_t pack_t2(float a, float b) {
+  __half2 v = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float t_lo(uint32_t v) { return __low2float(*reinterpret_cast<const __half2*>(&v)); }
+__device__ __forceinline__ float t_hi(uint32_t v) { return __high2float(*reinterpret_cast<const __half2*>(&v)); }
+#endif
+// "element > 0" on the packed bits (sign-magnitude formats: positive iff the 16 bits, read as a signed integer, are > 0; NaN never
+// occurs in a ReLU output) -- the ReLU-mask tests of the backward epilogues need no conversion
+__device__ __forceinline__ bool t_pos_lo(uint32_t v) { return static_cast<int32_t>(v << 16) > 0; }
+__device__ __forceinline__ bool t_pos_hi(uint32_t v) { return static_cast<int32_t>(v & 0xFFFF0000u) > 0; }
 
 // ----------------------------------------------------------------------------- counter-based dropout (rb_dropout)
 struct DropK {  // device-side form of rb_dropout; seed == nullptr: off

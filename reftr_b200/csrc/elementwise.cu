@@ -33,7 +33,7 @@ __global__ void stem_im2col_kernel(const float* __restrict__ img, uint4* __restr
     v[e] = x;
   }
   uint4 o;
-  o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]); o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+  o.x = pack_t2(v[0], v[1]); o.y = pack_t2(v[2], v[3]); o.z = pack_t2(v[4], v[5]); o.w = pack_t2(v[6], v[7]);
   out[idx] = o;
 }
 
@@ -61,11 +61,11 @@ __global__ void maxpool_kernel(const uint4* __restrict__ in, uint4* __restrict__
         const int x = x0 + dx;
         if (x < 0 || x >= W1) continue;
         const uint4 t = __ldg(in + ((static_cast<long long>(b) * H1 + y) * W1 + x) * C8 + c);
-        m[0] = fmaxf(m[0], bf16_lo(t.x)); m[1] = fmaxf(m[1], bf16_hi(t.x)); m[2] = fmaxf(m[2], bf16_lo(t.y)); m[3] = fmaxf(m[3], bf16_hi(t.y));
-        m[4] = fmaxf(m[4], bf16_lo(t.z)); m[5] = fmaxf(m[5], bf16_hi(t.z)); m[6] = fmaxf(m[6], bf16_lo(t.w)); m[7] = fmaxf(m[7], bf16_hi(t.w));
+        m[0] = fmaxf(m[0], t_lo(t.x)); m[1] = fmaxf(m[1], t_hi(t.x)); m[2] = fmaxf(m[2], t_lo(t.y)); m[3] = fmaxf(m[3], t_hi(t.y));
+        m[4] = fmaxf(m[4], t_lo(t.z)); m[5] = fmaxf(m[5], t_hi(t.z)); m[6] = fmaxf(m[6], t_lo(t.w)); m[7] = fmaxf(m[7], t_hi(t.w));
       }
     }
-    o.x = pack_bf16x2(m[0], m[1]); o.y = pack_bf16x2(m[2], m[3]); o.z = pack_bf16x2(m[4], m[5]); o.w = pack_bf16x2(m[6], m[7]);
+    o.x = pack_t2(m[0], m[1]); o.y = pack_t2(m[2], m[3]); o.z = pack_t2(m[4], m[5]); o.w = pack_t2(m[6], m[7]);
   }
   out[idx] = o;
 }
@@ -107,20 +107,20 @@ __global__ void parity_merge_kernel(const uint4* __restrict__ dxs, const uint4* 
     uint4 t = make_uint4(0, 0, 0, 0);
     if (only_plane < 0) t = __ldg(dxs + (((static_cast<long long>(plane) * B + b) * Hs + (y >> 1)) * Ws + (xx >> 1)) * C8 + c);
     else if (plane == only_plane) t = __ldg(dxs + ((static_cast<long long>(b) * Hs + (y >> 1)) * Ws + (xx >> 1)) * C8 + c);
-    float f[8] = {bf16_lo(t.x), bf16_hi(t.x), bf16_lo(t.y), bf16_hi(t.y), bf16_lo(t.z), bf16_hi(t.z), bf16_lo(t.w), bf16_hi(t.w)};
+    float f[8] = {t_lo(t.x), t_hi(t.x), t_lo(t.y), t_hi(t.y), t_lo(t.z), t_hi(t.z), t_lo(t.w), t_hi(t.w)};
     if (add) {
       const uint4 a = __ldg(add + idx);
-      f[0] += bf16_lo(a.x); f[1] += bf16_hi(a.x); f[2] += bf16_lo(a.y); f[3] += bf16_hi(a.y);
-      f[4] += bf16_lo(a.z); f[5] += bf16_hi(a.z); f[6] += bf16_lo(a.w); f[7] += bf16_hi(a.w);
+      f[0] += t_lo(a.x); f[1] += t_hi(a.x); f[2] += t_lo(a.y); f[3] += t_hi(a.y);
+      f[4] += t_lo(a.z); f[5] += t_hi(a.z); f[6] += t_lo(a.w); f[7] += t_hi(a.w);
     }
     if (mask_src) {
       const uint4 m = __ldg(mask_src + idx);
-      const float g[8] = {bf16_lo(m.x), bf16_hi(m.x), bf16_lo(m.y), bf16_hi(m.y), bf16_lo(m.z), bf16_hi(m.z), bf16_lo(m.w), bf16_hi(m.w)};
+      const float g[8] = {t_lo(m.x), t_hi(m.x), t_lo(m.y), t_hi(m.y), t_lo(m.z), t_hi(m.z), t_lo(m.w), t_hi(m.w)};
 #pragma unroll
       for (int e = 0; e < 8; ++e)
         if (!(g[e] > 0.f)) f[e] = 0.f;
     }
-    o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]); o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
+    o.x = pack_t2(f[0], f[1]); o.y = pack_t2(f[2], f[3]); o.z = pack_t2(f[4], f[5]); o.w = pack_t2(f[6], f[7]);
   }
   dx[idx] = o;
 }
@@ -131,8 +131,8 @@ __global__ void parity_merge_kernel(const uint4* __restrict__ dxs, const uint4* 
 //   dgr  bf16 [Cin, kh*kw*Cout]      column ((kh-1-r)*kw+(kw-1-s))*Cout + co   (taps flipped: dgrad == conv with same shifts)
 //   scale[co] = w*rsqrt(rv+eps), bias[co] = b - rm*scale  (scale = 1, bias = conv bias when there is no BN)
 __global__ void pack_conv_kernel(const float* __restrict__ w, int Cout, int Cin, int kh, int kw, const float* bn_w, const float* bn_b,
-                                 const float* bn_rm, const float* bn_rv, float eps, const float* conv_bias, __nv_bfloat16* fwd, int ldk,
-                                 __nv_bfloat16* dgr, float* scale_out, float* bias_out) {
+                                 const float* bn_rm, const float* bn_rv, float eps, const float* conv_bias, rb_t* fwd, int ldk,
+                                 rb_t* dgr, float* scale_out, float* bias_out) {
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long total = static_cast<long long>(Cout) * ldk;
   if (idx >= total) return;
@@ -151,13 +151,13 @@ __global__ void pack_conv_kernel(const float* __restrict__ w, int Cout, int Cin,
   if (k < taps * Cin) {
     const int ci = k % Cin, t = k / Cin, s = t % kw, r = t / kw;
     v = w[((static_cast<long long>(co) * Cin + ci) * kh + r) * kw + s] * sc;
-    if (dgr) dgr[static_cast<long long>(ci) * taps * Cout + (static_cast<long long>((kh - 1 - r) * kw + (kw - 1 - s))) * Cout + co] = __float2bfloat16(v);
+    if (dgr) dgr[static_cast<long long>(ci) * taps * Cout + (static_cast<long long>((kh - 1 - r) * kw + (kw - 1 - s))) * Cout + co] = f2t(v);
   }
-  fwd[idx] = __float2bfloat16(v);
+  fwd[idx] = f2t(v);
 }
 
 // Linear weight fp32 [N,K] -> wb bf16 [N,K] and (optionally) wt bf16 [K,N].
-__global__ void pack_linear_kernel(const float* __restrict__ w, int N, int K, __nv_bfloat16* wb, long long ldwb, __nv_bfloat16* wt, long long ldwt) {
+__global__ void pack_linear_kernel(const float* __restrict__ w, int N, int K, rb_t* wb, long long ldwb, rb_t* wt, long long ldwt) {
   __shared__ float tile[32][33];
   const int k0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -165,7 +165,7 @@ __global__ void pack_linear_kernel(const float* __restrict__ w, int N, int K, __
     float v = 0.f;
     if (n < N && k < K) {
       v = w[static_cast<long long>(n) * K + k];
-      if (wb) wb[static_cast<long long>(n) * ldwb + k] = __float2bfloat16(v);
+      if (wb) wb[static_cast<long long>(n) * ldwb + k] = f2t(v);
     }
     tile[i][threadIdx.x] = v;
   }
@@ -173,7 +173,7 @@ __global__ void pack_linear_kernel(const float* __restrict__ w, int N, int K, __
   if (wt) {
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
       const int k = k0 + i, n = n0 + threadIdx.x;
-      if (n < N && k < K) wt[static_cast<long long>(k) * ldwt + n] = __float2bfloat16(tile[threadIdx.x][i]);
+      if (n < N && k < K) wt[static_cast<long long>(k) * ldwt + n] = f2t(tile[threadIdx.x][i]);
     }
   }
 }
@@ -191,15 +191,15 @@ __global__ void unpack_conv_grad_kernel(const float* __restrict__ dwf, const flo
 }
 
 // ------------------------------------------------------------------------------------------------ casts / reductions
-__global__ void cast_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n) {
+__global__ void cast_bf16_kernel(const float* __restrict__ in, rb_t* __restrict__ out, long long n) {
   const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
   if (i + 3 < n) {
     const float4 v = *reinterpret_cast<const float4*>(in + i);
     uint2 o;
-    o.x = pack_bf16x2(v.x, v.y); o.y = pack_bf16x2(v.z, v.w);
+    o.x = pack_t2(v.x, v.y); o.y = pack_t2(v.z, v.w);
     *reinterpret_cast<uint2*>(out + i) = o;
   } else {
-    for (long long j = i; j < n; ++j) out[j] = __float2bfloat16(in[j]);
+    for (long long j = i; j < n; ++j) out[j] = f2t(in[j]);
   }
 }
 
@@ -234,8 +234,8 @@ __global__ void colsum_vec_kernel(const T* __restrict__ x, long long ld, long lo
         if (rr < r1) {
           if (sizeof(T) == 2) {
             const uint4 v = *reinterpret_cast<const uint4*>(x + rr * ld + n0);
-            acc[0] += bf16_lo(v.x); acc[1] += bf16_hi(v.x); acc[2] += bf16_lo(v.y); acc[3] += bf16_hi(v.y);
-            acc[4 % VEC] += bf16_lo(v.z); acc[5 % VEC] += bf16_hi(v.z); acc[6 % VEC] += bf16_lo(v.w); acc[7 % VEC] += bf16_hi(v.w);
+            acc[0] += t_lo(v.x); acc[1] += t_hi(v.x); acc[2] += t_lo(v.y); acc[3] += t_hi(v.y);
+            acc[4 % VEC] += t_lo(v.z); acc[5 % VEC] += t_hi(v.z); acc[6 % VEC] += t_lo(v.w); acc[7 % VEC] += t_hi(v.w);
           } else {
             const float4 v = *reinterpret_cast<const float4*>(x + rr * ld + n0);
             acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
@@ -259,12 +259,12 @@ __global__ void colsum_vec_kernel(const T* __restrict__ x, long long ld, long lo
 }
 
 // y = a + b (fp32), optional bf16 copy
-__global__ void add_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ y, __nv_bfloat16* __restrict__ yb, long long n) {
+__global__ void add_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ y, rb_t* __restrict__ yb, long long n) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float v = a[i] + (b ? b[i] : 0.f);
   if (y) y[i] = v;
-  if (yb) yb[i] = __float2bfloat16(v);
+  if (yb) yb[i] = f2t(v);
 }
 
 }  // namespace rb
@@ -331,14 +331,14 @@ extern "C" int rb_pack_conv(const float* w, int Cout, int Cin, int kh, int kw, c
   if (ldk < kh * kw * Cin) return rb_fail("rb_pack_conv: ldk too small");
   const long long total = static_cast<long long>(Cout) * ldk;
   pack_conv_kernel<<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(w, Cout, Cin, kh, kw, bn_w, bn_b, bn_rm, bn_rv, eps, conv_bias,
-                                                                                          static_cast<__nv_bfloat16*>(fwd), ldk, static_cast<__nv_bfloat16*>(dgr), scale_out, bias_out);
+                                                                                          static_cast<rb_t*>(fwd), ldk, static_cast<rb_t*>(dgr), scale_out, bias_out);
   RB_CHECK_LAUNCH();
   return 0;
 }
 
 extern "C" int rb_pack_linear(const float* w, int N, int K, void* wb, long long ldwb, void* wt, long long ldwt, void* stream) {
   dim3 grid((K + 31) / 32, (N + 31) / 32);
-  pack_linear_kernel<<<grid, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(w, N, K, static_cast<__nv_bfloat16*>(wb), ldwb, static_cast<__nv_bfloat16*>(wt), ldwt);
+  pack_linear_kernel<<<grid, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(w, N, K, static_cast<rb_t*>(wb), ldwb, static_cast<rb_t*>(wt), ldwt);
   RB_CHECK_LAUNCH();
   return 0;
 }
@@ -352,7 +352,7 @@ extern "C" int rb_unpack_conv_grad(const float* dwf, const float* scale, float* 
 
 extern "C" int rb_cast_bf16(const float* in, void* out, long long n, void* stream) {
   if (n <= 0) return 0;
-  cast_bf16_kernel<<<blocks_for((n + 3) / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(in, static_cast<__nv_bfloat16*>(out), n);
+  cast_bf16_kernel<<<blocks_for((n + 3) / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(in, static_cast<rb_t*>(out), n);
   RB_CHECK_LAUNCH();
   return 0;
 }
@@ -367,7 +367,7 @@ extern "C" int rb_colsum(const void* x, int is_bf16, long long ld, long long row
     rpb = rpb < 64 ? 64 : ((rpb + 31) / 32) * 32;
     dim3 g(gx, static_cast<unsigned>((rows + rpb - 1) / rpb));
     if (is_bf16)
-      colsum_vec_kernel<__nv_bfloat16, 8><<<g, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(x), ld, rows, N, out, static_cast<int>(rpb));
+      colsum_vec_kernel<rb_t, 8><<<g, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const rb_t*>(x), ld, rows, N, out, static_cast<int>(rpb));
     else
       colsum_vec_kernel<float, 4><<<g, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const float*>(x), ld, rows, N, out, static_cast<int>(rpb));
     RB_CHECK_LAUNCH();
@@ -377,7 +377,7 @@ extern "C" int rb_colsum(const void* x, int is_bf16, long long ld, long long row
   ysplit = ysplit < 1 ? 1 : (ysplit > 64 ? 64 : ysplit);
   dim3 grid((N + 127) / 128, ysplit);
   if (is_bf16)
-    colsum_kernel<__nv_bfloat16><<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(x), ld, rows, N, out);
+    colsum_kernel<rb_t><<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const rb_t*>(x), ld, rows, N, out);
   else
     colsum_kernel<float><<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const float*>(x), ld, rows, N, out);
   RB_CHECK_LAUNCH();
@@ -386,7 +386,7 @@ extern "C" int rb_colsum(const void* x, int is_bf16, long long ld, long long row
 
 extern "C" int rb_add(const float* a, const float* b, float* y, void* yb, long long n, void* stream) {
   if (n <= 0) return 0;
-  add_kernel<<<blocks_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, b, y, static_cast<__nv_bfloat16*>(yb), n);
+  add_kernel<<<blocks_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, b, y, static_cast<rb_t*>(yb), n);
   RB_CHECK_LAUNCH();
   return 0;
 }

@@ -21,6 +21,7 @@
 #include "common.cuh"
 #include "host.h"
 
+#include <stdlib.h>
 #include <string.h>
 
 namespace rb {
@@ -60,6 +61,7 @@ struct GemmKParams {
   int drop_gshift;     // the site's element of output column n is n >> drop_gshift
   uint32_t drop_wpr;   // 32-bit random words per row of the site
   float mask_scale;    // multiplies what mask_src keeps
+  int debug;           // RB_GEMM_DEBUG (timing experiments only, results are wrong): 1 = no output stores, 4 = no epilogue math
 };
 
 __device__ __forceinline__ bool row_is_interior(const rb_geom& g, long long row) {
@@ -191,7 +193,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else if (warp == 1) {
     // ------------------------------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(BM, bn, MODE, MODE);
+      const uint32_t idesc = umma_idesc_t(BM, bn, MODE, MODE);
       // The issuing thread is instruction-bound (one thread, dependent issue): descriptors are formed by ADDING 16-byte-unit
       // offsets to a base descriptor (the start-address field is the low 14 bits; shared memory is < 256 KB so no carry-out).
       const uint32_t smem_base = smem_u32(smem);
@@ -212,9 +214,9 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           tc_fence_after();
           const uint64_t ad = a_desc0 + static_cast<uint64_t>(s * stage_units);
           const uint64_t bd = ad + b_units;
-          umma_bf16_ss(d_tmem, ad, bd, idesc, k != 0);
+          umma_f16_ss(d_tmem, ad, bd, idesc, k != 0);
 #pragma unroll
-          for (int kk = 1; kk < BK / 16; ++kk) umma_bf16_ss(d_tmem, ad + kk * kstep, bd + kk * kstep, idesc, 1);
+          for (int kk = 1; kk < BK / 16; ++kk) umma_f16_ss(d_tmem, ad + kk * kstep, bd + kk * kstep, idesc, 1);
           umma_commit(&empty[s]);
           if (++s == p.stages) { s = 0; ph ^= 1; }
         }
@@ -290,14 +292,19 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           named_bar_sync(1 + team, 128);
         }
         uint32_t vv[2][32];
+        if (p.debug & 4) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) vv[0][j] = vv[1][j] = 0u;
+        } else {
         tmem_ld_32x32(tmem_base + lane_addr + as * bn + ch * 64, vv[0]);
         tmem_ld_32x32(tmem_base + lane_addr + as * bn + ch * 64 + 32, vv[1]);
         tmem_ld_wait();
+        }
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           const int hc0 = col0 + half * 32;
           const uint32_t (&v)[32] = vv[half];
-          if (hc0 >= p.N) continue;  // warp-uniform
+          if (hc0 >= p.N || (p.debug & 4)) continue;  // warp-uniform
           float f[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
@@ -356,8 +363,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const uint4 tt = *reinterpret_cast<const uint4*>(row + (((half * 4 + j) ^ sw128) << 4));
-              f[8 * j] += bf16_lo(tt.x); f[8 * j + 1] += bf16_hi(tt.x); f[8 * j + 2] += bf16_lo(tt.y); f[8 * j + 3] += bf16_hi(tt.y);
-              f[8 * j + 4] += bf16_lo(tt.z); f[8 * j + 5] += bf16_hi(tt.z); f[8 * j + 6] += bf16_lo(tt.w); f[8 * j + 7] += bf16_hi(tt.w);
+              f[8 * j] += t_lo(tt.x); f[8 * j + 1] += t_hi(tt.x); f[8 * j + 2] += t_lo(tt.y); f[8 * j + 3] += t_hi(tt.y);
+              f[8 * j + 4] += t_lo(tt.z); f[8 * j + 5] += t_hi(tt.z); f[8 * j + 6] += t_lo(tt.w); f[8 * j + 7] += t_hi(tt.w);
             }
           }
           if (p.has_res32) {
@@ -380,8 +387,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               const uint32_t w[4] = {tt.x, tt.y, tt.z, tt.w};
 #pragma unroll
               for (int ee = 0; ee < 4; ++ee) {
-                f[8 * j + 2 * ee] = (bf16_lo(w[ee]) > 0.f) ? f[8 * j + 2 * ee] * p.mask_scale : 0.f;
-                f[8 * j + 2 * ee + 1] = (bf16_hi(w[ee]) > 0.f) ? f[8 * j + 2 * ee + 1] * p.mask_scale : 0.f;
+                f[8 * j + 2 * ee] = t_pos_lo(w[ee]) ? f[8 * j + 2 * ee] * p.mask_scale : 0.f;
+                f[8 * j + 2 * ee + 1] = t_pos_hi(w[ee]) ? f[8 * j + 2 * ee + 1] * p.mask_scale : 0.f;
               }
             }
           }
@@ -394,8 +401,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               uint4 tt;
-              tt.x = pack_bf16x2(f[8 * j], f[8 * j + 1]); tt.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
-              tt.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]); tt.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+              tt.x = pack_t2(f[8 * j], f[8 * j + 1]); tt.y = pack_t2(f[8 * j + 2], f[8 * j + 3]);
+              tt.z = pack_t2(f[8 * j + 4], f[8 * j + 5]); tt.w = pack_t2(f[8 * j + 6], f[8 * j + 7]);
               *reinterpret_cast<uint4*>(row + (((half * 4 + j) ^ sw128) << 4)) = tt;
             }
           }
@@ -416,7 +423,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // here (instead of before writing) needs a single barrier per chunk
         if (two_slots && store_thread) tma_store_wait_read<0>();
         named_bar_sync(1 + team, 128);
-        if (store_thread) {
+        if (store_thread && !(p.debug & 1)) {
           if (p.has_out) tma_store_2d(&tmOut, oslot, col0, c.m0);
           if (p.has_out32) {
             tma_store_2d(&tmOut32, oslot + p.out_off_f32, col0, c.m0);
@@ -486,6 +493,10 @@ extern "C" int rb_gemm(const rb_gemm_args* a, void* stream) {
   kp.bias = a->bias;
   kp.relu = a->relu; kp.atomic = a->atomic; kp.geom = a->geom;
   kp.kblocks = (a->K + BK - 1) / BK;
+  {
+    const char* dbg = getenv("RB_GEMM_DEBUG");
+    kp.debug = dbg ? atoi(dbg) : 0;
+  }
   kp.drop = make_dropk(a->drop);
   kp.drop_gshift = a->drop_gshift;
   kp.mask_scale = a->mask_scale == 0.f ? 1.f : a->mask_scale;
@@ -570,11 +581,11 @@ extern "C" int rb_gemm(const rb_gemm_args* a, void* stream) {
   }
   tmOut = tmA; tmOut32 = tmA; tmRes = tmA; tmRes32 = tmA; tmMask = tmA;  // placeholders for unused maps
   const uint64_t M64 = static_cast<uint64_t>(a->M), N64 = static_cast<uint64_t>(a->N);
-  if (kp.has_out && make_tmap_2d(&tmOut, static_cast<const __nv_bfloat16*>(a->out) + a->out_row_off * a->ldo, N64, M64, a->ldo * 2, 64, BM)) return 1;
+  if (kp.has_out && make_tmap_2d(&tmOut, static_cast<const rb_t*>(a->out) + a->out_row_off * a->ldo, N64, M64, a->ldo * 2, 64, BM)) return 1;
   if (kp.has_out32 && make_tmap_2d_f32(&tmOut32, a->out32 + a->out_row_off * a->ldo32, N64, M64, a->ldo32 * 4, 32, BM)) return 1;
-  if (kp.has_res && make_tmap_2d(&tmRes, static_cast<const __nv_bfloat16*>(a->res) + a->out_row_off * a->ldres, N64, M64, a->ldres * 2, 64, BM)) return 1;
+  if (kp.has_res && make_tmap_2d(&tmRes, static_cast<const rb_t*>(a->res) + a->out_row_off * a->ldres, N64, M64, a->ldres * 2, 64, BM)) return 1;
   if (kp.has_res32 && make_tmap_2d_f32(&tmRes32, a->res32 + a->out_row_off * a->ldres32, N64, M64, a->ldres32 * 4, 32, BM)) return 1;
-  if (kp.has_mask && make_tmap_2d(&tmMask, static_cast<const __nv_bfloat16*>(a->mask_src) + a->out_row_off * a->ldmask, N64, M64, a->ldmask * 2, 64, BM)) return 1;
+  if (kp.has_mask && make_tmap_2d(&tmMask, static_cast<const rb_t*>(a->mask_src) + a->out_row_off * a->ldmask, N64, M64, a->ldmask * 2, 64, BM)) return 1;
 
   static bool configured[2] = {false, false};
   const int grid = kp.tiles_total < nsm ? kp.tiles_total : nsm;

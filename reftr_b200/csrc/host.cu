@@ -54,7 +54,7 @@ static int make_tmap_2d_impl(CUtensorMap* out, const void* ptr, uint64_t inner, 
 
 int make_tmap_2d(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t rows, uint64_t pitch_bytes, uint32_t box_inner,
                  uint32_t box_rows) {
-  return make_tmap_2d_impl(out, ptr, inner, rows, pitch_bytes, box_inner, box_rows, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2);
+  return make_tmap_2d_impl(out, ptr, inner, rows, pitch_bytes, box_inner, box_rows, rb::RB_ACT_DTYPE ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2);
 }
 
 int make_tmap_2d_f32(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t rows, uint64_t pitch_bytes, uint32_t box_inner,
@@ -74,4 +74,5 @@ int sm_count() {
 }  // namespace rb
 
 extern "C" const char* rb_last_error(void) { return rb::g_err; }
-extern "C" int rb_version(void) { return 1; }
+extern "C" int rb_version(void) { return 2; }
+extern "C" int rb_act_dtype(void) { return rb::RB_ACT_DTYPE; }

@@ -18,8 +18,8 @@ constexpr int LN_D = 256;
 // y = LN(x)*gamma+beta (optionally ReLU'd); writes fp32 y, bf16 y and bf16 (y + pos) at mapped rows; saves mean/rstd.
 // Replaces nn.LayerNorm at transformer.py:176/:181/:242/:248/:252, reftr_transformer.py:17/:21/:38.
 __global__ void layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, long long rows,
-                                     float eps, float* __restrict__ y32, __nv_bfloat16* __restrict__ yb, const float* __restrict__ pos32,
-                                     __nv_bfloat16* __restrict__ ypb, int relu, float* __restrict__ mean_out, float* __restrict__ rstd_out, RowMap map,
+                                     float eps, float* __restrict__ y32, rb_t* __restrict__ yb, const float* __restrict__ pos32,
+                                     rb_t* __restrict__ ypb, int relu, float* __restrict__ mean_out, float* __restrict__ rstd_out, RowMap map,
                                      DropK drop) {
   const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -66,14 +66,14 @@ __global__ void layernorm_fwd_kernel(const float* __restrict__ x, const float* _
   }
   if (yb) {
     uint4 o;
-    o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]); o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+    o.x = pack_t2(v[0], v[1]); o.y = pack_t2(v[2], v[3]); o.z = pack_t2(v[4], v[5]); o.w = pack_t2(v[6], v[7]);
     *reinterpret_cast<uint4*>(yb + orow * LN_D + lane * 8) = o;
   }
   if (ypb) {
     const float4 p0 = *reinterpret_cast<const float4*>(pos32 + orow * LN_D + lane * 8), p1 = *reinterpret_cast<const float4*>(pos32 + orow * LN_D + lane * 8 + 4);
     uint4 o;
-    o.x = pack_bf16x2(v[0] + p0.x, v[1] + p0.y); o.y = pack_bf16x2(v[2] + p0.z, v[3] + p0.w);
-    o.z = pack_bf16x2(v[4] + p1.x, v[5] + p1.y); o.w = pack_bf16x2(v[6] + p1.z, v[7] + p1.w);
+    o.x = pack_t2(v[0] + p0.x, v[1] + p0.y); o.y = pack_t2(v[2] + p0.z, v[3] + p0.w);
+    o.z = pack_t2(v[4] + p1.x, v[5] + p1.y); o.w = pack_t2(v[6] + p1.z, v[7] + p1.w);
     *reinterpret_cast<uint4*>(ypb + orow * LN_D + lane * 8) = o;
   }
 }
@@ -83,7 +83,7 @@ __global__ void layernorm_fwd_kernel(const float* __restrict__ x, const float* _
 // dx = rstd*(g - mean(g) - xhat*mean(g*xhat)), g = dy*gamma; dgamma += dy*xhat, dbeta += dy (atomics, once per warp).
 __global__ void layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ dy2, const float* __restrict__ y_relu, float relu_scale,
                                      const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ mean,
-                                     const float* __restrict__ rstd, long long rows, float* __restrict__ dx32, __nv_bfloat16* __restrict__ dxb,
+                                     const float* __restrict__ rstd, long long rows, float* __restrict__ dx32, rb_t* __restrict__ dxb,
                                      float* __restrict__ dgamma, float* __restrict__ dbeta, RowMap map, DropK odrop) {
   const int lane = threadIdx.x & 31;
   const uint32_t okey = odrop.seed ? drop_key(odrop) : 0u;
@@ -144,7 +144,7 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ dy, const float* 
         }
       }
       uint4 p;
-      p.x = pack_bf16x2(o[0], o[1]); p.y = pack_bf16x2(o[2], o[3]); p.z = pack_bf16x2(o[4], o[5]); p.w = pack_bf16x2(o[6], o[7]);
+      p.x = pack_t2(o[0], o[1]); p.y = pack_t2(o[2], o[3]); p.z = pack_t2(o[4], o[5]); p.w = pack_t2(o[6], o[7]);
       *reinterpret_cast<uint4*>(dxb + row * LN_D + lane * 8) = p;
     }
   }
@@ -172,8 +172,8 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ dy, const float* 
 // [B, h+2, w+2, 256]; one CTA per (sample, group of 8 channels) normalises over the h*w interior pixels and writes
 // token rows b*S + L + (y*w + x): fp32, bf16 and bf16(+pos).
 __global__ void groupnorm_tokens_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, int h, int w,
-                                            int S, int L, float eps, float* __restrict__ y32, __nv_bfloat16* __restrict__ yb,
-                                            const float* __restrict__ pos32, __nv_bfloat16* __restrict__ ypb, float* __restrict__ mean_out,
+                                            int S, int L, float eps, float* __restrict__ y32, rb_t* __restrict__ yb,
+                                            const float* __restrict__ pos32, rb_t* __restrict__ ypb, float* __restrict__ mean_out,
                                             float* __restrict__ rstd_out) {
   const int b = blockIdx.x, grp = blockIdx.y;
   const int hw = h * w, wp = w + 2;
@@ -218,12 +218,12 @@ __global__ void groupnorm_tokens_fwd_kernel(const float* __restrict__ x, const f
     o4[0] = make_float4(v[0], v[1], v[2], v[3]);
     o4[1] = make_float4(v[4], v[5], v[6], v[7]);
     uint4 t;
-    t.x = pack_bf16x2(v[0], v[1]); t.y = pack_bf16x2(v[2], v[3]); t.z = pack_bf16x2(v[4], v[5]); t.w = pack_bf16x2(v[6], v[7]);
+    t.x = pack_t2(v[0], v[1]); t.y = pack_t2(v[2], v[3]); t.z = pack_t2(v[4], v[5]); t.w = pack_t2(v[6], v[7]);
     *reinterpret_cast<uint4*>(yb + o) = t;
     if (ypb) {
       const float4 p0 = *reinterpret_cast<const float4*>(pos32 + o), p1 = *reinterpret_cast<const float4*>(pos32 + o + 4);
-      t.x = pack_bf16x2(v[0] + p0.x, v[1] + p0.y); t.y = pack_bf16x2(v[2] + p0.z, v[3] + p0.w);
-      t.z = pack_bf16x2(v[4] + p1.x, v[5] + p1.y); t.w = pack_bf16x2(v[6] + p1.z, v[7] + p1.w);
+      t.x = pack_t2(v[0] + p0.x, v[1] + p0.y); t.y = pack_t2(v[2] + p0.z, v[3] + p0.w);
+      t.z = pack_t2(v[4] + p1.x, v[5] + p1.y); t.w = pack_t2(v[6] + p1.z, v[7] + p1.w);
       *reinterpret_cast<uint4*>(ypb + o) = t;
     }
   }
@@ -233,7 +233,7 @@ __global__ void groupnorm_tokens_fwd_kernel(const float* __restrict__ x, const f
 // caller zero-fills the buffer once), dgamma/dbeta accumulated atomically.
 __global__ void groupnorm_tokens_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ dy2, const float* __restrict__ x,
                                             const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd, int h, int w,
-                                            int S, int L, __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                                            int S, int L, rb_t* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta) {
   const int b = blockIdx.x, grp = blockIdx.y;
   const int hw = h * w, wp = w + 2;
   const long long img_off = static_cast<long long>(b) * (h + 2) * wp * LN_D + grp * 8;
@@ -311,7 +311,7 @@ __global__ void groupnorm_tokens_bwd_kernel(const float* __restrict__ dy, const 
 #pragma unroll
     for (int i = 0; i < 8; ++i) ov[i] = rs * (d[i] * g[i] - ms1 - xh[i] * ms2);
     uint4 t;
-    t.x = pack_bf16x2(ov[0], ov[1]); t.y = pack_bf16x2(ov[2], ov[3]); t.z = pack_bf16x2(ov[4], ov[5]); t.w = pack_bf16x2(ov[6], ov[7]);
+    t.x = pack_t2(ov[0], ov[1]); t.y = pack_t2(ov[2], ov[3]); t.z = pack_t2(ov[4], ov[5]); t.w = pack_t2(ov[6], ov[7]);
     *reinterpret_cast<uint4*>(dx + xi) = t;
   }
 }
@@ -415,7 +415,7 @@ extern "C" int rb_layernorm_fwd(const float* x, const float* gamma, const float*
   if (ypb && !pos32) return rb_fail("rb_layernorm_fwd: ypb needs pos32");
   RowMap m{map_group, map_stride, map_offset};
   layernorm_fwd_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, gamma, beta, rows, eps, y32, static_cast<__nv_bfloat16*>(yb), pos32, static_cast<__nv_bfloat16*>(ypb), relu, mean, rstd, m, make_dropk(drop));
+      x, gamma, beta, rows, eps, y32, static_cast<rb_t*>(yb), pos32, static_cast<rb_t*>(ypb), relu, mean, rstd, m, make_dropk(drop));
   RB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -429,7 +429,7 @@ extern "C" int rb_layernorm_bwd(const float* dy, const float* dy2, const float* 
   long long blocks = (rows + 7) / 8;
   if (blocks > 148) blocks = 148;  // one per SM; warps stride over rows, dgamma/dbeta cost one atomic per column per block
   layernorm_bwd_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      dy, dy2, y_relu, relu_scale == 0.f ? 1.f : relu_scale, x, gamma, mean, rstd, rows, dx32, static_cast<__nv_bfloat16*>(dxb), dgamma, dbeta, m,
+      dy, dy2, y_relu, relu_scale == 0.f ? 1.f : relu_scale, x, gamma, mean, rstd, rows, dx32, static_cast<rb_t*>(dxb), dgamma, dbeta, m,
       make_dropk(dxb_drop));
   RB_CUDA(cudaGetLastError());
   return 0;
@@ -437,8 +437,8 @@ extern "C" int rb_layernorm_bwd(const float* dy, const float* dy2, const float* 
 
 extern "C" int rb_groupnorm_tokens_fwd(const float* x, const float* gamma, const float* beta, int B, int h, int w, int S, int L, float eps, float* y32,
                                        void* yb, const float* pos32, void* ypb, float* mean, float* rstd, void* stream) {
-  groupnorm_tokens_fwd_kernel<<<dim3(B, 32), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, gamma, beta, h, w, S, L, eps, y32, static_cast<__nv_bfloat16*>(yb),
-                                                                                       pos32, static_cast<__nv_bfloat16*>(ypb), mean, rstd);
+  groupnorm_tokens_fwd_kernel<<<dim3(B, 32), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, gamma, beta, h, w, S, L, eps, y32, static_cast<rb_t*>(yb),
+                                                                                       pos32, static_cast<rb_t*>(ypb), mean, rstd);
   RB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -446,7 +446,7 @@ extern "C" int rb_groupnorm_tokens_fwd(const float* x, const float* gamma, const
 extern "C" int rb_groupnorm_tokens_bwd(const float* dy, const float* dy2, const float* x, const float* gamma, const float* mean, const float* rstd,
                                        int B, int h, int w, int S, int L, void* dx, float* dgamma, float* dbeta, void* stream) {
   groupnorm_tokens_bwd_kernel<<<dim3(B, 32), 256, 0, static_cast<cudaStream_t>(stream)>>>(dy, dy2, x, gamma, mean, rstd, h, w, S, L,
-                                                                                       static_cast<__nv_bfloat16*>(dx), dgamma, dbeta);
+                                                                                       static_cast<rb_t*>(dx), dgamma, dbeta);
   RB_CUDA(cudaGetLastError());
   return 0;
 }

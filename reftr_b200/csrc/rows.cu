@@ -21,7 +21,7 @@ static RowMap4 host_map(const int* m) {
 
 // y[my(r), c] = a[ma(r), c] + b[mb(r), c]; one thread per 4 columns
 __global__ void rows_add_kernel(const float* __restrict__ a, long long lda, RowMap4 ma, const float* __restrict__ b, long long ldb, RowMap4 mb,
-                                float* __restrict__ y32, long long ldy, __nv_bfloat16* __restrict__ yb, long long ldyb, RowMap4 my, long long rows,
+                                float* __restrict__ y32, long long ldy, rb_t* __restrict__ yb, long long ldyb, RowMap4 my, long long rows,
                                 int D4) {
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= rows * D4) return;
@@ -36,7 +36,7 @@ __global__ void rows_add_kernel(const float* __restrict__ a, long long lda, RowM
   if (y32) *reinterpret_cast<float4*>(y32 + o * ldy + c) = v;
   if (yb) {
     uint2 t;
-    t.x = pack_bf16x2(v.x, v.y); t.y = pack_bf16x2(v.z, v.w);
+    t.x = pack_t2(v.x, v.y); t.y = pack_t2(v.z, v.w);
     *reinterpret_cast<uint2*>(yb + o * ldyb + c) = t;
   }
 }
@@ -62,7 +62,7 @@ extern "C" int rb_rows_add(const float* a, long long lda, const int* map_a, cons
   if ((lda % 4) || (b && (ldb % 4)) || (y32 && (ldy % 4)) || (yb && (ldyb % 4))) return rb_fail("rb_rows_add: pitches must be multiples of 4 elements");
   const long long total = rows * (D / 4);
   rows_add_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      a, lda, host_map(map_a), b, ldb, host_map(map_b), y32, ldy, static_cast<__nv_bfloat16*>(yb), ldyb, host_map(map_y), rows, D / 4);
+      a, lda, host_map(map_a), b, ldb, host_map(map_b), y32, ldy, static_cast<rb_t*>(yb), ldyb, host_map(map_y), rows, D / 4);
   RB_CUDA(cudaGetLastError());
   return 0;
 }

@@ -7,7 +7,7 @@
 namespace rb {
 
 // ------------------------------------------------------------------------------------------------ tokens <-> grid
-__global__ void tokens_to_grid_kernel(const float* __restrict__ tok, int S, int L, int h, int w, int C, __nv_bfloat16* __restrict__ grid, long long ld,
+__global__ void tokens_to_grid_kernel(const float* __restrict__ tok, int S, int L, int h, int w, int C, rb_t* __restrict__ grid, long long ld,
                                       int col0, long long total) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total) return;
@@ -17,14 +17,14 @@ __global__ void tokens_to_grid_kernel(const float* __restrict__ tok, int S, int 
   const int b = static_cast<int>(t / (h * w));
   const int y = p / w, x = p - y * w;
   const float4 v = *reinterpret_cast<const float4*>(tok + (static_cast<long long>(b) * S + L + p) * C + c4 * 4);
-  __nv_bfloat16* dst = grid + ((static_cast<long long>(b) * (h + 2) + y + 1) * (w + 2) + x + 1) * ld + col0 + c4 * 4;
+  rb_t* dst = grid + ((static_cast<long long>(b) * (h + 2) + y + 1) * (w + 2) + x + 1) * ld + col0 + c4 * 4;
   uint2 o;
-  o.x = pack_bf16x2(v.x, v.y);
-  o.y = pack_bf16x2(v.z, v.w);
+  o.x = pack_t2(v.x, v.y);
+  o.y = pack_t2(v.z, v.w);
   *reinterpret_cast<uint2*>(dst) = o;
 }
 
-__global__ void grid_to_tokens_kernel(const __nv_bfloat16* __restrict__ grid, long long ld, int col0, int S, int L, int h, int w, int C,
+__global__ void grid_to_tokens_kernel(const rb_t* __restrict__ grid, long long ld, int col0, int S, int L, int h, int w, int C,
                                       float* __restrict__ dtok, long long total) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total) return;
@@ -34,14 +34,14 @@ __global__ void grid_to_tokens_kernel(const __nv_bfloat16* __restrict__ grid, lo
   const int b = static_cast<int>(t / (h * w));
   const int y = p / w, x = p - y * w;
   const uint2 v = *reinterpret_cast<const uint2*>(grid + ((static_cast<long long>(b) * (h + 2) + y + 1) * (w + 2) + x + 1) * ld + col0 + c4 * 4);
-  *reinterpret_cast<float4*>(dtok + (static_cast<long long>(b) * S + L + p) * C + c4 * 4) = make_float4(bf16_lo(v.x), bf16_hi(v.x), bf16_lo(v.y), bf16_hi(v.y));
+  *reinterpret_cast<float4*>(dtok + (static_cast<long long>(b) * S + L + p) * C + c4 * 4) = make_float4(t_lo(v.x), t_hi(v.x), t_lo(v.y), t_hi(v.y));
 }
 
 // ------------------------------------------------------------------------------------------------ attention map
 // one CTA per sample; 8 warps = 8 heads; logits live in shared memory [8][hw]
 __global__ void __launch_bounds__(256)
 attn_map_fwd_kernel(const float* __restrict__ q, const float* __restrict__ k, const uint8_t* __restrict__ kpm, int S, int L, int hw, int w, float scale,
-                    float* __restrict__ att, __nv_bfloat16* __restrict__ grid, long long ld, int col0) {
+                    float* __restrict__ att, rb_t* __restrict__ grid, long long ld, int col0) {
   extern __shared__ float sm[];
   float* lg = sm;  // [8][hw]
   __shared__ float red[8];
@@ -88,12 +88,12 @@ attn_map_fwd_kernel(const float* __restrict__ q, const float* __restrict__ k, co
     const float a = lg[i] * inv;
     att[(static_cast<long long>(b) * 8 + nn) * hw + p] = a;
     const int y = p / w, x = p - y * w;
-    grid[((static_cast<long long>(b) * (h + 2) + y + 1) * (w + 2) + x + 1) * ld + col0 + nn] = __float2bfloat16(a);
+    grid[((static_cast<long long>(b) * (h + 2) + y + 1) * (w + 2) + x + 1) * ld + col0 + nn] = f2t(a);
   }
 }
 
 __global__ void __launch_bounds__(256)
-attn_map_bwd_kernel(const float* __restrict__ datt_ext, const __nv_bfloat16* __restrict__ dgrid, long long ld, int col0, const float* __restrict__ att,
+attn_map_bwd_kernel(const float* __restrict__ datt_ext, const rb_t* __restrict__ dgrid, long long ld, int col0, const float* __restrict__ att,
                     const float* __restrict__ q, const float* __restrict__ k, int S, int L, int hw, int w, float scale, float* __restrict__ dq,
                     float* __restrict__ dk) {
   extern __shared__ float sm[];
@@ -106,7 +106,7 @@ attn_map_bwd_kernel(const float* __restrict__ datt_ext, const __nv_bfloat16* __r
   for (int i = threadIdx.x; i < 8 * hw; i += 256) {
     const int nn = i / hw, p = i - nn * hw;
     const int y = p / w, x = p - y * w;
-    float d = __bfloat162float(dgrid[((static_cast<long long>(b) * (h + 2) + y + 1) * (w + 2) + x + 1) * ld + col0 + nn]);
+    float d = t2f(dgrid[((static_cast<long long>(b) * (h + 2) + y + 1) * (w + 2) + x + 1) * ld + col0 + nn]);
     if (datt_ext) d += datt_ext[(static_cast<long long>(b) * 8 + nn) * hw + p];
     dl[i] = d;
     dot += d * att[static_cast<long long>(b) * 8 * hw + i];
@@ -151,7 +151,7 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 // one CTA per (sample, group); thread t walks pixels t, t+blockDim, ... and the Cg channels of the group
 __global__ void __launch_bounds__(256)
 groupnorm_nhwc_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, int H, int W, int C, int G,
-                          float eps, int relu, __nv_bfloat16* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+                          float eps, int relu, rb_t* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out) {
   __shared__ float red[8];
   const int b = blockIdx.x, g = blockIdx.y;
   const int Cg = C / G, Wp = W + 2, Hp = H + 2;
@@ -184,15 +184,15 @@ groupnorm_nhwc_fwd_kernel(const float* __restrict__ x, const float* __restrict__
         v = (x[o + c] - mu) * rs * gamma[g * Cg + c] + beta[g * Cg + c];
         if (relu) v = fmaxf(v, 0.f);
       }
-      y[o + c] = __float2bfloat16(v);
+      y[o + c] = f2t(v);
     }
   }
 }
 
 __global__ void __launch_bounds__(256)
-groupnorm_nhwc_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y, const float* __restrict__ x,
+groupnorm_nhwc_bwd_kernel(const rb_t* __restrict__ dy, const rb_t* __restrict__ y, const float* __restrict__ x,
                           const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd, int H, int W, int C, int G,
-                          int relu, __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                          int relu, rb_t* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta) {
   __shared__ float red[8];
   extern __shared__ float csum[];  // [2][Cg] per-channel partial sums (dgamma, dbeta) of this CTA
   const int b = blockIdx.x, g = blockIdx.y;
@@ -209,8 +209,8 @@ groupnorm_nhwc_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloa
     for (int p = threadIdx.x; p < H * W; p += blockDim.x) {
       const int yy = p / W, xx = p - yy * W;
       const long long o = (base + static_cast<long long>(yy + 1) * Wp + xx + 1) * C + g * Cg + c;
-      float d = __bfloat162float(dy[o]);
-      if (relu && !(__bfloat162float(y[o]) > 0.f)) d = 0.f;
+      float d = t2f(dy[o]);
+      if (relu && !(t2f(y[o]) > 0.f)) d = 0.f;
       const float xh = (x[o] - mu) * rs;
       dg += d * xh;
       db += d;
@@ -238,12 +238,12 @@ groupnorm_nhwc_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloa
     for (int c = 0; c < Cg; ++c) {
       float v = 0.f;
       if (interior) {
-        float d = __bfloat162float(dy[o + c]);
-        if (relu && !(__bfloat162float(y[o + c]) > 0.f)) d = 0.f;
+        float d = t2f(dy[o + c]);
+        if (relu && !(t2f(y[o + c]) > 0.f)) d = 0.f;
         const float xh = (x[o + c] - mu) * rs;
         v = rs * (d * gamma[g * Cg + c] - m1 - xh * m2);
       }
-      dx[o + c] = __float2bfloat16(v);
+      dx[o + c] = f2t(v);
     }
   }
 }
@@ -271,10 +271,10 @@ __global__ void upsample_add_kernel(const uint4* __restrict__ lo, const uint4* _
     const int sy = nearest_src(Y - 1, h, H), sx = nearest_src(X - 1, w, W);
     const uint4 a = lo[((static_cast<long long>(b) * (h + 2) + sy + 1) * (w + 2) + sx + 1) * C8 + c];
     const uint4 d = cur[i];
-    o.x = pack_bf16x2(bf16_lo(a.x) + bf16_lo(d.x), bf16_hi(a.x) + bf16_hi(d.x));
-    o.y = pack_bf16x2(bf16_lo(a.y) + bf16_lo(d.y), bf16_hi(a.y) + bf16_hi(d.y));
-    o.z = pack_bf16x2(bf16_lo(a.z) + bf16_lo(d.z), bf16_hi(a.z) + bf16_hi(d.z));
-    o.w = pack_bf16x2(bf16_lo(a.w) + bf16_lo(d.w), bf16_hi(a.w) + bf16_hi(d.w));
+    o.x = pack_t2(t_lo(a.x) + t_lo(d.x), t_hi(a.x) + t_hi(d.x));
+    o.y = pack_t2(t_lo(a.y) + t_lo(d.y), t_hi(a.y) + t_hi(d.y));
+    o.z = pack_t2(t_lo(a.z) + t_lo(d.z), t_hi(a.z) + t_hi(d.z));
+    o.w = pack_t2(t_lo(a.w) + t_lo(d.w), t_hi(a.w) + t_hi(d.w));
   }
   y[i] = o;
 }
@@ -299,13 +299,13 @@ __global__ void upsample_bwd_kernel(const uint4* __restrict__ dy, uint4* __restr
       for (int X = X0; X <= X1; ++X) {
         if (nearest_src(X, w, W) != sx) continue;
         const uint4 v = dy[((static_cast<long long>(b) * (H + 2) + Y + 1) * (W + 2) + X + 1) * C8 + c];
-        acc[0] += bf16_lo(v.x); acc[1] += bf16_hi(v.x); acc[2] += bf16_lo(v.y); acc[3] += bf16_hi(v.y);
-        acc[4] += bf16_lo(v.z); acc[5] += bf16_hi(v.z); acc[6] += bf16_lo(v.w); acc[7] += bf16_hi(v.w);
+        acc[0] += t_lo(v.x); acc[1] += t_hi(v.x); acc[2] += t_lo(v.y); acc[3] += t_hi(v.y);
+        acc[4] += t_lo(v.z); acc[5] += t_hi(v.z); acc[6] += t_lo(v.w); acc[7] += t_hi(v.w);
       }
     }
   }
   uint4 o;
-  o.x = pack_bf16x2(acc[0], acc[1]); o.y = pack_bf16x2(acc[2], acc[3]); o.z = pack_bf16x2(acc[4], acc[5]); o.w = pack_bf16x2(acc[6], acc[7]);
+  o.x = pack_t2(acc[0], acc[1]); o.y = pack_t2(acc[2], acc[3]); o.z = pack_t2(acc[4], acc[5]); o.w = pack_t2(acc[6], acc[7]);
   dlo[i] = o;
 }
 
@@ -318,7 +318,7 @@ static unsigned nblocks(long long total, int threads) { return static_cast<unsig
 extern "C" int rb_tokens_to_grid(const float* tok, int B, int S, int L, int h, int w, int C, void* grid, long long ld, int col0, void* stream) {
   if (C % 4 || col0 % 4 || ld % 4) return rb_fail("rb_tokens_to_grid: C, col0 and ld must be multiples of 4");
   const long long total = static_cast<long long>(B) * h * w * (C / 4);
-  tokens_to_grid_kernel<<<nblocks(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(tok, S, L, h, w, C, static_cast<__nv_bfloat16*>(grid), ld, col0, total);
+  tokens_to_grid_kernel<<<nblocks(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(tok, S, L, h, w, C, static_cast<rb_t*>(grid), ld, col0, total);
   RB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -326,7 +326,7 @@ extern "C" int rb_tokens_to_grid(const float* tok, int B, int S, int L, int h, i
 extern "C" int rb_grid_to_tokens(const void* grid, long long ld, int col0, int B, int S, int L, int h, int w, int C, float* dtok, void* stream) {
   if (C % 4 || col0 % 4 || ld % 4) return rb_fail("rb_grid_to_tokens: C, col0 and ld must be multiples of 4");
   const long long total = static_cast<long long>(B) * h * w * (C / 4);
-  grid_to_tokens_kernel<<<nblocks(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(grid), ld, col0, S, L, h, w, C, dtok, total);
+  grid_to_tokens_kernel<<<nblocks(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const rb_t*>(grid), ld, col0, S, L, h, w, C, dtok, total);
   RB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -338,7 +338,7 @@ extern "C" int rb_attn_map_fwd(const float* q, const float* k, const void* kpm, 
   static bool cfg = false;
   if (!cfg) { RB_CUDA(cudaFuncSetAttribute(attn_map_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); cfg = true; }
   attn_map_fwd_kernel<<<B, 256, sm, static_cast<cudaStream_t>(stream)>>>(q, k, static_cast<const uint8_t*>(kpm), S, L, hw, w, scale, att,
-                                                                        static_cast<__nv_bfloat16*>(grid), ld, col0);
+                                                                        static_cast<rb_t*>(grid), ld, col0);
   RB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -349,7 +349,7 @@ extern "C" int rb_attn_map_bwd(const float* datt_ext, const void* dgrid, long lo
   if (sm > 200 * 1024) return rb_fail("rb_attn_map_bwd: %d visual tokens exceed the shared-memory plan", hw);
   static bool cfg = false;
   if (!cfg) { RB_CUDA(cudaFuncSetAttribute(attn_map_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); cfg = true; }
-  attn_map_bwd_kernel<<<B, 256, sm, static_cast<cudaStream_t>(stream)>>>(datt_ext, static_cast<const __nv_bfloat16*>(dgrid), ld, col0, att, q, k, S, L, hw, w,
+  attn_map_bwd_kernel<<<B, 256, sm, static_cast<cudaStream_t>(stream)>>>(datt_ext, static_cast<const rb_t*>(dgrid), ld, col0, att, q, k, S, L, hw, w,
                                                                         scale, dq, dk);
   RB_CUDA(cudaGetLastError());
   return 0;
@@ -358,7 +358,7 @@ extern "C" int rb_attn_map_bwd(const float* datt_ext, const void* dgrid, long lo
 extern "C" int rb_groupnorm_nhwc_fwd(const float* x, const float* gamma, const float* beta, int B, int H, int W, int C, int G, float eps, int relu, void* y,
                                      float* mean, float* rstd, void* stream) {
   if (C % G) return rb_fail("rb_groupnorm_nhwc_fwd: C %% G != 0");
-  groupnorm_nhwc_fwd_kernel<<<dim3(B, G), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, gamma, beta, H, W, C, G, eps, relu, static_cast<__nv_bfloat16*>(y),
+  groupnorm_nhwc_fwd_kernel<<<dim3(B, G), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, gamma, beta, H, W, C, G, eps, relu, static_cast<rb_t*>(y),
                                                                                       mean, rstd);
   RB_CUDA(cudaGetLastError());
   return 0;
@@ -369,7 +369,7 @@ extern "C" int rb_groupnorm_nhwc_bwd(const void* dy, const void* y, const float*
   if (C % G) return rb_fail("rb_groupnorm_nhwc_bwd: C %% G != 0");
   const size_t sm = static_cast<size_t>(2) * (C / G) * sizeof(float);
   groupnorm_nhwc_bwd_kernel<<<dim3(B, G), 256, sm, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(y), x, gamma, mean, rstd, H, W, C, G, relu, static_cast<__nv_bfloat16*>(dx),
+      static_cast<const rb_t*>(dy), static_cast<const rb_t*>(y), x, gamma, mean, rstd, H, W, C, G, relu, static_cast<rb_t*>(dx),
       dgamma, dbeta);
   RB_CUDA(cudaGetLastError());
   return 0;

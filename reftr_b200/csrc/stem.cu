@@ -21,7 +21,7 @@ constexpr int ST_K = 147, ST_KB = 3;            // 147 real columns in three 64-
 constexpr int ST_SMEM = ST_KB * 16384 + ST_KB * 8192 + 3 * ST_PH * ST_PWP * 4 + 64 + 1024;
 
 __global__ void __launch_bounds__(128)
-stem_conv_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restrict__ img, const float* __restrict__ bias, __nv_bfloat16* __restrict__ out,
+stem_conv_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restrict__ img, const float* __restrict__ bias, rb_t* __restrict__ out,
                  int H, int W, int H1, int W1) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -92,7 +92,7 @@ stem_conv_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restric
         }
       }
       uint4 t;
-      t.x = pack_bf16x2(v[0], v[1]); t.y = pack_bf16x2(v[2], v[3]); t.z = pack_bf16x2(v[4], v[5]); t.w = pack_bf16x2(v[6], v[7]);
+      t.x = pack_t2(v[0], v[1]); t.y = pack_t2(v[2], v[3]); t.z = pack_t2(v[4], v[5]); t.w = pack_t2(v[6], v[7]);
       *reinterpret_cast<uint4*>(row + ((j ^ (tid & 7)) << 4)) = t;
     }
   }
@@ -102,13 +102,13 @@ stem_conv_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restric
   if (tid == 0) {
     mbar_wait(&bars[0], 0);
     tc_fence_after();
-    constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 0, 0);
+    constexpr uint32_t idesc = umma_idesc_t(128, 64, 0, 0);
 #pragma unroll
     for (int kb = 0; kb < ST_KB; ++kb) {
       const uint32_t a_base = smem_u32(sA + kb * 16384), b_base = smem_u32(sW + kb * 8192);
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk)
-        umma_bf16_ss(tmem, umma_smem_desc(a_base + kk * 32, 16, 1024, SWZ_128B), umma_smem_desc(b_base + kk * 32, 16, 1024, SWZ_128B), idesc, (kb | kk) != 0);
+        umma_f16_ss(tmem, umma_smem_desc(a_base + kk * 32, 16, 1024, SWZ_128B), umma_smem_desc(b_base + kk * 32, 16, 1024, SWZ_128B), idesc, (kb | kk) != 0);
     }
     umma_commit(&bars[1]);
   }
@@ -119,7 +119,7 @@ stem_conv_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restric
   const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
   const int oy = oy0 + ly, ox = ox0 + lx;
   const bool ok = oy < H1 && ox < W1;
-  __nv_bfloat16* orow = out + ((static_cast<long long>(b) * H1 + oy) * W1 + ox) * 64;
+  rb_t* orow = out + ((static_cast<long long>(b) * H1 + oy) * W1 + ox) * 64;
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
     uint32_t v[32];
@@ -132,7 +132,7 @@ stem_conv_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restric
 #pragma unroll
         for (int e = 0; e < 8; ++e) f[e] = fmaxf(__uint_as_float(v[8 * j + e]) + __ldg(bias + half * 32 + 8 * j + e), 0.f);
         uint4 t;
-        t.x = pack_bf16x2(f[0], f[1]); t.y = pack_bf16x2(f[2], f[3]); t.z = pack_bf16x2(f[4], f[5]); t.w = pack_bf16x2(f[6], f[7]);
+        t.x = pack_t2(f[0], f[1]); t.y = pack_t2(f[2], f[3]); t.z = pack_t2(f[4], f[5]); t.w = pack_t2(f[6], f[7]);
         *reinterpret_cast<uint4*>(orow + half * 32 + 8 * j) = t;
       }
     }
@@ -153,7 +153,7 @@ extern "C" int rb_stem_conv(const float* img, const void* wf, int ldk, const flo
   static bool cfg = false;
   if (!cfg) { RB_CUDA(cudaFuncSetAttribute(stem_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM)); cfg = true; }
   dim3 grid((W1 + ST_TW - 1) / ST_TW, (H1 + ST_TH - 1) / ST_TH, B);
-  stem_conv_kernel<<<grid, 128, ST_SMEM, static_cast<cudaStream_t>(stream)>>>(tmW, img, bias, static_cast<__nv_bfloat16*>(out), H, W, H1, W1);
+  stem_conv_kernel<<<grid, 128, ST_SMEM, static_cast<cudaStream_t>(stream)>>>(tmW, img, bias, static_cast<rb_t*>(out), H, W, H1, W1);
   RB_CUDA(cudaGetLastError());
   return 0;
 }

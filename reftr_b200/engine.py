@@ -69,7 +69,7 @@ class Workspace:
         self.bufs = {}
 
     def get(self, name, shape, dtype=None, zero=False):
-        dtype = dtype or torch.bfloat16
+        dtype = dtype or ops.t16()
         shape = tuple(int(s) for s in shape)
         t = self.bufs.get(name)
         if t is None or tuple(t.shape) != shape or t.dtype != dtype:
@@ -206,6 +206,9 @@ class RefTREngine:
         self.force_eager = False  # bench.py: run the next steps launch by launch on the graphed workspace (profiling)
         self.launches = 0
         # ---- dropout (train mode): counter-based, nothing stored; ONE device seed rewritten before every forward --------
+        # static loss scale of the backward pass: activation gradients are stored in 16 bits (IEEE half by default), so the incoming
+        # gradient is multiplied by 2^k on entry and the parameter gradients by 2^-k on exit (exact); fp32 paths are unaffected
+        self.grad_scale = float(os.environ.get("REFTR_B200_GRAD_SCALE", "1024"))
         self.p_drop = float(vt.dropout)
         self.train_mode = False
         self.seed_dev = None
@@ -338,17 +341,18 @@ class RefTREngine:
         st = self._cur
         self.ws = ws = st["ws"]
         self.saved, self.dims = st["saved"], st["dims"]
+        S = self.grad_scale
         gl = ws.get("in.g_logits", g_logits.shape, torch.float32)
-        gl.copy_(g_logits)
+        torch.mul(g_logits, S, out=gl)
         gm = ga = None
         if g_masks is not None:
             gm = ws.get("in.g_masks", g_masks.shape, torch.float32)
-            gm.copy_(g_masks)
+            torch.mul(g_masks, S, out=gm)
             ga = ws.get("in.g_att", self.seghead.out_att.shape, torch.float32)
             if g_att is None:
                 ga.zero_()
             else:
-                ga.copy_(g_att)
+                torch.mul(g_att, S, out=ga)
         if self.force_eager:
             st["bouts"] = self.backward(gl, gm, ga)
         elif st["bwd"] is not None:
@@ -368,8 +372,8 @@ class RefTREngine:
         d_sent, d_pooled = st["bouts"]
         import time as _t
         _t0 = _t.perf_counter()
-        # fresh storage per step: autograd may keep these as .grad of leaf tensors
-        flat = self.gflat[:self.n_grad].clone()
+        # fresh storage per step: autograd may keep these as .grad of leaf tensors (the copy also undoes the loss scale)
+        flat = self.gflat[:self.n_grad] * (1.0 / S)
         _t1 = _t.perf_counter()
         if getattr(self.model, "engine_allreduce", False) and torch.distributed.is_available() and torch.distributed.is_initialized():
             world = torch.distributed.get_world_size()
@@ -383,7 +387,7 @@ class RefTREngine:
         self.host_ms = {"clone": (_t1 - _t0) * 1e3, "allreduce": (_t.perf_counter() - _t1) * 1e3}
         if self.bert is not None:
             return None, None, flat
-        return d_sent.clone(), d_pooled.clone(), flat
+        return d_sent * (1.0 / S), d_pooled * (1.0 / S), flat
 
     def G(self, name_or_param):
         n = name_or_param if isinstance(name_or_param, str) else self.pnames[id(name_or_param)]

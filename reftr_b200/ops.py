@@ -22,6 +22,17 @@ def launch_count():
     return _lib.LAUNCHES
 
 
+_T16 = None
+
+
+def t16():
+    """torch dtype of the library's 16-bit operand / activation type (rb_act_dtype: IEEE half by default, bf16 with -DRB_ACT_BF16)."""
+    global _T16
+    if _T16 is None:
+        _T16 = torch.float16 if _lib.lib().rb_act_dtype() == 0 else torch.bfloat16
+    return _T16
+
+
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -68,8 +79,8 @@ def gemm(A, B, M, N, K, *, mode=0, taps=((0, 0),), bias=None, res=None, res32=No
          out=None, out32=None, atomic=False, splits=1, geom=None, out_row_off=0, out32_z_stride=0, block_n=0, drop=None, drop_gshift=0,
          mask_scale=1.0):
     """See rb_gemm in include/reftr_b200.h.  ``taps`` is a sequence of (a_rowoff, b_koff) pairs."""
-    _check_2d(A, torch.bfloat16, "A")
-    _check_2d(B, torch.bfloat16, "B")
+    _check_2d(A, t16(), "A")
+    _check_2d(B, t16(), "B")
     a = GemmArgs()
     a.mode = mode
     a.A, a.a_rows, a.a_cols, a.lda = A.data_ptr(), A.shape[0], A.shape[1], A.stride(0)
@@ -86,16 +97,16 @@ def gemm(A, B, M, N, K, *, mode=0, taps=((0, 0),), bias=None, res=None, res32=No
         assert bias.dtype == torch.float32 and bias.is_contiguous()
         a.bias = bias.data_ptr()
     if res is not None:
-        _check_2d(res, torch.bfloat16, "res")
+        _check_2d(res, t16(), "res")
         a.res, a.ldres = res.data_ptr(), res.stride(0)
     if res32 is not None:
         _check_2d(res32, torch.float32, "res32")
         a.res32, a.ldres32 = res32.data_ptr(), res32.stride(0)
     if mask_src is not None:
-        _check_2d(mask_src, torch.bfloat16, "mask_src")
+        _check_2d(mask_src, t16(), "mask_src")
         a.mask_src, a.ldmask = mask_src.data_ptr(), mask_src.stride(0)
     if out is not None:
-        _check_2d(out, torch.bfloat16, "out")
+        _check_2d(out, t16(), "out")
         a.out, a.ldo = out.data_ptr(), out.stride(0)
     if out32 is not None:
         assert out32.dtype == torch.float32 and out32.is_cuda
@@ -179,7 +190,7 @@ def unpack_conv_grad(dwf, scale, grad, Cout, Cin, taps):
 def cast_bf16(x, out=None):
     assert x.dtype == torch.float32 and x.is_contiguous()
     if out is None:
-        out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+        out = torch.empty(x.shape, dtype=t16(), device=x.device)
     _lib.call("rb_cast_bf16", _p(x), _p(out), x.numel(), _s())
     return out
 
@@ -188,7 +199,7 @@ def colsum(x, out, rows=None, N=None):
     """out[N] += column sums of x [rows, N] (bf16 or fp32)."""
     rows = x.shape[0] if rows is None else rows
     N = x.shape[1] if N is None else N
-    _lib.call("rb_colsum", _p(x), int(x.dtype == torch.bfloat16), x.stride(0), rows, N, _p(out), _s())
+    _lib.call("rb_colsum", _p(x), int(x.dtype == t16()), x.stride(0), rows, N, _p(out), _s())
 
 
 def add(a, b, y=None, yb=None):

@@ -36,8 +36,8 @@ class PackedConv:
             return
         dev = w.device
         if self.wf is None or self.wf.device != dev:
-            self.wf = torch.empty(self.Cout, self.ldk, dtype=torch.bfloat16, device=dev)
-            self.wd = torch.empty(self.Cin, self.taps * self.Cout, dtype=torch.bfloat16, device=dev) if self.need_dgrad else None
+            self.wf = torch.empty(self.Cout, self.ldk, dtype=ops.t16(), device=dev)
+            self.wd = torch.empty(self.Cin, self.taps * self.Cout, dtype=ops.t16(), device=dev) if self.need_dgrad else None
             self.scale = torch.empty(self.Cout, dtype=torch.float32, device=dev)
             self.bias = torch.empty(self.Cout, dtype=torch.float32, device=dev)
         ops.pack_conv(w.detach(), bn, cb.detach() if cb is not None else None, self.wf, self.ldk, self.wd, self.scale, self.bias,
@@ -62,8 +62,8 @@ class PackedLinear:
             return
         dev = self.weight.device
         if self.wb is None or self.wb.device != dev:
-            self.wb = torch.zeros(self.Np, self.K, dtype=torch.bfloat16, device=dev)
-            self.wt = torch.zeros(self.K, self.Np, dtype=torch.bfloat16, device=dev)
+            self.wb = torch.zeros(self.Np, self.K, dtype=ops.t16(), device=dev)
+            self.wt = torch.zeros(self.K, self.Np, dtype=ops.t16(), device=dev)
             if self.Np != self.N:
                 self.bias = torch.zeros(self.Np, dtype=torch.float32, device=dev)
         ops.pack_linear(self.weight.detach(), self.wb, self.wt)
@@ -93,8 +93,8 @@ class PackedStack:
         dev = self.weights[0].device
         N = self.n * self.nrows
         if self.wb is None or self.wb.device != dev:
-            self.wb = torch.empty(N, self.K, dtype=torch.bfloat16, device=dev)
-            self.wt = torch.empty(self.K, N, dtype=torch.bfloat16, device=dev)
+            self.wb = torch.empty(N, self.K, dtype=ops.t16(), device=dev)
+            self.wt = torch.empty(self.K, N, dtype=ops.t16(), device=dev)
             self.bias = torch.empty(N, dtype=torch.float32, device=dev)
         for i, (w, b) in enumerate(zip(self.weights, self.biases)):
             sl = slice(i * self.nrows, (i + 1) * self.nrows)

@@ -38,8 +38,8 @@ class PackedConvPadded:
         if self.wf is None or self.wf.device != dev:
             self.w_pad = torch.zeros(self.Cp, self.Cin, self.kh, self.kw, dtype=torch.float32, device=dev)
             self.b_pad = torch.zeros(self.Cp, dtype=torch.float32, device=dev)
-            self.wf = torch.zeros(self.Cp, self.taps * self.Cin, dtype=torch.bfloat16, device=dev)
-            self.wd = torch.zeros(self.Cin, self.taps * self.Cp, dtype=torch.bfloat16, device=dev)
+            self.wf = torch.zeros(self.Cp, self.taps * self.Cin, dtype=ops.t16(), device=dev)
+            self.wd = torch.zeros(self.Cin, self.taps * self.Cp, dtype=ops.t16(), device=dev)
             self.scale = torch.empty(self.Cp, dtype=torch.float32, device=dev)
             self.bias = torch.empty(self.Cp, dtype=torch.float32, device=dev)
         self.w_pad[:self.Cout].copy_(w.detach())

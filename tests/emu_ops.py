@@ -14,11 +14,15 @@ _LAUNCHES = [0]
 # EXACT mode: "bf16" buffers are allocated as fp32 by the test (see test_engine_emulated.py) and nothing is rounded, so the
 # engine's wiring can be checked against the oracle to ~1e-5 instead of to bf16 noise.
 EXACT = [False]
-_BF = torch.bfloat16
+_BF = torch.float16  # the default build of the library (rb_act_dtype() == 0: IEEE half)
 
 
 def _lp():
     return torch.float32 if EXACT[0] else _BF
+
+
+def t16():
+    return _lp()
 
 
 def launch_count():

@@ -10,7 +10,8 @@ import emu_ops  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 dev = "cuda"
-BF = torch.bfloat16
+from reftr_b200 import ops as _ops
+BF = _ops.t16()
 
 
 def _close(a, b, tol):

@@ -6,6 +6,8 @@ import torch
 import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
+from reftr_b200 import ops as _ops
+T16 = _ops.t16()  # the library's 16-bit operand type (IEEE half by default)
 
 
 def _rel(a, b):
@@ -17,11 +19,11 @@ def _rel(a, b):
 def test_gemm_nt_linear(M, N, K, bn):
     from reftr_b200 import ops
     g = torch.Generator(device="cuda").manual_seed(M + N + K)
-    A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
-    B = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).bfloat16()
+    A = torch.randn(M, K, device="cuda", generator=g).to(T16)
+    B = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).to(T16)
     bias = torch.randn(N, device="cuda", generator=g)
-    res = torch.randn(M, N, device="cuda", generator=g).bfloat16()
-    out = torch.full((M, N), 7.0, device="cuda", dtype=torch.bfloat16)
+    res = torch.randn(M, N, device="cuda", generator=g).to(T16)
+    out = torch.full((M, N), 7.0, device="cuda", dtype=T16)
     out32 = torch.full((M, N), 7.0, device="cuda")
     ops.gemm(A, B, M, N, K, bias=bias, res=res, relu=True, out=out, out32=out32, block_n=bn)
     ref = torch.relu(A.float() @ B.float().t() + bias + res.float())
@@ -32,9 +34,9 @@ def test_gemm_nt_linear(M, N, K, bn):
 def test_gemm_nt_ragged_n_and_res32():
     from reftr_b200 import ops
     M, N, K = 50, 4, 256
-    A = torch.randn(M, K, device="cuda").bfloat16()
-    B = torch.zeros(8, K, device="cuda", dtype=torch.bfloat16)
-    B[:N] = (torch.randn(N, K, device="cuda") / 16).bfloat16()
+    A = torch.randn(M, K, device="cuda").to(T16)
+    B = torch.zeros(8, K, device="cuda", dtype=T16)
+    B[:N] = (torch.randn(N, K, device="cuda") / 16).to(T16)
     bias = torch.randn(N, device="cuda")
     res32 = torch.randn(M, N, device="cuda")
     out32 = torch.zeros(M, N, device="cuda")
@@ -44,7 +46,7 @@ def test_gemm_nt_ragged_n_and_res32():
 
 
 def _pad_nhwc(x):  # NCHW fp32 -> padded NHWC bf16 [N, H+2, W+2, C]
-    return F.pad(x.permute(0, 2, 3, 1), (0, 0, 1, 1, 1, 1)).bfloat16().contiguous()
+    return F.pad(x.permute(0, 2, 3, 1), (0, 0, 1, 1, 1, 1)).to(T16).contiguous()
 
 
 @pytest.mark.parametrize("Nb,H,W,Cin,Cout", [(2, 20, 20, 64, 64), (3, 14, 10, 128, 256), (1, 40, 40, 256, 128)])
@@ -56,9 +58,9 @@ def test_conv3x3_as_shifted_gemm(Nb, H, W, Cin, Cout):
     xp = _pad_nhwc(x)
     Wp, Hp = W + 2, H + 2
     R = Nb * Hp * Wp
-    wk = w.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).bfloat16().contiguous()  # [Cout, (r,s), Cin]
+    wk = w.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).to(T16).contiguous()  # [Cout, (r,s), Cin]
     taps = [((r - 1) * Wp + (s - 1), (r * 3 + s) * Cin) for r in range(3) for s in range(3)]
-    out = torch.full((R, Cout), 5.0, device="cuda", dtype=torch.bfloat16)
+    out = torch.full((R, Cout), 5.0, device="cuda", dtype=T16)
     ops.gemm(xp.view(R, Cin), wk, R, Cout, Cin, taps=taps, bias=bias, relu=True, out=out,
              geom=ops.make_geom(1, Wp, Hp * Wp, H, W))
     ref = F.relu(F.conv2d(xp[:, 1:-1, 1:-1].permute(0, 3, 1, 2).float(), wk.view(Cout, 3, 3, Cin).permute(0, 3, 1, 2).float(),
@@ -74,8 +76,8 @@ def test_conv3x3_as_shifted_gemm(Nb, H, W, Cin, Cout):
                                              (333, 512, 256, 2, 256)])
 def test_gemm_tn_wgrad(R, Mo, No, splits, bn):
     from reftr_b200 import ops
-    dY = torch.randn(R, Mo, device="cuda").bfloat16()
-    X = torch.randn(R, No, device="cuda").bfloat16()
+    dY = torch.randn(R, Mo, device="cuda").to(T16)
+    X = torch.randn(R, No, device="cuda").to(T16)
     out32 = torch.zeros(Mo, No, device="cuda")
     ops.gemm(dY, X, Mo, No, R, mode=1, out32=out32, atomic=True, splits=splits, block_n=bn)
     ref = dY.float().t() @ X.float()

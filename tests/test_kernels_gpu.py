@@ -6,6 +6,8 @@ import torch
 import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
+from reftr_b200 import ops as _ops
+T16 = _ops.t16()  # the library's 16-bit operand type (IEEE half by default)
 dev = "cuda"
 
 
@@ -21,7 +23,7 @@ def test_layernorm_fwd_bwd():
     b = 0.1 * torch.randn(D, device=dev)
     pos = torch.randn(rows, D, device=dev)
     for relu in (False, True):
-        y32 = torch.empty(rows, D, device=dev); yb = torch.empty(rows, D, device=dev, dtype=torch.bfloat16)
+        y32 = torch.empty(rows, D, device=dev); yb = torch.empty(rows, D, device=dev, dtype=T16)
         ypb = torch.empty_like(yb); mean = torch.empty(rows, device=dev); rstd = torch.empty(rows, device=dev)
         ops.layernorm_fwd(x, g, b, rows, y32=y32, yb=yb, pos32=pos, ypb=ypb, relu=relu, mean=mean, rstd=rstd)
         xr = x.clone().requires_grad_(); gr = g.clone().requires_grad_(); br = b.clone().requires_grad_()
@@ -32,7 +34,7 @@ def test_layernorm_fwd_bwd():
         assert _rel(yb, ref) < 8e-3 and _rel(ypb, ref + pos) < 8e-3
         dy = torch.randn(rows, D, device=dev)
         ref.backward(dy)
-        dx = torch.empty(rows, D, device=dev); dxb = torch.empty(rows, D, device=dev, dtype=torch.bfloat16)
+        dx = torch.empty(rows, D, device=dev); dxb = torch.empty(rows, D, device=dev, dtype=T16)
         dg = torch.zeros(D, device=dev); db = torch.zeros(D, device=dev)
         ops.layernorm_bwd(dy, x, g, mean, rstd, rows, y_relu=y32 if relu else None, dx32=dx, dxb=dxb, dgamma=dg, dbeta=db)
         assert _rel(dx, xr.grad) < 1e-4 and _rel(dg, gr.grad) < 1e-4 and _rel(db, br.grad) < 1e-4
@@ -59,7 +61,7 @@ def test_groupnorm_tokens():
     g = 1 + 0.1 * torch.randn(256, device=dev); be = 0.1 * torch.randn(256, device=dev)
     xp = F.pad(x.permute(0, 2, 3, 1), (0, 0, 1, 1, 1, 1)).contiguous()
     pos = torch.randn(B * S, 256, device=dev)
-    y32 = torch.zeros(B * S, 256, device=dev); yb = torch.zeros(B * S, 256, device=dev, dtype=torch.bfloat16); ypb = torch.zeros_like(yb)
+    y32 = torch.zeros(B * S, 256, device=dev); yb = torch.zeros(B * S, 256, device=dev, dtype=T16); ypb = torch.zeros_like(yb)
     mean = torch.empty(B * 32, device=dev); rstd = torch.empty(B * 32, device=dev)
     ops.groupnorm_tokens_fwd(xp, g, be, B, h, w, S, L, y32, yb, pos, ypb, mean, rstd)
     xr = x.clone().requires_grad_(); gr = g.clone().requires_grad_(); br = be.clone().requires_grad_()
@@ -70,7 +72,7 @@ def test_groupnorm_tokens():
     assert _rel(ypb.view(B, S, 256)[:, L:], ref_tok + pos.view(B, S, 256)[:, L:]) < 8e-3
     dy = torch.randn(B * S, 256, device=dev)
     ref_tok.backward(dy.view(B, S, 256)[:, L:])
-    dx = torch.zeros(B, h + 2, w + 2, 256, device=dev, dtype=torch.bfloat16)
+    dx = torch.zeros(B, h + 2, w + 2, 256, device=dev, dtype=T16)
     dg = torch.zeros(256, device=dev); db = torch.zeros(256, device=dev)
     ops.groupnorm_tokens_bwd(dy, None, xp, g, mean, rstd, B, h, w, S, L, dx, dg, db)
     assert _rel(dx[:, 1:-1, 1:-1].permute(0, 3, 1, 2), xr.grad) < 1e-2
@@ -97,18 +99,18 @@ def test_attention_fwd_bwd(B, H, Tq, Sk):
     from reftr_b200 import ops
     d = H * 32
     scale = 32 ** -0.5
-    q = torch.randn(B, Tq, d, device=dev).bfloat16(); k = torch.randn(B, Sk, d, device=dev).bfloat16(); v = torch.randn(B, Sk, d, device=dev).bfloat16()
+    q = torch.randn(B, Tq, d, device=dev).to(T16); k = torch.randn(B, Sk, d, device=dev).to(T16); v = torch.randn(B, Sk, d, device=dev).to(T16)
     kpm = torch.zeros(B, Sk, dtype=torch.uint8, device=dev)
     kpm[:, Sk - Sk // 4:] = 1
     kpm[0, 1::3] = 1
     kpm[:, 0] = 0
-    o = torch.empty(B * Tq, d, device=dev, dtype=torch.bfloat16)
+    o = torch.empty(B * Tq, d, device=dev, dtype=T16)
     lse = torch.empty(B, H, Tq, device=dev)
     ops.attn_fwd(q.view(-1, d), k.view(-1, d), v.view(-1, d), kpm, o, lse, B, H, Tq, Sk, scale)
     qr, kr, vr = (t.float().requires_grad_() for t in (q, k, v))
     ref = _attn_ref(qr, kr, vr, kpm, H, scale)
     assert _rel(o.view(B, Tq, d), ref) < 1e-2
-    do = torch.randn(B, Tq, d, device=dev).bfloat16()
+    do = torch.randn(B, Tq, d, device=dev).to(T16)
     ref.backward(do.float())
     dq = torch.empty_like(q).view(-1, d); dk = torch.empty_like(k).view(-1, d); dv = torch.empty_like(v).view(-1, d)
     Dbuf = torch.empty(B, H, Tq, device=dev)
@@ -173,16 +175,16 @@ def test_stem_maxpool_parity_pack():
     bn = [1 + 0.1 * torch.randn(64, device=dev), 0.1 * torch.randn(64, device=dev), 0.1 * torch.randn(64, device=dev), 0.5 + torch.rand(64, device=dev)]
     H1, W1 = (H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1
     H2, W2 = (H1 + 2 - 3) // 2 + 1, (W1 + 2 - 3) // 2 + 1
-    col = torch.empty(B * H1 * W1, 160, device=dev, dtype=torch.bfloat16)
+    col = torch.empty(B * H1 * W1, 160, device=dev, dtype=T16)
     ops.stem_im2col(img, col, B, H, W, H1, W1)
-    wf = torch.empty(64, 160, device=dev, dtype=torch.bfloat16); sc = torch.empty(64, device=dev); bi = torch.empty(64, device=dev)
+    wf = torch.empty(64, 160, device=dev, dtype=T16); sc = torch.empty(64, device=dev); bi = torch.empty(64, device=dev)
     ops.pack_conv(w, bn, None, wf, 160, None, sc, bi)
-    c1 = torch.empty(B * H1 * W1, 64, device=dev, dtype=torch.bfloat16)
+    c1 = torch.empty(B * H1 * W1, 64, device=dev, dtype=T16)
     ops.gemm(col, wf, B * H1 * W1, 64, 160, bias=bi, relu=True, out=c1)
     scale = bn[0] * (bn[3] + 1e-5).rsqrt()
     ref = F.relu(F.conv2d(img, w, stride=2, padding=3) * scale.view(1, -1, 1, 1) + (bn[1] - bn[2] * scale).view(1, -1, 1, 1))
     assert _rel(c1.view(B, H1, W1, 64).permute(0, 3, 1, 2), ref) < 2e-2
-    pooled = torch.empty(B, H2 + 2, W2 + 2, 64, device=dev, dtype=torch.bfloat16)
+    pooled = torch.empty(B, H2 + 2, W2 + 2, 64, device=dev, dtype=T16)
     ops.maxpool_3x3s2(c1, pooled, B, H1, W1, 64, H2, W2)
     refp = F.max_pool2d(c1.view(B, H1, W1, 64).permute(0, 3, 1, 2).float(), 3, 2, 1)
     assert _rel(pooled[:, 1:-1, 1:-1].permute(0, 3, 1, 2), refp) == 0
@@ -190,7 +192,7 @@ def test_stem_maxpool_parity_pack():
     # parity split / merge round trip on an odd-sized grid
     Hh, Ww, C = H2, W2, 64
     Ho, Wo = (Hh + 1) // 2, (Ww + 1) // 2
-    xs = torch.empty(4, B, Ho + 2, Wo + 2, C, device=dev, dtype=torch.bfloat16)
+    xs = torch.empty(4, B, Ho + 2, Wo + 2, C, device=dev, dtype=T16)
     ops.parity_split(pooled, xs, B, Hh, Ww, C, Ho, Wo)
     for p in range(2):
         for q in range(2):
@@ -201,23 +203,23 @@ def test_stem_maxpool_parity_pack():
     assert torch.equal(back, pooled)
     # 3x3 pack: dgrad copy is the flipped transpose
     w3 = torch.randn(128, 64, 3, 3, device=dev)
-    wf3 = torch.empty(128, 576, device=dev, dtype=torch.bfloat16); wd3 = torch.empty(64, 9 * 128, device=dev, dtype=torch.bfloat16)
+    wf3 = torch.empty(128, 576, device=dev, dtype=T16); wd3 = torch.empty(64, 9 * 128, device=dev, dtype=T16)
     ops.pack_conv(w3, None, None, wf3, 576, wd3, None, None)
-    assert torch.equal(wf3.view(128, 3, 3, 64), w3.permute(0, 2, 3, 1).bfloat16())
-    assert torch.equal(wd3.view(64, 3, 3, 128), w3.flip(2, 3).permute(1, 2, 3, 0).bfloat16())
+    assert torch.equal(wf3.view(128, 3, 3, 64), w3.permute(0, 2, 3, 1).to(T16))
+    assert torch.equal(wd3.view(64, 3, 3, 128), w3.flip(2, 3).permute(1, 2, 3, 0).to(T16))
     # linear pack + colsum + cast
     wl = torch.randn(100, 72, device=dev)
-    wb = torch.empty(100, 72, device=dev, dtype=torch.bfloat16); wt = torch.empty(72, 100, device=dev, dtype=torch.bfloat16)
+    wb = torch.empty(100, 72, device=dev, dtype=T16); wt = torch.empty(72, 100, device=dev, dtype=T16)
     ops.pack_linear(wl, wb, wt)
-    assert torch.equal(wb, wl.bfloat16()) and torch.equal(wt, wl.t().bfloat16())
+    assert torch.equal(wb, wl.to(T16)) and torch.equal(wt, wl.t().to(T16))
     x = torch.randn(1000, 72, device=dev)
     cs = torch.zeros(72, device=dev)
     ops.colsum(x, cs)
     assert _rel(cs, x.sum(0)) < 1e-5
-    assert torch.equal(ops.cast_bf16(x), x.bfloat16())
+    assert torch.equal(ops.cast_bf16(x), x.to(T16))
 
 
-@pytest.mark.parametrize("rows,N,dt", [(6720, 256, torch.bfloat16), (6720, 768, torch.bfloat16), (107584, 128, torch.bfloat16), (321, 2048, torch.bfloat16),
+@pytest.mark.parametrize("rows,N,dt", [(6720, 256, T16), (6720, 768, T16), (107584, 128, T16), (321, 2048, T16),
                                        (6720, 256, torch.float32), (96, 4, torch.float32), (33, 72, torch.float32)])
 def test_colsum(rows, N, dt):
     from reftr_b200 import ops
@@ -272,9 +274,9 @@ def test_stem_conv_fused(B, H, W):
     img = torch.randn(B, 3, H, W, device=dev)
     w = torch.randn(64, 3, 7, 7, device=dev) * 0.1
     bias = torch.randn(64, device=dev) * 0.1
-    wf = torch.zeros(64, 160, device=dev, dtype=torch.bfloat16)
-    wf[:, :147] = w.permute(0, 2, 3, 1).reshape(64, 147).bfloat16()
-    out = torch.empty(B * H1 * W1, 64, device=dev, dtype=torch.bfloat16)
+    wf = torch.zeros(64, 160, device=dev, dtype=T16)
+    wf[:, :147] = w.permute(0, 2, 3, 1).reshape(64, 147).to(T16)
+    out = torch.empty(B * H1 * W1, 64, device=dev, dtype=T16)
     ops.stem_conv(img, wf, bias, out, B, H, W, H1, W1)
-    ref = F.relu(F.conv2d(img.bfloat16().float(), w.bfloat16().float(), bias, stride=2, padding=3)).permute(0, 2, 3, 1).reshape(B * H1 * W1, 64)
+    ref = F.relu(F.conv2d(img.to(T16).float(), w.to(T16).float(), bias, stride=2, padding=3)).permute(0, 2, 3, 1).reshape(B * H1 * W1, 64)
     assert _rel(out, ref) < 1e-2

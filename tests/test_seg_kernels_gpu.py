@@ -9,7 +9,8 @@ import emu_ops
 
 pytestmark = pytest.mark.gpu
 dev = "cuda"
-BF = torch.bfloat16
+from reftr_b200 import ops as _ops
+BF = _ops.t16()
 
 
 def _close(a, b, tol):

@@ -3,13 +3,14 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from reftr_b200 import ops
+T16 = ops.t16()
 B, H, S = 16, 8, 420
 d = 256
 dev = "cuda"
-qkv = torch.randn(B * S, 3 * d, device=dev).bfloat16()
+qkv = torch.randn(B * S, 3 * d, device=dev).to(T16)
 kpm = torch.zeros(B, S, dtype=torch.uint8, device=dev)
-o = torch.empty(B * S, d, device=dev, dtype=torch.bfloat16)
-do = torch.randn(B * S, d, device=dev).bfloat16()
+o = torch.empty(B * S, d, device=dev, dtype=T16)
+do = torch.randn(B * S, d, device=dev).to(T16)
 dqkv = torch.empty_like(qkv)
 lse = torch.empty(B, H, S, device=dev); Dbuf = torch.empty(B, H, S, device=dev)
 q, k, v = qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:]

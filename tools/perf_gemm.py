@@ -3,6 +3,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from reftr_b200 import ops
+T16 = ops.t16()
 dev = "cuda"
 def run(name, fn, flops, bytes_):
     for _ in range(3): fn()
@@ -16,12 +17,12 @@ def run(name, fn, flops, bytes_):
     print(f"{name:44s} {us:8.1f} us  {flops / us / 1e6:7.1f} TFLOP/s  {bytes_ / us / 1e3:7.0f} GB/s", flush=True)
 
 def nt(M, N, K, taps=1, res=False, mask=False, relu=True, f32=False, res32=False):
-    A = torch.randn(M + 2048, K, device=dev).bfloat16()[1024:1024 + M]
-    W = torch.randn(N, K * taps, device=dev).bfloat16()
+    A = torch.randn(M + 2048, K, device=dev).to(T16)[1024:1024 + M]
+    W = torch.randn(N, K * taps, device=dev).to(T16)
     bias = torch.randn(N, device=dev)
-    out = torch.empty(M, N, device=dev, dtype=torch.float32 if f32 else torch.bfloat16)
-    r = torch.randn(M, N, device=dev).bfloat16() if res else None
-    m = torch.randn(M, N, device=dev).bfloat16() if mask else None
+    out = torch.empty(M, N, device=dev, dtype=torch.float32 if f32 else T16)
+    r = torch.randn(M, N, device=dev).to(T16) if res else None
+    m = torch.randn(M, N, device=dev).to(T16) if mask else None
     r32 = torch.randn(M, N, device=dev) if res32 else None
     tp = [((t // 3 - 1) * 162 + (t % 3 - 1), t * K) for t in range(taps)] if taps > 1 else [(0, 0)]
     kw = dict(out32=out) if f32 else dict(out=out)
@@ -30,8 +31,8 @@ def nt(M, N, K, taps=1, res=False, mask=False, relu=True, f32=False, res32=False
     run(f"NT M{M} N{N} K{K} t{taps} res{int(res)} mask{int(mask)} f32{int(f32)}", fn, 2.0 * M * N * K * taps, by)
 
 def tn(R, Mo, No, taps=1, splits=1):
-    dY = torch.randn(R + 2048, Mo, device=dev).bfloat16()[1024:1024 + R]
-    X = torch.randn(R + 2048, No, device=dev).bfloat16()[1024:1024 + R]
+    dY = torch.randn(R + 2048, Mo, device=dev).to(T16)[1024:1024 + R]
+    X = torch.randn(R + 2048, No, device=dev).to(T16)[1024:1024 + R]
     out = torch.zeros(Mo, taps * No, device=dev)
     tp = [(0, (t // 3 - 1) * 42 + (t % 3 - 1)) for t in range(taps)] if taps > 1 else [(0, 0)]
     fn = lambda: ops.gemm(dY, X, Mo, No, R, mode=1, taps=tp, out32=out, atomic=True, splits=splits, out32_z_stride=No)

@@ -3,6 +3,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from reftr_b200 import ops
+T16 = ops.t16()
 dev = "cuda"
 def timed_graph(fn, n=20):
     fn(); torch.cuda.synchronize()
@@ -15,8 +16,8 @@ def timed_graph(fn, n=20):
     return e0.elapsed_time(e1) / n * 1e3
 for M, N in ((320, 768), (128, 64), (128, 256), (18944, 64), (18944, 256)):
     for K in (256, 1024, 3072):
-        A = torch.randn(M, K, device=dev).bfloat16(); W = torch.randn(N, K, device=dev).bfloat16()
-        out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+        A = torch.randn(M, K, device=dev).to(T16); W = torch.randn(N, K, device=dev).to(T16)
+        out = torch.empty(M, N, device=dev, dtype=T16)
         for bn in (64, 128, 256):
             if bn > N and bn > 64: continue
             us = timed_graph(lambda: ops.gemm(A, W, M, N, K, out=out, block_n=bn))

@@ -10,7 +10,7 @@ import bench
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 dev = torch.device("cuda", 0)
 model, crit, _ = bench.build_ours(dev)
-model.eval()
+model.train() if os.environ.get("REFTR_B200_BENCH_EVAL") != "1" else model.eval()
 s, t = bench.host_batch(B, pinned=False)
 s, t = bench.to_device(s, t, dev)
 
