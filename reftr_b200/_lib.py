@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libreftr_b200.so")
+LIB_PATH = os.environ.get("REFTR_B200_LIB") or os.path.join(_HERE, "libreftr_b200.so")  # (override: kernel experiments)
 
 
 class Geom(C.Structure):

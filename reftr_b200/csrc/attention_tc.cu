@@ -79,7 +79,7 @@ constexpr int ATC_SMEM_DQ = 51200 + 1024;    // dQ: + rowB (dO)
 constexpr int ATC_SMEM_DKV = 67584 + 1024;   // dKV: + tileB (dS^T)
 
 __device__ __forceinline__ AtcSmem carve(uint8_t* raw) {
-  uint8_t* p = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* p = raw + ((1024u - (smem_u32(raw) & 1023u)) & 1023u);
   AtcSmem s;
   s.tileA = p;
   s.rowA = p + 16384;

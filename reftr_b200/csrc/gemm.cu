@@ -56,12 +56,14 @@ struct GemmKParams {
   uint32_t off_ein, ein_slot_bytes, ein_off_mask, ein_off_res32;
   uint32_t off_out, out_slot_bytes, out_off_f32;         // out_slots per team, 2 teams
   uint32_t off_bars;
+  uint32_t off_bias;   // bias staged in shared memory (bias_n floats, zero padded to whole tiles); bias_n == 0: read it from global
+  int bias_n;
   rb_geom geom;
   DropK drop;          // dropout on relu?(acc + bias), before the residuals
   int drop_gshift;     // the site's element of output column n is n >> drop_gshift
   uint32_t drop_wpr;   // 32-bit random words per row of the site
   float mask_scale;    // multiplies what mask_src keeps
-  int debug;           // RB_GEMM_DEBUG (timing experiments only, results are wrong): 1 = no output stores, 4 = no epilogue math
+  int debug;           // RB_GEMM_DEBUG (timing experiments only, results are wrong): 1 = no output stores, 4 = no epilogue math, 8 = no TMEM loads, 16 = no staging writes, 32 = no fence / barrier
 };
 
 __device__ __forceinline__ bool row_is_interior(const rb_geom& g, long long row) {
@@ -107,13 +109,16 @@ __device__ __forceinline__ TileCoord tile_coord(const GemmKParams& p, int t) {
   return c;
 }
 
-template <int MODE>
+// EPI selects how much of the epilogue is compiled in (the full body is ~40 KB of SASS, which thrashes the instruction cache of
+// the 8 epilogue warps): 0 = every feature (linear layers: fp32 output / residual, dropout, ...); 1 = the convolution path
+// (16-bit output; bias, 16-bit residual, ReLU, ReLU-mask, border zeroing only); 2 = split-K atomic accumulation only.
+template <int MODE, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
                  const __grid_constant__ CUtensorMap tmOut32, const __grid_constant__ CUtensorMap tmRes, const __grid_constant__ CUtensorMap tmRes32,
                  const __grid_constant__ CUtensorMap tmMask, const __grid_constant__ GemmKParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_bars);
   uint64_t* full = bars;                       // [MAX_STAGES]
   uint64_t* empty = bars + MAX_STAGES;         // [MAX_STAGES]
@@ -126,7 +131,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int bn = p.bn;
-  const bool has_ein = p.has_res | p.has_res32 | p.has_mask;
+  const bool f_atomic = EPI == 2 ? true : (EPI == 1 ? false : p.atomic != 0);
+  const bool f_res = EPI != 2 && p.has_res != 0, f_mask = EPI != 2 && p.has_mask != 0, f_res32 = EPI == 0 && p.has_res32 != 0;
+  const bool f_out = EPI == 1 ? true : (EPI == 2 ? false : p.has_out != 0), f_out32 = EPI == 0 && p.has_out32 != 0;
+  const bool has_ein = f_res | f_res32 | f_mask;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
@@ -146,6 +154,9 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
+  // the bias is read by every epilogue thread for every chunk: a global (L1-thrashed) load there costs an L2 round trip per chunk
+  float* sbias = reinterpret_cast<float*>(smem + p.off_bias);
+  for (int i = threadIdx.x; i < p.bias_n; i += GEMM_THREADS) sbias[i] = i < p.N ? __ldg(p.bias + i) : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -227,8 +238,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     __syncwarp();
   } else if (warp == 10) {
     // ------------------------------------------------------------------------------------------ epilogue-input producer
-    if (lane == 0 && has_ein && !p.atomic) {
-      const uint32_t tx = (p.has_res ? 16384u : 0u) + (p.has_mask ? 16384u : 0u) + (p.has_res32 ? 32768u : 0u);
+    if (lane == 0 && has_ein && !f_atomic) {
+      const uint32_t tx = (f_res ? 16384u : 0u) + (f_mask ? 16384u : 0u) + (f_res32 ? 32768u : 0u);
       int g = 0;
       for (int t = blockIdx.x; t < p.tiles_total; t += gridDim.x) {
         const TileCoord c = tile_coord(p, t);
@@ -240,9 +251,9 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_wait(&ein_empty[s], ((g / p.ein_slots) & 1) ^ 1);
           mbar_expect_tx(&ein_full[s], tx);
           uint8_t* dst = smem + p.off_ein + s * p.ein_slot_bytes;
-          if (p.has_res) tma_load_2d(dst, &tmRes, &ein_full[s], col0, c.m0);
-          if (p.has_mask) tma_load_2d(dst + p.ein_off_mask, &tmMask, &ein_full[s], col0, c.m0);
-          if (p.has_res32) {
+          if (f_res) tma_load_2d(dst, &tmRes, &ein_full[s], col0, c.m0);
+          if (f_mask) tma_load_2d(dst + p.ein_off_mask, &tmMask, &ein_full[s], col0, c.m0);
+          if (f_res32) {
             tma_load_2d(dst + p.ein_off_res32, &tmRes32, &ein_full[s], col0, c.m0);
             tma_load_2d(dst + p.ein_off_res32 + 16384, &tmRes32, &ein_full[s], col0 + 32, c.m0);
           }
@@ -258,8 +269,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
     const bool store_thread = (threadIdx.x == 64 + team * 128);
     const int sw128 = r & 7;
-    const bool use_ein = has_ein && !p.atomic;
-    const bool use_drop = p.drop.seed != nullptr;
+    const bool use_ein = has_ein && !f_atomic;
+    const bool use_drop = EPI == 0 && p.drop.seed != nullptr;
     const uint32_t dkey = use_drop ? drop_key(p.drop) : 0u;
     int tcount = 0, g = 0, o = 0;
     for (int t = blockIdx.x; t < p.tiles_total; t += gridDim.x) {
@@ -287,14 +298,29 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const bool two_slots = p.out_slots == 2;
         uint8_t* oslot = smem + p.off_out + (team * p.out_slots + (two_slots ? (o & 1) : 0)) * p.out_slot_bytes;
         ++o;
-        if (!p.atomic && !two_slots) {
+        if (!f_atomic && !two_slots) {
           if (store_thread) tma_store_wait_read<0>();  // the previous store of this team has finished reading the slot
           named_bar_sync(1 + team, 128);
         }
-        uint32_t vv[2][32];
-        if (p.debug & 4) {
+#ifdef RB_EPI_ROLLED
+        // one 32-column half at a time, NOT unrolled: half the epilogue code (instruction-cache footprint) and fewer registers
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+          const int hc0 = col0 + half * 32;
+          if (hc0 >= p.N || (p.debug & 4)) continue;  // warp-uniform
+          uint32_t v[32];
+          if (p.debug & 8) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) vv[0][j] = vv[1][j] = 0u;
+            for (int j = 0; j < 32; ++j) v[j] = static_cast<uint32_t>(r + j);
+          } else {
+            tmem_ld_32x32(tmem_base + lane_addr + as * bn + ch * 64 + half * 32, v);
+            tmem_ld_wait();
+          }
+#else
+        uint32_t vv[2][32];
+        if (p.debug & (4 | 8)) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) vv[0][j] = vv[1][j] = static_cast<uint32_t>(r + j);  // (not a constant: keeps the math alive)
         } else {
         tmem_ld_32x32(tmem_base + lane_addr + as * bn + ch * 64, vv[0]);
         tmem_ld_32x32(tmem_base + lane_addr + as * bn + ch * 64 + 32, vv[1]);
@@ -305,10 +331,11 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int hc0 = col0 + half * 32;
           const uint32_t (&v)[32] = vv[half];
           if (hc0 >= p.N || (p.debug & 4)) continue;  // warp-uniform
+#endif
           float f[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-          if (p.atomic) {
+          if (f_atomic) {
             if (row_ok) {
               float* dst = p.out32 + static_cast<long long>(c.z_tap) * p.out32_z_stride + orow * p.ldo32 + hc0;
               if (hc0 + 32 <= p.N && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
@@ -322,7 +349,14 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
             continue;
           }
-          if (p.bias) {
+          if (EPI != 2 && p.bias_n) {
+            const float4* b4 = reinterpret_cast<const float4*>(sbias + hc0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 b = b4[j];
+              f[4 * j] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
+            }
+          } else if (EPI != 2 && p.bias) {
             if (hc0 + 32 <= p.N) {
               const float4* b4 = reinterpret_cast<const float4*>(p.bias + hc0);
 #pragma unroll
@@ -358,7 +392,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               for (int j = 0; j < 32; ++j) f[j] *= ks;
             }
           }
-          if (p.has_res) {
+          if (f_res) {
             const uint8_t* row = ein + r * 128;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -367,7 +401,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               f[8 * j + 4] += t_lo(tt.z); f[8 * j + 5] += t_hi(tt.z); f[8 * j + 6] += t_lo(tt.w); f[8 * j + 7] += t_hi(tt.w);
             }
           }
-          if (p.has_res32) {
+          if (f_res32) {
             const uint8_t* row = ein + p.ein_off_res32 + half * 16384 + r * 128;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -379,7 +413,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
           }
-          if (p.has_mask) {
+          if (f_mask) {
             const uint8_t* row = ein + p.ein_off_mask + r * 128;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -396,7 +430,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = 0.f;
           }
-          if (p.has_out) {
+          if (f_out && !(p.debug & 16)) {
             uint8_t* row = oslot + r * 128;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -406,26 +440,26 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               *reinterpret_cast<uint4*>(row + (((half * 4 + j) ^ sw128) << 4)) = tt;
             }
           }
-          if (p.has_out32) {
+          if (f_out32) {
             uint8_t* row = oslot + p.out_off_f32 + half * 16384 + r * 128;
 #pragma unroll
             for (int j = 0; j < 8; ++j)
               *reinterpret_cast<float4*>(row + ((j ^ sw128) << 4)) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
           }
         }
-        if (p.atomic) continue;
+        if (f_atomic) continue;
         if (ein) {  // this warp is done with the input slot
           __syncwarp();
           if (lane == 0) mbar_arrive(&ein_empty[es]);
         }
-        fence_proxy_async_smem();
+        if (!(p.debug & 32)) fence_proxy_async_smem();
         // two slots: the store issued one chunk ago must have read ITS slot before the next chunk overwrites it; checking that
         // here (instead of before writing) needs a single barrier per chunk
-        if (two_slots && store_thread) tma_store_wait_read<0>();
-        named_bar_sync(1 + team, 128);
+        if (two_slots && store_thread && !(p.debug & 32)) tma_store_wait_read<0>();
+        if (!(p.debug & 32)) named_bar_sync(1 + team, 128);
         if (store_thread && !(p.debug & 1)) {
-          if (p.has_out) tma_store_2d(&tmOut, oslot, col0, c.m0);
-          if (p.has_out32) {
+          if (f_out) tma_store_2d(&tmOut, oslot, col0, c.m0);
+          if (f_out32) {
             tma_store_2d(&tmOut32, oslot + p.out_off_f32, col0, c.m0);
             if (col0 + 32 < p.N) tma_store_2d(&tmOut32, oslot + p.out_off_f32 + 16384, col0 + 32, c.m0);
           }
@@ -536,15 +570,22 @@ extern "C" int rb_gemm(const rb_gemm_args* a, void* stream) {
   kp.ein_slot_bytes = kp.ein_off_res32 + (kp.has_res32 ? 32768 : 0);
   kp.out_off_f32 = kp.has_out ? 16384 : 0;
   kp.out_slot_bytes = kp.out_off_f32 + (kp.has_out32 ? 32768 : 0);
-  const uint32_t bars_bytes = 512;
+  const long long bias_pad = static_cast<long long>(kp.tiles_n) * bn;
+  kp.bias_n = (a->bias && !a->atomic && bias_pad <= 2048) ? static_cast<int>(bias_pad) : 0;
+  uint32_t bars_bytes = 512 + static_cast<uint32_t>(kp.bias_n) * 4;
   // short main loops do not need a deep ring: the room goes to the epilogue rings instead (HBM-bound 1x1 convolutions, where
   // the residual / mask stream is as large as the output)
   const int want_stages = k_iters * 2 < 4 ? 4 : static_cast<int>(k_iters * 2 > MAX_STAGES ? MAX_STAGES : k_iters * 2);
   int stages = 0;
   kp.ein_slots = 0;
   kp.out_slots = 2;
-  for (int pass = 0; pass < 2 && stages < 2; ++pass) {
-    kp.out_slots = 2 - pass;  // second pass: one staging slot per team
+  for (int pass = 0; pass < 3 && stages < 2; ++pass) {
+    kp.out_slots = pass == 0 ? 2 : 1;  // second pass: one staging slot per team
+    if (pass == 2) {                   // third pass: the bias stays in global memory as well
+      if (!kp.bias_n) break;
+      kp.bias_n = 0;
+      bars_bytes = 512;
+    }
     const long long room = static_cast<long long>(SMEM_LIMIT) - (2LL * kp.out_slots * kp.out_slot_bytes + bars_bytes + 1024 /* alignment slack */);
     if (has_ein) {
       // the epilogue-input ring is what keeps HBM busy when the main loop is short: give it up to MAX_EIN slots after a minimal
@@ -567,6 +608,7 @@ extern "C" int rb_gemm(const rb_gemm_args* a, void* stream) {
   kp.off_ein = stages * kp.stage_bytes;
   kp.off_out = kp.off_ein + kp.ein_slots * kp.ein_slot_bytes;
   kp.off_bars = kp.off_out + 2 * kp.out_slots * kp.out_slot_bytes;
+  kp.off_bias = kp.off_bars + 512;
   const int smem_bytes = static_cast<int>(kp.off_bars + bars_bytes + 1024);
   if (smem_bytes > SMEM_LIMIT) return rb_fail("rb_gemm: shared-memory plan exceeds the limit (%d B)", smem_bytes);
 
@@ -587,21 +629,19 @@ extern "C" int rb_gemm(const rb_gemm_args* a, void* stream) {
   if (kp.has_res32 && make_tmap_2d_f32(&tmRes32, a->res32 + a->out_row_off * a->ldres32, N64, M64, a->ldres32 * 4, 32, BM)) return 1;
   if (kp.has_mask && make_tmap_2d(&tmMask, static_cast<const rb_t*>(a->mask_src) + a->out_row_off * a->ldmask, N64, M64, a->ldmask * 2, 64, BM)) return 1;
 
-  static bool configured[2] = {false, false};
   const int grid = kp.tiles_total < nsm ? kp.tiles_total : nsm;
-  if (a->mode == 0) {
-    if (!configured[0]) {
-      RB_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-      configured[0] = true;
-    }
-    umma_gemm_kernel<0><<<grid, GEMM_THREADS, smem_bytes, st>>>(tmA, tmB, tmOut, tmOut32, tmRes, tmRes32, tmMask, kp);
-  } else {
-    if (!configured[1]) {
-      RB_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-      configured[1] = true;
-    }
-    umma_gemm_kernel<1><<<grid, GEMM_THREADS, smem_bytes, st>>>(tmA, tmB, tmOut, tmOut32, tmRes, tmRes32, tmMask, kp);
+  const bool lean = !a->atomic && kp.has_out && !kp.has_out32 && !kp.has_res32 && !kp.drop.seed;
+  const int epi = a->atomic ? 2 : (lean ? 1 : 0);
+  typedef void (*KernelFn)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, GemmKParams);
+  static const KernelFn kernels[2][3] = {{umma_gemm_kernel<0, 0>, umma_gemm_kernel<0, 1>, umma_gemm_kernel<0, 2>},
+                                         {umma_gemm_kernel<1, 0>, umma_gemm_kernel<1, 1>, umma_gemm_kernel<1, 2>}};
+  static bool configured[2][3] = {{false, false, false}, {false, false, false}};
+  const KernelFn kern = kernels[a->mode][epi];
+  if (!configured[a->mode][epi]) {
+    RB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    configured[a->mode][epi] = true;
   }
+  kern<<<grid, GEMM_THREADS, smem_bytes, st>>>(tmA, tmB, tmOut, tmOut32, tmRes, tmRes32, tmMask, kp);
   RB_CUDA(cudaGetLastError());
   return 0;
 }

@@ -24,7 +24,7 @@ __global__ void __launch_bounds__(128)
 stem_conv_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restrict__ img, const float* __restrict__ bias, rb_t* __restrict__ out,
                  int H, int W, int H1, int W1) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sA = smem;                                  // 3 x [128 x 64] bf16, SW128
   uint8_t* sW = smem + ST_KB * 16384;                  // 3 x [64 x 64] bf16, SW128
   uint64_t* bars = reinterpret_cast<uint64_t*>(sW + ST_KB * 8192);

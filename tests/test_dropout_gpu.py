@@ -229,9 +229,9 @@ def test_e2e_train_mode_matches_oracle_with_same_masks(name):
         assert set(hook.seen) == set(eng._drops)
         err = (out_c["pred_boxes"].cpu() - out_o["pred_boxes"]).abs().max().item()
         print(name, "train step", step, "pred_boxes max abs err", err, "rel-L2", rel_l2(out_c["pred_boxes"], out_o["pred_boxes"]))
-        assert err < 1.5e-2
+        assert err < 4e-3 and rel_l2(out_c["pred_boxes"], out_o["pred_boxes"]) < 2e-3  # measured 0.7e-3..1.5e-3 / 0.8e-3..1.1e-3
         for a, b in zip(out_c["aux_outputs"], out_o["aux_outputs"]):
-            assert (a["pred_boxes"].cpu() - b["pred_boxes"]).abs().max().item() < 1.5e-2
+            assert (a["pred_boxes"].cpu() - b["pred_boxes"]).abs().max().item() < 4e-3
         if prev is not None:  # a new seed gives a new output, also from a replayed graph
             assert (out_c["pred_boxes"] - prev).abs().max().item() > 1e-4
         prev = out_c["pred_boxes"].detach().clone()
@@ -242,7 +242,7 @@ def test_e2e_train_mode_matches_oracle_with_same_masks(name):
         print(name, "train step", step, "worst grads", sorted(live.items(), key=lambda kv: -kv[1])[:6])
         bad = {n: e for n, e in live.items() if e != e or e > 0.9}
         assert not bad, bad
-        assert sorted(live.values())[len(live) // 2] < 0.5
+        assert sorted(live.values())[len(live) // 2] < 0.15
     if eng.use_graphs:
         assert any(st["fwd"] is not None and st["bwd"] is not None for st in eng._states.values())
     # eval mode afterwards: dropout off again, deterministic

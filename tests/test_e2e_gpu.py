@@ -77,23 +77,28 @@ def test_e2e_matches_oracle(name):
         err = (out_c["pred_boxes"].cpu() - out_o["pred_boxes"]).abs().max().item()
         rel = rel_l2(out_c["pred_boxes"], out_o["pred_boxes"])
         print(name, "step", step, "pred_boxes max abs err", err, "rel-L2", rel)
-        # tolerance: bf16 tensor-core operands with fp32 accumulation / residual stream; the oracle under bf16 autocast is
-        # 5e-3..7e-3 off itself on these cases, boxes are in (0,1)
-        assert err < 1.5e-2
+        # tolerance = the north star's 1e-3 relative (BASELINE.json), as rel-L2 over the boxes; IEEE-half tensor-core operands with
+        # fp32 accumulation / residual stream measure 4.6e-4..8.4e-4 on these cases (the oracle under bf16 autocast is 5e-3..7e-3 off
+        # itself).  Boxes are in (0,1): the largest single-coordinate error is bounded as well.
+        assert rel < 1e-3
+        assert err < 2.5e-3
         if "aux_outputs" in out_o:
             for a, b in zip(out_c["aux_outputs"], out_o["aux_outputs"]):
-                assert (a["pred_boxes"].cpu() - b["pred_boxes"]).abs().max().item() < 1.5e-2
+                assert (a["pred_boxes"].cpu() - b["pred_boxes"]).abs().max().item() < 2.5e-3
         if "pred_masks" in out_o:
-            assert rel_l2(out_c["pred_masks"], out_o["pred_masks"]) < 3e-2
-            assert rel_l2(out_c["mask_att"], out_o["mask_att"]) < 3e-2
+            print(name, "pred_masks rel-L2", rel_l2(out_c["pred_masks"], out_o["pred_masks"]), "mask_att rel-L2", rel_l2(out_c["mask_att"], out_o["mask_att"]))
+            assert rel_l2(out_c["pred_masks"], out_o["pred_masks"]) < 5e-3
+            assert rel_l2(out_c["mask_att"], out_o["mask_att"]) < 5e-3
         errs = compare_grads(cand, oracle)
         live = {n: e for n, e in errs.items() if norms[n] > 1e-6 * big}
         worst = sorted(live.items(), key=lambda kv: -kv[1])[:6]
         print(name, "step", step, "worst grads", worst)
         assert len(errs) > 150
-        bad = {n: (e, floor.get(n)) for n, e in live.items() if e != e or e > max(0.75, 3.0 * min(floor.get(n, 0.0), 0.6))}
+        bad = {n: (e, floor.get(n)) for n, e in live.items() if e != e or e > max(0.3, 3.0 * min(floor.get(n, 0.0), 0.6))}
         assert not bad, bad
-        assert sorted(live.values())[len(live) // 2] < 0.5
+        med = sorted(live.values())[len(live) // 2]
+        print(name, "step", step, "median grad rel-L2", med)
+        assert med < 0.1
     eng = cand.engine()
     assert eng.launches > 0
     if eng.use_graphs:

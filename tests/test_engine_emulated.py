@@ -84,13 +84,13 @@ def test_engine_on_emulated_kernels_matches_oracle(name, emulated):
     assert torch.equal(out_c["phrase_mask"], out_o["phrase_mask"])
     err = (out_c["pred_boxes"] - out_o["pred_boxes"]).abs().max().item()
     print(name, "pred_boxes max abs err", err)
-    assert err < 1.5e-2  # bf16 operand noise floor: the oracle under bf16 autocast is 5e-3..7e-3 off itself on these cases
+    assert err < 2.5e-3  # IEEE-half operand rounding (measured 3e-4..9e-4); the oracle under bf16 autocast is 5e-3..7e-3 off itself
     if "aux_outputs" in out_o:
         for a, b in zip(out_c["aux_outputs"], out_o["aux_outputs"]):
-            assert (a["pred_boxes"] - b["pred_boxes"]).abs().max().item() < 1.5e-2
+            assert (a["pred_boxes"] - b["pred_boxes"]).abs().max().item() < 2.5e-3
     if "pred_masks" in out_o:
-        assert rel_l2(out_c["pred_masks"], out_o["pred_masks"]) < 3e-2
-        assert rel_l2(out_c["mask_att"], out_o["mask_att"]) < 3e-2
+        assert rel_l2(out_c["pred_masks"], out_o["pred_masks"]) < 5e-3
+        assert rel_l2(out_c["mask_att"], out_o["mask_att"]) < 5e-3
     errs = compare_grads(cand, oracle)
     worst = sorted(errs.items(), key=lambda kv: -kv[1])[:8]
     print(name, "worst grads", worst)
@@ -104,7 +104,7 @@ def test_engine_on_emulated_kernels_matches_oracle(name, emulated):
     live = {n: e for n, e in errs.items() if norms[n] > 1e-6 * big}
     bad = {n: e for n, e in live.items() if e > 0.75}
     assert not bad, bad
-    assert sorted(live.values())[len(live) // 2] < 0.5
+    assert sorted(live.values())[len(live) // 2] < 0.1
 
 
 def _linear_loss(out):
