@@ -542,6 +542,7 @@ extern "C" int rb_gemm(const rb_gemm_args* a, void* stream) {
     kp.drop_wpr = static_cast<uint32_t>((cols + 1) >> 1);
     if ((static_cast<long long>(a->M) + a->out_row_off) * kp.drop_wpr >= (1LL << 32)) return rb_fail("rb_gemm: dropout site too large for a 32-bit counter");
   }
+  if (gemm_skinny_eligible(a) && !(getenv("RB_GEMM_NO_SKINNY"))) return gemm_skinny_launch(a, kp.drop, static_cast<int>(kp.drop_wpr), st);
   const int nsm = sm_count();
   const long long tiles_m = (a->M + BM - 1) / BM;
   const long long k_iters = a->mode == 0 ? static_cast<long long>(a->taps) * kp.kblocks : (kp.kblocks + kp.splits - 1) / kp.splits;

@@ -31,6 +31,9 @@ inline DropK make_dropk(const rb_dropout* d) {
   }
   return k;
 }
+// skinny (M <= 128) linear layers on mma.sync (gemm_skinny.cu); rb_gemm dispatches to it
+bool gemm_skinny_eligible(const rb_gemm_args* a);
+int gemm_skinny_launch(const rb_gemm_args* a, const DropK& drop, int drop_wpr, cudaStream_t st);
 // SIMT attention (attention.cu); the C-ABI entry points in attention_tc.cu fall back to these for short query counts
 int attn_fwd_simt(const void* Q, const void* K, const void* V, const void* kpm, void* O, float* LSE, int B, int H, int dh, int Tq, int Sk, long long ldq,
                   long long ldk, long long ldv, long long ldo, float scale, const rb_dropout* drop, void* stream);

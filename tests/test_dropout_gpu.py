@@ -208,6 +208,14 @@ def test_e2e_train_mode_matches_oracle_with_same_masks(name):
     cand = build_candidate(case, device=dev).train()
     eng = cand.engine()
     prev = None
+
+    def smooth_loss(out, device):
+        # a fixed random linear functional of every layer's boxes: L1 + GIoU has a sign() in its gradient, so a coordinate that
+        # lands within the forward tolerance of its target flips a whole gradient component -- which seed does that is luck
+        g = torch.Generator().manual_seed(5)
+        boxes = [out["pred_boxes"]] + [a["pred_boxes"] for a in out.get("aux_outputs", [])]
+        return sum((b * torch.randn(b.shape, generator=g).to(device)).sum() for b in boxes)
+
     for step in range(3):
         seed = (SEED + 7919 * step) & 0x7FFFFFFFFFFFFFFF
         oracle = build_oracle(case).train()
@@ -216,14 +224,14 @@ def test_e2e_train_mode_matches_oracle_with_same_masks(name):
         orc.DROPOUT_HOOK = hook
         try:
             out_o = oracle(s_cpu)
-            total_box_loss(out_o, synthetic_targets(case["inputs"]["B"], n_ph)).backward()
+            smooth_loss(out_o, "cpu").backward()
         finally:
             orc.DROPOUT_HOOK = None
             undo()
         cand.zero_grad(set_to_none=True)
         eng.next_seed = seed
         out_c = cand(s)
-        total_box_loss(out_c, synthetic_targets(case["inputs"]["B"], n_ph, device=dev)).backward()
+        smooth_loss(out_c, dev).backward()
         torch.cuda.synchronize()
         assert eng.train_mode and eng.last_seed == seed
         assert set(hook.seen) == set(eng._drops)

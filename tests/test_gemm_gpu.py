@@ -101,3 +101,52 @@ def test_conv3x3_wgrad_taps():
     F.conv2d(xr, wz, padding=1).backward(dyp[:, 1:-1, 1:-1].permute(0, 3, 1, 2).float())
     ref = wz.grad.permute(0, 2, 3, 1).reshape(Cout, 9, Cin)
     assert _rel(out32, ref) < 2e-3
+
+
+@pytest.mark.parametrize("M,N,K", [(16, 256, 256), (16, 2048, 256), (16, 256, 2048), (96, 64, 256), (96, 256, 64), (5, 4, 256), (80, 768, 768), (128, 256, 512),
+                                   (1, 256, 256)])
+def test_gemm_skinny_matches_torch_and_big_kernel(M, N, K):
+    """M <= 128 rows dispatch to the mma.sync latency kernel (gemm_skinny.cu): same results as torch and as the tcgen05 kernel for
+    every epilogue combination the decoder / query encoder / box head use."""
+    import os
+    from reftr_b200 import ops
+    import dropout_ref
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N + K)
+    A = torch.randn(M, K, device="cuda", generator=g).to(T16)
+    W = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).to(T16)
+    bias = torch.randn(N, device="cuda", generator=g)
+    pad = (N + 7) // 8 * 8  # 16-bit operands of the epilogue need a 16-byte row pitch
+    res = torch.randn(M, pad, device="cuda", generator=g).to(T16)[:, :N]
+    res32 = torch.randn(M, pad, device="cuda", generator=g)[:, :N]
+    msk = torch.randn(M, pad, device="cuda", generator=g).to(T16)[:, :N]
+    lin = A.float() @ W.float().t() + bias
+    seed = torch.full((1,), 1234567, dtype=torch.int64, device="cuda")
+    cases = [
+        (dict(bias=bias, res=res, relu=True), torch.relu(lin + res.float())),
+        (dict(bias=bias, res32=res32), lin + res32),
+        (dict(mask_src=msk, mask_scale=1.5), torch.where(msk.float() > 0, (lin - bias) * 1.5, torch.zeros((), device="cuda"))),
+    ]
+    if N % 2 == 0:
+        d1 = ops.Drop(seed, "sk.a", 0.1)
+        m1 = dropout_ref.mask_scale(1234567, "sk.a", M, N, 0.1, device="cuda")
+        cases.append((dict(bias=bias, res32=res32, drop=d1), res32 + lin * m1))
+        cases.append((dict(bias=bias, relu=True, drop=d1), torch.relu(lin) * m1))
+    if N % 32 == 0:
+        d2 = ops.Drop(seed, "sk.h", 0.3)
+        m2 = dropout_ref.mask_scale(1234567, "sk.h", M, N // 32, 0.3, device="cuda").repeat_interleave(32, dim=1)
+        cases.append((dict(bias=bias, drop=d2, drop_gshift=5), lin * m2))
+    for kw, ref in cases:
+        outs = []
+        for no_skinny in ("", "1"):
+            if no_skinny:
+                os.environ["RB_GEMM_NO_SKINNY"] = "1"
+            try:
+                ob = torch.full((M, pad), 3.0, device="cuda", dtype=T16)[:, :N]
+                o32 = torch.full((M, pad), 3.0, device="cuda")[:, :N]
+                ops.gemm(A, W, M, N, K, out=ob, out32=o32, **kw)
+            finally:
+                os.environ.pop("RB_GEMM_NO_SKINNY", None)
+            assert _rel(o32, ref) < 2e-3, (kw.keys(), no_skinny)
+            assert _rel(ob, ref) < 8e-3
+            outs.append(o32)
+        assert _rel(outs[0], outs[1]) < 1e-4  # the two kernels agree to fp32 summation order
