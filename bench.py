@@ -2,7 +2,8 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference|stock-gpu]
 
-A "step" is one forward + criterion + backward pass (no optimizer step) over one synthetic batch of
+A "step" is one forward + criterion + backward pass in TRAIN mode (every dropout of the reference active; no optimizer step, as
+in SURVEY.md 8(d)) over one synthetic batch of
 BASELINE.json configs[1]: ResNet-50 + 6+6-layer RefTR, 640x640 images, 20-token phrases, batch 16 PER GPU (the
 reference's --batch_size is per process, main_vg.py:208-209; weak scaling), random-init weights of that architecture.
 Under torchrun (N > 1) the model is wrapped in DistributedDataParallel (NCCL gradient all-reduce, as main_vg.py:293-296).
@@ -32,12 +33,14 @@ if ROOT not in sys.path:
 import torch  # noqa: E402
 
 GF_FWD_BWD = 207.83  # algorithmic GFLOP per sample, fwd+bwd, config 2 (FlopCounterMode on the reference)
-GEMM_TRAFFIC_PER_LAUNCH_MB = 26.49  # measured with ncu, see roofline.traffic_note
+GEMM_TRAFFIC_PER_LAUNCH_MB = 27.32  # measured with ncu, see roofline.traffic_note
 # encoder self-attention kernel (the metric's "encoder-MHA TC util%"): ncu --set full, profiles/r01_ncu_full_prof_final_misc.csv
-ENCODER_MHA = {"kernel": "attn_fwd_tc_kernel (QK^T and PV on tcgen05, S=420, head_dim 32, B*H=128)", "duration_us": 32.8,
-               "tensor_pipe_active_pct": 6.3, "dram_pct_of_peak": 3.9,
-               "note": "exp/latency-bound at head_dim 32 (SURVEY 7.2); the projections are separate GEMM launches, see DESIGN.md section 8",
-               "source": "profiles/r01_ncu_full_prof_final_misc.csv"}
+ENCODER_MHA = {"kernel": "attn_fwd_tc_kernel (QK^T and PV on tcgen05, S=420, head_dim 32, B*H=128, train mode: dropout on P)", "duration_us": 43.3,
+               "tensor_pipe_active_pct": 4.8, "issue_active_pct": 44.0, "dram_pct_of_peak": 2.9,
+               "eval_mode": {"duration_us": 32.8, "tensor_pipe_active_pct": 6.3, "source": "profiles/r01_ncu_full_prof_final_misc.csv"},
+               "note": "ALU (softmax + dropout hash) / latency-bound at head_dim 32: 2 CTAs per SM (119 registers), 44 % issue-slot "
+                       "utilisation; the projections are separate GEMM launches, see DESIGN.md section 8",
+               "source": "profiles/r01b_ncu_full_attention_stem.csv"}
 GF_BY_WORKLOAD = {"cfg2": 207.83, "cfg3": 220.77, "cfg4": 304.78, "cfg5": 616.74}
 WORKLOAD = dict(B=16, H=640, W=640, L=20)
 METRIC = "samples/sec fwd+bwd (640x640, 20-tok phrase, bs16/GPU)"
@@ -376,9 +379,10 @@ def main():
         ach = g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
         out["roofline"] = {"bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                            "frac": ach / pk["bf16_tflops_sustained"], "traffic": GEMM_TRAFFIC_PER_LAUNCH_MB * 1e6,
-                           "traffic_note": "bytes per launch = (dram__bytes_read.sum + dram__bytes_write.sum) summed over the 594 GEMM launches of one "
-                                           "cfg2 step / 594, ncu capture profiles/r01_gemm_dram_final.csv (15.74 GB per step; reads 14.0 GB)",
-                           "kernel": "umma_gemm_kernel (every GEMM / implicit-conv launch of one step: conv fwd+dgrad+wgrad, linear layers)",
+                           "traffic_note": "bytes per launch = (dram__bytes_read.sum + dram__bytes_write.sum) summed over the 576 GEMM launches of one "
+                                           "cfg2 train-mode step / 576, ncu capture profiles/r01b_gemm_dram_train.csv (15.74 GB per step; reads 14.0 GB)",
+                           "kernel": "rb_gemm: umma_gemm_kernel (tcgen05; every conv fwd+dgrad+wgrad and linear layer of one step) + gemm_skinny_kernel "
+                                     "(mma.sync, the M <= 128 decoder / head layers, 0.3 % of the FLOPs)",
                            "launches": len(rec), "avg_launch_us": g_ms * 1e3 / max(len(rec), 1), "gemm_ms_per_step": g_ms,
                            "gemm_gflop_per_step": g_fl / 1e9, "peak_source": pk_src + " (sustained)",
                            "note": "the path is mixed: conv1/layer1/layer2 GEMMs are HBM-bound (SURVEY 8(d)); see DESIGN.md section 5",
