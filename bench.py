@@ -183,6 +183,64 @@ def oracle_cpu_rate(B_sample, steps, warmup):
     return B_sample * len(times) / sum(times), threads, sum(times) / len(times)
 
 
+def optimizer_diag(model, step_fn, device):
+    """SURVEY 8(f) row N3 (NOT part of the metric's timed region): the reference's per-iteration clip_grad_norm_(0.1) + AdamW.step()
+    (engine_vg.py:62-67, main_vg.py:234-268) as torch runs it vs reftr_b200.optim on flat buffers, on the gradients of one step; and
+    a whole training iteration (fwd + bwd + clip + step, which also re-packs every folded 16-bit weight copy)."""
+    from reftr_b200 import optim as ro
+
+    def groups(named):
+        bb = [p for n, p in named if "img_backbone.0" in n]
+        bert = [p for n, p in named if "lang_backbone" in n]
+        rest = [p for n, p in named if "img_backbone.0" not in n and "lang_backbone" not in n]
+        return [{"params": rest, "lr": 1e-4}, {"params": bb, "lr": 1e-5}, {"params": bert, "lr": 1e-5}]
+
+    def timed_ms(fn, n):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
+    step_fn()
+    twin = [(n, torch.nn.Parameter(p.detach().clone())) for n, p in named]
+    for (_, t), (_, p) in zip(twin, named):
+        t.grad = p.grad.detach().clone()
+    opt_t = torch.optim.AdamW(groups(twin), lr=1e-4, weight_decay=1e-4)
+    tp = [t for _, t in twin]
+
+    def torch_step():
+        torch.nn.utils.clip_grad_norm_(tp, 0.1)
+        opt_t.step()
+    torch_step()
+    ms_torch = timed_ms(torch_step, 5)
+    del opt_t, twin, tp
+    opt = ro.FusedAdamW.for_model(model, groups(named), lr=1e-6, weight_decay=1e-4)
+    params = [p for _, p in named]
+
+    def fused_step():
+        ro.clip_grad_norm_(params, 0.1)
+        opt.step()
+    step_fn()
+    fused_step()
+    zero_copy = opt.flat_g is None
+    ms_fused = timed_ms(fused_step, 5)
+
+    def train_iter():
+        step_fn()
+        fused_step()
+    for _ in range(3):
+        train_iter()
+    ms_iter = timed_ms(train_iter, 5)
+    return {"torch_clip_adamw_ms": ms_torch, "fused_clip_adamw_ms": ms_fused, "params": sum(p.numel() for p in params),
+            "zero_copy_gradients": zero_copy, "train_iteration_ms": ms_iter,
+            "note": "train_iteration = fwd + criterion + bwd + clip + AdamW, incl. the re-pack of all folded 16-bit weights after each update"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -389,6 +447,8 @@ def main():
                            "top_groups": [{"ms": round(m_, 4), "launches": n_, "mode_M_N_K_taps": list(sg[:5]),
                                            "tflops": round(f_ / (m_ * 1e-3) / 1e12, 1)} for m_, n_, sg, f_ in top[:6]]}
         out["encoder_mha"] = ENCODER_MHA
+        if world == 1 and a.workload == "cfg2" and os.environ.get("REFTR_B200_BENCH_OPTIM", "1") == "1":
+            out["next_rows"] = {"N3_optimizer_step": optimizer_diag(model, step_resident, device)}
         if rank == 0 and a.gpus == 1 and not a.no_cpu_baseline:
             bs = 8
             rate, threads, sec = oracle_cpu_rate(bs, 1, 1)

@@ -250,6 +250,29 @@ int rb_attn_small_bwd(const void* Q, const void* K, const void* V, const void* d
 int rb_box_loss(const float* boxes, const float* tgt, const void* valid, int n_layers, int N, float inv_norm, const float* inv_norm_dev, float* losses,
                 float* dl1, float* dgiou, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Optimizer step on device-flat buffers (engine_vg.py:62-67, main_vg.py:234-268): global-norm clip
+ * (torch.nn.utils.clip_grad_norm_) + torch.optim.AdamW over ALL parameters in two launches.  p / g / m / v are flat fp32 buffers
+ * of n elements (n % 4 == 0, 16-byte aligned) holding every parameter, its gradient and its two moments at the same offsets;
+ * `segs` (HOST pointer) maps element ranges to parameter groups (per-group lr / weight decay, read on the host every step, so LR
+ * schedulers work unchanged).
+ * ------------------------------------------------------------------------------------------------------------- */
+#define RB_ADAMW_MAX_SEGMENTS 32
+#define RB_ADAMW_MAX_GROUPS 8
+typedef struct {
+  int nseg;
+  long long end[RB_ADAMW_MAX_SEGMENTS]; /* segment s = elements [end[s-1], end[s]), multiples of 4 */
+  int group[RB_ADAMW_MAX_SEGMENTS];
+  float lr[RB_ADAMW_MAX_GROUPS];
+  float weight_decay[RB_ADAMW_MAX_GROUPS];
+} rb_adamw_segments;
+/* *out += sum of squares of x[0..n)  (out: device scalar, zeroed by the caller) */
+int rb_sumsq(const float* x, long long n, float* out, void* stream);
+/* One AdamW step (amsgrad off).  `step` counts from 1 (bias corrections are computed on the host in double).  If sumsq != NULL and
+ * max_norm > 0 the gradient is multiplied by min(1, max_norm / (sqrt(*sumsq) + 1e-6)) first (clip_grad_norm_, no host sync). */
+int rb_adamw_flat(float* p, const float* g, float* m, float* v, long long n, const rb_adamw_segments* segs, float beta1, float beta2, float eps, int step,
+                  const float* sumsq, float max_norm, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -47,6 +47,11 @@ class GemmArgs(C.Structure):
     ]
 
 
+class AdamwSegments(C.Structure):
+    """rb_adamw_segments"""
+    _fields_ = [("nseg", C.c_int), ("end", C.c_longlong * 32), ("group", C.c_int * 32), ("lr", C.c_float * 8), ("weight_decay", C.c_float * 8)]
+
+
 _lib = None
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "reftr_b200.h")
 

@@ -364,3 +364,23 @@ def attn_small_bwd(Q, K, V, dO, P, dQ, dK, dV, B, H, S, scale, drop=None):
 def box_loss(boxes, tgt, valid, inv_norm, inv_norm_dev, losses, dl1, dgiou):
     n_layers, N = boxes.shape[0], boxes.shape[1]
     _lib.call("rb_box_loss", _p(boxes), _p(tgt), _p(valid), n_layers, N, float(inv_norm), _p(inv_norm_dev), _p(losses), _p(dl1), _p(dgiou), _s())
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# optimizer step on flat buffers (reftr_b200/optim.py)
+# ---------------------------------------------------------------------------------------------------------------
+def sumsq(x, out):
+    """out (device scalar) += sum(x^2); x: flat fp32, numel % 4 == 0."""
+    _lib.call("rb_sumsq", _p(x), x.numel(), _p(out), _s())
+
+
+def adamw_flat(p, g, m, v, seg_end, seg_group, lrs, wds, beta1, beta2, eps, step, sumsq_dev=None, max_norm=0.0):
+    segs = _lib.AdamwSegments()
+    segs.nseg = len(seg_end)
+    for i, (e, grp) in enumerate(zip(seg_end, seg_group)):
+        segs.end[i] = e
+        segs.group[i] = grp
+    for i, (lr, wd) in enumerate(zip(lrs, wds)):
+        segs.lr[i] = lr
+        segs.weight_decay[i] = wd
+    _lib.call("rb_adamw_flat", _p(p), _p(g), _p(m), _p(v), p.numel(), C.addressof(segs), beta1, beta2, eps, int(step), _p(sumsq_dev), float(max_norm), _s())

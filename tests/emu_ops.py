@@ -686,3 +686,28 @@ def attn_small_bwd(Q, K, V, dO, P, dQ, dK, dV, B, H, S, scale, drop=None):
     dk = ds.transpose(-1, -2) @ q
     for dst, src in ((dQ, dq), (dK, dk), (dV, dv)):
         dst.copy_(src.transpose(1, 2).reshape(B * S, H * 64).to(_lp()))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# optimizer step on flat buffers
+# ---------------------------------------------------------------------------------------------------------------
+def sumsq(x, out):
+    _LAUNCHES[0] += 1
+    out += (x.double() ** 2).sum().float()
+
+
+def adamw_flat(p, g, m, v, seg_end, seg_group, lrs, wds, beta1, beta2, eps, step, sumsq_dev=None, max_norm=0.0):
+    _LAUNCHES[0] += 1
+    clip = 1.0
+    if sumsq_dev is not None and max_norm > 0:
+        clip = min(1.0, max_norm / (float(sumsq_dev.sqrt()) + 1e-6))
+    bc1, bc2 = 1 - beta1 ** step, 1 - beta2 ** step
+    lo = 0
+    for end, grp in zip(seg_end, seg_group):
+        sl = slice(lo, end)
+        lr, wd = lrs[grp], wds[grp]
+        gg = g[sl] * clip
+        m[sl] = beta1 * m[sl] + (1 - beta1) * gg
+        v[sl] = beta2 * v[sl] + (1 - beta2) * gg * gg
+        p[sl] = p[sl] * (1 - lr * wd) - (lr / bc1) * m[sl] / (v[sl].sqrt() / math.sqrt(bc2) + eps)
+        lo = end
