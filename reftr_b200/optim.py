@@ -100,9 +100,11 @@ class FusedAdamW(torch.optim.Optimizer):
         if g0 is not None and g0.dtype == torch.float32 and g0.is_contiguous():
             st = g0.untyped_storage()
             first = g0.storage_offset() - self._off[id(ps[0])]  # element offset of slot 0 inside that storage
-            if first >= 0 and st.nbytes() >= 4 * (first + self.n) and (st.data_ptr() + 4 * first) % 16 == 0 and all(
-                    p.grad is not None and p.grad.dtype == torch.float32 and p.grad.is_contiguous()
-                    and p.grad.untyped_storage().data_ptr() == st.data_ptr() and p.grad.storage_offset() == first + self._off[id(p)] for p in ps):
+            base = st.data_ptr()
+            # every gradient must sit at its slot of that one storage (checked in full: ~0.3 ms of host time for 470 tensors)
+            if first >= 0 and st.nbytes() >= 4 * (first + self.n) and (base + 4 * first) % 16 == 0 and all(
+                    p.grad is not None and p.grad.data_ptr() == base + 4 * (first + self._off[id(p)]) and p.grad.is_contiguous()
+                    and p.grad.dtype == torch.float32 for p in ps):
                 return torch.empty(0, dtype=torch.float32, device=self.device).set_(st, first, (self.n,), (1,))
         return self._gather(ps)
 
@@ -143,12 +145,15 @@ class FusedAdamW(torch.optim.Optimizer):
         ops.adamw_flat(self.flat_p, g, self.flat_m, self.flat_v, self.seg_end, self.seg_group,
                        [grp["lr"] for grp in self.param_groups], [grp["weight_decay"] for grp in self.param_groups],
                        g0["betas"][0], g0["betas"][1], g0["eps"], self._step, sumsq, max_norm)
-        for st in self.state.values():
-            st["step"] += 1
         # the kernel wrote the parameters behind autograd's back: bump their version counters so that version-tracking consumers
         # (the engine's packed 16-bit weight copies, reftr_b200/pack.py) see the change, exactly as after torch's in-place update
         torch.autograd.graph.increment_version([p for _, p in self._plist])
         return loss
+
+    def state_dict(self):
+        for st in self.state.values():  # torch's per-parameter step counters are materialised only when somebody looks
+            st["step"].fill_(self._step)
+        return super().state_dict()
 
     def load_state_dict(self, state_dict):
         super().load_state_dict(state_dict)
