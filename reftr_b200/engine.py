@@ -209,6 +209,7 @@ class RefTREngine:
         self._side2, self._side2_used = None, False
         self._tracked = [t for t in list(model.parameters()) + list(model.buffers())]
         self._vsig, self._pack_dev = None, None
+        self._repack_graphs, self._repack_seen = {}, None
         self.force_eager = False  # bench.py: run the next steps launch by launch on the graphed workspace (profiling)
         self.launches = 0
         # ---- dropout (train mode): counter-based, nothing stored; ONE device seed rewritten before every forward --------
@@ -254,6 +255,7 @@ class RefTREngine:
         if self._dev != device or sig != self._sig:
             self._dev, self._sig = device, sig
             self._vsig = None
+            self._repack_graphs, self._repack_seen = {}, None  # graphs hold raw parameter addresses
             self._states = {}
             self.gflat = torch.zeros(self.n_flat, dtype=torch.float32, device=device)
             self.seed_dev = torch.zeros(1, dtype=torch.int64, device=device)
@@ -261,9 +263,34 @@ class RefTREngine:
         # cheap change detection first (one tuple compare); the per-pack refresh walk only runs when something moved
         vsig = tuple(t._version for t in self._tracked)
         if vsig != self._vsig or device != self._pack_dev:
+            self._refresh_packs(device)
+            self._vsig, self._pack_dev = tuple(t._version for t in self._tracked), device
+
+    def _refresh_packs(self, device):
+        """Re-packs the 16-bit kernel-layout copies of every weight whose master changed.  After an optimizer step that is ALL
+        trainable weights (~150 small launches every iteration), so the second time the same set is stale the launches are captured
+        into one CUDA graph (sources and destinations are fixed addresses) and replayed from then on."""
+        stale = [p for p in self.packs if getattr(p, "_key", None) != p.current_key()] if all(hasattr(p, "current_key") for p in self.packs) else None
+        if stale is None or device.type != "cuda" or not self.use_graphs or device != self._pack_dev or not stale:
             for p in self.packs:
                 p.refresh()
-            self._vsig, self._pack_dev = tuple(t._version for t in self._tracked), device
+            return
+        ids = tuple(id(p) for p in stale)
+        g = self._repack_graphs.get(ids)
+        if g is None and self._repack_seen == ids and len(stale) > 8:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for p in stale:
+                    p.refresh()
+            self._repack_graphs = {ids: g}
+        self._repack_seen = ids
+        if g is None:
+            for p in stale:
+                p.refresh()
+        else:
+            g.replay()
+            for p in stale:
+                p._key = p.current_key()
 
     # ------------------------------------------------------------------------------------------------------------
     # step driver: eager on the first step of a shape, CUDA-graph capture on the second, replay afterwards

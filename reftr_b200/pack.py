@@ -25,6 +25,10 @@ class PackedConv:
         self._key = None
         self.wf = self.wd = self.scale = self.bias = None
 
+    def current_key(self):
+        bn = (self.bn.weight, self.bn.bias, self.bn.running_mean, self.bn.running_var) if self.bn is not None else ()
+        return _ver(self.conv.weight, getattr(self.conv, "bias", None), *bn)
+
     def refresh(self):
         w = self.conv.weight
         bn = None
@@ -56,6 +60,9 @@ class PackedLinear:
         self._key = None
         self.wb = self.wt = self.bias = None
 
+    def current_key(self):
+        return _ver(self.weight, self.bias_p)
+
     def refresh(self):
         key = _ver(self.weight, self.bias_p)
         if key == self._key:
@@ -85,6 +92,9 @@ class PackedStack:
         self.n = len(weights)
         self._key = None
         self.wb = self.wt = self.bias = None
+
+    def current_key(self):
+        return _ver(*self.weights, *self.biases)
 
     def refresh(self):
         key = _ver(*self.weights, *self.biases)

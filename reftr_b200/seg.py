@@ -29,6 +29,9 @@ class PackedConvPadded:
         self._key = None
         self.wf = self.wd = self.scale = self.bias = self.w_pad = self.b_pad = None
 
+    def current_key(self):
+        return _ver(self.conv.weight, self.conv.bias)
+
     def refresh(self):
         w, b = self.conv.weight, self.conv.bias
         key = _ver(w, b)

@@ -144,6 +144,13 @@ def test_fused_adamw_on_the_engine_flat_gradients_gpu():
         opt.step()
         opt_t.step()
     torch.cuda.synchronize()
+    # the engine's packed 16-bit weight copies followed the updates (re-packed from a captured graph from the 2nd update on): the
+    # updated model computes what a freshly built model with the same state_dict computes
+    assert model.engine()._repack_graphs
+    fresh = build_candidate(case, device="cuda")
+    fresh.load_state_dict(model.state_dict())
+    with torch.no_grad():
+        assert torch.equal(model(s)["pred_boxes"], fresh(s)["pred_boxes"])
     moved = 0
     for n, p in model.named_parameters():
         if p.requires_grad:
