@@ -822,7 +822,8 @@ class RefTREngine:
         self.wgrad_linear(dqkv[:, :2 * D], xpb, gw[:2 * D], 2 * D, D, rows)
         self.wgrad_linear(dqkv[:, 2 * D:], xb, gw[2 * D:], D, D, rows)
         ops.gemm(dqkv, e.inp.wt, rows, D, 3 * D, res32=dy1, out32=g_out)
-        ops.gemm(dqkv[:, :2 * D], e.inp.wt[:, :2 * D], rows, D, 2 * D, res32=dpos, out32=dpos)
+        with self._off():  # d(pos) of the encoder layers only feeds the embedding gradients at the very end: off the critical path
+            ops.gemm(dqkv[:, :2 * D], e.inp.wt[:, :2 * D], rows, D, 2 * D, res32=dpos, out32=dpos)
 
     # ------------------------------------------------------------------------------------------------------------
     # query encoder (reftr_transformer.py:41-66)
