@@ -273,6 +273,15 @@ int rb_sumsq(const float* x, long long n, float* out, void* stream);
 int rb_adamw_flat(float* p, const float* g, float* m, float* v, long long n, const rb_adamw_segments* segs, float beta1, float beta2, float eps, int step,
                   const float* sumsq, float max_norm, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Input pipeline on the GPU: torchvision to_tensor + Normalize (datasets/transforms.py:233-250) and the
+ * pad-to-batch NestedTensor build of util/collate_fn.py:24-41 in one launch.  packed: the raw uint8 HWC images back to back;
+ * table int64 [B,3] = {byte offset, h, w} (device); out fp32 [B,3,H,W] = ((x / 255) - mean) / std inside the image, 0 in the
+ * padding; mask bool/u8 [B,H,W], 1 = padding.
+ * ------------------------------------------------------------------------------------------------------------- */
+int rb_collate_u8(const void* packed, const long long* table, int B, int H, int W, float mean0, float mean1, float mean2, float std0, float std1,
+                  float std2, float* out, void* mask, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -384,3 +384,8 @@ def adamw_flat(p, g, m, v, seg_end, seg_group, lrs, wds, beta1, beta2, eps, step
         segs.lr[i] = lr
         segs.weight_decay[i] = wd
     _lib.call("rb_adamw_flat", _p(p), _p(g), _p(m), _p(v), p.numel(), C.addressof(segs), beta1, beta2, eps, int(step), _p(sumsq_dev), float(max_norm), _s())
+
+
+def collate_u8(packed, table, B, H, W, mean, std, out, mask):
+    _lib.call("rb_collate_u8", _p(packed), _p(table), B, H, W, float(mean[0]), float(mean[1]), float(mean[2]), float(std[0]), float(std[1]),
+              float(std[2]), _p(out), _p(mask), _s())

@@ -1,0 +1,40 @@
+"""GPU input pipeline (reftr_b200/data.py) against the reference's CPU path restated in torch (to_tensor + Normalize,
+datasets/transforms.py:233-250; nested_tensor_from_tensor_list, util/collate_fn.py:24-41): bit-exact, ragged sizes included."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("sizes", [[(640, 640)] * 4, [(480, 640), (640, 427), (333, 500), (17, 9), (640, 640)], [(1, 1)], [(224, 224), (200, 300)]])
+def test_collate_u8_matches_reference_cpu_path(sizes):
+    from reftr_b200.data import DeviceCollator, reference_collate
+    g = torch.Generator().manual_seed(len(sizes))
+    images = [torch.randint(0, 256, (h, w, 3), dtype=torch.uint8, generator=g) for h, w in sizes]
+    ref = reference_collate(images)
+    col = DeviceCollator("cuda")
+    for _ in range(2):  # second call reuses the staging buffers
+        got = col(images)
+        torch.cuda.synchronize()
+        assert got.tensors.shape == ref.tensors.shape and got.mask.dtype == torch.bool
+        assert torch.equal(got.mask.cpu(), ref.mask)
+        assert torch.equal(got.tensors.cpu(), ref.tensors)  # same fp32 operations in the same order: bit-exact
+    side = torch.cuda.Stream()
+    got = col(images, stream=side)
+    side.synchronize()
+    assert torch.equal(got.tensors.cpu(), ref.tensors)
+
+
+def test_collated_batch_feeds_the_model():
+    from oracle.cases import CASES
+    from reftr_b200.data import DeviceCollator
+    from reftr_b200.synthetic import synthetic_samples
+    from util_build import build_candidate
+    case = CASES["pad_box"]
+    g = torch.Generator().manual_seed(0)
+    images = [torch.randint(0, 256, (192, 256, 3), dtype=torch.uint8, generator=g), torch.randint(0, 256, (192, 200, 3), dtype=torch.uint8, generator=g)]
+    s = synthetic_samples(**case["inputs"], device="cuda")
+    s["img"] = DeviceCollator("cuda")(images)
+    model = build_candidate(case, device="cuda")
+    out = model(s)
+    assert torch.isfinite(out["pred_boxes"]).all() and out["pred_boxes"].shape[0] == 2
