@@ -40,14 +40,12 @@ __global__ void stem_im2col_kernel(const float* __restrict__ img, uint4* __restr
 // ------------------------------------------------------------------------------------------------ max-pool 3x3/2 pad 1
 // in: bf16 NHWC [B,H1,W1,C] (un-padded, post-ReLU so >= 0) -> out: padded NHWC [B,H2+2,W2+2,C] with zero border.
 __global__ void maxpool_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B, int H1, int W1, int C8, int H2, int W2) {
-  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int Hp = H2 + 2, Wp = W2 + 2;
-  const long long total = static_cast<long long>(B) * Hp * Wp * C8;
-  if (idx >= total) return;
-  const int c = static_cast<int>(idx % C8);
-  const long long pix = idx / C8;
-  const int v = static_cast<int>(pix % Wp), u = static_cast<int>((pix / Wp) % Hp);
-  const int b = static_cast<int>(pix / (static_cast<long long>(Wp) * Hp));
+  const unsigned i = blockIdx.y * 256u + threadIdx.x;  // grid: x = padded output row (b, u), y = chunks of the row's Wp*C8 vectors
+  if (i >= static_cast<unsigned>(Wp * C8)) return;
+  const int u = static_cast<int>(blockIdx.x % static_cast<unsigned>(Hp)), b = static_cast<int>(blockIdx.x / static_cast<unsigned>(Hp));
+  const int v = static_cast<int>(i / static_cast<unsigned>(C8)), c = static_cast<int>(i - static_cast<unsigned>(v) * C8);
+  const long long idx = static_cast<long long>(blockIdx.x) * (Wp * C8) + i;
   uint4 o = make_uint4(0, 0, 0, 0);
   if (u >= 1 && u <= H2 && v >= 1 && v <= W2) {
     float m[8];
@@ -73,34 +71,32 @@ __global__ void maxpool_kernel(const uint4* __restrict__ in, uint4* __restrict__
 // ------------------------------------------------------------------------------------------------ parity split / merge
 // x padded [B,H+2,W+2,C] -> xs [4,B,Hs,Ws,C] (Hs=Ho+2, Ws=Wo+2); plane (p,q) cell (u,v) = x[2u+p, 2v+q] or 0.
 // only_plane < 0: all four planes (xs = [4, ...]); otherwise only that plane is produced (xs = that plane's [B, Hs, Ws, C] block)
-__global__ void parity_split_kernel(const uint4* __restrict__ x, uint4* __restrict__ xs, int B, int H, int W, int C8, int Hs, int Ws, int only_plane) {
-  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const long long per_plane = static_cast<long long>(B) * Hs * Ws * C8;
-  if (idx >= (only_plane < 0 ? 4 : 1) * per_plane) return;
-  const int plane = only_plane < 0 ? static_cast<int>(idx / per_plane) : only_plane;
-  long long r = only_plane < 0 ? idx - plane * per_plane : idx;
-  const int c = static_cast<int>(r % C8); r /= C8;
-  const int v = static_cast<int>(r % Ws); r /= Ws;
-  const int u = static_cast<int>(r % Hs);
-  const int b = static_cast<int>(r / Hs);
+// grid: x = row (plane, b, u), y = 256-element chunks of the row's Ws*C8 vectors -- no per-thread 64-bit divisions (those made
+// these copy kernels ALU-bound: ~200 instructions per 16 bytes)
+__global__ void __launch_bounds__(256) parity_split_kernel(const uint4* __restrict__ x, uint4* __restrict__ xs, int B, int H, int W, int C8, int Hs, int Ws, int only_plane) {
+  const unsigned i = blockIdx.y * 256u + threadIdx.x;
+  if (i >= static_cast<unsigned>(Ws * C8)) return;
+  unsigned row = blockIdx.x;                      // (plane', b, u), plane' = 0 when a single plane is produced
+  const int u = static_cast<int>(row % static_cast<unsigned>(Hs)); row /= static_cast<unsigned>(Hs);
+  const int b = static_cast<int>(row % static_cast<unsigned>(B));
+  const int plane = only_plane < 0 ? static_cast<int>(row / static_cast<unsigned>(B)) : only_plane;
+  const int v = static_cast<int>(i / static_cast<unsigned>(C8)), c = static_cast<int>(i - static_cast<unsigned>(v) * C8);
   const int y = 2 * u + (plane >> 1), xx = 2 * v + (plane & 1);
   uint4 o = make_uint4(0, 0, 0, 0);
   if (y <= H + 1 && xx <= W + 1) o = __ldg(x + ((static_cast<long long>(b) * (H + 2) + y) * (W + 2) + xx) * C8 + c);
-  xs[idx] = o;
+  xs[static_cast<long long>(blockIdx.x) * (Ws * C8) + i] = o;
 }
 
 // dx[b,y,x,:] = relu_mask(dxs[plane(y&1,x&1), b, y>>1, x>>1, :] (+ add[b,y,x,:])) on interior pixels, 0 on the border.
 // only_plane >= 0: dxs is that single plane's block and the three other planes are zero
-__global__ void parity_merge_kernel(const uint4* __restrict__ dxs, const uint4* __restrict__ add, const uint4* __restrict__ mask_src,
+__global__ void __launch_bounds__(256) parity_merge_kernel(const uint4* __restrict__ dxs, const uint4* __restrict__ add, const uint4* __restrict__ mask_src,
                                     uint4* __restrict__ dx, int B, int H, int W, int C8, int Hs, int Ws, int only_plane) {
-  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int Hp = H + 2, Wp = W + 2;
-  const long long total = static_cast<long long>(B) * Hp * Wp * C8;
-  if (idx >= total) return;
-  const int c = static_cast<int>(idx % C8);
-  const long long pix = idx / C8;
-  const int xx = static_cast<int>(pix % Wp), y = static_cast<int>((pix / Wp) % Hp);
-  const int b = static_cast<int>(pix / (static_cast<long long>(Wp) * Hp));
+  const unsigned i = blockIdx.y * 256u + threadIdx.x;  // grid: x = padded row (b, y), y = chunks of the row's Wp*C8 vectors
+  if (i >= static_cast<unsigned>(Wp * C8)) return;
+  const int y = static_cast<int>(blockIdx.x % static_cast<unsigned>(Hp)), b = static_cast<int>(blockIdx.x / static_cast<unsigned>(Hp));
+  const int xx = static_cast<int>(i / static_cast<unsigned>(C8)), c = static_cast<int>(i - static_cast<unsigned>(xx) * C8);
+  const long long idx = static_cast<long long>(blockIdx.x) * (Wp * C8) + i;
   uint4 o = make_uint4(0, 0, 0, 0);
   if (y >= 1 && y <= H && xx >= 1 && xx <= W) {
     const int plane = ((y & 1) << 1) | (xx & 1);
@@ -282,16 +278,14 @@ extern "C" int rb_stem_im2col(const float* img, void* out, int B, int H, int W, 
 
 extern "C" int rb_maxpool_3x3s2(const void* in, void* out, int B, int H1, int W1, int C, int H2, int W2, void* stream) {
   if (C % 8) return rb_fail("rb_maxpool_3x3s2: C must be a multiple of 8");
-  const long long total = static_cast<long long>(B) * (H2 + 2) * (W2 + 2) * (C / 8);
-  maxpool_kernel<<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint4*>(in), static_cast<uint4*>(out), B, H1, W1, C / 8, H2, W2);
+  maxpool_kernel<<<dim3(static_cast<unsigned>(B * (H2 + 2)), blocks_for(static_cast<long long>(W2 + 2) * (C / 8), 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint4*>(in), static_cast<uint4*>(out), B, H1, W1, C / 8, H2, W2);
   RB_CHECK_LAUNCH();
   return 0;
 }
 
 extern "C" int rb_parity_split(const void* x, void* xs, int B, int H, int W, int C, int Ho, int Wo, void* stream) {
   if (C % 8) return rb_fail("rb_parity_split: C must be a multiple of 8");
-  const long long total = 4ll * B * (Ho + 2) * (Wo + 2) * (C / 8);
-  parity_split_kernel<<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint4*>(x), static_cast<uint4*>(xs), B, H, W, C / 8, Ho + 2, Wo + 2, -1);
+  parity_split_kernel<<<dim3(static_cast<unsigned>(4 * B * (Ho + 2)), blocks_for(static_cast<long long>(Wo + 2) * (C / 8), 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint4*>(x), static_cast<uint4*>(xs), B, H, W, C / 8, Ho + 2, Wo + 2, -1);
   RB_CHECK_LAUNCH();
   return 0;
 }
@@ -299,8 +293,7 @@ extern "C" int rb_parity_split(const void* x, void* xs, int B, int H, int W, int
 extern "C" int rb_parity_split_plane(const void* x, void* xs_plane, int B, int H, int W, int C, int Ho, int Wo, int plane, void* stream) {
   if (C % 8) return rb_fail("rb_parity_split_plane: C must be a multiple of 8");
   if (plane < 0 || plane > 3) return rb_fail("rb_parity_split_plane: plane must be 0..3");
-  const long long total = static_cast<long long>(B) * (Ho + 2) * (Wo + 2) * (C / 8);
-  parity_split_kernel<<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint4*>(x), static_cast<uint4*>(xs_plane), B, H, W, C / 8, Ho + 2, Wo + 2, plane);
+  parity_split_kernel<<<dim3(static_cast<unsigned>(B * (Ho + 2)), blocks_for(static_cast<long long>(Wo + 2) * (C / 8), 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint4*>(x), static_cast<uint4*>(xs_plane), B, H, W, C / 8, Ho + 2, Wo + 2, plane);
   RB_CHECK_LAUNCH();
   return 0;
 }
@@ -309,8 +302,7 @@ extern "C" int rb_parity_merge_plane(const void* dxs_plane, int plane, const voi
                                      void* stream) {
   if (C % 8) return rb_fail("rb_parity_merge_plane: C must be a multiple of 8");
   if (plane < 0 || plane > 3) return rb_fail("rb_parity_merge_plane: plane must be 0..3");
-  const long long total = static_cast<long long>(B) * (H + 2) * (W + 2) * (C / 8);
-  parity_merge_kernel<<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  parity_merge_kernel<<<dim3(static_cast<unsigned>(B * (H + 2)), blocks_for(static_cast<long long>(W + 2) * (C / 8), 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint4*>(dxs_plane), static_cast<const uint4*>(add), static_cast<const uint4*>(mask_src), static_cast<uint4*>(dx), B, H, W, C / 8, Ho + 2, Wo + 2, plane);
   RB_CHECK_LAUNCH();
   return 0;
@@ -318,8 +310,7 @@ extern "C" int rb_parity_merge_plane(const void* dxs_plane, int plane, const voi
 
 extern "C" int rb_parity_merge(const void* dxs, const void* add, const void* mask_src, void* dx, int B, int H, int W, int C, int Ho, int Wo, void* stream) {
   if (C % 8) return rb_fail("rb_parity_merge: C must be a multiple of 8");
-  const long long total = static_cast<long long>(B) * (H + 2) * (W + 2) * (C / 8);
-  parity_merge_kernel<<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  parity_merge_kernel<<<dim3(static_cast<unsigned>(B * (H + 2)), blocks_for(static_cast<long long>(W + 2) * (C / 8), 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint4*>(dxs), static_cast<const uint4*>(add), static_cast<const uint4*>(mask_src), static_cast<uint4*>(dx), B, H, W, C / 8, Ho + 2, Wo + 2, -1);
   RB_CHECK_LAUNCH();
   return 0;
