@@ -385,9 +385,9 @@ def main():
 
     value = world * B * a.steps / ms * 1e3
     e2e = world * B * a.steps / ms_e2e * 1e3
-    out = dict(base, value=value, ms_per_step=ms / a.steps, dtype="bf16",
+    out = dict(base, value=value, ms_per_step=ms / a.steps, dtype="f16",
                config={"workload": CONFIG["workload"] if a.workload == "cfg2" else f"{a.workload} (NOT the metric's configuration): {wl_shape}", "global_batch": world * B, "parallelism": f"dp{world}", "mode": CONFIG["mode"] if model.training else "eval+grad (dropout inactive; diagnostic)",
-                       "bert": "BERT-base on the same C-ABI kernels (bf16 operands, fp32 residual/LN), inside the step graphs",
+                       "bert": "BERT-base on the same C-ABI kernels (IEEE-half operands, fp32 accumulate / residual / LN), inside the step graphs", "operands": "IEEE half (fp16) tensor-core operands and saved activations, fp32 accumulation, residual stream, normalisation and softmax; static 2^10 loss scale in the backward",
                        "l2": "per-step working set (saved activations, several GB) far exceeds the 126 MB L2; no explicit flush"},
                e2e={"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": nbytes(s_host, t_host), "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / a.steps},

@@ -195,6 +195,16 @@ __device__ __forceinline__ uint32_t pack_t2(float a, float b) {
 __device__ __forceinline__ float t_lo(uint32_t v) { return __low2float(*reinterpret_cast<const __half2*>(&v)); }
 __device__ __forceinline__ float t_hi(uint32_t v) { return __high2float(*reinterpret_cast<const __half2*>(&v)); }
 #endif
+// max(x, 0) folded into the conversion (cvt.rn.relu): ReLU costs no instruction of its own in a 16-bit-output epilogue
+__device__ __forceinline__ uint32_t pack_t2_relu(float a, float b) {
+  uint32_t d;
+#ifdef RB_ACT_BF16
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+#else
+  asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+#endif
+  return d;
+}
 // "element > 0" on the packed bits (sign-magnitude formats: positive iff the 16 bits, read as a signed integer, are > 0; NaN never
 // occurs in a ReLU output) -- the ReLU-mask tests of the backward epilogues need no conversion
 __device__ __forceinline__ bool t_pos_lo(uint32_t v) { return static_cast<int32_t>(v << 16) > 0; }

@@ -409,7 +409,9 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               f[4 * j] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
             }
           }
-          if (p.relu && !use_drop) {
+          // convolution path (16-bit output only): the ReLU rides on the f32 -> 16-bit conversion below
+          const bool relu_in_pack = EPI == 1 && p.relu;
+          if (p.relu && !use_drop && !relu_in_pack) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
           }
@@ -426,18 +428,30 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               }
             }
           }
-          if (!interior) {
+          if (__any_sync(0xffffffffu, !interior)) {  // a real (warp-uniform) branch: 4 warps in 5 hold no border pixel and skip 32 selects
+            if (!interior) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = 0.f;
+              for (int j = 0; j < 32; ++j) f[j] = 0.f;
+            }
           }
           if (f_out && !(p.debug & 16)) {
             uint8_t* row = oslot + r * 128;
+            if (relu_in_pack) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 tt;
-              tt.x = pack_t2(f[8 * j], f[8 * j + 1]); tt.y = pack_t2(f[8 * j + 2], f[8 * j + 3]);
-              tt.z = pack_t2(f[8 * j + 4], f[8 * j + 5]); tt.w = pack_t2(f[8 * j + 6], f[8 * j + 7]);
-              *reinterpret_cast<uint4*>(row + (((half * 4 + j) ^ sw128) << 4)) = tt;
+              for (int j = 0; j < 4; ++j) {
+                uint4 tt;
+                tt.x = pack_t2_relu(f[8 * j], f[8 * j + 1]); tt.y = pack_t2_relu(f[8 * j + 2], f[8 * j + 3]);
+                tt.z = pack_t2_relu(f[8 * j + 4], f[8 * j + 5]); tt.w = pack_t2_relu(f[8 * j + 6], f[8 * j + 7]);
+                *reinterpret_cast<uint4*>(row + (((half * 4 + j) ^ sw128) << 4)) = tt;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                uint4 tt;
+                tt.x = pack_t2(f[8 * j], f[8 * j + 1]); tt.y = pack_t2(f[8 * j + 2], f[8 * j + 3]);
+                tt.z = pack_t2(f[8 * j + 4], f[8 * j + 5]); tt.w = pack_t2(f[8 * j + 6], f[8 * j + 7]);
+                *reinterpret_cast<uint4*>(row + (((half * 4 + j) ^ sw128) << 4)) = tt;
+              }
             }
           }
           if (f_out32) {
