@@ -28,7 +28,15 @@ namespace rb {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int GEMM_THREADS = 352;
+#ifdef RB_EPI16
+// EXPERIMENTAL build variant (tools/build_variant.sh, not the default): 16 epilogue warps -- two teams of 8, the two 4-warp halves of
+// a team take the two 32-column halves of the team's 64-column chunk -- because the epilogue is bound by the instruction stream of
+// its warps.  Needs <= 96 registers per thread (640 threads).
+constexpr int GEMM_THREADS = 640, EPI_WARP0 = 4, EIN_WARP = 2, TEAM_WARPS = 8;
+#define RB_EPI_ROLLED
+#else
+constexpr int GEMM_THREADS = 352, EPI_WARP0 = 2, EIN_WARP = 10, TEAM_WARPS = 4;
+#endif
 constexpr int MAX_STAGES = 8;
 constexpr int MAX_EIN = 8;
 constexpr int A_BYTES = BM * BK * 2;
@@ -145,11 +153,11 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], 8);
+      mbar_init(&acc_empty[s], 2 * TEAM_WARPS);
     }
     for (int s = 0; s < MAX_EIN; ++s) {
       mbar_init(&ein_full[s], 1);
-      mbar_init(&ein_empty[s], 4);
+      mbar_init(&ein_empty[s], TEAM_WARPS);
     }
     fence_barrier_init();
   }
@@ -236,7 +244,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
     __syncwarp();
-  } else if (warp == 10) {
+  } else if (warp == EIN_WARP) {
     // ------------------------------------------------------------------------------------------ epilogue-input producer
     if (lane == 0 && has_ein && !f_atomic) {
       const uint32_t tx = (f_res ? 16384u : 0u) + (f_mask ? 16384u : 0u) + (f_res32 ? 32768u : 0u);
@@ -261,13 +269,18 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
     __syncwarp();
-  } else {
+  } else if (warp >= EPI_WARP0) {
     // ------------------------------------------------------------------------------------------ epilogue (2 teams)
-    const int team = (warp - 2) >> 2;
+    const int team = (warp - EPI_WARP0) / TEAM_WARPS;
     const int q = warp & 3;  // TMEM lane quarter this warp may access
+#ifdef RB_EPI16
+    const int half_lo = ((warp - EPI_WARP0) >> 2) & 1, half_hi = half_lo;  // this warp's 32-column half of the team's chunk
+#elif defined(RB_EPI_ROLLED)
+    const int half_lo = 0, half_hi = 1;
+#endif
     const int r = q * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
-    const bool store_thread = (threadIdx.x == 64 + team * 128);
+    const bool store_thread = (threadIdx.x == (EPI_WARP0 + team * TEAM_WARPS) * 32);
     const int sw128 = r & 7;
     const bool use_ein = has_ein && !f_atomic;
     const bool use_drop = EPI == 0 && p.drop.seed != nullptr;
@@ -300,12 +313,12 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         ++o;
         if (!f_atomic && !two_slots) {
           if (store_thread) tma_store_wait_read<0>();  // the previous store of this team has finished reading the slot
-          named_bar_sync(1 + team, 128);
+          named_bar_sync(1 + team, TEAM_WARPS * 32);
         }
 #ifdef RB_EPI_ROLLED
         // one 32-column half at a time, NOT unrolled: half the epilogue code (instruction-cache footprint) and fewer registers
 #pragma unroll 1
-        for (int half = 0; half < 2; ++half) {
+        for (int half = half_lo; half <= half_hi; ++half) {
           const int hc0 = col0 + half * 32;
           if (hc0 >= p.N || (p.debug & 4)) continue;  // warp-uniform
           uint32_t v[32];
@@ -470,7 +483,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // two slots: the store issued one chunk ago must have read ITS slot before the next chunk overwrites it; checking that
         // here (instead of before writing) needs a single barrier per chunk
         if (two_slots && store_thread && !(p.debug & 32)) tma_store_wait_read<0>();
-        if (!(p.debug & 32)) named_bar_sync(1 + team, 128);
+        if (!(p.debug & 32)) named_bar_sync(1 + team, TEAM_WARPS * 32);
         if (store_thread && !(p.debug & 1)) {
           if (f_out) tma_store_2d(&tmOut, oslot, col0, c.m0);
           if (f_out32) {
