@@ -323,8 +323,11 @@ class RefTR(nn.Module):
         params = eng.param_list()
         ph_ids = samples.get("phrase") if isinstance(samples, dict) else None
         ph_mask = samples.get("phrase_mask") if ph_ids is not None else None
-        outs = HotPathFunction.apply(eng, tensors, mask, samples["sentence_mask"], mask_context, query_mask, n_ph, want_seg,
-                                     sent_feat, pooled, samples["sentence"], ph_ids, ph_mask, *params)
+        # enqueue the GPU work first, then let autograd do its (host-side) bookkeeping while the GPU is already running
+        eng.run_forward(tensors, mask, samples["sentence_mask"], mask_context, query_mask, n_ph, want_seg,
+                        sent_feat.detach() if sent_feat is not None else None, pooled.detach() if pooled is not None else None,
+                        samples["sentence"], ph_ids, ph_mask)
+        outs = HotPathFunction.apply(eng, want_seg, sent_feat, pooled, *params)
         return outs, query_mask, n_ph
 
     def forward(self, samples):
