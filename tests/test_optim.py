@@ -157,3 +157,48 @@ def test_fused_adamw_on_the_engine_flat_gradients_gpu():
             assert torch.allclose(p, twin[n], rtol=1e-5, atol=1e-8), (n, (p - twin[n]).abs().max().item())
             moved += int((p - init[n]).abs().max().item() > 0)
     assert moved > 150, moved
+
+
+def test_fused_adamw_on_the_engine_layout_cpu(monkeypatch):
+    """Host logic of the engine <-> optimizer hand-over without a GPU (kernels emulated in torch): the optimizer adopts the engine's
+    gradient-slot layout, the gradients HotPathFunction returns are consumed in place (no gather), the language backbone's slots are
+    one contiguous slice (what the overlapped all-reduce relies on), and two steps match torch.optim.AdamW + clip_grad_norm_."""
+    import reftr_b200.bert as rbert
+    import reftr_b200.engine as rengine
+    import reftr_b200.optim as ro
+    import reftr_b200.pack as rpack
+    from oracle.cases import CASES
+    from reftr_b200.synthetic import synthetic_samples
+    from util_build import build_candidate
+    for m in (rengine, rpack, rbert, ro):
+        monkeypatch.setattr(m, "ops", emu_ops)
+    case = CASES["cfg1_box"]
+    model = build_candidate(case)
+    eng = model.engine()
+    named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
+    b0, b1 = eng._bert_slice
+    for n, _ in named:
+        off = eng.slots[n][0]
+        assert (b0 <= off < b1) == n.startswith("lang_backbone."), n
+    groups = [{"params": [p for n, p in named if "lang_backbone" not in n], "lr": 1e-3},
+              {"params": [p for n, p in named if "lang_backbone" in n], "lr": 1e-4}]
+    opt = ro.FusedAdamW.for_model(model, groups, lr=1e-3, weight_decay=1e-2)
+    assert all(opt._off[id(p)] == eng.slots[n][0] for n, p in named) and opt.n == eng.n_grad
+    twin = {n: torch.nn.Parameter(p.detach().clone()) for n, p in named}
+    opt_t = torch.optim.AdamW([{"params": [twin[n] for n, _ in named if "lang_backbone" not in n], "lr": 1e-3},
+                               {"params": [twin[n] for n, _ in named if "lang_backbone" in n], "lr": 1e-4}], lr=1e-3, weight_decay=1e-2)
+    s = synthetic_samples(**case["inputs"])
+    for _ in range(2):
+        opt.zero_grad()
+        out = model(s)
+        (out["pred_boxes"] * torch.linspace(-1, 1, out["pred_boxes"].numel()).view_as(out["pred_boxes"])).sum().mul(30.0).backward()
+        for n, p in named:
+            twin[n].grad = p.grad.detach().clone()
+        n_f = ro.clip_grad_norm_([p for _, p in named], 0.1)
+        assert opt.flat_g is None  # zero-copy: the gradients are views of the engine's flat buffer at the optimizer's offsets
+        n_t = torch.nn.utils.clip_grad_norm_(list(twin.values()), 0.1)
+        assert abs(float(n_f) - float(n_t)) < 1e-4 * float(n_t) and float(n_t) > 0.1
+        opt.step()
+        opt_t.step()
+    for n, p in named:
+        assert torch.allclose(p, twin[n], rtol=2e-5, atol=1e-7), n
