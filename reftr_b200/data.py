@@ -66,19 +66,3 @@ class _null:
 
 def collate_images_u8(images, device, mean=IMAGENET_MEAN, std=IMAGENET_STD, stream=None):
     return DeviceCollator(device, mean, std)(images, stream)
-
-
-def reference_collate(images, mean=IMAGENET_MEAN, std=IMAGENET_STD):
-    """What the reference computes on the CPU for the same raw images (to_tensor + Normalize + nested_tensor_from_tensor_list);
-    used by the tests as the checker and by nothing else."""
-    B = len(images)
-    H, W = max(im.shape[0] for im in images), max(im.shape[1] for im in images)
-    m, s = torch.tensor(mean).view(3, 1, 1), torch.tensor(std).view(3, 1, 1)
-    out = torch.zeros(B, 3, H, W)
-    mask = torch.ones(B, H, W, dtype=torch.bool)
-    for b, im in enumerate(images):
-        t = im.permute(2, 0, 1).to(torch.float32).div(255)
-        t = t.sub(m).div(s)
-        out[b, :, :im.shape[0], :im.shape[1]] = t
-        mask[b, :im.shape[0], :im.shape[1]] = False
-    return ImageList(out, mask)

@@ -8,7 +8,8 @@ pytestmark = pytest.mark.gpu
 
 @pytest.mark.parametrize("sizes", [[(640, 640)] * 4, [(480, 640), (640, 427), (333, 500), (17, 9), (640, 640)], [(1, 1)], [(224, 224), (200, 300)]])
 def test_collate_u8_matches_reference_cpu_path(sizes):
-    from reftr_b200.data import DeviceCollator, reference_collate
+    from data_ref import reference_collate
+    from reftr_b200.data import DeviceCollator
     g = torch.Generator().manual_seed(len(sizes))
     images = [torch.randint(0, 256, (h, w, 3), dtype=torch.uint8, generator=g) for h, w in sizes]
     ref = reference_collate(images)
