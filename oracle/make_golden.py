@@ -23,6 +23,8 @@ sys.path.insert(0, REF)
 from reftr_b200.synthetic import synthetic_samples, synthetic_targets, synthetic_weights  # noqa: E402
 from oracle.cases import CASES, bert_config  # noqa: E402
 
+TRAIN_CASES = ("cfg1_box", "multi_phrase")
+
 
 def load_reference():
     import numpy as np  # noqa: F401  (main_vg's parser uses np.pi)
@@ -51,19 +53,33 @@ def load_reference():
     return models, ns["get_args_parser"], NestedTensor, _FakeBert
 
 
-def run_case(name, case, models, get_args_parser, NestedTensor, fake_bert):
+TRAIN_SEED = 11  # seed of oracle/det_dropout.py for the train-mode fixtures
+
+
+def run_case(name, case, models, get_args_parser, NestedTensor, fake_bert, train=False):
+    """train=True: the reference runs in train mode (--dropout 0.1) under oracle/det_dropout.py, and the fixture also stores the
+    sequence of dropout calls (index, shape, p) -- it pins WHERE the oracle applies dropout, not just the eval-mode arithmetic."""
+    import contextlib
+    from oracle.det_dropout import deterministic_dropout
     from oracle.reftr_oracle import total_box_loss
     parser = argparse.ArgumentParser(parents=[get_args_parser()])
-    args = parser.parse_args(case["flags"] + ["--device", "cpu"])
+    flags = list(case["flags"])
+    if train:
+        flags[flags.index("--dropout") + 1] = "0.1"
+    args = parser.parse_args(flags + ["--device", "cpu"])
     fake_bert.cfg = bert_config(case)
+    if train:
+        fake_bert.cfg._attn_implementation = "eager"  # sdpa draws its dropout inside a fused kernel; the eager path calls F.dropout
     torch.manual_seed(0)
     model, criterion, post = models.build_reftr(args)
     synthetic_weights(model, seed=case["wseed"])
-    model.eval()  # dropout inactive: parity is only defined without it
+    model.train() if train else model.eval()  # eval: dropout inactive
     s = synthetic_samples(**case["inputs"])
     samples = dict(s)
     samples["img"] = NestedTensor(s["img"].tensors, s["img"].mask)
-    out = model(samples)
+    ctx = deterministic_dropout(TRAIN_SEED) if train else contextlib.nullcontext()
+    with ctx as dstate:
+        out = model(samples)
     n_ph = max(case["inputs"].get("n_ph", 0), 1)
     tgt = synthetic_targets(case["inputs"]["B"], n_ph)
     loss = total_box_loss(out, tgt)
@@ -83,6 +99,9 @@ def run_case(name, case, models, get_args_parser, NestedTensor, fake_bert):
     gold["grads"] = grads
     gold["n_params_with_grad"] = sum(1 for _, p in model.named_parameters() if p.grad is not None)
     gold["state_dict_keys"] = [(k, tuple(v.shape)) for k, v in model.state_dict().items()]
+    if train:
+        gold["dropout_calls"] = dstate["log"]
+        name = name + "_train"
     path = os.path.join(ROOT, "tests", "golden", f"{name}.pt")
     torch.save(gold, path)
     print(name, "loss", float(loss), "boxes", gold["pred_boxes"].flatten()[:4].tolist(), "->", path,
@@ -95,3 +114,6 @@ if __name__ == "__main__":
     only = sys.argv[1:] or list(CASES)
     for name in only:
         run_case(name, CASES[name], *ref)
+    for name in TRAIN_CASES:
+        if name in only:
+            run_case(name, CASES[name], *ref, train=True)
