@@ -186,6 +186,16 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const uint32_t mb0 = s.maskbits[2 * j], mb1 = s.maskbits[2 * j + 1];
       float p0[32], p1[32];
       float mx = -INFINITY;
+#ifdef RB_ATTN_FAST
+      if ((mb0 | mb1) == 0u) {  // EXPERIMENTAL variant (tools/build_variant.sh): no key of this block is masked -> no selects
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          p0[i] = __uint_as_float(v0[i]) * c;
+          p1[i] = __uint_as_float(v1[i]) * c;
+          mx = fmaxf(mx, fmaxf(p0[i], p1[i]));
+        }
+      } else
+#endif
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
         p0[i] = ((mb0 >> i) & 1u) ? -INFINITY : __uint_as_float(v0[i]) * c;
@@ -365,6 +375,12 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
             dv[2 * i + 1] = drop_keep(w, 1, drop.thr) ? __float_as_uint(__uint_as_float(dv[2 * i + 1]) * drop.scale) : 0u;
           }
         }
+#ifdef RB_ATTN_FAST
+        if (mb == 0u) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) ds[i] = ex2(__uint_as_float(sv[i]) * c - lse2) * (__uint_as_float(dv[i]) - D) * scale;
+        } else
+#endif
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           const float p = ((mb >> i) & 1u) ? 0.f : ex2(__uint_as_float(sv[i]) * c - lse2);
@@ -501,7 +517,18 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         for (int t = 0; t < 32; ++t) {
           const float pv = key_ok ? ex2(__uint_as_float(sv[t]) * c - cl[half * 32 + t]) : 0.f;
           float mk = 1.f;
+#ifdef RB_ATTN_FAST
+          if (use_drop) {  // the even thread hashes the even query rows, the odd thread the odd ones; one shuffle hands the word over
+            uint32_t w = 0;
+            if ((t & 1) == (lane & 1)) w = drop_word(dkey, ctr);
+            const uint32_t wo = __shfl_xor_sync(0xffffffffu, w, 1);
+            if ((t & 1) != (lane & 1)) w = wo;
+            mk = drop_keep(w, key & 1, drop.thr) ? drop.scale : 0.f;
+            ctr += wpr;
+          }
+#else
           if (use_drop) { mk = drop_keep(drop_word(dkey, ctr), key & 1, drop.thr) ? drop.scale : 0.f; ctr += wpr; }
+#endif
           p[t] = pv * mk;  // dV uses the dropped probabilities
           ds[t] = pv * (__uint_as_float(dv[t]) * mk - cd[half * 32 + t]) * scale;
         }

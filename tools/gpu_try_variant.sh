@@ -8,7 +8,7 @@ name=${1:-var16}
 LIBV=$PWD/build/$name/libreftr_b200.so
 mkdir -p gpurun_out
 [ -f "$LIBV" ] || { echo "missing $LIBV (run tools/build_variant.sh $name ... before gpurun)"; exit 1; }
-REFTR_B200_LIB=$LIBV timeout 900 python -m pytest tests/test_gemm_gpu.py tests/test_dropout_gpu.py tests/test_e2e_gpu.py tests/test_seg_kernels_gpu.py -x -q > gpurun_out/pytest_$name.log 2>&1
+REFTR_B200_LIB=$LIBV timeout 900 python -m pytest tests/test_gemm_gpu.py tests/test_kernels_gpu.py tests/test_dropout_gpu.py tests/test_e2e_gpu.py tests/test_seg_kernels_gpu.py -x -q > gpurun_out/pytest_$name.log 2>&1
 echo "variant tests rc=$?"; tail -3 gpurun_out/pytest_$name.log
 python tools/perf_gemm.py > gpurun_out/perf_gemm_default.log 2>&1
 REFTR_B200_LIB=$LIBV python tools/perf_gemm.py > gpurun_out/perf_gemm_$name.log 2>&1
