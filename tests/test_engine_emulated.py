@@ -205,3 +205,40 @@ def test_dropout_generator_statistics():
     for a, b in ((m1, m2), (m1, m3), (m1[:, 0::2], m1[:, 1::2]), (m1[:-1], m1[1:])):
         both = (~a & ~b).float().mean().item()  # P(both dropped) = p^2 when independent
         assert abs(both - p * p) < 1.5e-3, both
+
+
+def test_engine_wiring_exact_two_queries_per_phrase(emulated_exact):
+    """--num_queries_per_phrase 2 with the multi-phrase input (T = n_ph * n_q = 6 decoder queries; the query encoder tiles every
+    phrase feature over the learned query embeddings, reftr_transformer.py:62-66): not a shipped config, but part of the surface."""
+    from transformers import BertModel
+    from oracle.cases import bert_config
+    from oracle.reftr_oracle import RefTROracle
+    from reftr_b200.modules import BackboneParams, Joiner, PositionEmbeddingSine, RefTR, VLTransformerParams
+    from reftr_b200.synthetic import synthetic_weights
+    case = CASES["multi_phrase"]
+    torch.set_num_threads(os.cpu_count())
+
+    def build(kind):
+        torch.manual_seed(1234)
+        b = BertModel(bert_config(case))
+        if kind == "oracle":
+            m = RefTROracle(b, enc=1, dec=2, dropout=0.0, aux_loss=True, n_q=2)
+        else:
+            m = RefTR(Joiner(BackboneParams("resnet50", True, False), PositionEmbeddingSine(128)), b,
+                      VLTransformerParams(256, 8, 1, 2, 2048, 0.0, 1, 128), num_queries_per_phrase=2, aux_loss=True)
+        synthetic_weights(m, seed=5)
+        return m.eval()
+
+    oracle, cand = build("oracle"), build("cand")
+    s = synthetic_samples(**case["inputs"])
+    out_o, out_c = oracle(s), cand(s)
+    assert out_c["pred_boxes"].shape == out_o["pred_boxes"].shape == (2, 3, 2, 4)
+    assert torch.equal(out_c["phrase_mask"], out_o["phrase_mask"])
+    assert (out_c["pred_boxes"] - out_o["pred_boxes"]).abs().max().item() < 2e-5
+    _linear_loss(out_o).backward()
+    _linear_loss(out_c).backward()
+    errs = compare_grads(cand, oracle)
+    norms = {n: p.grad.norm().item() for n, p in oracle.named_parameters() if p.grad is not None}
+    big = max(norms.values())
+    bad = {n: e for n, e in errs.items() if e > 1e-2 and norms[n] > 1e-6 * big}
+    assert not bad, bad
