@@ -242,3 +242,24 @@ def test_engine_wiring_exact_two_queries_per_phrase(emulated_exact):
     big = max(norms.values())
     bad = {n: e for n, e in errs.items() if e > 1e-2 and norms[n] > 1e-6 * big}
     assert not bad, bad
+
+
+def test_engine_wiring_exact_frozen_bert(emulated_exact):
+    """--freeze_bert (reftr_transformer.py:319-321): the language backbone runs on the kernels but receives no gradients and the
+    backward skips it; every other gradient is unchanged."""
+    case = CASES["cfg1_box"]
+    torch.set_num_threads(os.cpu_count())
+    oracle, cand = build_oracle(case), build_candidate(case)
+    for m in (oracle, cand):
+        for p in m.lang_backbone.parameters():
+            p.requires_grad_(False)
+    s = synthetic_samples(**case["inputs"])
+    out_o, out_c = oracle(s), cand(s)
+    _linear_loss(out_o).backward()
+    _linear_loss(out_c).backward()
+    assert cand.engine().bert is not None and not cand.engine().bert.trainable
+    assert all(p.grad is None for p in cand.lang_backbone.parameters())
+    errs = compare_grads(cand, oracle)
+    norms = {n: p.grad.norm().item() for n, p in oracle.named_parameters() if p.grad is not None}
+    big = max(norms.values())
+    assert len(errs) > 100 and not {n: e for n, e in errs.items() if e > 1e-2 and norms[n] > 1e-6 * big}
