@@ -245,8 +245,9 @@ def test_engine_wiring_exact_two_queries_per_phrase(emulated_exact):
 
 
 def test_engine_wiring_exact_frozen_bert(emulated_exact):
-    """--freeze_bert (reftr_transformer.py:319-321): the language backbone runs on the kernels but receives no gradients and the
-    backward skips it; every other gradient is unchanged."""
+    """A frozen language backbone (requires_grad False on every lang_backbone parameter, set by the training script; the reference's
+    own --freeze_bert flag is stored but never applied, reftr_transformer.py:128, :152-157): BERT still runs on the kernels, receives
+    no gradients, its backward is skipped, and every other gradient is unchanged."""
     case = CASES["cfg1_box"]
     torch.set_num_threads(os.cpu_count())
     oracle, cand = build_oracle(case), build_candidate(case)
