@@ -35,7 +35,8 @@ def load_lang_backbone(name):
     cls = RobertaModel if name.split("-")[0] == "roberta" else BertModel
     if os.environ.get("REFTR_B200_RANDOM_BERT") == "1":
         torch.manual_seed(1234)
-        return BertModel(BertConfig())
+        layers = int(os.environ.get("REFTR_B200_RANDOM_BERT_LAYERS", "12"))  # (tests shrink the random BERT to keep CPU runs short)
+        return BertModel(BertConfig(num_hidden_layers=layers))
     return cls.from_pretrained(name)
 
 
