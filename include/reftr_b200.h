@@ -268,6 +268,13 @@ typedef struct {
 } rb_adamw_segments;
 /* *out += sum of squares of x[0..n)  (out: device scalar, zeroed by the caller) */
 int rb_sumsq(const float* x, long long n, float* out, void* stream);
+/* Hand-over of the flat gradient buffer at the end of the backward pass (replaces the reference's implicit per-tensor .grad
+ * tensors, engine_vg.py:61): dst[i] = src[i] * scale (undoes the static loss scale of the 16-bit backward) and *flag |= 1 if any
+ * src[i] is inf / NaN -- the finite check the reference only does on the loss (engine_vg.py:55-58), at no extra memory traffic.
+ * n % 4 == 0, 16-byte aligned buffers; flag is a device int the caller zeroes. */
+int rb_scale_copy_check(const float* src, float* dst, long long n, float scale, int* flag, void* stream);
+/* If *flag != 0: x[0..n) = 0 and *counter += 1 (counter may be NULL).  If *flag == 0 the launch does nothing. */
+int rb_zero_if(float* x, long long n, const int* flag, float* counter, void* stream);
 /* One AdamW step (amsgrad off).  `step` counts from 1 (bias corrections are computed on the host in double).  If sumsq != NULL and
  * max_norm > 0 the gradient is multiplied by min(1, max_norm / (sqrt(*sumsq) + 1e-6)) first (clip_grad_norm_, no host sync). */
 int rb_adamw_flat(float* p, const float* g, float* m, float* v, long long n, const rb_adamw_segments* segs, float beta1, float beta2, float eps, int step,

@@ -20,7 +20,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, REF)
 
-from reftr_b200.synthetic import synthetic_samples, synthetic_targets, synthetic_weights  # noqa: E402
+from reftr_b200.synthetic import (criterion_targets, synthetic_mask_targets, synthetic_samples, synthetic_targets,  # noqa: E402
+                                  synthetic_weights)
 from oracle.cases import CASES, bert_config  # noqa: E402
 
 TRAIN_CASES = ("cfg1_box", "multi_phrase")
@@ -92,6 +93,8 @@ def run_case(name, case, models, get_args_parser, NestedTensor, fake_bert, train
     if "pred_masks" in out:
         gold["pred_masks"] = out["pred_masks"].detach()
         gold["mask_att"] = out["mask_att"].detach()
+    if not train:
+        gold.update(reference_criterion_and_postprocess(case, out, tgt, criterion, post))
     grads = {}
     for pname, p in model.named_parameters():
         if p.grad is not None and case["grad_filter"](pname):
@@ -106,6 +109,53 @@ def run_case(name, case, models, get_args_parser, NestedTensor, fake_bert, train
     torch.save(gold, path)
     print(name, "loss", float(loss), "boxes", gold["pred_boxes"].flatten()[:4].tolist(), "->", path,
           os.path.getsize(path), "bytes")
+
+
+def reference_criterion_and_postprocess(case, out, tgt, criterion, post):
+    """Pins SURVEY 8(f) N2 and the discrete outputs of 3.4 to the REFERENCE: runs the reference's own criterion
+    (models/criterion.py:101-202; CriterionVGOnePhraseSeg reftr_segmentation.py:305-337 for --masks) on the reference model's
+    outputs, storing every entry of its loss dict, the weighted total (engine_vg.py:42-43) and its gradient w.r.t. every layer's boxes
+    (and the mask logits); then the reference's post-processors and the decisions engine_vg.evaluate takes from them:
+    ``iou > 0.5`` per sample (engine_vg.py:131-140) and ``sigmoid > 0.5`` masks (reftr_segmentation.py:288-302) + mask IoU (:152)."""
+    from util.box_ops import box_cxcywh_to_xyxy, box_iou, mask_iou
+    inp = case["inputs"]
+    B, H, W = inp["B"], inp["H"], inp["W"]
+    aux = out.get("aux_outputs") or []
+    boxes_all = torch.stack([a["pred_boxes"].detach() for a in aux] + [out["pred_boxes"].detach()]).requires_grad_(True)
+    pm = out["phrase_mask"]
+    o2 = {"pred_boxes": boxes_all[-1], "phrase_mask": pm}
+    if aux:
+        o2["aux_outputs"] = [{"pred_boxes": boxes_all[i], "phrase_mask": pm} for i in range(len(aux))]
+    masks = None
+    if "pred_masks" in out:
+        masks = synthetic_mask_targets(B, H, W)
+        o2["pred_masks"] = out["pred_masks"].detach().requires_grad_(True)
+        o2["mask_att"] = out["mask_att"].detach()
+    targets = criterion_targets(tgt, pm if tgt.shape[1] > 1 else None, masks, sizes=(H, W))
+    ld = criterion(o2, targets)
+    wd = criterion.weight_dict
+    total = sum(ld[k] * wd[k] for k in ld if k in wd)
+    total.backward()
+    res = {"crit_losses": {k: v.detach().clone() for k, v in ld.items()}, "crit_weight_dict": dict(wd), "crit_total": total.detach(),
+           "crit_grad_boxes": boxes_all.grad.clone()}
+    if masks is not None:
+        res["crit_grad_masks"] = o2["pred_masks"].grad.clone()
+    with torch.no_grad():
+        sizes = torch.stack([t["orig_size"] for t in targets])
+        results = post["bbox"](o2, sizes)
+        ious = []
+        for i, r in enumerate(results):
+            iou, _ = box_iou(box_cxcywh_to_xyxy(targets[i]["boxes"]), r["boxes"])
+            ious.append(torch.diag(iou))
+        res["post_boxes"] = [r["boxes"].clone() for r in results]
+        res["post_boxes_scaled"] = [r["boxes"].clone() for r in post["bbox"](o2, sizes, scale_to_original_shape=True)]
+        res["iou"] = torch.cat(ious)
+        res["iou_gt_half"] = res["iou"] > 0.5
+        if "segm" in post:
+            results = post["segm"](results, o2, sizes, sizes)
+            res["post_masks"] = torch.stack([r["masks"][0, 0] for r in results])
+            res["seg_iou"] = torch.stack([mask_iou(r["masks"][0][0], targets[i]["masks"]) for i, r in enumerate(results)])
+    return res
 
 
 if __name__ == "__main__":

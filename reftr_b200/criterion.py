@@ -74,9 +74,32 @@ class CriterionVGMultiPhrase(nn.Module):
         self.weight_dict = weight_dict
         self.losses = losses
 
-    def _fused_boxes(self, outputs, targets, num_boxes):
-        """All layers' box losses from ``outputs["_boxes_all"]`` ([n_layers, B, n_ph, k, 4], last layer last) -- sync-free."""
-        allb = outputs["_boxes_all"]
+    @staticmethod
+    def _all_layer_boxes(outputs):
+        """[n_layers, B, n_ph, k, 4] (last layer last) when the model's per-layer ``pred_boxes`` are slices of ONE tensor (reftr_b200's
+        modules: ``coord[-1]`` and ``coord[i]`` of the same sigmoid output), else None.  Found through ``Tensor._base`` so the output
+        dict keeps exactly the reference's keys (reftr_transformer.py:293-304)."""
+        pb = outputs["pred_boxes"]
+        aux = outputs.get("aux_outputs") or []
+        if not pb.is_cuda:
+            return None
+        if not aux:
+            return pb.unsqueeze(0)
+        base = pb._base
+        nl = len(aux) + 1
+        if base is None or base.dim() != pb.dim() + 1 or base.shape[0] != nl or tuple(base.shape[1:]) != tuple(pb.shape) or not base.is_contiguous():
+            return None
+        step = base[0].numel() * base.element_size()
+        if pb.data_ptr() != base.data_ptr() + (nl - 1) * step:
+            return None
+        for i, a in enumerate(aux):
+            ab = a["pred_boxes"]
+            if ab._base is not base or ab.data_ptr() != base.data_ptr() + i * step:
+                return None
+        return base
+
+    def _fused_boxes(self, allb, outputs, targets, num_boxes):
+        """All layers' box losses in one kernel from the stacked boxes [n_layers, B, n_ph, k, 4] (last layer last) -- sync-free."""
         nl, b, n_ph, k, _ = allb.shape
         tgt = torch.cat([t["boxes"] for t in targets], dim=0).to(torch.float32)
         valid = None
@@ -131,9 +154,9 @@ class CriterionVGMultiPhrase(nn.Module):
         else:
             num_boxes = max(num_boxes, 1.0)
         losses = {}
-        fused = "_boxes_all" in outputs and outputs["_boxes_all"].is_cuda and "boxes" in self.losses
-        if fused:
-            losses.update(self._fused_boxes(outputs, targets, num_boxes))
+        allb = self._all_layer_boxes(outputs) if "boxes" in self.losses else None
+        if allb is not None:
+            losses.update(self._fused_boxes(allb, outputs, targets, num_boxes))
             for loss in self.losses:
                 if loss != "boxes":
                     losses.update(self.get_loss(loss, outputs, targets, num_boxes))

@@ -447,9 +447,10 @@ __global__ void box_loss_kernel(const float* __restrict__ boxes, const float* __
 
 extern "C" int rb_box_loss(const float* boxes, const float* tgt, const void* valid, int n_layers, int N, float inv_norm, const float* inv_norm_dev,
                            float* losses, float* dl1, float* dgiou, void* stream) {
-  if (n_layers <= 0 || N <= 0) return 0;
+  if (n_layers <= 0) return 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   RB_CUDA(cudaMemsetAsync(losses, 0, sizeof(float) * 2 * n_layers, st));
+  if (N <= 0) return 0;  // no boxes: every loss is exactly 0 (the caller allocates `losses` uninitialised)
   rb::box_loss_kernel<<<dim3((N + 127) / 128, n_layers), 128, 0, st>>>(boxes, tgt, static_cast<const uint8_t*>(valid), n_layers, N, inv_norm, inv_norm_dev, losses,
                                                                      dl1, dgiou);
   RB_CHECK_LAUNCH();

@@ -24,6 +24,31 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float4* __restrict__ x
   }
 }
 
+// Hand-over of the flat gradient buffer (engine.run_backward): dst = src * scale (undoes the static loss scale of the 16-bit
+// backward, and gives autograd fresh storage) and, in the same pass, a non-finite detector: *flag is set to 1 when any element of
+// src is inf / NaN.  No extra memory traffic; the decision is taken by zero_if_kernel below.
+__global__ void __launch_bounds__(256) scale_copy_check_kernel(const float4* __restrict__ src, float4* __restrict__ dst, long long n4, float scale,
+                                                               int* __restrict__ flag) {
+  bool bad = false;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float4 v = __ldg(src + i);
+    // x - x is 0 for finite x and NaN for inf / NaN
+    bad |= !((v.x - v.x) == 0.f) | !((v.y - v.y) == 0.f) | !((v.z - v.z) == 0.f) | !((v.w - v.w) == 0.f);
+    v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+    dst[i] = v;
+  }
+  if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(flag, 1);
+}
+
+// If *flag != 0: x[0..n) = 0 (a skipped step) and, once, *counter += 1.  If *flag == 0 (every normal step) each block reads one word
+// and exits.
+__global__ void __launch_bounds__(256) zero_if_kernel(float4* __restrict__ x, long long n4, const int* __restrict__ flag, float* __restrict__ counter) {
+  if (*flag == 0) return;
+  if (counter && blockIdx.x == 0 && threadIdx.x == 0) *counter += 1.f;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += static_cast<long long>(gridDim.x) * blockDim.x)
+    x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
 struct AdamSegs {  // segment s covers elements [s == 0 ? 0 : end[s-1], end[s]) and belongs to parameter group `group[s]`
   long long end[RB_ADAMW_MAX_SEGMENTS];
   int group[RB_ADAMW_MAX_SEGMENTS];
@@ -69,6 +94,29 @@ extern "C" int rb_sumsq(const float* x, long long n, float* out, void* stream) {
   long long blocks = (n / 4 + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
   sumsq_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const float4*>(x), n / 4, out);
+  RB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int rb_scale_copy_check(const float* src, float* dst, long long n, float scale, int* flag, void* stream) {
+  if (n % 4 || ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15)) return rb_fail("rb_scale_copy_check: n %% 4 != 0 or unaligned buffers");
+  if (!flag) return rb_fail("rb_scale_copy_check: flag is NULL");
+  if (n <= 0) return 0;
+  long long blocks = (n / 4 + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  scale_copy_check_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const float4*>(src),
+                                                                                                    reinterpret_cast<float4*>(dst), n / 4, scale, flag);
+  RB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int rb_zero_if(float* x, long long n, const int* flag, float* counter, void* stream) {
+  if (n % 4 || (reinterpret_cast<uintptr_t>(x) & 15)) return rb_fail("rb_zero_if: n %% 4 != 0 or unaligned buffer");
+  if (!flag) return rb_fail("rb_zero_if: flag is NULL");
+  if (n <= 0) return 0;
+  long long blocks = (n / 4 + 255) / 256;
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  zero_if_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<float4*>(x), n / 4, flag, counter);
   RB_CUDA(cudaGetLastError());
   return 0;
 }

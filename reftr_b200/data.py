@@ -19,41 +19,68 @@ IMAGENET_STD = (0.229, 0.224, 0.225)
 class DeviceCollator:
     """Reusable pinned staging buffers + device buffers for one data loader (one instance per process)."""
 
+    N_SLOTS = 2  # pinned staging slots: batch i+1 is packed on the host while the DMA of batch i may still be in flight
+
     def __init__(self, device, mean=IMAGENET_MEAN, std=IMAGENET_STD):
         self.device = torch.device(device)
         self.mean, self.std = tuple(mean), tuple(std)
-        self._pinned = self._table = None
+        self._slots = [dict(pinned=None, table=None, event=None) for _ in range(self.N_SLOTS)]
+        self._next = 0
 
-    def __call__(self, images, stream=None):
+    def __call__(self, images, stream=None, consumer_stream=None):
         """images: list of uint8 tensors [h_i, w_i, 3] on the host.  Returns ImageList(tensors fp32 [B,3,H,W], mask bool [B,H,W])
         on the device (the NestedTensor contract of util/misc.py:308-332).  The copies and the kernel are enqueued on ``stream``
-        (default: the current stream), nothing synchronises."""
+        (default: the current stream).
+
+        Hazards handled here (the host runs far ahead of the GPU under CUDA-graph replay): (1) a pinned staging slot is rewritten
+        only after the H2D copies that last read it have EXECUTED -- each slot carries a CUDA event recorded after its copies, and
+        ``event.synchronize()`` is called before the slot is reused (with two slots that wait is normally already over); (2) the
+        returned tensors are allocated on ``stream`` but consumed elsewhere: ``record_stream`` is called for ``consumer_stream``
+        (default: the stream that is current when the collator is called), as engine_vg.data_prefetcher does (engine_vg.py:271-283);
+        the caller still has to make the consumer wait for ``stream`` (``wait_stream`` / the returned ``ImageList.ready`` event)."""
         B = len(images)
         if B == 0 or any(im.dtype != torch.uint8 or im.dim() != 3 or im.shape[2] != 3 or not im.device.type == "cpu" for im in images):
             raise ValueError("collate_images_u8 expects a non-empty list of host uint8 [h, w, 3] tensors")
         H, W = max(im.shape[0] for im in images), max(im.shape[1] for im in images)
         total = sum(im.numel() for im in images)
-        if self._pinned is None or self._pinned.numel() < total:
-            self._pinned = torch.empty(max(total, 1 << 20), dtype=torch.uint8).pin_memory() if torch.cuda.is_available() else torch.empty(total, dtype=torch.uint8)
-        if self._table is None or self._table.shape[0] < B:
-            self._table = torch.empty(B, 3, dtype=torch.int64)
-            if torch.cuda.is_available():
-                self._table = self._table.pin_memory()
+        cuda = torch.cuda.is_available()
+        slot = self._slots[self._next]
+        self._next = (self._next + 1) % self.N_SLOTS
+        if slot["event"] is not None:
+            slot["event"].synchronize()  # the DMA that last read this slot has finished
+        if slot["pinned"] is None or slot["pinned"].numel() < total:
+            slot["pinned"] = torch.empty(max(total, 1 << 20), dtype=torch.uint8).pin_memory() if cuda else torch.empty(total, dtype=torch.uint8)
+        if slot["table"] is None or slot["table"].shape[0] < B:
+            slot["table"] = torch.empty(B, 3, dtype=torch.int64).pin_memory() if cuda else torch.empty(B, 3, dtype=torch.int64)
+        pinned, tab = slot["pinned"], slot["table"]
         off = 0
         for b, im in enumerate(images):
             n = im.numel()
-            self._pinned[off:off + n].copy_(im.reshape(-1))
-            self._table[b, 0], self._table[b, 1], self._table[b, 2] = off, im.shape[0], im.shape[1]
+            pinned[off:off + n].copy_(im.reshape(-1))
+            tab[b, 0], tab[b, 1], tab[b, 2] = off, im.shape[0], im.shape[1]
             off += n
+        consumer = consumer_stream if consumer_stream is not None else (torch.cuda.current_stream(self.device) if cuda else None)
         ctx = torch.cuda.stream(stream) if stream is not None else _null()
         with ctx:
-            packed = self._pinned[:total].to(self.device, non_blocking=True)
-            table = self._table[:B].to(self.device, non_blocking=True)
+            packed = pinned[:total].to(self.device, non_blocking=True)
+            table = tab[:B].to(self.device, non_blocking=True)
+            if cuda:
+                slot["event"] = torch.cuda.Event()
+                slot["event"].record()  # on `stream`: after both copies
             out = torch.empty(B, 3, H, W, dtype=torch.float32, device=self.device)
             mask = torch.empty(B, H, W, dtype=torch.bool, device=self.device)
             ops.require_device(out)
             ops.collate_u8(packed, table, B, H, W, self.mean, self.std, out, mask)
-        return ImageList(out, mask)
+            ready = None
+            if cuda:
+                ready = torch.cuda.Event()
+                ready.record()
+        if cuda and stream is not None and consumer is not None and consumer != stream:
+            for t in (out, mask):
+                t.record_stream(consumer)
+        res = ImageList(out, mask)
+        res.ready = ready  # consumer: torch.cuda.current_stream().wait_event(res.ready)
+        return res
 
 
 class _null:

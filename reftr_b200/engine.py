@@ -208,6 +208,11 @@ class RefTREngine:
         self._side, self._side_used = None, False
         self._side2, self._side2_used = None, False
         self._tracked = [t for t in list(model.parameters()) + list(model.buffers())]
+        self._rg_sig = tuple(p.requires_grad for p in model.parameters())
+        self._synced = False
+        # overflow sentinel of the 16-bit backward (see run_backward): [0] = number of non-finite steps seen so far (device counter)
+        self.overflow_dev = None
+        self.skip_nonfinite = os.environ.get("REFTR_B200_SKIP_NONFINITE", "1") != "0"
         self._vsig, self._pack_dev = None, None
         self._repack_graphs, self._repack_seen = {}, None
         self.force_eager = False  # bench.py: run the next steps launch by launch on the graphed workspace (profiling)
@@ -251,6 +256,11 @@ class RefTREngine:
     def _prepare(self, device):
         """Re-packs weights whose master copy changed (optimizer step / load_state_dict) and drops captured graphs when
         any parameter storage moved (graphs hold raw device addresses)."""
+        if tuple(p.requires_grad for p in self.model.parameters()) != self._rg_sig:
+            raise RuntimeError("reftr_b200: requires_grad of a parameter changed after the engine was built (the gradient slots, the DDP "
+                               "ignore list and the frozen-layer plan are fixed at construction); freeze / unfreeze parameters BEFORE the "
+                               "first forward, or call model.reset_engine() after changing them")
+        self._sync_initial_state()
         sig = tuple(p.data_ptr() for _, p in self.named)
         if self._dev != device or sig != self._sig:
             self._dev, self._sig = device, sig
@@ -265,6 +275,28 @@ class RefTREngine:
         if vsig != self._vsig or device != self._pack_dev:
             self._refresh_packs(device)
             self._vsig, self._pack_dev = tuple(t._version for t in self._tracked), device
+
+    def _sync_initial_state(self):
+        """DistributedDataParallel broadcasts rank 0's parameters and buffers at construction (main_vg.py:293-296) -- but it SKIPS
+        what ``_ddp_params_and_buffers_to_ignore`` names, i.e. everything this engine owns (modules.RefTR._mark_ddp_ignored).  The
+        reference seeds every rank with ``seed + rank`` before ``build_reftr`` (main_vg.py:173-177), so without this the replicas would
+        start from different decoder / query-encoder / head weights and never converge to each other (only gradients are averaged).
+        Once, at the first forward after a process group exists: ONE flat broadcast of every ignored floating-point tensor from
+        rank 0 (a no-op for tensors that already agree)."""
+        if self._synced or self._dist_world() <= 1:
+            return
+        self._synced = True
+        ignored = set(getattr(self.model, "_ddp_params_and_buffers_to_ignore", []) or [])
+        ts = [t.data for n, t in list(self.model.named_parameters()) + list(self.model.named_buffers()) if n in ignored and t.is_floating_point()]
+        if not ts:
+            return
+        with torch.no_grad():
+            flat = torch.cat([t.reshape(-1).to(torch.float32) for t in ts])
+            torch.distributed.broadcast(flat, 0)
+            off = 0
+            for t in ts:
+                t.copy_(flat[off:off + t.numel()].view_as(t))
+                off += t.numel()
 
     def _refresh_packs(self, device):
         """Re-packs the 16-bit kernel-layout copies of every weight whose master changed.  After an optimizer step that is ALL
@@ -409,7 +441,8 @@ class RefTREngine:
         import time as _t
         _t0 = _t.perf_counter()
         # fresh storage per step: autograd may keep these as .grad of leaf tensors (the copy also undoes the loss scale)
-        flat = self.gflat[:self.n_grad] * (1.0 / S)
+        flat = torch.empty(self.n_grad, dtype=torch.float32, device=self.gflat.device)
+        self._handover(0, self.n_grad, flat)
         _t1 = _t.perf_counter()
         if getattr(self.model, "engine_allreduce", False) and torch.distributed.is_available() and torch.distributed.is_initialized():
             world = torch.distributed.get_world_size()
@@ -420,10 +453,39 @@ class RefTREngine:
                 else:
                     torch.distributed.all_reduce(flat)
                     flat.mul_(1.0 / world)
+        self._finish_guard(flat)
         self.host_ms = {"clone": (_t1 - _t0) * 1e3, "allreduce": (_t.perf_counter() - _t1) * 1e3}
         if self.bert is not None:
             return None, None, flat
         return d_sent * (1.0 / S), d_pooled * (1.0 / S), flat
+
+    def _handover(self, lo, hi, flat):
+        """flat[lo:hi] = gflat[lo:hi] / grad_scale into fresh storage, and the overflow sentinel of the 16-bit backward in the same
+        pass.  Activation gradients are IEEE half under a static loss scale, so an overflow (real checkpoints, exploding loss) would
+        put inf / NaN into the flat gradient and from there into clip_grad_norm_ and the AdamW moments.  rb_scale_copy_check raises
+        a device flag when it copies a non-finite value (no extra traffic); ``_finish_guard`` then zeroes the whole gradient of the
+        step (the update becomes a no-op apart from weight decay, like a GradScaler-skipped step) and counts it -- all on the
+        device, no host synchronisation.  REFTR_B200_SKIP_NONFINITE=0 only counts (the reference's behaviour: engine_vg.py:55-58
+        checks the loss, not the gradients)."""
+        if self.overflow_dev is None or self.overflow_dev.device != flat.device:
+            self.overflow_dev = torch.zeros(1, dtype=torch.float32, device=flat.device)
+            self._flag = torch.zeros(1, dtype=torch.int32, device=flat.device)
+        ops.scale_copy_check(self.gflat[lo:hi], flat[lo:hi], 1.0 / self.grad_scale, self._flag)
+
+    def _finish_guard(self, flat):
+        """After the last hand-over (and, under data parallelism, after the all-reduces: a rank that overflowed has already spread its
+        inf / NaN to every replica's sum, so the flags are combined first and every rank takes the same decision)."""
+        if self._dist_world() > 1:
+            torch.distributed.all_reduce(self._flag, op=torch.distributed.ReduceOp.MAX)
+        if self.skip_nonfinite:
+            ops.zero_if(flat, self._flag, self.overflow_dev)
+        else:
+            self.overflow_dev.add_(self._flag.to(torch.float32))
+        self._flag.zero_()
+
+    def overflow_steps(self):
+        """Number of steps whose gradient was non-finite so far (synchronises; for logging)."""
+        return 0 if self.overflow_dev is None else int(self.overflow_dev.item())
 
     def _dist_world(self):
         if getattr(self.model, "engine_allreduce", False) and torch.distributed.is_available() and torch.distributed.is_initialized():
@@ -475,14 +537,15 @@ class RefTREngine:
         br.wait_event(ev)
         with torch.cuda.stream(br):
             gB.replay()
-            torch.mul(self.gflat[b0:b1], 1.0 / S, out=flat[b0:b1])   # fresh storage + undo the loss scale (as in run_backward)
+            self._handover(b0, b1, flat)   # fresh storage + undo the loss scale + overflow sentinel (as in run_backward)
             self._allreduce_(flat[b0:b1])
         gC.replay()
         for lo, hi in ((0, b0), (b1, self.n_grad)):
             if hi > lo:
-                torch.mul(self.gflat[lo:hi], 1.0 / S, out=flat[lo:hi])
+                self._handover(lo, hi, flat)
                 self._allreduce_(flat[lo:hi])
         main.wait_stream(br)
+        self._finish_guard(flat)
         st["nb"] += 1
         self.launches += st["bl"]
         self.host_ms = {"clone": 0.0, "allreduce": 0.0}

@@ -274,6 +274,12 @@ class RefTR(nn.Module):
             self._engine = RefTREngine(self)
         return self._engine
 
+    def reset_engine(self):
+        """Rebuilds the engine and the DDP ignore list after ``requires_grad`` flags were changed (e.g. freezing BERT by hand after
+        construction).  Call it BEFORE wrapping the module in DistributedDataParallel."""
+        self._engine = None
+        self._mark_ddp_ignored()
+
     def _language(self, samples):
         """BERT + the phrase / context masks of reftr_transformer.py:197-248, vectorised (no host syncs)."""
         sentence, sentence_mask = samples["sentence"], samples["sentence_mask"]
@@ -338,7 +344,8 @@ class RefTR(nn.Module):
         out = {"pred_boxes": coord[-1], "phrase_mask": pm}
         if self.aux_loss:
             out["aux_outputs"] = [{"pred_boxes": b, "phrase_mask": pm} for b in coord[:-1]]
-            out["_boxes_all"] = coord  # every layer's boxes in one tensor: lets reftr_b200's criterion fuse all box losses
+            # (every layer's boxes are slices of ONE tensor: reftr_b200's criterion finds it through Tensor._base and computes all box
+            # losses in one kernel; the dict holds exactly the reference's keys, reftr_transformer.py:293-304)
         return out
 
 

@@ -374,6 +374,17 @@ def sumsq(x, out):
     _lib.call("rb_sumsq", _p(x), x.numel(), _p(out), _s())
 
 
+def scale_copy_check(src, dst, scale, flag):
+    """dst = src * scale; flag (device int32[1]) |= any(src non-finite)."""
+    assert src.numel() == dst.numel() and flag.dtype == torch.int32
+    _lib.call("rb_scale_copy_check", _p(src), _p(dst), src.numel(), float(scale), _p(flag), _s())
+
+
+def zero_if(x, flag, counter=None):
+    """x = 0 and counter += 1 when flag != 0; nothing otherwise."""
+    _lib.call("rb_zero_if", _p(x), x.numel(), _p(flag), _p(counter), _s())
+
+
 def adamw_flat(p, g, m, v, seg_end, seg_group, lrs, wds, beta1, beta2, eps, step, sumsq_dev=None, max_norm=0.0):
     segs = _lib.AdamwSegments()
     segs.nseg = len(seg_end)

@@ -10,6 +10,11 @@ Drop-in use (no reference file edited):
     grad_total_norm = reftr_b200.optim.clip_grad_norm_(model.parameters(), max_norm)   # deferred into optimizer.step()
     optimizer.step()
 LR schedulers (StepLR / LambdaLR, main_vg.py:269-287) work unchanged: ``param_groups[i]["lr"]`` is read on every step.
+
+Semantics that differ from the torch pair, on purpose: (1) ``clip_grad_norm_`` is DEFERRED -- it returns the total norm, but ``p.grad``
+itself stays unclipped; the coefficient is applied inside ``step()`` (read ``p.grad`` after clipping only through the optimizer).
+(2) every optimized parameter must have a gradient at ``step()``: torch skips gradient-less parameters, a flat pass cannot, so that
+case raises instead of silently applying weight decay to them.
 """
 import weakref
 
@@ -112,14 +117,14 @@ class FusedAdamW(torch.optim.Optimizer):
         if self.flat_g is None:
             self.flat_g = torch.zeros(self.n, dtype=torch.float32, device=self.device)
             self._gviews = [self.flat_g[self._off[id(p)]:self._off[id(p)] + p.numel()].view(p.shape) for p in ps]
-        src, dst = [], []
-        for p, v in zip(ps, self._gviews):
-            if p.grad is None:
-                v.zero_()
-            else:
-                src.append(p.grad)
-                dst.append(v)
-        torch._foreach_copy_(dst, src)
+        missing = [p for p in ps if p.grad is None]
+        if missing:
+            # torch.optim.AdamW SKIPS a parameter without a gradient (no weight decay, no moment decay, its step counter stands
+            # still); one flat pass cannot, and treating "no gradient" as a zero gradient would silently decay such weights.
+            raise RuntimeError(f"FusedAdamW: {len(missing)} of {len(ps)} optimized parameters have no gradient (first shape "
+                               f"{tuple(missing[0].shape)}); optimize only parameters that receive one every step (the engine hands a "
+                               "gradient to every requires_grad parameter), or use torch.optim.AdamW")
+        torch._foreach_copy_(self._gviews, [p.grad for p in ps])
         return self.flat_g
 
     def defer_clip(self, max_norm):
@@ -166,6 +171,8 @@ class FusedAdamW(torch.optim.Optimizer):
                     st[key] = view
         steps = [int(st["step"]) for st in self.state.values()]
         self._step = max(steps) if steps else 0
+        for st in self.state.values():  # older checkpoints store the step as a python int
+            st["step"] = torch.as_tensor(float(st["step"]), dtype=torch.float32)
 
 
 def clip_grad_norm_(parameters, max_norm, norm_type=2.0):

@@ -111,3 +111,34 @@ def synthetic_targets(B, n_ph=1, seed=2, device="cpu"):
     c = 0.25 + 0.5 * torch.rand(B, n_ph, 2, generator=g)
     wh = 0.1 + 0.3 * torch.rand(B, n_ph, 2, generator=g)
     return torch.cat([c, wh], -1).to(device)
+
+
+def synthetic_mask_targets(B, H, W, seed=4, device="cpu"):
+    """bool [B, 1, H, W] random rectangles (targets["masks"] of the segmentation criterion)."""
+    g = torch.Generator().manual_seed(seed)
+    m = torch.zeros(B, 1, H, W, dtype=torch.bool)
+    for b in range(B):
+        y0, x0 = int(torch.randint(0, H // 2, (1,), generator=g)), int(torch.randint(0, W // 2, (1,), generator=g))
+        hh, ww = int(torch.randint(H // 8, H // 2, (1,), generator=g)), int(torch.randint(W // 8, W // 2, (1,), generator=g))
+        m[b, 0, y0:y0 + hh, x0:x0 + ww] = True
+    return m.to(device)
+
+
+def criterion_targets(boxes, phrase_mask=None, masks=None, sizes=None):
+    """The reference's target format (list of per-sample dicts, refer_dataset.py:186-194 / criterion.py:113-130) from the dense
+    synthetic targets: ``boxes`` [B, n_ph, 4]; ``phrase_mask`` bool [B, n_ph(*k)] selects the valid phrases of a multi-phrase batch."""
+    B, n_ph = boxes.shape[:2]
+    out = []
+    for b in range(B):
+        if phrase_mask is not None:
+            pm = phrase_mask[b].view(n_ph, -1)[:, 0]
+            bx = boxes[b][pm]
+        else:
+            bx = boxes[b]
+        t = {"boxes": bx, "labels": torch.zeros(bx.shape[0], dtype=torch.long, device=boxes.device)}
+        if masks is not None:
+            t["masks"] = masks[b]
+        if sizes is not None:
+            t["orig_size"] = t["size"] = torch.tensor(sizes, device=boxes.device)
+        out.append(t)
+    return out

@@ -696,6 +696,21 @@ def sumsq(x, out):
     out += (x.double() ** 2).sum().float()
 
 
+def scale_copy_check(src, dst, scale, flag):
+    _LAUNCHES[0] += 1
+    if not bool(torch.isfinite(src).all()):
+        flag.fill_(1)
+    dst.copy_(src * scale)
+
+
+def zero_if(x, flag, counter=None):
+    _LAUNCHES[0] += 1
+    if int(flag.item()) != 0:
+        x.zero_()
+        if counter is not None:
+            counter += 1
+
+
 def adamw_flat(p, g, m, v, seg_end, seg_group, lrs, wds, beta1, beta2, eps, step, sumsq_dev=None, max_norm=0.0):
     _LAUNCHES[0] += 1
     clip = 1.0

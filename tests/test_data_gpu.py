@@ -26,6 +26,29 @@ def test_collate_u8_matches_reference_cpu_path(sizes):
     assert torch.equal(got.tensors.cpu(), ref.tensors)
 
 
+def test_collator_staging_is_not_overwritten_while_a_copy_is_in_flight():
+    """The host runs ahead of the GPU: batch i+1 (and i+2, which reuses batch i's pinned slot) is packed while the stream is still
+    busy with earlier work.  Every batch must arrive intact."""
+    from data_ref import reference_collate
+    from reftr_b200.data import DeviceCollator
+    g = torch.Generator().manual_seed(3)
+    batches = [[torch.randint(0, 256, (320, 320, 3), dtype=torch.uint8, generator=g) for _ in range(4)] for _ in range(6)]
+    refs = [reference_collate(b) for b in batches]
+    col = DeviceCollator("cuda")
+    side = torch.cuda.Stream()
+    busy = torch.empty(64 << 20, device="cuda")
+    outs = []
+    for b in batches:
+        with torch.cuda.stream(side):
+            for _ in range(20):
+                busy.add_(1.0)          # keep the copy stream backed up so the host gets ahead of the DMA
+        outs.append(col(b, stream=side))
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    for got, ref in zip(outs, refs):
+        assert torch.equal(got.tensors.cpu(), ref.tensors) and torch.equal(got.mask.cpu(), ref.mask)
+
+
 def test_collated_batch_feeds_the_model():
     from oracle.cases import CASES
     from reftr_b200.data import DeviceCollator

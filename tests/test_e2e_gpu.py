@@ -140,58 +140,3 @@ def test_split_backward_graphs_match_single_graph(name, monkeypatch):
     for n in a:
         if a[n].norm().item() > 1e-6 * big:
             assert rel_l2(b[n], a[n]) < 2e-3, n  # fp32 atomics order is the only difference
-
-
-def test_full_size_config_matches_oracle_on_gpu():
-    """BASELINE.json configs[1] at full size (ResNet-50, 6+6 layers, 640x640, 20-token phrase, aux loss; 4 samples of the bs16 batch
-    to bound memory): the CUDA path against the fp32 oracle run on the same GPU with TF32 off.  Forward tolerance as in the small
-    cases (rel-L2 < 1e-3 on every decoder layer's boxes); the size-independent backward property checked here is that every one of
-    the reference's trainable parameters receives a finite gradient whose norm agrees with the oracle's (the per-tensor rel-L2
-    comparison is done at small sizes above, where ReLU-mask flips do not dominate)."""
-    from transformers import BertConfig, BertModel
-    from oracle.reftr_oracle import RefTROracle
-    from reftr_b200.synthetic import synthetic_weights
-    from reftr_b200.modules import BackboneParams, Joiner, PositionEmbeddingSine, RefTR, VLTransformerParams
-    tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
-    torch.backends.cuda.matmul.allow_tf32 = False
-    torch.backends.cudnn.allow_tf32 = False
-    try:
-        torch.manual_seed(1234)
-        oracle = RefTROracle(BertModel(BertConfig()), enc=6, dec=6, dropout=0.1, aux_loss=True)
-        synthetic_weights(oracle, seed=0)
-        oracle = oracle.cuda().eval()
-        torch.manual_seed(1234)
-        cand = RefTR(Joiner(BackboneParams("resnet50", True, False), PositionEmbeddingSine(128)), BertModel(BertConfig()),
-                     VLTransformerParams(256, 8, 6, 6, 2048, 0.1, 1, 128), aux_loss=True)
-        synthetic_weights(cand, seed=0)
-        cand = cand.cuda().eval()
-        s = synthetic_samples(B=4, H=640, W=640, L=20, device="cuda")
-        tgt = synthetic_targets(4, 1, device="cuda")
-        out_o = oracle(s)
-        total_box_loss(out_o, tgt).backward()
-        out_c = cand(s)
-        total_box_loss(out_c, tgt).backward()
-        torch.cuda.synchronize()
-        assert torch.equal(out_c["phrase_mask"], out_o["phrase_mask"])
-        layers_c = [out_c["pred_boxes"]] + [a["pred_boxes"] for a in out_c["aux_outputs"]]
-        layers_o = [out_o["pred_boxes"]] + [a["pred_boxes"] for a in out_o["aux_outputs"]]
-        rels = [rel_l2(a, b) for a, b in zip(layers_c, layers_o)]
-        print("full-size cfg2 (B=4): pred_boxes rel-L2 [last layer, aux layers 0..4]", rels)
-        # measured: 5.6e-4 on the model's output (last decoder layer); 4.2e-4..1.1e-3 on the five auxiliary layers -- 62 layers deep
-        # (50 convolutions + 6 + 6 transformer layers) the 16-bit operand rounding of one auxiliary layer lands just above 1e-3
-        assert rels[0] < 1e-3 and max(rels) < 1.5e-3
-        og = {n: p.grad for n, p in oracle.named_parameters() if p.grad is not None}
-        cg = {n: p.grad for n, p in cand.named_parameters() if p.grad is not None}
-        print("params with grad: oracle", len(og), "candidate", len(cg), "missing in candidate", sorted(set(og) - set(cg))[:5])
-        assert set(og) <= set(cg) and len(og) > 400  # every parameter the reference trains receives a gradient
-        big = max(g.norm().item() for g in og.values())
-        ratios = []
-        for n, g in og.items():
-            assert torch.isfinite(cg[n]).all(), n
-            if g.norm().item() > 1e-5 * big:
-                ratios.append(cg[n].norm().item() / g.norm().item())
-        ratios.sort()
-        print("gradient norm ratio candidate/oracle: min %.3f median %.3f max %.3f over %d tensors" % (ratios[0], ratios[len(ratios) // 2], ratios[-1], len(ratios)))
-        assert 0.97 < ratios[len(ratios) // 2] < 1.03 and ratios[0] > 0.5 and ratios[-1] < 2.0
-    finally:
-        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32

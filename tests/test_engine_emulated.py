@@ -264,3 +264,56 @@ def test_engine_wiring_exact_frozen_bert(emulated_exact):
     norms = {n: p.grad.norm().item() for n, p in oracle.named_parameters() if p.grad is not None}
     big = max(norms.values())
     assert len(errs) > 100 and not {n: e for n, e in errs.items() if e > 1e-2 and norms[n] > 1e-6 * big}
+
+
+def test_backward_of_a_stale_forward_raises(emulated):
+    """The engine keeps the activations of the LAST forward only: a second forward (an evaluation inside the training loop, another
+    micro-batch) before the first one's backward must fail loudly instead of pairing the wrong saved activations."""
+    case = CASES["cfg1_box"]
+    cand = build_candidate(case)
+    s = synthetic_samples(**case["inputs"])
+    out_a = cand(s)
+    with torch.no_grad():
+        cand(s)
+    with pytest.raises(RuntimeError, match="stale forward"):
+        _loss(out_a, case).backward()
+    out_b = cand(s)                      # a fresh forward / backward pair still works afterwards
+    _loss(out_b, case).backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in cand.parameters() if p.requires_grad)
+
+
+def test_nonfinite_gradient_step_is_zeroed_and_counted(emulated):
+    """Overflow sentinel (engine._handover / _finish_guard): with an absurd loss scale the 16-bit activation gradients overflow to inf;
+    the flat gradient of that step must come out as exact zeros (a skipped step), the counter must say 1, and the next, normal step
+    must be unaffected."""
+    case = CASES["cfg1_box"]
+    cand = build_candidate(case)
+    s = synthetic_samples(**case["inputs"])
+    eng = cand.engine()
+    eng.grad_scale = 1e30
+    _loss(cand(s), case).backward()
+    assert eng.overflow_steps() == 1
+    for n, p in cand.named_parameters():
+        if p.requires_grad:
+            assert p.grad is not None and not p.grad.any(), n
+    eng.grad_scale = 1024.0
+    cand.zero_grad(set_to_none=True)
+    _loss(cand(s), case).backward()
+    assert eng.overflow_steps() == 1
+    g = cand.bbox_embed.layers[0].weight.grad
+    assert torch.isfinite(g).all() and g.abs().sum() > 0
+
+
+def test_changing_requires_grad_after_the_first_forward_raises(emulated):
+    case = CASES["cfg1_box"]
+    cand = build_candidate(case)
+    s = synthetic_samples(**case["inputs"])
+    cand(s)
+    for p in cand.lang_backbone.parameters():
+        p.requires_grad_(False)
+    with pytest.raises(RuntimeError, match="requires_grad"):
+        cand(s)
+    cand.reset_engine()
+    _loss(cand(s), case).backward()
+    assert all(p.grad is None for p in cand.lang_backbone.parameters())
+    assert cand.bbox_embed.layers[0].weight.grad is not None

@@ -254,9 +254,12 @@ def test_fused_box_criterion_matches_torch(padded):
     res = {}
     for fused in (False, True):
         bx = boxes.clone().requires_grad_()
-        out = {"pred_boxes": bx[-1], "phrase_mask": pm, "aux_outputs": [{"pred_boxes": x, "phrase_mask": pm} for x in bx[:-1]]}
-        if fused:
-            out["_boxes_all"] = bx
+        if fused:   # slices of one tensor, as reftr_b200.modules.RefTR.forward returns them: the criterion takes the one-kernel path
+            out = {"pred_boxes": bx[-1], "phrase_mask": pm, "aux_outputs": [{"pred_boxes": bx[i], "phrase_mask": pm} for i in range(nl - 1)]}
+            assert crit._all_layer_boxes(out) is not None
+        else:       # separate tensors per layer (what the reference's model returns): the plain-torch restatement runs
+            out = {"pred_boxes": bx[-1] * 1.0, "phrase_mask": pm, "aux_outputs": [{"pred_boxes": bx[i] * 1.0, "phrase_mask": pm} for i in range(nl - 1)]}
+            assert crit._all_layer_boxes(out) is None
         ld = crit(out, targets)
         w = torch.linspace(0.5, 1.5, len(ld)).tolist()
         sum(v * wi for v, wi in zip((ld[k_] for k_ in sorted(ld)), w)).backward()
