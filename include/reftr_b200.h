@@ -60,6 +60,7 @@ typedef struct {
  * mode 1 ("TN"): D[m, n] = sum_r A[r + a_rowoff[z], m] * B[r + b_rowoff[z], n], r in [0, K) ; used for
  *      weight gradients (contraction over pixels / tokens), one z per tap, split-K over `splits` CTAs with
  *      fp32 atomic accumulation into out32 + z * out32_z_stride (replaces autograd's conv/linear wgrad).
+ *      Optional bias gradient / per-row scale: see bias_grad, row_scale, out_scale below.
  * Epilogue (mode 0, and mode 1 when atomic=0): v = acc + bias[n] + res[row, n] + res32[row, n];
  *      relu; v = mask_src[row, n] > 0 ? v : 0; rows that are padding per `geom` -> 0; written as bf16 (out)
  *      and/or fp32 (out32).  row = m + out_row_off for out/res/mask_src addressing and geometry.
@@ -76,7 +77,7 @@ typedef struct {
   int taps;
   int a_rowoff[16];
   int b_koff[16]; /* mode 0: k offset into B per tap; mode 1: row offset into B per z */
-  int splits;     /* mode 1 */
+  int splits;     /* mode 1: K splits; <= 0 with atomic accumulation = chosen by the library together with the tile width */
   int block_n;    /* 0 = auto, else 32/64/128/256 */
   long long out_row_off;
   const float* bias;
@@ -92,6 +93,13 @@ typedef struct {
   const rb_dropout* drop; /* HOST pointer, nullable */
   int drop_gshift;
   float mask_scale;
+  /* atomic accumulation only (weight gradients): everything accumulated is multiplied by out_scale (0 = 1) and row m by
+   * row_scale[m] (nullable; the FrozenBatchNorm fold of a convolution's weight gradient, backbone.py:70-80); mode 1 only:
+   * bias_grad[m] += out_scale * sum_r A[r + a_rowoff[0], m] (nullable) -- the bias gradient of the same layer, contracted on the
+   * tensor cores against a block of ones next to the weight gradient (replaces a separate column-sum pass over dY) */
+  float* bias_grad;
+  const float* row_scale;
+  float out_scale;
 } rb_gemm_args;
 
 int rb_gemm(const rb_gemm_args* args, void* stream);

@@ -44,6 +44,9 @@ class GemmArgs(C.Structure):
         ("drop", C.c_void_p),
         ("drop_gshift", C.c_int),
         ("mask_scale", C.c_float),
+        ("bias_grad", C.c_void_p),
+        ("row_scale", C.c_void_p),
+        ("out_scale", C.c_float),
     ]
 
 

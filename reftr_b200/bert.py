@@ -125,8 +125,7 @@ class BertEngine:
             dpre = ws.get(f"bertb.{tag}.dpre", [Bn, D], f32)
             dpreb = ws.get(f"bertb.{tag}.dpreb", [Bn, D])
             ops.tanh_bwd(d_pooled.reshape(Bn, D), pooled, dx=dpre, dxb=dpreb)
-            eng.colsum(dpre, G(bert.pooler.dense.bias))
-            eng.wgrad_linear(dpreb, cls_b, G(bert.pooler.dense.weight), D, D, Bn)
+            eng.wgrad_linear(dpreb, cls_b, G(bert.pooler.dense.weight), D, D, Bn, bias=G(bert.pooler.dense.bias))
             dcls = ws.get(f"bertb.{tag}.dcls", [Bn, D], f32)
             ops.gemm(dpreb, self.pool.wt, Bn, D, D, out32=dcls)
             ops.rows_scatter_add(dcls, g, Bn, D, map_dst=(1, L, 0, 0))
@@ -141,20 +140,17 @@ class BertEngine:
             k = f"bert.{tag}.{li}"
             dr1, dr2 = eng.drop(k + ".drop1", self.p_hidden), eng.drop(k + ".drop2", self.p_hidden)
             ops.ln_wide_bwd(g, y2, ln2.weight, m2, r2, rows, dx32=dy2, dxb=dy2b, dgamma=G(ln2.weight), dbeta=G(ln2.bias), dxb_drop=dr2)
-            eng.colsum(dy2b if dr2 is not None else dy2, G(lay.output.dense.bias))
-            eng.wgrad_linear(dy2b, h, G(lay.output.dense.weight), D, FF, rows)
+            eng.wgrad_linear(dy2b, h, G(lay.output.dense.weight), D, FF, rows, bias=G(lay.output.dense.bias))
             dh = ws.get(f"bertb.{tag}.{li}.dh", [rows, FF])
             ops.gemm(dy2b, l.o2.wt, rows, FF, D, out=dh)
             dhp = ws.get(f"bertb.{tag}.{li}.dhp", [rows, FF])
             ops.gelu_bwd(dh, hpre, dhp)
-            eng.colsum(dhp, G(lay.intermediate.dense.bias))
-            eng.wgrad_linear(dhp, x1b, G(lay.intermediate.dense.weight), FF, D, rows)
+            eng.wgrad_linear(dhp, x1b, G(lay.intermediate.dense.weight), FF, D, rows, bias=G(lay.intermediate.dense.bias))
             g1 = ws.get(f"bertb.{tag}.{li}.g1", [rows, D], f32)
             ops.gemm(dhp, l.i.wt, rows, D, FF, res32=dy2, out32=g1)
             dy1, dy1b = ws.get(f"bertb.{tag}.{li}.dy1", [rows, D], f32), ws.get(f"bertb.{tag}.{li}.dy1b", [rows, D])
             ops.ln_wide_bwd(g1, y1, ln1.weight, m1, r1, rows, dx32=dy1, dxb=dy1b, dgamma=G(ln1.weight), dbeta=G(ln1.bias), dxb_drop=dr1)
-            eng.colsum(dy1b if dr1 is not None else dy1, G(a.output.dense.bias))
-            eng.wgrad_linear(dy1b, ctx, G(a.output.dense.weight), D, D, rows)
+            eng.wgrad_linear(dy1b, ctx, G(a.output.dense.weight), D, D, rows, bias=G(a.output.dense.bias))
             dctx = ws.get(f"bertb.{tag}.{li}.dctx", [rows, D])
             ops.gemm(dy1b, l.o.wt, rows, D, D, out=dctx)
             dqkv = ws.get(f"bertb.{tag}.{li}.dqkv", [rows, 3 * D])
@@ -162,8 +158,7 @@ class BertEngine:
                                drop=eng.drop(k + ".attn", self.p_attn))
             for j, lin in enumerate((a.self.query, a.self.key, a.self.value)):
                 sl = dqkv[:, j * D:(j + 1) * D]
-                eng.colsum(sl, G(lin.bias))
-                eng.wgrad_linear(sl, xb, G(lin.weight), D, D, rows)
+                eng.wgrad_linear(sl, xb, G(lin.weight), D, D, rows, bias=G(lin.bias))
             g_in = gbuf[1] if g is gbuf[0] else gbuf[0]
             ops.gemm(dqkv, l.qkv.wt, rows, D, 3 * D, res32=dy1, out32=g_in)
             g = g_in

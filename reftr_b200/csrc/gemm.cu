@@ -71,6 +71,10 @@ struct GemmKParams {
   int drop_gshift;     // the site's element of output column n is n >> drop_gshift
   uint32_t drop_wpr;   // 32-bit random words per row of the site
   float mask_scale;    // multiplies what mask_src keeps
+  float* bias_grad;    // TN + atomic only: bias_grad[m] += out_scale * sum_r A[r, m] (an extra N=16 MMA against a block of ones)
+  const float* row_scale;  // atomic only: row m of the result is multiplied by row_scale[m] (FrozenBN fold of a conv weight gradient)
+  float out_scale;     // atomic only: multiplies everything that is accumulated
+  uint32_t off_ones;   // 8 KB of 1.0 (the B operand of the bias-gradient MMA)
   int debug;           // RB_GEMM_DEBUG (timing experiments only, results are wrong): 1 = no output stores, 4 = no epilogue math, 8 = no TMEM loads, 16 = no staging writes, 32 = no fence / barrier
 };
 
@@ -165,6 +169,13 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   // the bias is read by every epilogue thread for every chunk: a global (L1-thrashed) load there costs an L2 round trip per chunk
   float* sbias = reinterpret_cast<float*>(smem + p.off_bias);
   for (int i = threadIdx.x; i < p.bias_n; i += GEMM_THREADS) sbias[i] = i < p.N ? __ldg(p.bias + i) : 0.f;
+  if (MODE == 1 && p.bias_grad) {  // every element of the block is 1.0, so its (swizzled, MN-major) layout does not matter
+    const rb_t one = f2t(1.f);
+    const uint32_t one2 = static_cast<uint32_t>(*reinterpret_cast<const uint16_t*>(&one)) * 0x10001u;
+    uint32_t* ones = reinterpret_cast<uint32_t*>(smem + p.off_ones);
+    for (int i = threadIdx.x; i < 8192 / 4; i += GEMM_THREADS) ones[i] = one2;
+    fence_proxy_async_smem();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -219,6 +230,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint64_t a_desc0 = (MODE == 0) ? umma_smem_desc(smem_base, 16, 1024, SWZ_128B) : umma_smem_desc(smem_base, 8192, 1024, SWZ_128B);
       const uint32_t stage_units = p.stage_bytes >> 4, b_units = A_BYTES >> 4;
       constexpr uint32_t kstep = (MODE == 0 ? 32 : 2048) >> 4;
+      const uint32_t idesc_cs = umma_idesc_t(BM, 16, 1, 1);
+      const uint64_t ones_desc = a_desc0 + static_cast<uint64_t>(p.off_ones >> 4);
       int s = 0, tcount = 0;
       uint32_t ph = 0;
       for (int t = blockIdx.x; t < p.tiles_total; t += gridDim.x) {
@@ -228,6 +241,9 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_wait(&acc_empty[as], ((tcount >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * bn;
+        // bias gradient (TN): the tiles of the first column block also contract A against ones into 16 spare TMEM columns
+        const bool colsum = MODE == 1 && p.bias_grad != nullptr && c.n0 == 0 && c.z_tap == 0;
+        const uint32_t cs_tmem = tmem_base + 2 * bn + as * 16;
         for (int k = 0; k < c.n_it; ++k) {
           mbar_wait(&full[s], ph);
           tc_fence_after();
@@ -236,6 +252,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           umma_f16_ss(d_tmem, ad, bd, idesc, k != 0);
 #pragma unroll
           for (int kk = 1; kk < BK / 16; ++kk) umma_f16_ss(d_tmem, ad + kk * kstep, bd + kk * kstep, idesc, 1);
+          if (colsum) {
+#pragma unroll
+            for (int kk = 0; kk < BK / 16; ++kk) umma_f16_ss(cs_tmem, ad + kk * kstep, ones_desc + kk * kstep, idesc_cs, (k | kk) != 0);
+          }
           umma_commit(&empty[s]);
           if (++s == p.stages) { s = 0; ph ^= 1; }
         }
@@ -301,6 +321,12 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int col0 = c.n0 + ch * 64;
         if (col0 >= p.N) { g += bn / 64 - ch; break; }
         if ((g & 1) != team) continue;
+        if (MODE == 1 && EPI == 2 && ch == 0 && p.bias_grad != nullptr && c.n0 == 0 && c.z_tap == 0) {
+          uint32_t cs;
+          tmem_ld_32x1(tmem_base + lane_addr + 2 * bn + as * 16, cs);
+          tmem_ld_wait();
+          if (row_ok) atomicAdd(p.bias_grad + gm, __uint_as_float(cs) * p.out_scale);
+        }
         const uint8_t* ein = nullptr;
         int es = 0;
         if (use_ein) {
@@ -350,6 +376,11 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
           if (f_atomic) {
             if (row_ok) {
+              if (p.row_scale != nullptr || p.out_scale != 1.f) {  // warp-uniform
+                const float rs = p.out_scale * (p.row_scale != nullptr ? __ldg(p.row_scale + gm) : 1.f);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] *= rs;
+              }
               float* dst = p.out32 + static_cast<long long>(c.z_tap) * p.out32_z_stride + orow * p.ldo32 + hc0;
               if (hc0 + 32 <= p.N && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
 #pragma unroll
@@ -527,6 +558,32 @@ static int pick_bn(int N, long long tiles_mz, long long k_iters, int nsm) {
   return best;
 }
 
+// Weight gradients (mode 1, split-K): tile width AND number of K splits together.  The kernel is persistent with a static tile
+// order, so its run time is waves x (time of one tile); a tile's time is its share of the L2 -> shared-memory operand stream
+// (k-blocks x (128 + bn) x 128 B: these GEMMs are bound by that stream) plus the atomic epilogue and a fixed
+// fill / drain cost.  Minimising that over (bn, splits) lands on single-wave configurations with 128..148 tiles instead of
+// e.g. 222 tiles in two half-empty waves.
+static void pick_tn(int M, int N, int taps, int kblocks, int nsm, bool no256, int fixed_bn, int* bn_out, int* splits_out) {
+  const int cands[3] = {256, 128, 64};
+  double best = 1e300;
+  *bn_out = 64; *splits_out = 1;
+  const long long tiles_m = (M + BM - 1) / BM;
+  for (int bn : cands) {
+    if (fixed_bn && bn != fixed_bn) continue;
+    if (!fixed_bn && ((bn >= 2 * N && bn > 64) || (no256 && bn == 256))) continue;
+    const long long base = tiles_m * ((N + bn - 1) / bn) * taps;
+    const int smax = kblocks / 2 > 1 ? (kblocks / 2 < 512 ? kblocks / 2 : 512) : 1;
+    for (int sp = 1; sp <= smax; ++sp) {
+      const long long tiles = base * sp;
+      const long long waves = (tiles + nsm - 1) / nsm;
+      const int k_it = (kblocks + sp - 1) / sp;
+      const double cost = static_cast<double>(waves) * (k_it * (128.0 + bn) * 0.125 + 1.5 * 0.5 * bn + 60.0);  // KB-equivalents
+      if (cost < best - 1e-9) { best = cost; *bn_out = bn; *splits_out = sp; }
+      if (waves > 4 && sp > 1) break;  // more splits only add waves from here on
+    }
+  }
+}
+
 extern "C" int rb_gemm(const rb_gemm_args* a, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (!a || !a->A || !a->B) return rb_fail("rb_gemm: null operand");
@@ -549,6 +606,13 @@ extern "C" int rb_gemm(const rb_gemm_args* a, void* stream) {
   memset(&kp, 0, sizeof(kp));
   kp.mode = a->mode;
   kp.M = a->M; kp.N = a->N; kp.taps = a->taps; kp.splits = a->splits < 1 ? 1 : a->splits;
+  int auto_bn = 0;
+  if (a->mode == 1 && a->atomic && a->splits <= 0) {  // splits <= 0: chosen here, together with the tile width
+    int bn_t = 0, sp_t = 1;
+    pick_tn(a->M, a->N, a->taps, (a->K + BK - 1) / BK, sm_count(), a->bias_grad != nullptr, a->block_n == 32 ? 64 : a->block_n, &bn_t, &sp_t);
+    kp.splits = sp_t;
+    auto_bn = bn_t;
+  }
   for (int i = 0; i < 16; ++i) { kp.a_rowoff[i] = a->a_rowoff[i]; kp.b_koff[i] = a->b_koff[i]; }
   kp.out_row_off = a->out_row_off;
   kp.bias = a->bias;
@@ -558,6 +622,11 @@ extern "C" int rb_gemm(const rb_gemm_args* a, void* stream) {
     const char* dbg = getenv("RB_GEMM_DEBUG");
     kp.debug = dbg ? atoi(dbg) : 0;
   }
+  kp.bias_grad = a->bias_grad;
+  kp.row_scale = a->row_scale;
+  kp.out_scale = a->out_scale == 0.f ? 1.f : a->out_scale;
+  if ((a->bias_grad || a->row_scale || kp.out_scale != 1.f) && !a->atomic) return rb_fail("rb_gemm: bias_grad / row_scale / out_scale need atomic accumulation");
+  if (a->bias_grad && a->mode != 1) return rb_fail("rb_gemm: bias_grad needs mode 1 (TN)");
   kp.drop = make_dropk(a->drop);
   kp.drop_gshift = a->drop_gshift;
   kp.mask_scale = a->mask_scale == 0.f ? 1.f : a->mask_scale;
@@ -573,10 +642,11 @@ extern "C" int rb_gemm(const rb_gemm_args* a, void* stream) {
   const int nsm = sm_count();
   const long long tiles_m = (a->M + BM - 1) / BM;
   const long long k_iters = a->mode == 0 ? static_cast<long long>(a->taps) * kp.kblocks : (kp.kblocks + kp.splits - 1) / kp.splits;
-  int bn = a->block_n ? a->block_n : pick_bn(a->N, tiles_m * (a->mode == 1 ? a->taps * kp.splits : 1), k_iters, nsm);
+  int bn = a->block_n ? a->block_n : (auto_bn ? auto_bn : pick_bn(a->N, tiles_m * (a->mode == 1 ? a->taps * kp.splits : 1), k_iters, nsm));
   // output/residual-dominated problems (short main loop + epilogue inputs): narrower tiles leave room for a deep input ring
   if (!a->block_n && bn == 256 && !a->atomic && (a->res || a->res32 || a->mask_src) && k_iters <= 4) bn = 128;
   if (bn == 32) bn = 64;
+  if (a->bias_grad && bn == 256) bn = 128;  // 2 x 16 TMEM columns for the bias-gradient accumulators next to 2 x bn
   if (bn != 64 && bn != 128 && bn != 256) return rb_fail("rb_gemm: unsupported block_n %d", bn);
   kp.bn = bn;
   kp.tiles_m = static_cast<int>(tiles_m);
@@ -600,7 +670,8 @@ extern "C" int rb_gemm(const rb_gemm_args* a, void* stream) {
   kp.out_slot_bytes = kp.out_off_f32 + (kp.has_out32 ? 32768 : 0);
   const long long bias_pad = static_cast<long long>(kp.tiles_n) * bn;
   kp.bias_n = (a->bias && !a->atomic && bias_pad <= 2048) ? static_cast<int>(bias_pad) : 0;
-  uint32_t bars_bytes = 512 + static_cast<uint32_t>(kp.bias_n) * 4;
+  const uint32_t ones_bytes = a->bias_grad ? 8192u + 1024u : 0u;
+  uint32_t bars_bytes = 512 + static_cast<uint32_t>(kp.bias_n) * 4 + ones_bytes;
   // short main loops do not need a deep ring: the room goes to the epilogue rings instead (HBM-bound 1x1 convolutions, where
   // the residual / mask stream is as large as the output)
   const int want_stages = k_iters * 2 < 4 ? 4 : static_cast<int>(k_iters * 2 > MAX_STAGES ? MAX_STAGES : k_iters * 2);
@@ -612,7 +683,7 @@ extern "C" int rb_gemm(const rb_gemm_args* a, void* stream) {
     if (pass == 2) {                   // third pass: the bias stays in global memory as well
       if (!kp.bias_n) break;
       kp.bias_n = 0;
-      bars_bytes = 512;
+      bars_bytes = 512 + ones_bytes;
     }
     const long long room = static_cast<long long>(SMEM_LIMIT) - (2LL * kp.out_slots * kp.out_slot_bytes + bars_bytes + 1024 /* alignment slack */);
     if (has_ein) {
@@ -637,6 +708,7 @@ extern "C" int rb_gemm(const rb_gemm_args* a, void* stream) {
   kp.off_out = kp.off_ein + kp.ein_slots * kp.ein_slot_bytes;
   kp.off_bars = kp.off_out + 2 * kp.out_slots * kp.out_slot_bytes;
   kp.off_bias = kp.off_bars + 512;
+  kp.off_ones = (kp.off_bias + static_cast<uint32_t>(kp.bias_n) * 4 + 1023u) & ~1023u;
   const int smem_bytes = static_cast<int>(kp.off_bars + bars_bytes + 1024);
   if (smem_bytes > SMEM_LIMIT) return rb_fail("rb_gemm: shared-memory plan exceeds the limit (%d B)", smem_bytes);
 

@@ -566,14 +566,6 @@ class RefTREngine:
     # ------------------------------------------------------------------------------------------------------------
     # generic helpers
     # ------------------------------------------------------------------------------------------------------------
-    @staticmethod
-    def _splits(M, N, taps, K):
-        bn = 128 if N >= 128 else 64
-        tiles = _cdiv(M, 128) * _cdiv(N, bn) * taps
-        kb = _cdiv(K, 64)
-        want = _cdiv(3 * 148, tiles)
-        return max(1, min(want, kb // 4 if kb >= 4 else 1))
-
     # ------------------------------------------------------------------------------------------------------------
     # Off-critical-path work.  In the backward pass the chain of INPUT gradients is the critical path; weight gradients, bias
     # gradients (column sums) and embedding scatters only feed the flat gradient buffer.  They are launched on a side stream
@@ -622,29 +614,32 @@ class RefTREngine:
         with self._off():
             ops.colsum(x, out, rows=rows, N=N)
 
-    def wgrad_linear(self, dY, X, gview, M, N, K):
-        """gview[M, N] += dY[:K, :M]^T X[:K, :N]   (TN GEMM, split-K, fp32 atomics; off the critical path)."""
+    def wgrad_linear(self, dY, X, gview, M, N, K, bias=None):
+        """gview[M, N] += dY[:K, :M]^T X[:K, :N]   (TN GEMM, split-K, fp32 atomics; off the critical path).
+        ``bias`` [M]: the layer's bias gradient, bias[m] += sum_r dY[r, m], produced by the SAME launch (an extra N=16 MMA against
+        ones in the tiles of the first column block) instead of a separate column-sum pass over dY."""
         with self._off():
-            ops.gemm(dY, X, M, N, K, mode=1, out32=gview, atomic=True, splits=self._splits(M, N, 1, K))
+            ops.gemm(dY, X, M, N, K, mode=1, out32=gview, atomic=True, splits=0, bias_grad=bias)  # splits 0: picked by rb_gemm
 
-    def wgrad_conv(self, pc, dY, X, K, key=None, b_offsets=None):
-        """Folded-layout weight gradient of a convolution; b_offsets = row offset of X per tap (None: 1x1, no shift)."""
+    def wgrad_conv(self, pc, dY, X, K, key=None, b_offsets=None, bias=None):
+        """Folded-layout weight gradient of a convolution; b_offsets = row offset of X per tap (None: 1x1, no shift);
+        ``bias``: the convolution's bias gradient from the same launch (see ``wgrad_linear``)."""
         with self._off():
-            self._wgrad_conv(pc, dY, X, K, key, b_offsets)
+            self._wgrad_conv(pc, dY, X, K, key, b_offsets, bias)
 
-    def _wgrad_conv(self, pc, dY, X, K, key=None, b_offsets=None):
+    def _wgrad_conv(self, pc, dY, X, K, key=None, b_offsets=None, bias=None):
         g = self.G(pc.conv.weight)
         Cout, Cin = pc.Cout, pc.Cin
         if b_offsets is None or len(b_offsets) == 1:
+            # 1x1: the parameter layout [Cout, Cin, 1, 1] IS the GEMM's [M, N]; the FrozenBN fold (x scale[co]) rides in the epilogue
             gv = g.view(Cout, Cin)
             ops.gemm(dY, X, Cout, Cin, K, mode=1, taps=[(0, b_offsets[0] if b_offsets else 0)], out32=gv, atomic=True,
-                     splits=self._splits(Cout, Cin, 1, K))
-            ops.unpack_conv_grad(gv, pc.scale, gv, Cout, Cin, 1)  # in-place x scale[co]  (FrozenBN fold)
+                     splits=0, row_scale=pc.scale if pc.bn is not None else None, bias_grad=bias)
         else:
             taps = len(b_offsets)
             sc = self.scratch_view(key).view(Cout, taps * Cin)
             ops.gemm(dY, X, Cout, Cin, K, mode=1, taps=[(0, o) for o in b_offsets], out32=sc, atomic=True,
-                     splits=self._splits(Cout, Cin, taps, K), out32_z_stride=Cin)
+                     splits=0, out32_z_stride=Cin, bias_grad=bias)
             ops.unpack_conv_grad(sc, pc.scale, g, Cout, Cin, taps)
 
     # ------------------------------------------------------------------------------------------------------------
@@ -788,8 +783,7 @@ class RefTREngine:
         d1b = ws.get(key + ".d1b", [rows, D])
         ops.layernorm_bwd(dy, y1, seq[5].weight, m1, r1, rows, y_relu=y32, dx32=d1, dxb=d1b, dgamma=self.G(seq[5].weight),
                           dbeta=self.G(seq[5].bias), rowmap=rowmap)
-        self.colsum(d1, self.G(seq[4].bias))
-        self.wgrad_linear(d1b, a1b, self.G(seq[4].weight), D, D, rows)
+        self.wgrad_linear(d1b, a1b, self.G(seq[4].weight), D, D, rows, bias=self.G(seq[4].bias))
         da1 = ws.get(key + ".da1", [rows, D], torch.float32)
         ops.gemm(d1b, packs[1].wt, rows, D, D, out32=da1)
         d0 = ws.get(key + ".d0", [rows, D], torch.float32)
@@ -797,8 +791,7 @@ class RefTREngine:
         dr = self.drop(key + ".drop", seq[3].p)  # a1 > 0 <=> ReLU passed AND kept; kept gradients are scaled by 1/(1-p)
         ops.layernorm_bwd(da1, y0, seq[1].weight, m0, r0, rows, y_relu=a1, relu_scale=dr.scale if dr else 1.0, dx32=d0, dxb=d0b,
                           dgamma=self.G(seq[1].weight), dbeta=self.G(seq[1].bias))
-        self.colsum(d0, self.G(seq[0].bias))
-        self.wgrad_linear(d0b, A, self.G(seq[0].weight), D, K, rows)
+        self.wgrad_linear(d0b, A, self.G(seq[0].weight), D, K, rows, bias=self.G(seq[0].bias))
         if not need_dA:
             return None
         dA = ws.get(key + ".dA", [rows, K], torch.float32)
@@ -846,12 +839,10 @@ class RefTREngine:
         dropped hidden activation, so h > 0 <=> ReLU passed and kept (``drop_h`` gives the 1/(1-p) scale)."""
         ws = self.ws
         dff = lin1.N
-        self.colsum(dyb if drop_out is not None else dy32, self.G(mod.linear2.bias))
-        self.wgrad_linear(dyb, h, self.G(mod.linear2.weight), D, dff, rows)
+        self.wgrad_linear(dyb, h, self.G(mod.linear2.weight), D, dff, rows, bias=self.G(mod.linear2.bias))
         dh = ws.get(key + ".dh", [rows, dff])
         ops.gemm(dyb, lin2.wt, rows, dff, D, mask_src=h, out=dh, mask_scale=drop_h.scale if drop_h is not None else 1.0)
-        self.colsum(dh, self.G(mod.linear1.bias))
-        self.wgrad_linear(dh, x_in_b, self.G(mod.linear1.weight), dff, D, rows)
+        self.wgrad_linear(dh, x_in_b, self.G(mod.linear1.weight), dff, D, rows, bias=self.G(mod.linear1.bias))
         ops.gemm(dh, lin1.wt, rows, D, dff, res32=dy32, out32=out32)
 
     def _enc_bwd(self, l, e, g, g_out, kpm, dpos, B, S):
@@ -872,18 +863,16 @@ class RefTREngine:
         dy1b = ws.get(f"encb{l}.dy1b", [rows, D])
         ops.layernorm_bwd(g1, y1, lay.norm1.weight, m1, r1, rows, dx32=dy1, dxb=dy1b, dgamma=self.G(lay.norm1.weight),
                           dbeta=self.G(lay.norm1.bias), dxb_drop=dr1)
-        self.colsum(dy1b if dr1 is not None else dy1, self.G(lay.self_attn.out_proj.bias))
-        self.wgrad_linear(dy1b, o, self.G(lay.self_attn.out_proj.weight), D, D, rows)
+        self.wgrad_linear(dy1b, o, self.G(lay.self_attn.out_proj.weight), D, D, rows, bias=self.G(lay.self_attn.out_proj.bias))
         do = ws.get(f"encb{l}.do", [rows, D])
         ops.gemm(dy1b, e.out.wt, rows, D, D, out=do)
         dqkv = ws.get(f"encb{l}.dqkv", [rows, 3 * D])
         dbuf = ws.get(f"encb{l}.dbuf", [B, NH, S], torch.float32)
         ops.attn_bwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], kpm, o, do, lse, dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:], dbuf,
                      B, NH, S, S, DH ** -0.5, drop=self.drop(k + ".attn"))
-        self.colsum(dqkv, self.G(lay.self_attn.in_proj_bias))
-        gw = self.G(lay.self_attn.in_proj_weight)
-        self.wgrad_linear(dqkv[:, :2 * D], xpb, gw[:2 * D], 2 * D, D, rows)
-        self.wgrad_linear(dqkv[:, 2 * D:], xb, gw[2 * D:], D, D, rows)
+        gw, gbi = self.G(lay.self_attn.in_proj_weight), self.G(lay.self_attn.in_proj_bias)
+        self.wgrad_linear(dqkv[:, :2 * D], xpb, gw[:2 * D], 2 * D, D, rows, bias=gbi[:2 * D])
+        self.wgrad_linear(dqkv[:, 2 * D:], xb, gw[2 * D:], D, D, rows, bias=gbi[2 * D:])
         ops.gemm(dqkv, e.inp.wt, rows, D, 3 * D, res32=dy1, out32=g_out)
         with self._off():  # d(pos) of the encoder layers only feeds the embedding gradients at the very end: off the critical path
             ops.gemm(dqkv[:, :2 * D], e.inp.wt[:, :2 * D], rows, D, 2 * D, res32=dpos, out32=dpos)
@@ -958,8 +947,7 @@ class RefTREngine:
         d_co = ws.get("qeb.d_co", [rp, D], torch.float32)
         d_cob = ws.get("qeb.d_cob", [rp, D])
         ops.layernorm_bwd(d_left, co32, ln.weight, mc, rc, rp, dx32=d_co, dxb=d_cob, dgamma=self.G(ln.weight), dbeta=self.G(ln.bias))
-        self.colsum(d_co, self.G(qe.context_out[0].bias))
-        self.wgrad_linear(d_cob, cb, self.G(qe.context_out[0].weight), D, D, rp)
+        self.wgrad_linear(d_cob, cb, self.G(qe.context_out[0].weight), D, D, rp, bias=self.G(qe.context_out[0].bias))
         d_c = ws.get("qeb.d_c", [rp, D], torch.float32)
         ops.gemm(d_cob, self.qe_cout.wt, rp, D, D, out32=d_c)
         dk = ws.get("qeb.dk", [B, D], torch.float32)
@@ -972,8 +960,7 @@ class RefTREngine:
         ops.cast_bf16(dv, dvb)
         for lin, mod, d32, db, x, n in ((self.qe_lin[0], qe.linear1, dk, dkb, cls_b, B), (self.qe_lin[1], qe.linear2, dq, dqb, ctxb, rl),
                                         (self.qe_lin[2], qe.linear3, dv, dvb, ctxb, rl)):
-            self.colsum(d32, self.G(mod.bias))
-            self.wgrad_linear(db, x, self.G(mod.weight), D, D, n)
+            self.wgrad_linear(db, x, self.G(mod.weight), D, D, n, bias=self.G(mod.bias))
         d_ctx = ws.get("qeb.d_ctx", [rl, D], torch.float32)
         ops.gemm(dqb, self.qe_lin[1].wt, rl, D, D, out32=d_ctx)
         ops.gemm(dvb, self.qe_lin[2].wt, rl, D, D, res32=d_ctx, out32=d_ctx)
@@ -1091,8 +1078,7 @@ class RefTREngine:
             ops.layernorm_bwd(g2, y2, lay.norm2.weight, m2, r2, rt, dx32=dy2, dxb=dy2b, dgamma=self.G(lay.norm2.weight),
                               dbeta=self.G(lay.norm2.bias), dxb_drop=dr2)
             # cross attention
-            self.colsum(dy2b if dr2 is not None else dy2, self.G(lay.multihead_attn.out_proj.bias))
-            self.wgrad_linear(dy2b, o_c, self.G(lay.multihead_attn.out_proj.weight), D, D, rt)
+            self.wgrad_linear(dy2b, o_c, self.G(lay.multihead_attn.out_proj.weight), D, D, rt, bias=self.G(lay.multihead_attn.out_proj.bias))
             do_c = ws.get(f"decb{l}.do_c", [rt, D])
             ops.gemm(dy2b, d.ca_out.wt, rt, D, D, out=do_c)
             dqc = ws.get(f"decb{l}.dqc", [rt, D])
@@ -1102,12 +1088,9 @@ class RefTREngine:
                          drop=self.drop(k + ".ca"))
             gw = self.G(lay.multihead_attn.in_proj_weight)
             gb = self.G(lay.multihead_attn.in_proj_bias)
-            self.colsum(dqc, gb[:D])
-            self.colsum(dkall[:, cs], gb[D:2 * D])
-            self.colsum(dvall[:, cs], gb[2 * D:])
-            self.wgrad_linear(dqc, t1qb, gw[:D], D, D, rt)
-            self.wgrad_linear(dkall[:, cs], mempb, gw[D:2 * D], D, D, rows)
-            self.wgrad_linear(dvall[:, cs], memb, gw[2 * D:], D, D, rows)
+            self.wgrad_linear(dqc, t1qb, gw[:D], D, D, rt, bias=gb[:D])
+            self.wgrad_linear(dkall[:, cs], mempb, gw[D:2 * D], D, D, rows, bias=gb[D:2 * D])
+            self.wgrad_linear(dvall[:, cs], memb, gw[2 * D:], D, D, rows, bias=gb[2 * D:])
             g1 = ws.get(f"decb{l}.g1", [rt, D], torch.float32)
             ops.gemm(dqc, d.ca.wt[:, :D], rt, D, D, res32=dy2, out32=g1)
             ops.gemm(dqc, d.ca.wt[:, :D], rt, D, D, res32=dqpos, out32=dqpos)
@@ -1116,8 +1099,7 @@ class RefTREngine:
             ops.layernorm_bwd(g1, y1, lay.norm1.weight, m1, r1, rt, dx32=dy1, dxb=dy1b, dgamma=self.G(lay.norm1.weight),
                               dbeta=self.G(lay.norm1.bias), dxb_drop=dr1)
             # self attention
-            self.colsum(dy1b if dr1 is not None else dy1, self.G(lay.self_attn.out_proj.bias))
-            self.wgrad_linear(dy1b, o_s, self.G(lay.self_attn.out_proj.weight), D, D, rt)
+            self.wgrad_linear(dy1b, o_s, self.G(lay.self_attn.out_proj.weight), D, D, rt, bias=self.G(lay.self_attn.out_proj.bias))
             do_s = ws.get(f"decb{l}.do_s", [rt, D])
             if T == 1:  # the head dropout of the forward shortcut, applied to d(attention output) = d(value projection)
                 ops.gemm(dy1b, d.sa_out.wt, rt, D, D, out=do_s, drop=self.drop(k + ".sa"), drop_gshift=5)
@@ -1126,16 +1108,15 @@ class RefTREngine:
             g_prev = gbuf[l & 1]
             gws = self.G(lay.self_attn.in_proj_weight)
             if T == 1:  # d(value projection) = d(attention output); q / k receive no gradient
-                self.colsum(do_s, self.G(lay.self_attn.in_proj_bias)[2 * D:])
-                self.wgrad_linear(do_s, tgtb, gws[2 * D:], D, D, rt)
+                self.wgrad_linear(do_s, tgtb, gws[2 * D:], D, D, rt, bias=self.G(lay.self_attn.in_proj_bias)[2 * D:])
                 ops.gemm(do_s, d.sa.wt[:, 2 * D:], rt, D, D, res32=dy1, out32=g_prev)
             else:
                 dqkv = ws.get(f"decb{l}.dqkv", [rt, 3 * D])
                 ops.attn_bwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], qmask, o_s, do_s, lse_s, dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:],
                              dbuf, B, NH, T, T, scale, drop=self.drop(k + ".sa"))
-                self.colsum(dqkv, self.G(lay.self_attn.in_proj_bias))
-                self.wgrad_linear(dqkv[:, :2 * D], tqb, gws[:2 * D], 2 * D, D, rt)
-                self.wgrad_linear(dqkv[:, 2 * D:], tgtb, gws[2 * D:], D, D, rt)
+                gbs = self.G(lay.self_attn.in_proj_bias)
+                self.wgrad_linear(dqkv[:, :2 * D], tqb, gws[:2 * D], 2 * D, D, rt, bias=gbs[:2 * D])
+                self.wgrad_linear(dqkv[:, 2 * D:], tgtb, gws[2 * D:], D, D, rt, bias=gbs[2 * D:])
                 ops.gemm(dqkv, d.sa.wt, rt, D, 3 * D, res32=dy1, out32=g_prev)
                 ops.gemm(dqkv[:, :2 * D], d.sa.wt[:, :2 * D], rt, D, 2 * D, res32=dqpos, out32=dqpos)
             g_next = g_prev
@@ -1245,16 +1226,13 @@ class RefTREngine:
         gl[:, :4].copy_(g_logits.reshape(rh, 4))
         glb = ws.get("bboxb.glb", [rh, 64])
         ops.cast_bf16(gl, glb)
-        self.colsum(gl, self.G(bl[2].bias), rows=rh, N=4)
-        self.wgrad_linear(glb, z1, self.G(bl[2].weight), 4, D, rh)
+        self.wgrad_linear(glb, z1, self.G(bl[2].weight), 4, D, rh, bias=self.G(bl[2].bias))
         dz1 = ws.get("bboxb.dz1", [rh, D])
         ops.gemm(glb, self.bbox[2].wt, rh, D, 64, mask_src=z1, out=dz1)
-        self.colsum(dz1, self.G(bl[1].bias))
-        self.wgrad_linear(dz1, z0, self.G(bl[1].weight), D, D, rh)
+        self.wgrad_linear(dz1, z0, self.G(bl[1].weight), D, D, rh, bias=self.G(bl[1].bias))
         dz0 = ws.get("bboxb.dz0", [rh, D])
         ops.gemm(dz1, self.bbox[1].wt, rh, D, D, mask_src=z0, out=dz0)
-        self.colsum(dz0, self.G(bl[0].bias))
-        self.wgrad_linear(dz0, hsb, self.G(bl[0].weight), D, D, rh)
+        self.wgrad_linear(dz0, hsb, self.G(bl[0].weight), D, D, rh, bias=self.G(bl[0].bias))
         d_hs = ws.get("bboxb.d_hs", [rh, D], torch.float32)
         ops.gemm(dz0, self.bbox[0].wt, rh, D, D, out32=d_hs)
         g_mem = ws.get("bwd.g_mem", [rows, D], torch.float32)
@@ -1307,8 +1285,7 @@ class RefTREngine:
         gn = m.input_proj[0][1]
         dproj = ws.get("iproj.dx", [g5.R, D], zero=True)
         ops.groupnorm_tokens_bwd(g, g_src, proj32, gn.weight, gmean, grstd, B, h, w, S, L, dproj, self.G(gn.weight), self.G(gn.bias))
-        self.colsum(dproj, self.G(m.input_proj[0][0].bias))
-        self.wgrad_conv(self.iproj, dproj, c5, g5.R)
+        self.wgrad_conv(self.iproj, dproj, c5, g5.R, bias=self.G(m.input_proj[0][0].bias))
         if self.blocks[-1].trainable:
             g5y = ws.get("iproj.gc5", [g5.R, 2048])
             ops.gemm(dproj, self.iproj.wd, g5.R, 2048, D, res=g_fpn.get(4), mask_src=c5, out=g5y)

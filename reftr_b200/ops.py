@@ -77,7 +77,7 @@ def _check_2d(t, dtype, name):
 
 def gemm(A, B, M, N, K, *, mode=0, taps=((0, 0),), bias=None, res=None, res32=None, mask_src=None, relu=False,
          out=None, out32=None, atomic=False, splits=1, geom=None, out_row_off=0, out32_z_stride=0, block_n=0, drop=None, drop_gshift=0,
-         mask_scale=1.0):
+         mask_scale=1.0, bias_grad=None, row_scale=None, out_scale=1.0):
     """See rb_gemm in include/reftr_b200.h.  ``taps`` is a sequence of (a_rowoff, b_koff) pairs."""
     _check_2d(A, t16(), "A")
     _check_2d(B, t16(), "B")
@@ -119,6 +119,13 @@ def gemm(A, B, M, N, K, *, mode=0, taps=((0, 0),), bias=None, res=None, res32=No
     if drop is not None:
         a.drop, a.drop_gshift = drop.ptr(), drop_gshift
     a.mask_scale = mask_scale
+    if bias_grad is not None:
+        assert bias_grad.dtype == torch.float32 and bias_grad.is_contiguous() and bias_grad.numel() >= M
+        a.bias_grad = bias_grad.data_ptr()
+    if row_scale is not None:
+        assert row_scale.dtype == torch.float32 and row_scale.is_contiguous() and row_scale.numel() >= M
+        a.row_scale = row_scale.data_ptr()
+    a.out_scale = out_scale
     if PROFILE is not None:  # bench.py: keep the launch descriptor so the launch can be re-issued and timed in isolation
         PROFILE.append((a, 2.0 * M * N * K * len(taps), (mode, M, N, K, len(taps), bool(atomic), res is not None, res32 is not None,
                                                        mask_src is not None, out32 is not None)))

@@ -156,7 +156,7 @@ class SegHead:
         sc = eng.scratch_view("seg.out").view(Cp, 9 * self.out.Cin)
         sh = g2.shifts()
         ops.gemm(dl, y4, Cp, self.out.Cin, g2.R, mode=1, taps=[(0, o) for o in sh], out32=sc, atomic=True,
-                 splits=eng._splits(Cp, self.out.Cin, 9, g2.R), out32_z_stride=self.out.Cin)
+                 splits=0, out32_z_stride=self.out.Cin)
         w8 = ws.get("segb.w8", [Cp, self.out.Cin, 3, 3], torch.float32)
         ops.unpack_conv_grad(sc, None, w8, Cp, self.out.Cin, 9)
         G(mh.out_lay.weight).add_(w8[:1])
@@ -170,9 +170,8 @@ class SegHead:
             xin, g, c32, y, mean, rstd = sv[i][:6]
             dc = ws.get(f"segb.dc{i}", [g.R, pc.Cout])
             ops.groupnorm_nhwc_bwd(dy, y, c32, gn.weight, mean, rstd, B, g.H, g.W, pc.Cout, gn.num_groups, dc, G(gn.weight), G(gn.bias), relu=True)
-            eng.colsum(dc, G(lay.bias))
             shg = g.shifts()
-            eng.wgrad_conv(pc, dc, xin, g.R, key=f"seg.lay{i + 1}", b_offsets=shg)
+            eng.wgrad_conv(pc, dc, xin, g.R, key=f"seg.lay{i + 1}", b_offsets=shg, bias=G(lay.bias))
             dxin = ws.get(f"segb.dxin{i}", [g.R, pc.Cin])
             ops.gemm(dc, pc.wd, g.R, pc.Cin, pc.Cout, taps=[(s, t * pc.Cout) for t, s in enumerate(shg)], out=dxin, geom=g.geom)
             if i >= 2:
@@ -181,8 +180,7 @@ class SegHead:
                 adm = getattr(mh, f"adapter{j + 1}")
                 glo, f = sv[i][6], sv[i][7]
                 layer = (3, 2, 1)[j]
-                eng.colsum(dxin, G(adm.bias))
-                eng.wgrad_conv(ad, dxin, f, g.R)
+                eng.wgrad_conv(ad, dxin, f, g.R, bias=G(adm.bias))
                 first_trainable_layer = min(b.layer for b in eng.blocks if b.trainable) if any(b.trainable for b in eng.blocks) else 99
                 if layer >= first_trainable_layer:  # gradient into the backbone feature (C2 = frozen layer1 output: none)
                     gf = ws.get(f"segb.gf{layer}", [g.R, ad.Cin])
@@ -205,13 +203,11 @@ class SegHead:
         ba = m.bbox_attention
         dkb = ws.get("segb.dkb", [rows, D])
         ops.cast_bf16(dk, dkb)
-        eng.colsum(dk, G(ba.k_linear.bias))
-        eng.wgrad_linear(dkb, memb, G(ba.k_linear.weight), D, D, rows)
+        eng.wgrad_linear(dkb, memb, G(ba.k_linear.weight), D, D, rows, bias=G(ba.k_linear.bias))
         ops.gemm(dkb, self.k.wt, rows, D, D, res32=g_mem, out32=g_mem)
         dqb = ws.get("segb.dqb", [B, D])
         ops.cast_bf16(dq, dqb)
-        eng.colsum(dq, G(ba.q_linear.bias))
-        eng.wgrad_linear(dqb, hs_last, G(ba.q_linear.weight), D, D, B)
+        eng.wgrad_linear(dqb, hs_last, G(ba.q_linear.weight), D, D, B, bias=G(ba.q_linear.bias))
         d_last = d_hs[(nl - 1) * B:nl * B]
         ops.gemm(dqb, self.q.wt, B, D, D, res32=d_last, out32=d_last)
         return g_mem, g_src, g_fpn

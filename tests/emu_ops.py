@@ -77,7 +77,8 @@ def _cols(Bm, n, k0, K):
 
 
 def gemm(A, B, M, N, K, *, mode=0, taps=((0, 0),), bias=None, res=None, res32=None, mask_src=None, relu=False, out=None, out32=None,
-         atomic=False, splits=1, geom=None, out_row_off=0, out32_z_stride=0, block_n=0, drop=None, drop_gshift=0, mask_scale=1.0):
+         atomic=False, splits=1, geom=None, out_row_off=0, out32_z_stride=0, block_n=0, drop=None, drop_gshift=0, mask_scale=1.0,
+         bias_grad=None, row_scale=None, out_scale=1.0):
     _LAUNCHES[0] += 1
     assert A.dtype == _lp() and B.dtype == _lp() and A.stride(1) == 1 and B.stride(1) == 1
     assert A.stride(0) % 8 == 0 and B.stride(0) % 8 == 0, "TMA pitch"
@@ -120,7 +121,11 @@ def gemm(A, B, M, N, K, *, mode=0, taps=((0, 0),), bias=None, res=None, res32=No
         for z, (ro, bo) in enumerate(taps):
             a = _rows(A, r + ro, M) * valid
             b = _rows(B, r + bo, N) * valid
-            d = a.t() @ b
+            d = a.t() @ b * out_scale
+            if row_scale is not None:
+                d = d * row_scale[:M, None]
+            if z == 0 and bias_grad is not None:
+                bias_grad[:M] += a.sum(0) * out_scale
             tgt = torch.as_strided(out32, (M, N), (out32.stride(-2), 1), out32.storage_offset() + z * out32_z_stride)
             tgt += d
     return out if out is not None else out32

@@ -84,6 +84,41 @@ def test_gemm_tn_wgrad(R, Mo, No, splits, bn):
     assert _rel(out32, ref) < 2e-3
 
 
+@pytest.mark.parametrize("R,Mo,No,splits,bn", [(1000, 128, 192, 3, 0), (6400, 256, 512, 8, 0), (200, 64, 64, 1, 64), (333, 768, 768, 2, 256),
+                                             (16, 4, 256, 1, 0), (6720, 2048, 256, 14, 0), (320, 3072, 768, 1, 0)])
+def test_gemm_tn_wgrad_with_bias_gradient_and_row_scale(R, Mo, No, splits, bn):
+    """bias_grad (column sums of dY from an extra N=16 MMA against ones in the same launch), row_scale and out_scale of the atomic
+    epilogue; the accumulation targets start non-zero (the kernel ADDS)."""
+    from reftr_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(R + Mo)
+    dY = torch.randn(R, max(Mo, 64), device="cuda", generator=g).to(T16)[:, :Mo]   # (row pitch stays a multiple of 16 bytes: the 4-wide box head)
+    X = torch.randn(R, No, device="cuda", generator=g).to(T16)
+    rs = torch.rand(Mo, device="cuda", generator=g) + 0.5
+    out32 = torch.full((Mo, No), 0.25, device="cuda")
+    bg = torch.full((Mo,), -1.0, device="cuda")
+    ops.gemm(dY, X, Mo, No, R, mode=1, out32=out32, atomic=True, splits=splits if bn else 0, block_n=bn, bias_grad=bg, row_scale=rs, out_scale=0.5)
+    ref = 0.25 + 0.5 * rs[:, None] * (dY.float().t() @ X.float())
+    assert _rel(out32, ref) < 2e-3
+    ref_b = -1.0 + 0.5 * dY.float().sum(0)
+    assert (bg - ref_b).abs().max().item() < 2e-3 * max(1.0, ref_b.abs().max().item())
+
+
+def test_conv3x3_wgrad_taps_with_bias_gradient():
+    """With several taps the bias gradient must be accumulated once (by tap 0's tiles), not once per tap."""
+    from reftr_b200 import ops
+    Nb, H, W, Cin, Cout = 2, 12, 9, 128, 128
+    Wp, Hp = W + 2, H + 2
+    R = Nb * Hp * Wp
+    dyp = _pad_nhwc(torch.randn(Nb, Cout, H, W, device="cuda"))
+    xp = _pad_nhwc(torch.randn(Nb, Cin, H, W, device="cuda"))
+    taps = [(0, (r - 1) * Wp + (s - 1)) for r in range(3) for s in range(3)]
+    out32 = torch.zeros(Cout, 9 * Cin, device="cuda")
+    bg = torch.zeros(Cout, device="cuda")
+    ops.gemm(dyp.view(R, Cout), xp.view(R, Cin), Cout, Cin, R, mode=1, taps=taps, out32=out32, atomic=True, splits=2, out32_z_stride=Cin, bias_grad=bg)
+    ref_b = dyp.view(R, Cout).float().sum(0)
+    assert (bg - ref_b).abs().max().item() < 2e-3 * ref_b.abs().max().item()
+
+
 def test_conv3x3_wgrad_taps():
     from reftr_b200 import ops
     Nb, H, W, Cin, Cout = 2, 12, 9, 128, 128

@@ -54,3 +54,8 @@ nt(T, 256, 768, relu=False, f32=True, res32=True)
 # wgrad
 tn(R3, 256, 256, taps=9, splits=13); tn(R3, 256, 1024, splits=28); tn(R3, 1024, 256, splits=28); tn(R2, 128, 128, taps=9, splits=12)
 tn(R2, 512, 128, splits=56); tn(R4, 512, 512, taps=9, splits=7); tn(T, 2048, 256, splits=14); tn(T, 256, 2048, splits=14); tn(T, 256, 256, splits=14)
+# round 2: splits = 0 -> tile width and K splits chosen together by rb_gemm (single-wave configurations)
+print("--- auto splits")
+tn(R3, 256, 256, taps=9, splits=0); tn(R3, 256, 1024, splits=0); tn(R3, 1024, 256, splits=0); tn(R2, 128, 128, taps=9, splits=0)
+tn(R2, 512, 128, splits=0); tn(R2, 128, 512, splits=0); tn(R4, 512, 512, taps=9, splits=0); tn(R4, 512, 2048, splits=0); tn(T, 2048, 256, splits=0); tn(T, 256, 2048, splits=0); tn(T, 256, 256, splits=0)
+tn(320, 768, 768, splits=0); tn(320, 3072, 768, splits=0); tn(320, 768, 3072, splits=0)

@@ -62,8 +62,7 @@ def main():
     torch.cuda.synchronize()
     from torch.profiler import ProfilerActivity, profile
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
-        for _ in range(a.steps):
-            step()
+        step()                      # ONE step between two synchronisations: the span below is that step's GPU timeline
         torch.cuda.synchronize()
     if rank != 0:
         return
@@ -74,16 +73,7 @@ def main():
     ks = [e for e in ev if e.get("cat") in ("kernel", "gpu_memset", "gpu_memcpy") and "dur" in e]
     ks.sort(key=lambda e: e["ts"])
     os.remove(trace)
-    # split into steps at the largest gaps between consecutive kernel starts on the union of streams; keep the LAST step
-    ends = 0.0
-    cuts = []
-    for i, e in enumerate(ks):
-        if i and e["ts"] - ends > 0:
-            cuts.append((e["ts"] - ends, i))
-        ends = max(ends, e["ts"] + e["dur"])
-    cuts.sort(reverse=True)
-    bounds = sorted(i for _, i in cuts[:a.steps - 1])
-    step_ks = ks[bounds[-1]:] if bounds else ks
+    step_ks = ks
     t0 = step_ks[0]["ts"]
     rows = [(e["ts"] - t0, e["dur"], e.get("args", {}).get("stream", e.get("tid")), e["name"]) for e in step_ks]
     with open(a.out + "_kernels.csv", "w") as f:
