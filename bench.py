@@ -261,6 +261,54 @@ def stock_and_parity(model, s_dev, t_dev, device, value):
     return res
 
 
+def verify_data_parallel(model, net, crit, device, world, rank, workload):
+    """Hardware check of the multi-GPU path (SURVEY section 4 "distributed" tier): the gradient that rank 0 holds after the split
+    backward + sliced NCCL all-reduce of a data-parallel step (every rank on its own shard) against the gradient of ONE process
+    running the global batch.  Eval mode (dropout off, so both runs are deterministic); every rank runs both passes (the criterion's
+    num_boxes all-reduce is collective).  rel-L2 over the whole flat gradient and the worst per-tensor rel-L2."""
+    import contextlib
+    from reftr_b200.synthetic import ImageList, synthetic_samples, synthetic_targets
+    shape = dict(WORKLOADS[workload][1])
+    bv = 4
+    shape["B"] = bv * world
+    s_all = synthetic_samples(**shape, seed=123, device=device)
+    n_ph = max(shape.get("n_ph", 0), 1)
+    t_all = synthetic_targets(bv * world, n_ph, seed=321, device=device)
+
+    def shard(lo, hi):
+        return {k: (ImageList(v.tensors[lo:hi], v.mask[lo:hi]) if k == "img" else v[lo:hi]) for k, v in s_all.items()}, t_all[lo:hi]
+
+    def run(module, s, t):
+        model.zero_grad(set_to_none=True)
+        ld = crit(module(s), targets_list(t, masks=False))
+        sum(ld[k] * crit.weight_dict[k] for k in ld if k in crit.weight_dict).backward()
+        torch.cuda.synchronize()
+        return {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}
+
+    was_training = model.training
+    model.eval()
+    try:
+        s_loc, t_loc = shard(rank * bv, (rank + 1) * bv)
+        for _ in range(3):                       # eager, capture, replay: the replayed split-graph path is the one compared
+            g_dp = run(net, s_loc, t_loc)
+        model.engine_allreduce = False
+        ctx = net.no_sync() if hasattr(net, "no_sync") else contextlib.nullcontext()
+        with ctx:
+            for _ in range(2):
+                g_one = run(model, s_all, t_all)
+        model.engine_allreduce = True
+    finally:
+        model.train(was_training)
+    num = sum(((g_dp[n].double() - g_one[n].double()) ** 2).sum() for n in g_one).sqrt().item()
+    den = sum((g_one[n].double() ** 2).sum() for n in g_one).sqrt().item()
+    big = max(g.norm().item() for g in g_one.values())
+    per = {n: ((g_dp[n] - g_one[n]).norm() / (g_one[n].norm() + 1e-20)).item() for n in g_one if g_one[n].norm().item() > 1e-4 * big}
+    worst = max(per.items(), key=lambda kv: kv[1])
+    return {"world": world, "samples_per_rank": bv, "rel_l2_flat_gradient": num / max(den, 1e-30), "worst_tensor": worst[0], "worst_tensor_rel_l2": worst[1],
+            "tensors_compared": len(per), "tolerance": 2e-3, "ok": num / max(den, 1e-30) < 2e-3,
+            "what": "rank 0's gradient after the split backward + sliced NCCL all-reduce (each rank on its shard) vs one process on the global batch; eval mode"}
+
+
 def optimizer_diag(model, step_fn, device):
     """SURVEY 8(f) row N3 (NOT part of the metric's timed region): the reference's per-iteration clip_grad_norm_(0.1) + AdamW.step()
     (engine_vg.py:62-67, main_vg.py:234-268) as torch runs it vs reftr_b200.optim on flat buffers, on the gradients of one step; and
@@ -408,9 +456,10 @@ def main():
         from reftr_b200.data import DeviceCollator
         collator = DeviceCollator(device)
         g8 = torch.Generator().manual_seed(7)
-        imgs_u8 = [torch.randint(0, 256, (wl_shape["H"], wl_shape["W"], 3), dtype=torch.uint8, generator=g8).pin_memory() for _ in range(B)]
+        imgs_u8 = [torch.randint(0, 256, (wl_shape["H"], wl_shape["W"], 3), dtype=torch.uint8, generator=g8) for _ in range(B)]
+        packed = DeviceCollator.pack(imgs_u8)   # the data-loader worker's part (pinned host memory), outside the step like the fp32 collate
         s_rest = {k: v for k, v in s_host.items() if k != "img"}
-        h2d_bytes = sum(im.numel() for im in imgs_u8) + sum(v.numel() * v.element_size() for v in s_rest.values()) + t_host.numel() * t_host.element_size()
+        h2d_bytes = packed.nbytes() + sum(v.numel() * v.element_size() for v in s_rest.values()) + t_host.numel() * t_host.element_size()
     else:
         h2d_bytes = nbytes(s_host, t_host)
 
@@ -418,7 +467,7 @@ def main():
         with torch.cuda.stream(copy_stream):
             if use_u8:
                 s = {k: v.to(device, non_blocking=True) for k, v in s_rest.items()}
-                s["img"] = collator(imgs_u8, stream=copy_stream)
+                s["img"] = collator.upload(packed, stream=copy_stream)
                 t = t_host.to(device, non_blocking=True)
             else:
                 s, t = to_device(s_host, t_host, device)
@@ -439,7 +488,33 @@ def main():
         prefetch()  # next step's inputs: the copy overlaps this step's compute
         loss.backward()
         net.zero_grad(set_to_none=True)  # (where optimizer.zero_grad() sits in a training loop: after the update, before logging)
-        return loss.item()  # D2H read of the step's result
+        # D2H read of the step's result, every step.  REFTR_B200_E2E_LAG=0: blocking read right here (engine_vg.py:53 style).  Default:
+        # the loss goes to pinned host memory asynchronously and is READ one step later, after the next step's forward has been
+        # enqueued (a logging lag of one iteration; the last one is read before the timed region closes) -- the GPU is not left idle
+        # while the host prepares the next step.
+        if lag_read:
+            prev = pending.pop("loss", None)
+            buf = loss_bufs[step_no[0] & 1]
+            buf.copy_(loss.detach(), non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            pending["loss"] = (buf, ev)
+            step_no[0] += 1
+            if prev is not None:
+                prev[1].synchronize()
+                return float(prev[0])
+            return None
+        return loss.item()
+
+    lag_read = os.environ.get("REFTR_B200_E2E_LAG", "1") != "0"
+    loss_bufs = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
+    step_no = [0]
+
+    def e2e_flush():
+        prev = pending.pop("loss", None)
+        if prev is not None:
+            prev[1].synchronize()
+            return float(prev[0])
 
     def barrier():
         if world > 1:
@@ -473,7 +548,21 @@ def main():
     clocks = sampler.summary()
     for _ in range(2):
         step_e2e()
-    win_e2e = sorted(timed(step_e2e, a.steps) for _ in range(max(1, a.windows)))
+    def timed_e2e():
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(a.steps):
+            step_e2e()
+        e2e_flush()   # the last step's loss is read inside the timed region too
+        e1.record()
+        barrier()
+        t_ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+        if world > 1:
+            torch.distributed.all_reduce(t_ms, op=torch.distributed.ReduceOp.MAX)
+        return t_ms.item()
+    e2e_flush()
+    win_e2e = sorted(timed_e2e() for _ in range(max(1, a.windows)))
     ms_e2e = win_e2e[len(win_e2e) // 2]
 
     # host-side cost of one step (diagnostic): time to enqueue a whole step without any sync, and time until the forward is enqueued
@@ -499,7 +588,8 @@ def main():
                e2e={"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / a.steps, "windows_ms_per_step": [round(w / a.steps, 4) for w in win_e2e],
                     "input": ("raw uint8 HWC images in pinned host memory -> one H2D -> rb_collate_u8 (normalise + pad + mask on the device), "
-                              "token ids / masks / targets as int64 / fp32") if use_u8 else "normalised fp32 batch in pinned host memory"},
+                              "token ids / masks / targets as int64 / fp32") if use_u8 else "normalised fp32 batch in pinned host memory",
+                    "loss_read": "every step's loss is copied to pinned host memory and read one step later (REFTR_B200_E2E_LAG=0: blocking read every step)" if lag_read else "blocking .item() every step"},
                windows_ms_per_step=[round(w / a.steps, 4) for w in win],
                gpu_launches=launches, clocks=clocks, host=host_ms)
     if a.impl == "stock-gpu":
@@ -572,6 +662,8 @@ def main():
             rate, threads, sec = oracle_cpu_rate(bs, 1, 1)
             out["cpu_baseline"] = {"value": rate, "unit": "samples/s", "cores": threads, "kind": "port",
                                    "sample": f"fp32 oracle fwd+loss+bwd, one {bs}-sample batch of the same workload after one warm-up batch, {threads} threads, {sec:.1f} s"}
+    if a.verify and world > 1 and a.impl == "ours":
+        out["verify"] = verify_data_parallel(model, net, crit, device, world, rank, a.workload)
     if rank == 0:
         print(json.dumps(out))
     if world > 1:

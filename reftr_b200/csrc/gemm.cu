@@ -75,6 +75,15 @@ struct GemmKParams {
   const float* row_scale;  // atomic only: row m of the result is multiplied by row_scale[m] (FrozenBN fold of a conv weight gradient)
   float out_scale;     // atomic only: multiplies everything that is accumulated
   uint32_t off_ones;   // 8 KB of 1.0 (the B operand of the bias-gradient MMA)
+  int cl;              // 1, or 2 = CTA pairs (cluster 2x1x1, tcgen05.mma.cta_group::2): a pair multiplies a 256 x bn tile; each CTA loads its
+                       // 128 rows of A and HALF of the B tile, the leader issues the MMAs, each CTA runs the epilogue of its own 128 rows.
+                       // The shared-memory fill per CTA and k-block shrinks from A + B to A + B/2 (these GEMMs are bound by
+                       // the bytes they can keep in flight, not by the tensor pipe)
+  int tiles_mp;        // cl == 2: pairs of row tiles
+  int bm;              // rows per tile: 128, or 256 ("tall" tiles, cl == 1 only): two 128-row MMAs per k-step share the B tile and
+                       // accumulate side by side in TMEM (no accumulator double buffering), so that the operand bytes pulled from L2
+                       // per FLOP drop by a third against 128 x 256 -- the chip-wide L2 -> SM throughput (~6300 B/clk) is what bounds the
+                       // long-K convolutions and weight gradients
   int debug;           // RB_GEMM_DEBUG (timing experiments only, results are wrong): 1 = no output stores, 4 = no epilogue math, 8 = no TMEM loads, 16 = no staging writes, 32 = no fence / barrier
 };
 
@@ -98,13 +107,19 @@ struct TileCoord {
   int m0, n0, z_tap, it_begin, n_it;
 };
 
-__device__ __forceinline__ TileCoord tile_coord(const GemmKParams& p, int t) {
+__device__ __forceinline__ TileCoord tile_coord(const GemmKParams& p, int t, int rank) {
   TileCoord c;
   const int tn = t % p.tiles_n;
   int rest = t / p.tiles_n;
-  const int tm = rest % p.tiles_m;
-  const int z = rest / p.tiles_m;
-  c.m0 = tm * BM;
+  int tm, z;
+  if (p.cl == 2) {  // t indexes PAIRS of row tiles; a row tile beyond tiles_m (odd tail) is all padding: loads read zeros, stores are clipped
+    tm = 2 * (rest % p.tiles_mp) + rank;
+    z = rest / p.tiles_mp;
+  } else {
+    tm = rest % p.tiles_m;
+    z = rest / p.tiles_m;
+  }
+  c.m0 = tm * p.bm;
   c.n0 = tn * p.bn;
   if (p.mode == 0) {
     c.z_tap = 0;
@@ -124,7 +139,9 @@ __device__ __forceinline__ TileCoord tile_coord(const GemmKParams& p, int t) {
 // EPI selects how much of the epilogue is compiled in (the full body is ~40 KB of SASS, which thrashes the instruction cache of
 // the 8 epilogue warps): 0 = every feature (linear layers: fp32 output / residual, dropout, ...); 1 = the convolution path
 // (16-bit output; bias, 16-bit residual, ReLU, ReLU-mask, border zeroing only); 2 = split-K atomic accumulation only.
-template <int MODE, int EPI>
+// CL = 1: one CTA per tile; CL = 2: CTA pairs (cluster 2x1x1, tcgen05 cta_group::2).  A compile-time parameter because a kernel that
+// contains cta_group::2 instructions can only be launched with an even cluster size.
+template <int MODE, int EPI, int CL>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
                  const __grid_constant__ CUtensorMap tmOut32, const __grid_constant__ CUtensorMap tmRes, const __grid_constant__ CUtensorMap tmRes32,
@@ -143,6 +160,12 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int bn = p.bn;
+  constexpr int cl = CL;
+  int rank = 0;
+  if constexpr (cl == 2) rank = static_cast<int>(cluster_ctarank());
+  const int nh = cl == 2 ? 1 : (p.bm >> 7);  // 128-row halves per tile
+  const int t_first = cl == 2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int t_step = cl == 2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
   const bool f_atomic = EPI == 2 ? true : (EPI == 1 ? false : p.atomic != 0);
   const bool f_res = EPI != 2 && p.has_res != 0, f_mask = EPI != 2 && p.has_mask != 0, f_res32 = EPI == 0 && p.has_res32 != 0;
   const bool f_out = EPI == 1 ? true : (EPI == 2 ? false : p.has_out != 0), f_out32 = EPI == 0 && p.has_out32 != 0;
@@ -152,12 +175,12 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < p.stages; ++s) {
-      mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
+      mbar_init(&full[s], 1);   // pairs: only the leader's is used; it collects the bytes of BOTH CTAs' loads
+      mbar_init(&empty[s], 1);  // pairs: the leader's commit arrives on both CTAs' barriers
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], 2 * TEAM_WARPS);
+      mbar_init(&acc_empty[s], cl * 2 * TEAM_WARPS);  // pairs: the leader's barrier counts the epilogue warps of both CTAs
     }
     for (int s = 0; s < MAX_EIN; ++s) {
       mbar_init(&ein_full[s], 1);
@@ -165,7 +188,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  if (warp == 1) {
+    if constexpr (cl == 2) tmem_alloc_cg2<512>(tmem_slot);
+    else tmem_alloc<512>(tmem_slot);
+  }
   // the bias is read by every epilogue thread for every chunk: a global (L1-thrashed) load there costs an L2 round trip per chunk
   float* sbias = reinterpret_cast<float*>(smem + p.off_bias);
   for (int i = threadIdx.x; i < p.bias_n; i += GEMM_THREADS) sbias[i] = i < p.N ? __ldg(p.bias + i) : 0.f;
@@ -178,17 +204,20 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (cl == 2) cluster_sync_all();  // the peer's barriers exist before anything is signalled on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     // ------------------------------------------------------------------------------------------ main-loop producer
     if (lane == 0) {
-      const uint32_t tx_bytes = p.stage_bytes;
+      const uint32_t tx_bytes = p.stage_bytes * static_cast<uint32_t>(cl);  // pairs: the leader's barrier expects both CTAs' stages
+      uint32_t lead_full0 = 0u;  // pairs: the LEADER's full barriers (shared::cluster address)
+      if constexpr (cl == 2) lead_full0 = mapa_u32(smem_u32(&full[0]), 0);
       int s = 0;         // ring position
       uint32_t ph = 0;   // ring phase
-      for (int t = blockIdx.x; t < p.tiles_total; t += gridDim.x) {
-        const TileCoord c = tile_coord(p, t);
+      for (int t = t_first; t < p.tiles_total; t += t_step) {
+        const TileCoord c = tile_coord(p, t, rank);
         // incremental (tap, k-block) counters: this single thread is instruction-bound, so no divisions in the loop
         int tap = 0, kc = 0;
         if (MODE == 0 && c.it_begin) { tap = c.it_begin / p.kblocks; kc = c.it_begin - tap * p.kblocks; }
@@ -197,12 +226,18 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int ra = (MODE == 1) ? p.a_rowoff[c.z_tap] : 0, rb = (MODE == 1) ? p.b_koff[c.z_tap] : 0;
         for (int k = 0; k < c.n_it; ++k) {
           mbar_wait(&empty[s], ph ^ 1);
-          mbar_expect_tx(&full[s], tx_bytes);
+          if (rank == 0) mbar_expect_tx(&full[s], tx_bytes);
           uint8_t* a_dst = smem + s * p.stage_bytes;
-          uint8_t* b_dst = a_dst + A_BYTES;
+          uint8_t* b_dst = a_dst + nh * A_BYTES;
           if (MODE == 0) {
-            tma_load_2d(a_dst, &tmA, &full[s], kc * BK, row_a);
-            tma_load_2d(b_dst, &tmB, &full[s], col_b + kc * BK, c.n0);
+            if constexpr (cl == 2) {
+              tma_load_2d_cg2(a_dst, &tmA, (lead_full0 + 8u * s), kc * BK, row_a);
+              tma_load_2d_cg2(b_dst, &tmB, (lead_full0 + 8u * s), col_b + kc * BK, c.n0 + rank * (bn >> 1));
+            } else {
+              tma_load_2d(a_dst, &tmA, &full[s], kc * BK, row_a);
+              if (nh == 2) tma_load_2d(a_dst + A_BYTES, &tmA, &full[s], kc * BK, row_a + BM);
+              tma_load_2d(b_dst, &tmB, &full[s], col_b + kc * BK, c.n0);
+            }
             if (++kc == p.kblocks) {
               kc = 0;
               ++tap;
@@ -210,9 +245,15 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               col_b = p.b_koff[tap & 15];
             }
           } else {
+            if constexpr (cl == 2) {
 #pragma unroll
-            for (int j = 0; j < BM / 64; ++j) tma_load_2d(a_dst + j * 8192, &tmA, &full[s], c.m0 + 64 * j, r0 + ra);
-            for (int j = 0; j < bn / 64; ++j) tma_load_2d(b_dst + j * 8192, &tmB, &full[s], c.n0 + 64 * j, r0 + rb);
+              for (int j = 0; j < BM / 64; ++j) tma_load_2d_cg2(a_dst + j * 8192, &tmA, (lead_full0 + 8u * s), c.m0 + 64 * j, r0 + ra);
+              const int nb = bn >> 7, nc0 = c.n0 + rank * (bn >> 1);  // this CTA's half of the B tile: nb boxes of 64 columns
+              for (int j = 0; j < nb; ++j) tma_load_2d_cg2(b_dst + j * 8192, &tmB, (lead_full0 + 8u * s), nc0 + 64 * j, r0 + rb);
+            } else {
+              for (int j = 0; j < nh * (BM / 64); ++j) tma_load_2d(a_dst + j * 8192, &tmA, &full[s], c.m0 + 64 * j, r0 + ra);
+              for (int j = 0; j < bn / 64; ++j) tma_load_2d(b_dst + j * 8192, &tmB, &full[s], c.n0 + 64 * j, r0 + rb);
+            }
             r0 += BK;
           }
           if (++s == p.stages) { s = 0; ph ^= 1; }
@@ -222,46 +263,57 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     __syncwarp();
   } else if (warp == 1) {
     // ------------------------------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_t(BM, bn, MODE, MODE);
+    if (lane == 0 && rank == 0) {  // pairs: the leader issues for both CTAs
       // The issuing thread is instruction-bound (one thread, dependent issue): descriptors are formed by ADDING 16-byte-unit
       // offsets to a base descriptor (the start-address field is the low 14 bits; shared memory is < 256 KB so no carry-out).
       const uint32_t smem_base = smem_u32(smem);
       const uint64_t a_desc0 = (MODE == 0) ? umma_smem_desc(smem_base, 16, 1024, SWZ_128B) : umma_smem_desc(smem_base, 8192, 1024, SWZ_128B);
-      const uint32_t stage_units = p.stage_bytes >> 4, b_units = A_BYTES >> 4;
+      const uint32_t stage_units = p.stage_bytes >> 4, b_units = static_cast<uint32_t>(nh * A_BYTES) >> 4;
       constexpr uint32_t kstep = (MODE == 0 ? 32 : 2048) >> 4;
-      const uint32_t idesc_cs = umma_idesc_t(BM, 16, 1, 1);
       const uint64_t ones_desc = a_desc0 + static_cast<uint64_t>(p.off_ones >> 4);
       int s = 0, tcount = 0;
       uint32_t ph = 0;
-      for (int t = blockIdx.x; t < p.tiles_total; t += gridDim.x) {
-        const TileCoord c = tile_coord(p, t);
-        if (c.n_it <= 0) continue;
-        const int as = tcount & 1;
-        mbar_wait(&acc_empty[as], ((tcount >> 1) & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * bn;
-        // bias gradient (TN): the tiles of the first column block also contract A against ones into 16 spare TMEM columns
-        const bool colsum = MODE == 1 && p.bias_grad != nullptr && c.n0 == 0 && c.z_tap == 0;
-        const uint32_t cs_tmem = tmem_base + 2 * bn + as * 16;
-        for (int k = 0; k < c.n_it; ++k) {
-          mbar_wait(&full[s], ph);
-          tc_fence_after();
-          const uint64_t ad = a_desc0 + static_cast<uint64_t>(s * stage_units);
-          const uint64_t bd = ad + b_units;
-          umma_f16_ss(d_tmem, ad, bd, idesc, k != 0);
-#pragma unroll
-          for (int kk = 1; kk < BK / 16; ++kk) umma_f16_ss(d_tmem, ad + kk * kstep, bd + kk * kstep, idesc, 1);
-          if (colsum) {
-#pragma unroll
-            for (int kk = 0; kk < BK / 16; ++kk) umma_f16_ss(cs_tmem, ad + kk * kstep, ones_desc + kk * kstep, idesc_cs, (k | kk) != 0);
-          }
-          umma_commit(&empty[s]);
-          if (++s == p.stages) { s = 0; ph ^= 1; }
-        }
-        umma_commit(&acc_full[as]);
-        ++tcount;
+      // the same loop twice (cta_group::1 / ::2) so that the per-MMA path carries no mode branch
+#define RB_MMA_LOOP(MMA, COMMIT, ROWS)                                                                                             \
+      {                                                                                                                            \
+        const uint32_t idesc = umma_idesc_t(ROWS, bn, MODE, MODE), idesc_cs = umma_idesc_t(ROWS, 16, 1, 1);                        \
+        for (int t = t_first; t < p.tiles_total; t += t_step) {                                                                    \
+          const TileCoord c = tile_coord(p, t, rank);                                                                              \
+          if (c.n_it <= 0) continue;                                                                                               \
+          /* tall tiles: both halves' accumulators fill TMEM side by side, ONE accumulator stage */                                \
+          const int as = nh == 2 ? 0 : (tcount & 1);                                                                               \
+          mbar_wait(&acc_empty[as], ((nh == 2 ? tcount : (tcount >> 1)) & 1) ^ 1);                                                 \
+          tc_fence_after();                                                                                                        \
+          const uint32_t d_tmem = tmem_base + as * bn;                                                                             \
+          /* bias gradient (TN): the tiles of the first column block also contract A against ones into 16 spare TMEM columns */    \
+          const bool colsum = MODE == 1 && p.bias_grad != nullptr && c.n0 == 0 && c.z_tap == 0;                                    \
+          const uint32_t cs_tmem = tmem_base + 2 * bn + as * 16;                                                                   \
+          for (int k = 0; k < c.n_it; ++k) {                                                                                       \
+            mbar_wait(&full[s], ph);                                                                                               \
+            tc_fence_after();                                                                                                      \
+            const uint64_t ad = a_desc0 + static_cast<uint64_t>(s * stage_units);                                                  \
+            const uint64_t bd = ad + b_units;                                                                                      \
+            MMA(d_tmem, ad, bd, idesc, k != 0);                                                                                    \
+            _Pragma("unroll") for (int kk = 1; kk < BK / 16; ++kk) MMA(d_tmem, ad + kk * kstep, bd + kk * kstep, idesc, 1);        \
+            if (nh == 2) {                                                                                                         \
+              const uint64_t ad2 = ad + (A_BYTES >> 4);                                                                            \
+              _Pragma("unroll") for (int kk = 0; kk < BK / 16; ++kk)                                                               \
+                  MMA(d_tmem + bn, ad2 + kk * kstep, bd + kk * kstep, idesc, (k | kk) != 0);                                       \
+            }                                                                                                                      \
+            if (colsum) {                                                                                                          \
+              _Pragma("unroll") for (int kk = 0; kk < BK / 16; ++kk)                                                               \
+                  MMA(cs_tmem, ad + kk * kstep, ones_desc + kk * kstep, idesc_cs, (k | kk) != 0);                                  \
+            }                                                                                                                      \
+            COMMIT(&empty[s]);                                                                                                     \
+            if (++s == p.stages) { s = 0; ph ^= 1; }                                                                               \
+          }                                                                                                                        \
+          COMMIT(&acc_full[as]);                                                                                                   \
+          ++tcount;                                                                                                                \
+        }                                                                                                                          \
       }
+      if constexpr (cl == 2) RB_MMA_LOOP(umma_f16_ss_cg2, umma_commit_cg2, 2 * BM)
+      else RB_MMA_LOOP(umma_f16_ss, umma_commit, BM)
+#undef RB_MMA_LOOP
     }
     __syncwarp();
   } else if (warp == EIN_WARP) {
@@ -269,21 +321,23 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0 && has_ein && !f_atomic) {
       const uint32_t tx = (f_res ? 16384u : 0u) + (f_mask ? 16384u : 0u) + (f_res32 ? 32768u : 0u);
       int g = 0;
-      for (int t = blockIdx.x; t < p.tiles_total; t += gridDim.x) {
-        const TileCoord c = tile_coord(p, t);
+      for (int t = t_first; t < p.tiles_total; t += t_step) {
+        const TileCoord c = tile_coord(p, t, rank);
         if (c.n_it <= 0) continue;
-        for (int ch = 0; ch < bn / 64; ++ch, ++g) {
-          const int col0 = c.n0 + ch * 64;
-          if (col0 >= p.N) { g += bn / 64 - ch; break; }
+        const int nch = bn / 64;
+        for (int cc = 0; cc < nh * nch; ++cc, ++g) {
+          const int sub = cc / nch, ch = cc - sub * nch;
+          const int col0 = c.n0 + ch * 64, m0s = c.m0 + sub * BM;
+          if (col0 >= p.N) { g += nch - ch - 1; cc += nch - ch - 1; continue; }
           const int s = g % p.ein_slots;
           mbar_wait(&ein_empty[s], ((g / p.ein_slots) & 1) ^ 1);
           mbar_expect_tx(&ein_full[s], tx);
           uint8_t* dst = smem + p.off_ein + s * p.ein_slot_bytes;
-          if (f_res) tma_load_2d(dst, &tmRes, &ein_full[s], col0, c.m0);
-          if (f_mask) tma_load_2d(dst + p.ein_off_mask, &tmMask, &ein_full[s], col0, c.m0);
+          if (f_res) tma_load_2d(dst, &tmRes, &ein_full[s], col0, m0s);
+          if (f_mask) tma_load_2d(dst + p.ein_off_mask, &tmMask, &ein_full[s], col0, m0s);
           if (f_res32) {
-            tma_load_2d(dst + p.ein_off_res32, &tmRes32, &ein_full[s], col0, c.m0);
-            tma_load_2d(dst + p.ein_off_res32 + 16384, &tmRes32, &ein_full[s], col0 + 32, c.m0);
+            tma_load_2d(dst + p.ein_off_res32, &tmRes32, &ein_full[s], col0, m0s);
+            tma_load_2d(dst + p.ein_off_res32 + 16384, &tmRes32, &ein_full[s], col0 + 32, m0s);
           }
         }
       }
@@ -306,21 +360,24 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const bool use_drop = EPI == 0 && p.drop.seed != nullptr;
     const uint32_t dkey = use_drop ? drop_key(p.drop) : 0u;
     int tcount = 0, g = 0, o = 0;
-    for (int t = blockIdx.x; t < p.tiles_total; t += gridDim.x) {
-      const TileCoord c = tile_coord(p, t);
+    for (int t = t_first; t < p.tiles_total; t += t_step) {
+      const TileCoord c = tile_coord(p, t, rank);
       if (c.n_it <= 0) continue;
-      const int as = tcount & 1;
-      const long long gm = static_cast<long long>(c.m0) + r;
-      const bool row_ok = gm < p.M;
-      const long long orow = gm + p.out_row_off;
-      const bool interior = row_ok && row_is_interior(p.geom, orow);
-      mbar_wait(&acc_full[as], (tcount >> 1) & 1);
+      const int as = nh == 2 ? 0 : (tcount & 1);
+      mbar_wait(&acc_full[as], (nh == 2 ? tcount : (tcount >> 1)) & 1);
       tc_fence_after();
+      const int nch = bn / 64;
 #pragma unroll 1
-      for (int ch = 0; ch < bn / 64; ++ch, ++g) {
-        const int col0 = c.n0 + ch * 64;
-        if (col0 >= p.N) { g += bn / 64 - ch; break; }
+      for (int cc = 0; cc < nh * nch; ++cc, ++g) {
+        const int sub = cc / nch, ch = cc - sub * nch;  // tall tiles: the second 128-row half follows the first, its accumulator bn columns further
+        const int col0 = c.n0 + ch * 64, m0s = c.m0 + sub * BM;
+        if (col0 >= p.N) { g += nch - ch - 1; cc += nch - ch - 1; continue; }
         if ((g & 1) != team) continue;
+        const uint32_t acc_col = static_cast<uint32_t>((nh == 2 ? sub : as) * bn);
+        const long long gm = static_cast<long long>(m0s) + r;
+        const bool row_ok = gm < p.M;
+        const long long orow = gm + p.out_row_off;
+        const bool interior = row_ok && row_is_interior(p.geom, orow);
         if (MODE == 1 && EPI == 2 && ch == 0 && p.bias_grad != nullptr && c.n0 == 0 && c.z_tap == 0) {
           uint32_t cs;
           tmem_ld_32x1(tmem_base + lane_addr + 2 * bn + as * 16, cs);
@@ -352,7 +409,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = static_cast<uint32_t>(r + j);
           } else {
-            tmem_ld_32x32(tmem_base + lane_addr + as * bn + ch * 64 + half * 32, v);
+            tmem_ld_32x32(tmem_base + lane_addr + acc_col + ch * 64 + half * 32, v);
             tmem_ld_wait();
           }
 #else
@@ -361,8 +418,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int j = 0; j < 32; ++j) vv[0][j] = vv[1][j] = static_cast<uint32_t>(r + j);  // (not a constant: keeps the math alive)
         } else {
-        tmem_ld_32x32(tmem_base + lane_addr + as * bn + ch * 64, vv[0]);
-        tmem_ld_32x32(tmem_base + lane_addr + as * bn + ch * 64 + 32, vv[1]);
+        tmem_ld_32x32(tmem_base + lane_addr + acc_col + ch * 64, vv[0]);
+        tmem_ld_32x32(tmem_base + lane_addr + acc_col + ch * 64 + 32, vv[1]);
         tmem_ld_wait();
         }
 #pragma unroll
@@ -516,10 +573,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (two_slots && store_thread && !(p.debug & 32)) tma_store_wait_read<0>();
         if (!(p.debug & 32)) named_bar_sync(1 + team, TEAM_WARPS * 32);
         if (store_thread && !(p.debug & 1)) {
-          if (f_out) tma_store_2d(&tmOut, oslot, col0, c.m0);
+          if (f_out) tma_store_2d(&tmOut, oslot, col0, m0s);
           if (f_out32) {
-            tma_store_2d(&tmOut32, oslot + p.out_off_f32, col0, c.m0);
-            if (col0 + 32 < p.N) tma_store_2d(&tmOut32, oslot + p.out_off_f32 + 16384, col0 + 32, c.m0);
+            tma_store_2d(&tmOut32, oslot + p.out_off_f32, col0, m0s);
+            if (col0 + 32 < p.N) tma_store_2d(&tmOut32, oslot + p.out_off_f32 + 16384, col0 + 32, m0s);
           }
           tma_store_commit();
         }
@@ -527,14 +584,25 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       // every TMEM read of this accumulator stage by this warp has completed (tcgen05.wait::ld): release it
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[as]);
+      if (lane == 0) {
+        if constexpr (cl == 2) {
+          if (rank == 0) mbar_arrive(&acc_empty[as]);
+          else mbar_arrive_cluster(mapa_u32(smem_u32(&acc_empty[as]), 0));  // pairs: the leader's MMA issuer waits for both CTAs' epilogues
+        } else {
+          mbar_arrive(&acc_empty[as]);
+        }
+      }
       ++tcount;
     }
     if (store_thread) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<512>(tmem_base);
+  if constexpr (cl == 2) cluster_sync_all();  // no CTA leaves while its peer may still signal its barriers / read its shared memory
+  if (warp == 1) {
+    if constexpr (cl == 2) tmem_dealloc_cg2<512>(tmem_base);
+    else tmem_dealloc<512>(tmem_base);
+  }
 }
 
 }  // namespace rb
@@ -558,28 +626,62 @@ static int pick_bn(int N, long long tiles_mz, long long k_iters, int nsm) {
   return best;
 }
 
+// Run-time model of one launch (clocks): the kernel is persistent with a static tile order, so it takes waves x (time of one tile); a
+// k-block of a tile costs max(MMA time, its operand bytes / the tile's share of the chip-wide L2 -> SM throughput) -- ~6300 B/clk
+// for the whole chip (measured: 128 x 128 tiles of the layer-3 3x3 convolution pull 32 KB per k-block in 795 clk on 148 SMs = 41 B/clk
+// per SM; the 128 x 256 weight-gradient tiles 48 KB in 1250 clk), i.e. the long-K GEMMs are bound by bytes per FLOP, which only a
+// larger tile lowers.  `overlap_epi`: the accumulator is double buffered (128-row tiles), so only part of the epilogue is exposed.
+static double tile_clocks(int bm, int bn, int cl, long long k_it, long long active, bool atomic_epi) {
+  // (the cap is per SM as much as chip-wide: a launch that leaves SMs idle does not speed up the busy ones -- 87 us against 53 us for
+  // the layer-2 3x3 weight gradient on 81 against 144 tiles)
+  double rate = 6300.0 / static_cast<double>(active < 1 ? 1 : active);
+  if (rate > 43.0) rate = 43.0;
+  const double mma = (bm / 128) * 2.0 * bn;
+  const double l2 = (bm + bn / cl) * 128.0 / rate;
+  const double epi = (bm / 128) * (bn / 64) * (atomic_epi ? 700.0 : 450.0);
+  return static_cast<double>(k_it) * (mma > l2 ? mma : l2) + (bm == 256 ? epi : 0.35 * epi) + 2500.0;
+}
+static double launch_clocks(int bm, int bn, int cl, long long tiles, long long k_it, int nsm, bool atomic_epi) {
+  const long long slots = cl == 2 ? nsm / 2 : nsm;
+  const long long full = tiles / slots, rem = tiles % slots;
+  double t = static_cast<double>(full) * tile_clocks(bm, bn, cl, k_it, nsm, atomic_epi);
+  if (rem) t += tile_clocks(bm, bn, cl, k_it, rem * cl, atomic_epi);
+  return t + 6000.0;  // launch, TMEM allocation, barrier setup, pipeline fill / drain
+}
+
 // Weight gradients (mode 1, split-K): tile width AND number of K splits together.  The kernel is persistent with a static tile
 // order, so its run time is waves x (time of one tile); a tile's time is its share of the L2 -> shared-memory operand stream
 // (k-blocks x (128 + bn) x 128 B: these GEMMs are bound by that stream) plus the atomic epilogue and a fixed
 // fill / drain cost.  Minimising that over (bn, splits) lands on single-wave configurations with 128..148 tiles instead of
 // e.g. 222 tiles in two half-empty waves.
-static void pick_tn(int M, int N, int taps, int kblocks, int nsm, bool no256, int fixed_bn, int* bn_out, int* splits_out) {
+static void pick_tn(int M, int N, int taps, int kblocks, int nsm, bool has_bias_grad, int fixed_bn, int cl_mode, int tall_mode, int* bn_out, int* splits_out,
+                    int* cl_out, int* bm_out) {
   const int cands[3] = {256, 128, 64};
   double best = 1e300;
-  *bn_out = 64; *splits_out = 1;
-  const long long tiles_m = (M + BM - 1) / BM;
-  for (int bn : cands) {
-    if (fixed_bn && bn != fixed_bn) continue;
-    if (!fixed_bn && ((bn >= 2 * N && bn > 64) || (no256 && bn == 256))) continue;
-    const long long base = tiles_m * ((N + bn - 1) / bn) * taps;
-    const int smax = kblocks / 2 > 1 ? (kblocks / 2 < 512 ? kblocks / 2 : 512) : 1;
-    for (int sp = 1; sp <= smax; ++sp) {
-      const long long tiles = base * sp;
-      const long long waves = (tiles + nsm - 1) / nsm;
-      const int k_it = (kblocks + sp - 1) / sp;
-      const double cost = static_cast<double>(waves) * (k_it * (128.0 + bn) * 0.125 + 1.5 * 0.5 * bn + 60.0);  // KB-equivalents
-      if (cost < best - 1e-9) { best = cost; *bn_out = bn; *splits_out = sp; }
-      if (waves > 4 && sp > 1) break;  // more splits only add waves from here on
+  *bn_out = 64; *splits_out = 1; *cl_out = 1; *bm_out = 128;
+  for (int bm = 128; bm <= 256; bm += 128) {
+    if (bm == 256 && (tall_mode == 0 || has_bias_grad || M <= 128)) continue;
+    const long long tiles_m = (M + bm - 1) / bm;
+    for (int bn : cands) {
+      if (fixed_bn && bn != fixed_bn) continue;
+      if (!fixed_bn && ((bn >= 2 * N && bn > 64) || (has_bias_grad && bn == 256))) continue;
+      for (int cl = 1; cl <= 2; ++cl) {  // cl_mode: 0 = never pairs, 1 = pairs wherever legal, 2 = by cost
+        const bool legal = bm == 128 && bn >= 128 && tiles_m >= 2;
+        if (cl == 2 && (!legal || cl_mode == 0)) continue;
+        if (cl == 1 && legal && cl_mode == 1) continue;
+        const long long base = (cl == 2 ? (tiles_m + 1) / 2 : tiles_m) * ((N + bn - 1) / bn) * taps;
+        const long long slots = cl == 2 ? nsm / 2 : nsm;
+        const int smax = kblocks / 2 > 1 ? (kblocks / 2 < 512 ? kblocks / 2 : 512) : 1;
+        for (int sp = 1; sp <= smax; ++sp) {
+          const long long tiles = base * sp;
+          const int k_it = (kblocks + sp - 1) / sp;
+          double cost = launch_clocks(bm, bn, cl, tiles, k_it, nsm, true);
+          if (cl == 2) cost *= 1.05;           // measured: pairs buy less than the byte count suggests (the peer's half crosses the same crossbar)
+          if (bm == 256 && tall_mode == 1) cost *= 0.5;  // RB_GEMM_TALL=1: tall tiles wherever legal (tests)
+          if (cost < best - 1e-9) { best = cost; *bn_out = bn; *splits_out = sp; *cl_out = cl; *bm_out = bm; }
+          if ((tiles + slots - 1) / slots > 4 && sp > 1) break;  // more splits only add waves from here on
+        }
+      }
     }
   }
 }
@@ -606,12 +708,19 @@ extern "C" int rb_gemm(const rb_gemm_args* a, void* stream) {
   memset(&kp, 0, sizeof(kp));
   kp.mode = a->mode;
   kp.M = a->M; kp.N = a->N; kp.taps = a->taps; kp.splits = a->splits < 1 ? 1 : a->splits;
-  int auto_bn = 0;
-  if (a->mode == 1 && a->atomic && a->splits <= 0) {  // splits <= 0: chosen here, together with the tile width
-    int bn_t = 0, sp_t = 1;
-    pick_tn(a->M, a->N, a->taps, (a->K + BK - 1) / BK, sm_count(), a->bias_grad != nullptr, a->block_n == 32 ? 64 : a->block_n, &bn_t, &sp_t);
+  int auto_bn = 0, auto_cl = 0, auto_bm = 0;
+  // RB_GEMM_CLUSTER: 0 = never use CTA pairs (cta_group::2), 1 = wherever legal, unset = by cost model
+  // RB_GEMM_TALL:    0 = never use 256-row tiles, 1 = wherever legal, unset = by cost model
+  static const int cl_mode = [] { const char* e = getenv("RB_GEMM_CLUSTER"); return e ? (atoi(e) ? 1 : 0) : 2; }();
+  static const int tall_mode = [] { const char* e = getenv("RB_GEMM_TALL"); return e ? (atoi(e) ? 1 : 0) : 2; }();
+  if (a->mode == 1 && a->atomic && a->splits <= 0) {  // splits <= 0: chosen here, together with the tile shape
+    int bn_t = 0, sp_t = 1, cl_t = 1, bm_t = 128;
+    pick_tn(a->M, a->N, a->taps, (a->K + BK - 1) / BK, sm_count(), a->bias_grad != nullptr, a->block_n == 32 ? 64 : a->block_n, cl_mode, tall_mode, &bn_t, &sp_t,
+            &cl_t, &bm_t);
     kp.splits = sp_t;
     auto_bn = bn_t;
+    auto_cl = cl_t;
+    auto_bm = bm_t;
   }
   for (int i = 0; i < 16; ++i) { kp.a_rowoff[i] = a->a_rowoff[i]; kp.b_koff[i] = a->b_koff[i]; }
   kp.out_row_off = a->out_row_off;
@@ -640,7 +749,7 @@ extern "C" int rb_gemm(const rb_gemm_args* a, void* stream) {
   }
   if (gemm_skinny_eligible(a) && !(getenv("RB_GEMM_NO_SKINNY"))) return gemm_skinny_launch(a, kp.drop, static_cast<int>(kp.drop_wpr), st);
   const int nsm = sm_count();
-  const long long tiles_m = (a->M + BM - 1) / BM;
+  long long tiles_m = (a->M + BM - 1) / BM;
   const long long k_iters = a->mode == 0 ? static_cast<long long>(a->taps) * kp.kblocks : (kp.kblocks + kp.splits - 1) / kp.splits;
   int bn = a->block_n ? a->block_n : (auto_bn ? auto_bn : pick_bn(a->N, tiles_m * (a->mode == 1 ? a->taps * kp.splits : 1), k_iters, nsm));
   // output/residual-dominated problems (short main loop + epilogue inputs): narrower tiles leave room for a deep input ring
@@ -648,10 +757,42 @@ extern "C" int rb_gemm(const rb_gemm_args* a, void* stream) {
   if (bn == 32) bn = 64;
   if (a->bias_grad && bn == 256) bn = 128;  // 2 x 16 TMEM columns for the bias-gradient accumulators next to 2 x bn
   if (bn != 64 && bn != 128 && bn != 256) return rb_fail("rb_gemm: unsupported block_n %d", bn);
+  // ---- 256-row tiles: long main loops only (the accumulator is not double buffered), never with the bias-gradient MMA --------------
+  kp.bm = BM;
+  if (auto_bm) {
+    kp.bm = auto_bm;
+  } else if (a->mode == 0 && tall_mode != 0 && !a->block_n && a->M > BM && k_iters >= 8 && !kp.drop.seed && !a->out32) {
+    // NT: compare the chosen 128-row shape with the tall candidates under the same model
+    const bool ein = a->res || a->res32 || a->mask_src;
+    double best = launch_clocks(BM, bn, 1, tiles_m * ((a->N + bn - 1) / bn), k_iters, nsm, false);
+    if (tall_mode == 1) best = 1e300;
+    const int tb[2] = {256, 128};
+    for (int b : tb) {
+      if (b >= 2 * a->N && b > 64) continue;
+      if (ein && b == 256) continue;  // epilogue inputs + 64 KB stages do not leave room for a useful ring
+      const long long tl = ((a->M + 255) / 256) * ((a->N + b - 1) / b);
+      const double c = launch_clocks(256, b, 1, tl, k_iters, nsm, false);
+      if (c < best) { best = c; kp.bm = 256; bn = b; }
+    }
+  }
+  if (kp.bm == 256) tiles_m = (a->M + 255) / 256;
   kp.bn = bn;
   kp.tiles_m = static_cast<int>(tiles_m);
   kp.tiles_n = (a->N + bn - 1) / bn;
-  const long long total = tiles_m * kp.tiles_n * (a->mode == 1 ? a->taps * kp.splits : 1);
+  // CTA pairs (cta_group::2): legal for bn >= 128 and at least two row tiles.  Weight gradients: decided by pick_tn's cost model;
+  // NT: wherever the main loop is long enough for the operand stream to matter (K per tile >= 256) and the padding of an odd last
+  // pair is small
+  kp.cl = 1;
+  {
+    const bool legal = kp.bm == BM && bn >= 128 && tiles_m >= 2 && nsm >= 2;
+    if (legal && cl_mode != 0) {
+      if (auto_cl) kp.cl = auto_cl;
+      else if (cl_mode == 1) kp.cl = 2;
+      // (NT, by default: no pairs -- measured neutral to slower on the convolution shapes, profiles/r02_gemm_pairs_tall.log)
+    }
+  }
+  kp.tiles_mp = static_cast<int>((tiles_m + 1) / 2);
+  const long long total = (kp.cl == 2 ? kp.tiles_mp : tiles_m) * kp.tiles_n * (a->mode == 1 ? a->taps * kp.splits : 1);
   if (total > 0x7fffffffLL) return rb_fail("rb_gemm: too many tiles");
   kp.tiles_total = static_cast<int>(total);
   if (a->atomic) {
@@ -661,7 +802,7 @@ extern "C" int rb_gemm(const rb_gemm_args* a, void* stream) {
     kp.has_res = a->res != nullptr; kp.has_res32 = a->res32 != nullptr; kp.has_mask = a->mask_src != nullptr;
   }
   // ---- shared-memory plan --------------------------------------------------------------------------------------
-  kp.stage_bytes = A_BYTES + bn * 128;
+  kp.stage_bytes = (kp.bm / BM) * A_BYTES + (bn / kp.cl) * 128;  // pairs: each CTA stages half of the B tile
   const bool has_ein = kp.has_res || kp.has_res32 || kp.has_mask;
   kp.ein_off_mask = kp.has_res ? 16384 : 0;
   kp.ein_off_res32 = kp.ein_off_mask + (kp.has_mask ? 16384 : 0);
@@ -679,7 +820,7 @@ extern "C" int rb_gemm(const rb_gemm_args* a, void* stream) {
   kp.ein_slots = 0;
   kp.out_slots = 2;
   for (int pass = 0; pass < 3 && stages < 2; ++pass) {
-    kp.out_slots = pass == 0 ? 2 : 1;  // second pass: one staging slot per team
+    kp.out_slots = (pass == 0 && kp.bm == BM) ? 2 : 1;  // second pass (and tall tiles): one staging slot per team
     if (pass == 2) {                   // third pass: the bias stays in global memory as well
       if (!kp.bias_n) break;
       kp.bias_n = 0;
@@ -716,7 +857,7 @@ extern "C" int rb_gemm(const rb_gemm_args* a, void* stream) {
   CUtensorMap tmA, tmB, tmOut, tmOut32, tmRes, tmRes32, tmMask;
   if (a->mode == 0) {
     if (make_tmap_2d(&tmA, a->A, static_cast<uint64_t>(a->a_cols), static_cast<uint64_t>(a->a_rows), a->lda * 2, 64, BM)) return 1;
-    if (make_tmap_2d(&tmB, a->B, static_cast<uint64_t>(a->b_cols), static_cast<uint64_t>(a->b_rows), a->ldb * 2, 64, bn)) return 1;
+    if (make_tmap_2d(&tmB, a->B, static_cast<uint64_t>(a->b_cols), static_cast<uint64_t>(a->b_rows), a->ldb * 2, 64, bn / kp.cl)) return 1;  // pairs: half a tile per CTA
   } else {
     if (make_tmap_2d(&tmA, a->A, static_cast<uint64_t>(a->a_cols), static_cast<uint64_t>(a->a_rows), a->lda * 2, 64, 64)) return 1;
     if (make_tmap_2d(&tmB, a->B, static_cast<uint64_t>(a->b_cols), static_cast<uint64_t>(a->b_rows), a->ldb * 2, 64, 64)) return 1;
@@ -729,19 +870,32 @@ extern "C" int rb_gemm(const rb_gemm_args* a, void* stream) {
   if (kp.has_res32 && make_tmap_2d_f32(&tmRes32, a->res32 + a->out_row_off * a->ldres32, N64, M64, a->ldres32 * 4, 32, BM)) return 1;
   if (kp.has_mask && make_tmap_2d(&tmMask, static_cast<const rb_t*>(a->mask_src) + a->out_row_off * a->ldmask, N64, M64, a->ldmask * 2, 64, BM)) return 1;
 
-  const int grid = kp.tiles_total < nsm ? kp.tiles_total : nsm;
+  const int slots = kp.cl == 2 ? nsm / 2 : nsm;
+  const int grid = kp.cl * (kp.tiles_total < slots ? kp.tiles_total : slots);
   const bool lean = !a->atomic && kp.has_out && !kp.has_out32 && !kp.has_res32 && !kp.drop.seed;
   const int epi = a->atomic ? 2 : (lean ? 1 : 0);
   typedef void (*KernelFn)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, GemmKParams);
-  static const KernelFn kernels[2][3] = {{umma_gemm_kernel<0, 0>, umma_gemm_kernel<0, 1>, umma_gemm_kernel<0, 2>},
-                                         {umma_gemm_kernel<1, 0>, umma_gemm_kernel<1, 1>, umma_gemm_kernel<1, 2>}};
-  static bool configured[2][3] = {{false, false, false}, {false, false, false}};
-  const KernelFn kern = kernels[a->mode][epi];
-  if (!configured[a->mode][epi]) {
+  static const KernelFn kernels[2][2][3] = {{{umma_gemm_kernel<0, 0, 1>, umma_gemm_kernel<0, 1, 1>, umma_gemm_kernel<0, 2, 1>},
+                                             {umma_gemm_kernel<1, 0, 1>, umma_gemm_kernel<1, 1, 1>, umma_gemm_kernel<1, 2, 1>}},
+                                            {{umma_gemm_kernel<0, 0, 2>, umma_gemm_kernel<0, 1, 2>, umma_gemm_kernel<0, 2, 2>},
+                                             {umma_gemm_kernel<1, 0, 2>, umma_gemm_kernel<1, 1, 2>, umma_gemm_kernel<1, 2, 2>}}};
+  static bool configured[2][2][3] = {};
+  const KernelFn kern = kernels[kp.cl - 1][a->mode][epi];
+  if (!configured[kp.cl - 1][a->mode][epi]) {
     RB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-    configured[a->mode][epi] = true;
+    configured[kp.cl - 1][a->mode][epi] = true;
   }
-  kern<<<grid, GEMM_THREADS, smem_bytes, st>>>(tmA, tmB, tmOut, tmOut32, tmRes, tmRes32, tmMask, kp);
+  if (kp.cl == 2) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    RB_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmOut, tmOut32, tmRes, tmRes32, tmMask, kp));
+  } else {
+    kern<<<grid, GEMM_THREADS, smem_bytes, st>>>(tmA, tmB, tmOut, tmOut32, tmRes, tmRes32, tmMask, kp);
+  }
   RB_CUDA(cudaGetLastError());
   return 0;
 }

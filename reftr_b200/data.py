@@ -27,6 +27,53 @@ class DeviceCollator:
         self._slots = [dict(pinned=None, table=None, event=None) for _ in range(self.N_SLOTS)]
         self._next = 0
 
+    @staticmethod
+    def pack(images):
+        """Host side of the collation, for the data-loader worker: the raw uint8 HWC images packed back to back into ONE pinned
+        buffer plus the (offset, h, w) table -- what ``upload`` ships.  Returns a ``PackedBatch``."""
+        B = len(images)
+        if B == 0 or any(im.dtype != torch.uint8 or im.dim() != 3 or im.shape[2] != 3 or not im.device.type == "cpu" for im in images):
+            raise ValueError("DeviceCollator.pack expects a non-empty list of host uint8 [h, w, 3] tensors")
+        total = sum(im.numel() for im in images)
+        cuda = torch.cuda.is_available()
+        buf = torch.empty(total, dtype=torch.uint8)
+        tab = torch.empty(B, 3, dtype=torch.int64)
+        if cuda:
+            buf, tab = buf.pin_memory(), tab.pin_memory()
+        off = 0
+        for b, im in enumerate(images):
+            n = im.numel()
+            buf[off:off + n].copy_(im.reshape(-1))
+            tab[b, 0], tab[b, 1], tab[b, 2] = off, im.shape[0], im.shape[1]
+            off += n
+        return PackedBatch(buf, tab, max(im.shape[0] for im in images), max(im.shape[1] for im in images))
+
+    def upload(self, packed, stream=None, consumer_stream=None):
+        """Device side: one H2D of the packed bytes (+ the table) and rb_collate_u8, on ``stream``.  ``packed`` (a ``PackedBatch``) owns
+        its pinned memory, so nothing here is reused across calls; the caller keeps ``packed`` alive until the returned
+        ``ImageList.ready`` event has passed (the bench keeps one batch for the whole run)."""
+        cuda = torch.cuda.is_available()
+        B = packed.table.shape[0]
+        consumer = consumer_stream if consumer_stream is not None else (torch.cuda.current_stream(self.device) if cuda else None)
+        ctx = torch.cuda.stream(stream) if stream is not None else _null()
+        with ctx:
+            dbuf = packed.buf.to(self.device, non_blocking=True)
+            dtab = packed.table.to(self.device, non_blocking=True)
+            out = torch.empty(B, 3, packed.H, packed.W, dtype=torch.float32, device=self.device)
+            mask = torch.empty(B, packed.H, packed.W, dtype=torch.bool, device=self.device)
+            ops.require_device(out)
+            ops.collate_u8(dbuf, dtab, B, packed.H, packed.W, self.mean, self.std, out, mask)
+            ready = None
+            if cuda:
+                ready = torch.cuda.Event()
+                ready.record()
+        if cuda and stream is not None and consumer is not None and consumer != stream:
+            for t in (out, mask):
+                t.record_stream(consumer)
+        res = ImageList(out, mask)
+        res.ready = ready
+        return res
+
     def __call__(self, images, stream=None, consumer_stream=None):
         """images: list of uint8 tensors [h_i, w_i, 3] on the host.  Returns ImageList(tensors fp32 [B,3,H,W], mask bool [B,H,W])
         on the device (the NestedTensor contract of util/misc.py:308-332).  The copies and the kernel are enqueued on ``stream``
@@ -81,6 +128,16 @@ class DeviceCollator:
         res = ImageList(out, mask)
         res.ready = ready  # consumer: torch.cuda.current_stream().wait_event(res.ready)
         return res
+
+
+class PackedBatch:
+    """Pinned host buffers of one collated batch: ``buf`` uint8 (all images back to back), ``table`` int64 [B, 3] = (offset, h, w)."""
+
+    def __init__(self, buf, table, H, W):
+        self.buf, self.table, self.H, self.W = buf, table, int(H), int(W)
+
+    def nbytes(self):
+        return self.buf.numel() + self.table.numel() * 8
 
 
 class _null:

@@ -194,6 +194,8 @@ class RefTREngine:
         after = [self.slots[n][0] for n, _ in self.named if not n.startswith("lang_backbone.") and bert_offs and self.slots[n][0] > bert_offs[0]]
         self._bert_slice = (min(bert_offs), min(after) if after else self.n_grad) if bert_offs else (0, 0)
         self._split_stream = None
+        self._comm_stream = None
+        self._bb_gy = None
         self._bw = None
         self.gflat = None
         self.ws = None
@@ -509,42 +511,94 @@ class RefTREngine:
                 torch.distributed.all_reduce(t)
                 t.mul_(1.0 / world)
 
+    def _split_plan(self):
+        """Parts of the split backward and the slices of the flat gradient buffer each one COMPLETES, in the order their all-reduces are
+        issued (identical on every rank).  The slots follow named_parameters(): img_backbone (layer2, layer3, layer4 -- conv1 / layer1 are
+        frozen and have no slot), lang_backbone, vl_transformer .. query_encoder, input_proj."""
+        def spans(pred):
+            """maximal runs of consecutive slots whose parameter name satisfies pred"""
+            runs = []
+            for n, p in self.named:
+                lo = self.slots[n][0]
+                hi = lo + _cdiv(p.numel(), 64) * 64
+                if pred(n):
+                    if runs and runs[-1][1] == lo:
+                        runs[-1] = (runs[-1][0], hi)
+                    else:
+                        runs.append((lo, hi))
+            return runs
+        b0, b1 = self._bert_slice
+        iproj = spans(lambda n: n.startswith("input_proj."))
+        rest = spans(lambda n: not n.startswith(("img_backbone.", "lang_backbone.", "input_proj.")))
+        plan = [("heads", rest)]
+        layers = sorted({b.layer for b in self.blocks if b.trainable}, reverse=True)
+        first = True
+        for li in layers:
+            sl = spans(lambda n, li=li: n.startswith(f"img_backbone.0.body.layer{li}."))
+            plan.append((f"bb:{li}", (iproj if first else []) + sl))
+            if first:
+                plan.append(("bert", [(b0, b1)] if b1 > b0 else []))
+            first = False
+        if not layers:  # frozen backbone: input_proj alone, then BERT
+            plan.append(("bb:0", iproj))
+            plan.append(("bert", [(b0, b1)] if b1 > b0 else []))
+        covered = sorted(sl for _, sls in plan for sl in sls)
+        pos = 0
+        for lo, hi in covered:  # every slot is handed over exactly once
+            assert lo == pos, (plan, pos)
+            pos = hi
+        assert pos == self.n_grad, (plan, pos, self.n_grad)
+        return plan
+
     def _run_backward_split(self, st, gl, gm, ga):
-        """Backward as THREE CUDA graphs so that the data-parallel exchange overlaps compute: the language backbone holds 72 % of
-        the gradient bytes (438 of 607 MB) and its backward finishes long before the conv backbone's, so its slice of the flat
-        gradient buffer is all-reduced on a second stream while the ResNet backward is still running; the rest follows at the end.
-        (One monolithic graph + one all-reduce after it left 1.2 ms of NVLink time exposed per step at 2..8 GPUs.)"""
-        S = self.grad_scale
+        """Backward as SEVERAL CUDA graphs so that the data-parallel exchange overlaps compute (one exchange step, 607 MB
+        of fp32 gradients).  Parts: heads + decoder + encoder | ResNet layer4 (+ input_proj) | BERT (on a second stream, next to the
+        ResNet) | layer3 | layer2.  As soon as a part has finished, its slice of the flat gradient buffer is handed over (scaled copy +
+        overflow check) and all-reduced on a communication stream while the following parts still compute; only layer2's 5 MB slice is
+        exchanged after the last kernel.  (Round 1 exchanged the whole non-BERT remainder, 169 MB, after the backbone: 1.85 ms exposed
+        per step at 8 GPUs.)  The all-reduces are issued in the same fixed order on every rank."""
         main = torch.cuda.current_stream()
         if self._split_stream is None:
             self._split_stream = torch.cuda.Stream(device=self._dev)
-        br = self._split_stream
+            self._comm_stream = torch.cuda.Stream(device=self._dev)
+        br, cs = self._split_stream, self._comm_stream
         if st.get("bwd3") is None:
-            graphs = []
-            for part in ("heads", "bert", "backbone"):
+            plan = self._split_plan()
+            graphs = {}
+            for part, _ in plan:
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
                     self.backward(gl, gm, ga, part=part)
-                graphs.append(g)
-            st["bwd3"] = graphs
-        gA, gB, gC = st["bwd3"]
-        b0, b1 = self._bert_slice
+                graphs[part] = g
+            st["bwd3"] = (plan, graphs)
+        plan, graphs = st["bwd3"]
         flat = torch.empty(self.n_grad, dtype=torch.float32, device=self._dev)
         flat.record_stream(br)
-        gA.replay()
-        ev = torch.cuda.Event()
-        ev.record(main)
-        br.wait_event(ev)
-        with torch.cuda.stream(br):
-            gB.replay()
-            self._handover(b0, b1, flat)   # fresh storage + undo the loss scale + overflow sentinel (as in run_backward)
-            self._allreduce_(flat[b0:b1])
-        gC.replay()
-        for lo, hi in ((0, b0), (b1, self.n_grad)):
-            if hi > lo:
-                self._handover(lo, hi, flat)
-                self._allreduce_(flat[lo:hi])
+        flat.record_stream(cs)
+
+        def exchange(after_stream, slices):
+            ev = torch.cuda.Event()
+            ev.record(after_stream)
+            cs.wait_event(ev)
+            with torch.cuda.stream(cs):
+                for lo, hi in slices:
+                    self._handover(lo, hi, flat)   # fresh storage + undo the loss scale + overflow sentinel (as in run_backward)
+                    self._allreduce_(flat[lo:hi])
+
+        bert_ev = None
+        for part, slices in plan:
+            if part == "bert":
+                ev = torch.cuda.Event()
+                ev.record(main)   # the heads part (which produced BERT's incoming gradient) precedes this point on the main stream
+                br.wait_event(ev)
+                with torch.cuda.stream(br):
+                    graphs[part].replay()
+                exchange(br, slices)
+            else:
+                graphs[part].replay()
+                exchange(main, slices)
         main.wait_stream(br)
+        main.wait_stream(cs)
         self._finish_guard(flat)
         st["nb"] += 1
         self.launches += st["bl"]
@@ -743,17 +797,21 @@ class RefTREngine:
                 feats[b.layer] = (x, g)
         return feats
 
-    def _backbone_bwd(self, gy, g_fpn):
-        """gy: masked gradient at the C5 output; g_fpn: {layer: unmasked bf16 gradient added at that layer's output}."""
+    def _backbone_bwd(self, gy, g_fpn, only_layer=None):
+        """gy: masked gradient at the output of the last block to process; g_fpn: {layer: unmasked bf16 gradient added at that layer's
+        output}.  ``only_layer``: process that ResNet layer's blocks only (split backward); returns the gradient for the layer below."""
         for b in reversed(self.blocks):
             if not b.trainable:
                 break
+            if only_layer is not None and b.layer != only_layer:
+                continue
             # a gradient arriving at a layer's output from the FPN adapters is injected where the NEXT layer's first
             # block forms its input gradient; that block is processed before this one, so look it up by layer index
             g_extra = g_fpn.get(b.layer - 1) if (b.ds is not None and b.need_gx) else None
             gy = self._block_bwd(b, gy, g_extra)
             if gy is None:
                 break
+        return gy
 
     # ------------------------------------------------------------------------------------------------------------
     # small fused pieces
@@ -1209,7 +1267,7 @@ class RefTREngine:
         ``part`` runs one third of the pass only (``_run_backward_split``: three CUDA graphs, so that the gradient all-reduce of
         the language backbone overlaps the conv backbone's backward): "heads" = box / mask heads, decoder, query encoder, encoder,
         map_sentence; "bert" = the language backbone; "backbone" = input_proj + ResNet.  None = everything, BERT on a branch."""
-        if part in ("bert", "backbone"):
+        if part is not None and part != "heads":
             return self._backward_tail(part)
         m = self.model
         ws = self.ws
@@ -1266,11 +1324,22 @@ class RefTREngine:
         return self._backward_tail(None)
 
     def _backward_tail(self, part):
+        """part None: everything after the heads (BERT on a branch stream); "bert": the language backbone only; "bb:<k>": the conv
+        backbone's layer k (the first such part also runs GroupNorm / input_proj backward and forms the gradient at C5)."""
         m = self.model
         ws = self.ws
         B, H, W, h, w, L, S, T, n_ph, n_q, native_bert, has_phrases = self.dims
         feats, c5, g5, pos32, kpm, mctx, qmask, proj32, gmean, grstd, mem32, memb, mempb, hs32, hsb, z0, z1 = self.saved["top"]
         g, g_src, g_fpn, d_sent, d_pooled = self._bw
+        if part is not None and part.startswith("bb:"):
+            layer = int(part[3:])
+            layers = sorted({b.layer for b in self.blocks if b.trainable}, reverse=True)
+            if not layers or layer == layers[0]:
+                self._bb_gy = self._iproj_bwd(g, g_src, g_fpn)
+            if layers and self._bb_gy is not None:
+                self._bb_gy = self._backbone_bwd(self._bb_gy, g_fpn, only_layer=layer)
+            self._join_side()
+            return None
         if native_bert and part in (None, "bert"):  # BERT's backward chain runs next to the backbone backward (independent of it)
             import contextlib
             with (self._branch() if part is None else contextlib.nullcontext()):
@@ -1282,17 +1351,29 @@ class RefTREngine:
         if part == "bert":
             self._join_side()
             return None
-        gn = m.input_proj[0][1]
-        dproj = ws.get("iproj.dx", [g5.R, D], zero=True)
-        ops.groupnorm_tokens_bwd(g, g_src, proj32, gn.weight, gmean, grstd, B, h, w, S, L, dproj, self.G(gn.weight), self.G(gn.bias))
-        self.wgrad_conv(self.iproj, dproj, c5, g5.R, bias=self.G(m.input_proj[0][0].bias))
-        if self.blocks[-1].trainable:
-            g5y = ws.get("iproj.gc5", [g5.R, 2048])
-            ops.gemm(dproj, self.iproj.wd, g5.R, 2048, D, res=g_fpn.get(4), mask_src=c5, out=g5y)
+        g5y = self._iproj_bwd(g, g_src, g_fpn)
+        if g5y is not None:
             self._backbone_bwd(g5y, g_fpn)
         self._join_branch()
         self._join_side()
         return d_sent.view(B, L, -1), d_pooled
+
+    def _iproj_bwd(self, g, g_src, g_fpn):
+        """GroupNorm + input_proj backward (reftr_transformer.py:172-175); returns the masked gradient at the C5 output, or None when
+        the backbone is frozen."""
+        m = self.model
+        ws = self.ws
+        B, H, W, h, w, L, S, T, n_ph, n_q, native_bert, has_phrases = self.dims
+        feats, c5, g5, pos32, kpm, mctx, qmask, proj32, gmean, grstd = self.saved["top"][:10]
+        gn = m.input_proj[0][1]
+        dproj = ws.get("iproj.dx", [g5.R, D], zero=True)
+        ops.groupnorm_tokens_bwd(g, g_src, proj32, gn.weight, gmean, grstd, B, h, w, S, L, dproj, self.G(gn.weight), self.G(gn.bias))
+        self.wgrad_conv(self.iproj, dproj, c5, g5.R, bias=self.G(m.input_proj[0][0].bias))
+        if not self.blocks[-1].trainable:
+            return None
+        g5y = ws.get("iproj.gc5", [g5.R, 2048])
+        ops.gemm(dproj, self.iproj.wd, g5.R, 2048, D, res=g_fpn.get(4), mask_src=c5, out=g5y)
+        return g5y
 
 
 class HotPathFunction(torch.autograd.Function):

@@ -26,6 +26,23 @@ def test_collate_u8_matches_reference_cpu_path(sizes):
     assert torch.equal(got.tensors.cpu(), ref.tensors)
 
 
+def test_pack_then_upload_matches_reference_cpu_path():
+    """The split form: DeviceCollator.pack in the loader worker (pinned host memory), DeviceCollator.upload on the copy stream."""
+    from data_ref import reference_collate
+    from reftr_b200.data import DeviceCollator
+    g = torch.Generator().manual_seed(11)
+    images = [torch.randint(0, 256, (h, w, 3), dtype=torch.uint8, generator=g) for h, w in [(480, 640), (640, 427), (64, 64)]]
+    ref = reference_collate(images)
+    packed = DeviceCollator.pack(images)
+    assert packed.buf.is_pinned() and packed.nbytes() == sum(im.numel() for im in images) + 3 * 3 * 8
+    side = torch.cuda.Stream()
+    col = DeviceCollator("cuda")
+    for _ in range(2):
+        got = col.upload(packed, stream=side)
+        torch.cuda.current_stream().wait_event(got.ready)
+        assert torch.equal(got.tensors.cpu(), ref.tensors) and torch.equal(got.mask.cpu(), ref.mask)
+
+
 def test_collator_staging_is_not_overwritten_while_a_copy_is_in_flight():
     """The host runs ahead of the GPU: batch i+1 (and i+2, which reuses batch i's pinned slot) is packed while the stream is still
     busy with earlier work.  Every batch must arrive intact."""

@@ -118,8 +118,8 @@ def test_missing_library_fails_loudly(monkeypatch):
 
 @pytest.mark.parametrize("name", ["cfg1_box", "multi_phrase"])
 def test_split_backward_graphs_match_single_graph(name, monkeypatch):
-    """The three-graph backward used under data parallelism (engine._run_backward_split: BERT's gradient slice is exchanged while
-    the conv backbone's backward still runs) must produce the gradients of the single-graph backward."""
+    """The multi-graph backward used under data parallelism (engine._run_backward_split: every part's gradient slice is exchanged while
+    the following parts still compute) must produce the gradients of the single-graph backward."""
     case = CASES[name]
     s = synthetic_samples(**case["inputs"], device="cuda")
 

@@ -317,3 +317,34 @@ def test_changing_requires_grad_after_the_first_forward_raises(emulated):
     _loss(cand(s), case).backward()
     assert all(p.grad is None for p in cand.lang_backbone.parameters())
     assert cand.bbox_embed.layers[0].weight.grad is not None
+
+
+@pytest.mark.parametrize("name", ["cfg1_box", "seg", "r101_box"])
+def test_split_backward_plan_partitions_the_flat_gradient(name):
+    """The data-parallel backward (engine._run_backward_split) exchanges the flat gradient buffer part by part; the plan's slices must
+    tile [0, n_grad) exactly once, each slice holding only parameters that the part completes."""
+    case = CASES[name]
+    if case["seg"] and not _have_seg():
+        pytest.skip("no seg head")
+    eng = build_candidate(case).engine()
+    plan = eng._split_plan()
+    assert [p for p, _ in plan][0] == "heads" and "bert" in [p for p, _ in plan]
+    slices = sorted(sl for _, sls in plan for sl in sls)
+    assert slices[0][0] == 0 and slices[-1][1] == eng.n_grad
+    assert all(a[1] == b[0] for a, b in zip(slices, slices[1:]))
+    owner = {}
+    for part, sls in plan:
+        for lo, hi in sls:
+            for n, _ in eng.named:
+                if lo <= eng.slots[n][0] < hi:
+                    owner[n] = part
+    assert len(owner) == len(eng.named)
+    for n, part in owner.items():
+        if n.startswith("lang_backbone."):
+            assert part == "bert", n
+        elif n.startswith("img_backbone."):
+            assert part == "bb:" + n.split("layer")[1][0], (n, part)
+        elif n.startswith("input_proj."):
+            assert part.startswith("bb:"), n
+        else:
+            assert part == "heads", (n, part)
