@@ -653,10 +653,10 @@ def main():
             if ns.get("encoder_mha"):
                 out["encoder_mha"] = dict(ns["encoder_mha"], source=f"{ns['file']} sha256 {ns['file_sha256']}", lib_sha256_capture=ns.get("lib_sha256"),
                                           lib_sha256_now=ns.get("lib_sha256_now"), stale=ns.get("stale"))
-        if world == 1 and a.workload == "cfg2" and os.environ.get("REFTR_B200_BENCH_OPTIM", "1") == "1":
-            out["next_rows"] = {"N3_optimizer_step": optimizer_diag(model, step_resident, device)}
         if world == 1 and a.workload == "cfg2" and os.environ.get("REFTR_B200_BENCH_STOCK", "1") == "1":
             out.update(stock_and_parity(model, s_dev, t_dev, device, value))
+        if world == 1 and a.workload == "cfg2" and os.environ.get("REFTR_B200_BENCH_OPTIM", "1") == "1":
+            out["next_rows"] = {"N3_optimizer_step": optimizer_diag(model, step_resident, device)}
         if rank == 0 and a.gpus == 1 and not a.no_cpu_baseline:
             bs = 8
             rate, threads, sec = oracle_cpu_rate(bs, 1, 1)

@@ -24,6 +24,14 @@ constexpr int ATC_ROWS = 128;  // rows (queries, or keys in the dKV kernel) per 
 constexpr int ATC_BLK = 64;    // columns (keys, or queries in the dKV kernel) per block
 constexpr int ATC_DH = 32;
 constexpr int ATC_MAXBLK = 64;  // up to 4096 columns
+// resident CTAs per SM the register allocation is held to (these kernels are latency chains MMA -> softmax -> MMA: other CTAs on the SM
+// are what hides them; un-bounded, ptxas took 119 registers for the forward = 2 CTAs and 185 for dK/dV = ONE CTA, i.e. 6 warps per SM)
+#ifndef ATC_FWD_CTAS
+#define ATC_FWD_CTAS 3
+#endif
+#ifndef ATC_DKV_CTAS
+#define ATC_DKV_CTAS 2
+#endif
 
 __device__ __forceinline__ float ex2(float x) {
   float y;
@@ -118,7 +126,7 @@ __device__ __forceinline__ void atc_init(const AtcSmem& s, int warp, int tmem_co
 // =====================================================================================================================
 // forward
 // =====================================================================================================================
-__global__ void __launch_bounds__(ATC_THREADS)
+__global__ void __launch_bounds__(ATC_THREADS, ATC_FWD_CTAS)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                    const uint8_t* __restrict__ kpm, rb_t* __restrict__ O, float* __restrict__ LSE, int H, int Tq, int Sk, long long ldo,
                    float scale, DropK drop) {
@@ -418,7 +426,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 // =====================================================================================================================
 // backward: dK, dV  (rows of the CTA = 128 keys; blocks = 64 queries)
 // =====================================================================================================================
-__global__ void __launch_bounds__(ATC_THREADS)
+__global__ void __launch_bounds__(ATC_THREADS, ATC_DKV_CTAS)
 attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                        const __grid_constant__ CUtensorMap tmdO, const uint8_t* __restrict__ kpm, const float* __restrict__ LSE,
                        const float* __restrict__ Dbuf, rb_t* __restrict__ dK, rb_t* __restrict__ dV, int H, int Tq, int Sk, long long lddk,

@@ -107,19 +107,20 @@ struct TileCoord {
   int m0, n0, z_tap, it_begin, n_it;
 };
 
+template <int CL, int NH>
 __device__ __forceinline__ TileCoord tile_coord(const GemmKParams& p, int t, int rank) {
   TileCoord c;
   const int tn = t % p.tiles_n;
   int rest = t / p.tiles_n;
   int tm, z;
-  if (p.cl == 2) {  // t indexes PAIRS of row tiles; a row tile beyond tiles_m (odd tail) is all padding: loads read zeros, stores are clipped
+  if constexpr (CL == 2) {  // t indexes PAIRS of row tiles; a row tile beyond tiles_m (odd tail) is all padding: loads read zeros, stores are clipped
     tm = 2 * (rest % p.tiles_mp) + rank;
     z = rest / p.tiles_mp;
   } else {
     tm = rest % p.tiles_m;
     z = rest / p.tiles_m;
   }
-  c.m0 = tm * p.bm;
+  c.m0 = tm * (NH * BM);
   c.n0 = tn * p.bn;
   if (p.mode == 0) {
     c.z_tap = 0;
@@ -141,7 +142,8 @@ __device__ __forceinline__ TileCoord tile_coord(const GemmKParams& p, int t, int
 // (16-bit output; bias, 16-bit residual, ReLU, ReLU-mask, border zeroing only); 2 = split-K atomic accumulation only.
 // CL = 1: one CTA per tile; CL = 2: CTA pairs (cluster 2x1x1, tcgen05 cta_group::2).  A compile-time parameter because a kernel that
 // contains cta_group::2 instructions can only be launched with an even cluster size.
-template <int MODE, int EPI, int CL>
+// NH = 128-row halves per tile: 1, or 2 = "tall" 256-row tiles (instantiated for the convolution path <0, 1, 1, 2> only).
+template <int MODE, int EPI, int CL, int NH>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
                  const __grid_constant__ CUtensorMap tmOut32, const __grid_constant__ CUtensorMap tmRes, const __grid_constant__ CUtensorMap tmRes32,
@@ -163,9 +165,12 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   constexpr int cl = CL;
   int rank = 0;
   if constexpr (cl == 2) rank = static_cast<int>(cluster_ctarank());
-  const int nh = cl == 2 ? 1 : (p.bm >> 7);  // 128-row halves per tile
-  const int t_first = cl == 2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
-  const int t_step = cl == 2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  constexpr int nh = NH;  // 128-row halves per tile
+  // (read blockIdx / gridDim at every tile loop instead of keeping them in variables: the compiler then proves the loop counters of the
+  // single-thread roles warp-uniform and keeps the MMA descriptors in uniform registers; held in a vector register they cost an
+  // ELECT + R2UR.BROADCAST waterfall per tcgen05.mma -- 10 % of the whole kernel, profiles/r02_gemm_uniform_regression.log)
+#define RB_T_FIRST (cl == 2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x))
+#define RB_T_STEP (cl == 2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x))
   const bool f_atomic = EPI == 2 ? true : (EPI == 1 ? false : p.atomic != 0);
   const bool f_res = EPI != 2 && p.has_res != 0, f_mask = EPI != 2 && p.has_mask != 0, f_res32 = EPI == 0 && p.has_res32 != 0;
   const bool f_out = EPI == 1 ? true : (EPI == 2 ? false : p.has_out != 0), f_out32 = EPI == 0 && p.has_out32 != 0;
@@ -216,8 +221,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if constexpr (cl == 2) lead_full0 = mapa_u32(smem_u32(&full[0]), 0);
       int s = 0;         // ring position
       uint32_t ph = 0;   // ring phase
-      for (int t = t_first; t < p.tiles_total; t += t_step) {
-        const TileCoord c = tile_coord(p, t, rank);
+      for (int t = RB_T_FIRST; t < p.tiles_total; t += RB_T_STEP) {
+        const TileCoord c = tile_coord<CL, NH>(p, t, rank);
         // incremental (tap, k-block) counters: this single thread is instruction-bound, so no divisions in the loop
         int tap = 0, kc = 0;
         if (MODE == 0 && c.it_begin) { tap = c.it_begin / p.kblocks; kc = c.it_begin - tap * p.kblocks; }
@@ -277,8 +282,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #define RB_MMA_LOOP(MMA, COMMIT, ROWS)                                                                                             \
       {                                                                                                                            \
         const uint32_t idesc = umma_idesc_t(ROWS, bn, MODE, MODE), idesc_cs = umma_idesc_t(ROWS, 16, 1, 1);                        \
-        for (int t = t_first; t < p.tiles_total; t += t_step) {                                                                    \
-          const TileCoord c = tile_coord(p, t, rank);                                                                              \
+        for (int t = RB_T_FIRST; t < p.tiles_total; t += RB_T_STEP) {                                                                    \
+          const TileCoord c = tile_coord<CL, NH>(p, t, rank);                                                                              \
           if (c.n_it <= 0) continue;                                                                                               \
           /* tall tiles: both halves' accumulators fill TMEM side by side, ONE accumulator stage */                                \
           const int as = nh == 2 ? 0 : (tcount & 1);                                                                               \
@@ -321,14 +326,14 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0 && has_ein && !f_atomic) {
       const uint32_t tx = (f_res ? 16384u : 0u) + (f_mask ? 16384u : 0u) + (f_res32 ? 32768u : 0u);
       int g = 0;
-      for (int t = t_first; t < p.tiles_total; t += t_step) {
-        const TileCoord c = tile_coord(p, t, rank);
+      for (int t = RB_T_FIRST; t < p.tiles_total; t += RB_T_STEP) {
+        const TileCoord c = tile_coord<CL, NH>(p, t, rank);
         if (c.n_it <= 0) continue;
-        const int nch = bn / 64;
-        for (int cc = 0; cc < nh * nch; ++cc, ++g) {
-          const int sub = cc / nch, ch = cc - sub * nch;
-          const int col0 = c.n0 + ch * 64, m0s = c.m0 + sub * BM;
-          if (col0 >= p.N) { g += nch - ch - 1; cc += nch - ch - 1; continue; }
+        for (int sub = 0; sub < nh; ++sub) {
+        const int m0s = c.m0 + sub * BM;
+        for (int ch = 0; ch < bn / 64; ++ch, ++g) {
+          const int col0 = c.n0 + ch * 64;
+          if (col0 >= p.N) { g += bn / 64 - ch; break; }
           const int s = g % p.ein_slots;
           mbar_wait(&ein_empty[s], ((g / p.ein_slots) & 1) ^ 1);
           mbar_expect_tx(&ein_full[s], tx);
@@ -339,6 +344,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tma_load_2d(dst + p.ein_off_res32, &tmRes32, &ein_full[s], col0, m0s);
             tma_load_2d(dst + p.ein_off_res32 + 16384, &tmRes32, &ein_full[s], col0 + 32, m0s);
           }
+        }
         }
       }
     }
@@ -360,24 +366,24 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const bool use_drop = EPI == 0 && p.drop.seed != nullptr;
     const uint32_t dkey = use_drop ? drop_key(p.drop) : 0u;
     int tcount = 0, g = 0, o = 0;
-    for (int t = t_first; t < p.tiles_total; t += t_step) {
-      const TileCoord c = tile_coord(p, t, rank);
+    for (int t = RB_T_FIRST; t < p.tiles_total; t += RB_T_STEP) {
+      const TileCoord c = tile_coord<CL, NH>(p, t, rank);
       if (c.n_it <= 0) continue;
       const int as = nh == 2 ? 0 : (tcount & 1);
       mbar_wait(&acc_full[as], (nh == 2 ? tcount : (tcount >> 1)) & 1);
       tc_fence_after();
-      const int nch = bn / 64;
+      for (int sub = 0; sub < nh; ++sub) {  // tall tiles: the second 128-row half follows the first, its accumulator bn columns further
+      const int m0s = c.m0 + sub * BM;
+      const uint32_t acc_col = static_cast<uint32_t>((nh == 2 ? sub : as) * bn);
+      const long long gm = static_cast<long long>(m0s) + r;
+      const bool row_ok = gm < p.M;
+      const long long orow = gm + p.out_row_off;
+      const bool interior = row_ok && row_is_interior(p.geom, orow);
 #pragma unroll 1
-      for (int cc = 0; cc < nh * nch; ++cc, ++g) {
-        const int sub = cc / nch, ch = cc - sub * nch;  // tall tiles: the second 128-row half follows the first, its accumulator bn columns further
-        const int col0 = c.n0 + ch * 64, m0s = c.m0 + sub * BM;
-        if (col0 >= p.N) { g += nch - ch - 1; cc += nch - ch - 1; continue; }
+      for (int ch = 0; ch < bn / 64; ++ch, ++g) {
+        const int col0 = c.n0 + ch * 64;
+        if (col0 >= p.N) { g += bn / 64 - ch; break; }
         if ((g & 1) != team) continue;
-        const uint32_t acc_col = static_cast<uint32_t>((nh == 2 ? sub : as) * bn);
-        const long long gm = static_cast<long long>(m0s) + r;
-        const bool row_ok = gm < p.M;
-        const long long orow = gm + p.out_row_off;
-        const bool interior = row_ok && row_is_interior(p.geom, orow);
         if (MODE == 1 && EPI == 2 && ch == 0 && p.bias_grad != nullptr && c.n0 == 0 && c.z_tap == 0) {
           uint32_t cs;
           tmem_ld_32x1(tmem_base + lane_addr + 2 * bn + as * 16, cs);
@@ -581,6 +587,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           tma_store_commit();
         }
       }
+      }
       // every TMEM read of this accumulator stage by this warp has completed (tcgen05.wait::ld): release it
       tc_fence_before();
       __syncwarp();
@@ -654,33 +661,29 @@ static double launch_clocks(int bm, int bn, int cl, long long tiles, long long k
 // (k-blocks x (128 + bn) x 128 B: these GEMMs are bound by that stream) plus the atomic epilogue and a fixed
 // fill / drain cost.  Minimising that over (bn, splits) lands on single-wave configurations with 128..148 tiles instead of
 // e.g. 222 tiles in two half-empty waves.
-static void pick_tn(int M, int N, int taps, int kblocks, int nsm, bool has_bias_grad, int fixed_bn, int cl_mode, int tall_mode, int* bn_out, int* splits_out,
-                    int* cl_out, int* bm_out) {
+static void pick_tn(int M, int N, int taps, int kblocks, int nsm, bool has_bias_grad, int fixed_bn, int cl_mode, int* bn_out, int* splits_out, int* cl_out) {
   const int cands[3] = {256, 128, 64};
   double best = 1e300;
-  *bn_out = 64; *splits_out = 1; *cl_out = 1; *bm_out = 128;
-  for (int bm = 128; bm <= 256; bm += 128) {
-    if (bm == 256 && (tall_mode == 0 || has_bias_grad || M <= 128)) continue;
-    const long long tiles_m = (M + bm - 1) / bm;
-    for (int bn : cands) {
-      if (fixed_bn && bn != fixed_bn) continue;
-      if (!fixed_bn && ((bn >= 2 * N && bn > 64) || (has_bias_grad && bn == 256))) continue;
-      for (int cl = 1; cl <= 2; ++cl) {  // cl_mode: 0 = never pairs, 1 = pairs wherever legal, 2 = by cost
-        const bool legal = bm == 128 && bn >= 128 && tiles_m >= 2;
-        if (cl == 2 && (!legal || cl_mode == 0)) continue;
-        if (cl == 1 && legal && cl_mode == 1) continue;
-        const long long base = (cl == 2 ? (tiles_m + 1) / 2 : tiles_m) * ((N + bn - 1) / bn) * taps;
-        const long long slots = cl == 2 ? nsm / 2 : nsm;
-        const int smax = kblocks / 2 > 1 ? (kblocks / 2 < 512 ? kblocks / 2 : 512) : 1;
-        for (int sp = 1; sp <= smax; ++sp) {
-          const long long tiles = base * sp;
-          const int k_it = (kblocks + sp - 1) / sp;
-          double cost = launch_clocks(bm, bn, cl, tiles, k_it, nsm, true);
-          if (cl == 2) cost *= 1.05;           // measured: pairs buy less than the byte count suggests (the peer's half crosses the same crossbar)
-          if (bm == 256 && tall_mode == 1) cost *= 0.5;  // RB_GEMM_TALL=1: tall tiles wherever legal (tests)
-          if (cost < best - 1e-9) { best = cost; *bn_out = bn; *splits_out = sp; *cl_out = cl; *bm_out = bm; }
-          if ((tiles + slots - 1) / slots > 4 && sp > 1) break;  // more splits only add waves from here on
-        }
+  *bn_out = 64; *splits_out = 1; *cl_out = 1;
+  const long long tiles_m = (M + BM - 1) / BM;
+  for (int bn : cands) {
+    if (fixed_bn && bn != fixed_bn) continue;
+    if (!fixed_bn && ((bn >= 2 * N && bn > 64) || (has_bias_grad && bn == 256))) continue;
+    for (int cl = 1; cl <= 2; ++cl) {  // cl_mode: 0 = never pairs, 1 = pairs wherever legal
+      const bool legal = bn >= 128 && tiles_m >= 2;
+      if (cl == 2 && (!legal || cl_mode == 0)) continue;
+      if (cl == 1 && legal && cl_mode == 1) continue;
+      const long long base = (cl == 2 ? (tiles_m + 1) / 2 : tiles_m) * ((N + bn - 1) / bn) * taps;
+      const long long slots = cl == 2 ? nsm / 2 : nsm;
+      const int smax = kblocks / 2 > 1 ? (kblocks / 2 < 512 ? kblocks / 2 : 512) : 1;
+      for (int sp = 1; sp <= smax; ++sp) {
+        const long long tiles = base * sp;
+        const long long waves = (tiles + slots - 1) / slots;
+        const int k_it = (kblocks + sp - 1) / sp;
+        // per CTA and k-block: A (128 columns) + its share of B, 128 B per column; + the atomic epilogue and a fixed fill / drain cost
+        const double cost = static_cast<double>(waves) * (k_it * (128.0 + bn / cl) * 0.125 + 1.5 * 0.5 * bn + 60.0);  // KB-equivalents
+        if (cost < best - 1e-9) { best = cost; *bn_out = bn; *splits_out = sp; *cl_out = cl; }
+        if (waves > 4 && sp > 1) break;  // more splits only add waves from here on
       }
     }
   }
@@ -711,16 +714,26 @@ extern "C" int rb_gemm(const rb_gemm_args* a, void* stream) {
   int auto_bn = 0, auto_cl = 0, auto_bm = 0;
   // RB_GEMM_CLUSTER: 0 = never use CTA pairs (cta_group::2), 1 = wherever legal, unset = by cost model
   // RB_GEMM_TALL:    0 = never use 256-row tiles, 1 = wherever legal, unset = by cost model
-  static const int cl_mode = [] { const char* e = getenv("RB_GEMM_CLUSTER"); return e ? (atoi(e) ? 1 : 0) : 2; }();
-  static const int tall_mode = [] { const char* e = getenv("RB_GEMM_TALL"); return e ? (atoi(e) ? 1 : 0) : 2; }();
+  // RB_GEMM_CLUSTER: 0 = never use CTA pairs (cta_group::2), 1 = wherever legal, unset = where they measured faster (below)
+  // RB_GEMM_TALL:    1 = 256-row tiles wherever legal (experiments), otherwise never
+  // Measured on the step's shapes (profiles/r02_gemm_pairs_tall.log, same box, CUDA events): pairs take 8..9 % off the 3x3 weight
+  // gradients and 12 % off the long-K input gradients whose only epilogue input is the ReLU mask, are neutral on the 1x1 weight
+  // gradients and up to 1.8x SLOWER on output-heavy 1x1 convolutions (the leader's MMA waits for both CTAs' epilogues); tall tiles
+  // are neutral to 6 % slower everywhere (no accumulator double buffering) -- a measured dead end, kept behind the switch.
+  static const int cl_env = [] { const char* e = getenv("RB_GEMM_CLUSTER"); return e ? (atoi(e) ? 1 : 0) : 2; }();
+  static const int tall_mode = [] { const char* e = getenv("RB_GEMM_TALL"); return (e && atoi(e)) ? 1 : 0; }();
+  int cl_mode = cl_env;
+  if (cl_env == 2) {
+    const int kb = (a->K + BK - 1) / BK;
+    if (a->mode == 1) cl_mode = a->taps >= 9 ? 1 : 0;
+    else cl_mode = (a->taps == 1 && kb >= 16 && a->mask_src && !a->res && !a->res32 && !a->out32) ? 1 : 0;
+  }
   if (a->mode == 1 && a->atomic && a->splits <= 0) {  // splits <= 0: chosen here, together with the tile shape
-    int bn_t = 0, sp_t = 1, cl_t = 1, bm_t = 128;
-    pick_tn(a->M, a->N, a->taps, (a->K + BK - 1) / BK, sm_count(), a->bias_grad != nullptr, a->block_n == 32 ? 64 : a->block_n, cl_mode, tall_mode, &bn_t, &sp_t,
-            &cl_t, &bm_t);
+    int bn_t = 0, sp_t = 1, cl_t = 1;
+    pick_tn(a->M, a->N, a->taps, (a->K + BK - 1) / BK, sm_count(), a->bias_grad != nullptr, a->block_n == 32 ? 64 : a->block_n, cl_mode, &bn_t, &sp_t, &cl_t);
     kp.splits = sp_t;
     auto_bn = bn_t;
     auto_cl = cl_t;
-    auto_bm = bm_t;
   }
   for (int i = 0; i < 16; ++i) { kp.a_rowoff[i] = a->a_rowoff[i]; kp.b_koff[i] = a->b_koff[i]; }
   kp.out_row_off = a->out_row_off;
@@ -761,7 +774,7 @@ extern "C" int rb_gemm(const rb_gemm_args* a, void* stream) {
   kp.bm = BM;
   if (auto_bm) {
     kp.bm = auto_bm;
-  } else if (a->mode == 0 && tall_mode != 0 && !a->block_n && a->M > BM && k_iters >= 8 && !kp.drop.seed && !a->out32) {
+  } else if (a->mode == 0 && tall_mode != 0 && !a->block_n && a->M > BM && k_iters >= 8 && !kp.drop.seed && !a->out32 && !a->res32 && a->out && !a->atomic) {
     // NT: compare the chosen 128-row shape with the tall candidates under the same model
     const bool ein = a->res || a->res32 || a->mask_src;
     double best = launch_clocks(BM, bn, 1, tiles_m * ((a->N + bn - 1) / bn), k_iters, nsm, false);
@@ -875,13 +888,21 @@ extern "C" int rb_gemm(const rb_gemm_args* a, void* stream) {
   const bool lean = !a->atomic && kp.has_out && !kp.has_out32 && !kp.has_res32 && !kp.drop.seed;
   const int epi = a->atomic ? 2 : (lean ? 1 : 0);
   typedef void (*KernelFn)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, GemmKParams);
-  static const KernelFn kernels[2][2][3] = {{{umma_gemm_kernel<0, 0, 1>, umma_gemm_kernel<0, 1, 1>, umma_gemm_kernel<0, 2, 1>},
-                                             {umma_gemm_kernel<1, 0, 1>, umma_gemm_kernel<1, 1, 1>, umma_gemm_kernel<1, 2, 1>}},
-                                            {{umma_gemm_kernel<0, 0, 2>, umma_gemm_kernel<0, 1, 2>, umma_gemm_kernel<0, 2, 2>},
-                                             {umma_gemm_kernel<1, 0, 2>, umma_gemm_kernel<1, 1, 2>, umma_gemm_kernel<1, 2, 2>}}};
+  static const KernelFn kernels[2][2][3] = {{{umma_gemm_kernel<0, 0, 1, 1>, umma_gemm_kernel<0, 1, 1, 1>, umma_gemm_kernel<0, 2, 1, 1>},
+                                             {umma_gemm_kernel<1, 0, 1, 1>, umma_gemm_kernel<1, 1, 1, 1>, umma_gemm_kernel<1, 2, 1, 1>}},
+                                            {{umma_gemm_kernel<0, 0, 2, 1>, umma_gemm_kernel<0, 1, 2, 1>, umma_gemm_kernel<0, 2, 2, 1>},
+                                             {umma_gemm_kernel<1, 0, 2, 1>, umma_gemm_kernel<1, 1, 2, 1>, umma_gemm_kernel<1, 2, 2, 1>}}};
   static bool configured[2][2][3] = {};
-  const KernelFn kern = kernels[kp.cl - 1][a->mode][epi];
-  if (!configured[kp.cl - 1][a->mode][epi]) {
+  static bool configured_tall = false;
+  KernelFn kern = kernels[kp.cl - 1][a->mode][epi];
+  if (kp.bm == 256) {
+    if (a->mode != 0 || epi != 1 || kp.cl != 1) return rb_fail("rb_gemm: 256-row tiles exist for the NT convolution path only");
+    kern = umma_gemm_kernel<0, 1, 1, 2>;
+    if (!configured_tall) {
+      RB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+      configured_tall = true;
+    }
+  } else if (!configured[kp.cl - 1][a->mode][epi]) {
     RB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     configured[kp.cl - 1][a->mode][epi] = true;
   }
