@@ -294,19 +294,36 @@ def verify_data_parallel(model, net, crit, device, world, rank, workload):
         model.engine_allreduce = False
         ctx = net.no_sync() if hasattr(net, "no_sync") else contextlib.nullcontext()
         with ctx:
+            # (a) the same arithmetic without any exchange: this process runs EVERY rank's shard itself and averages the gradients
+            g_ref = None
+            for r in range(world):
+                s_r, t_r = shard(r * bv, (r + 1) * bv)
+                for _ in range(2):
+                    g_r = run(model, s_r, t_r)
+                g_ref = g_r if g_ref is None else {n: g_ref[n] + g_r[n] for n in g_ref}
+            g_ref = {n: g / world for n, g in g_ref.items()}
+            # (b) one process on the global batch (different batch size => 1 / num_boxes scales the 16-bit activation gradients differently)
             for _ in range(2):
                 g_one = run(model, s_all, t_all)
         model.engine_allreduce = True
     finally:
         model.train(was_training)
-    num = sum(((g_dp[n].double() - g_one[n].double()) ** 2).sum() for n in g_one).sqrt().item()
-    den = sum((g_one[n].double() ** 2).sum() for n in g_one).sqrt().item()
-    big = max(g.norm().item() for g in g_one.values())
-    per = {n: ((g_dp[n] - g_one[n]).norm() / (g_one[n].norm() + 1e-20)).item() for n in g_one if g_one[n].norm().item() > 1e-4 * big}
-    worst = max(per.items(), key=lambda kv: kv[1])
-    return {"world": world, "samples_per_rank": bv, "rel_l2_flat_gradient": num / max(den, 1e-30), "worst_tensor": worst[0], "worst_tensor_rel_l2": worst[1],
-            "tensors_compared": len(per), "tolerance": 2e-3, "ok": num / max(den, 1e-30) < 2e-3,
-            "what": "rank 0's gradient after the split backward + sliced NCCL all-reduce (each rank on its shard) vs one process on the global batch; eval mode"}
+
+    def cmp(ga, gb):
+        num = sum(((ga[n].double() - gb[n].double()) ** 2).sum() for n in gb).sqrt().item()
+        den = sum((gb[n].double() ** 2).sum() for n in gb).sqrt().item()
+        big = max(g.norm().item() for g in gb.values())
+        per = {n: ((ga[n] - gb[n]).norm() / (gb[n].norm() + 1e-20)).item() for n in gb if gb[n].norm().item() > 1e-4 * big}
+        worst = max(per.items(), key=lambda kv: kv[1])
+        return num / max(den, 1e-30), worst, len(per)
+    rel, worst, n = cmp(g_dp, g_ref)
+    rel_g, worst_g, _ = cmp(g_dp, g_one)
+    return {"world": world, "samples_per_rank": bv, "rel_l2_flat_gradient": rel, "worst_tensor": worst[0], "worst_tensor_rel_l2": worst[1],
+            "tensors_compared": n, "tolerance": 1e-4, "ok": rel < 1e-4,
+            "vs_one_process_on_the_global_batch": {"rel_l2_flat_gradient": rel_g, "worst_tensor": worst_g[0], "worst_tensor_rel_l2": worst_g[1],
+                                                   "note": "not the same arithmetic: the global batch halves 1/num_boxes, i.e. the magnitude of every 16-bit activation gradient"},
+            "what": "rank 0's gradient after the split backward + sliced NCCL all-reduces (each rank on its shard) vs the average of the per-shard "
+                    "gradients computed by ONE process without any exchange (same kernels, same batch shapes; only fp32 atomic order differs); eval mode"}
 
 
 def optimizer_diag(model, step_fn, device):

@@ -223,6 +223,11 @@ class RefTREngine:
         # static loss scale of the backward pass: activation gradients are stored in 16 bits (IEEE half by default), so the incoming
         # gradient is multiplied by 2^k on entry and the parameter gradients by 2^-k on exit (exact); fp32 paths are unaffected
         self.grad_scale = float(os.environ.get("REFTR_B200_GRAD_SCALE", "1024"))
+        # dynamic adjustment (GradScaler-style, but lazy): every SCALE_CHECK_EVERY backward passes the overflow counter is read (ONE host
+        # synchronisation per interval -- the reference's own loop synchronises every step, engine_vg.py:53); new overflows halve the
+        # scale, SCALE_GROWTH_INTERVAL clean steps double it (up to 2^16).  REFTR_B200_DYNAMIC_SCALE=0 keeps the scale fixed.
+        self.dynamic_scale = os.environ.get("REFTR_B200_DYNAMIC_SCALE", "1") != "0"
+        self._scale_seen, self._scale_clean, self._bwd_calls = 0, 0, 0
         self.p_drop = float(vt.dropout)
         self.train_mode = False
         self.seed_dev = None
@@ -270,6 +275,7 @@ class RefTREngine:
             self._repack_graphs, self._repack_seen = {}, None  # graphs hold raw parameter addresses
             self._states = {}
             self.gflat = torch.zeros(self.n_flat, dtype=torch.float32, device=device)
+            self._gflat_clean = True
             self.seed_dev = torch.zeros(1, dtype=torch.int64, device=device)
             self._drops = {}
         # cheap change detection first (one tuple compare); the per-pack refresh walk only runs when something moved
@@ -408,6 +414,7 @@ class RefTREngine:
         st = self._cur
         self.ws = ws = st["ws"]
         self.saved, self.dims = st["saved"], st["dims"]
+        self._maybe_adjust_scale()
         S = self.grad_scale
         gl = ws.get("in.g_logits", g_logits.shape, torch.float32)
         torch.mul(g_logits, S, out=gl)
@@ -420,6 +427,7 @@ class RefTREngine:
                 ga.zero_()
             else:
                 torch.mul(g_att, S, out=ga)
+        self._ensure_gflat_clean()
         split = self._split_wanted()
         if split and not self.force_eager and (st.get("bwd3") is not None or (st["graphed"] and st["fwd"] is not None and st["nb"] >= 1)):
             return self._run_backward_split(st, gl, gm, ga)
@@ -456,6 +464,7 @@ class RefTREngine:
                     torch.distributed.all_reduce(flat)
                     flat.mul_(1.0 / world)
         self._finish_guard(flat)
+        self._clear_gflat()
         self.host_ms = {"clone": (_t1 - _t0) * 1e3, "allreduce": (_t.perf_counter() - _t1) * 1e3}
         if self.bert is not None:
             return None, None, flat
@@ -484,6 +493,53 @@ class RefTREngine:
         else:
             self.overflow_dev.add_(self._flag.to(torch.float32))
         self._flag.zero_()
+
+    SCALE_CHECK_EVERY = 50
+    SCALE_GROWTH_INTERVAL = 2000
+    SCALE_MAX, SCALE_MIN = 65536.0, 1.0
+
+    def _maybe_adjust_scale(self):
+        """Called at the start of every backward (before the incoming gradient is scaled)."""
+        self._bwd_calls += 1
+        if not self.dynamic_scale or self._bwd_calls % self.SCALE_CHECK_EVERY or self.overflow_dev is None:
+            return
+        n = self.overflow_steps()          # the one synchronisation of the interval
+        if n > self._scale_seen:
+            self.grad_scale = max(self.SCALE_MIN, self.grad_scale * 0.5 ** min(n - self._scale_seen, 4))
+            self._scale_seen, self._scale_clean = n, 0
+        else:
+            self._scale_clean += self.SCALE_CHECK_EVERY
+            if self._scale_clean >= self.SCALE_GROWTH_INTERVAL and self.grad_scale < self.SCALE_MAX:
+                self.grad_scale *= 2.0
+                self._scale_clean = 0
+
+    def _ensure_gflat_clean(self):
+        """The weight-gradient GEMMs ACCUMULATE (split-K atomics) into ``gflat``, so it must be zero when a backward starts.  Normally
+        ``_clear_gflat`` has already done that behind the previous step; after an interrupted backward (exception) it is done here."""
+        if not getattr(self, "_gflat_clean", False):
+            self.gflat.zero_()
+        ev = getattr(self, "_gflat_ev", None)
+        if ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
+            self._gflat_ev = None
+        self._gflat_clean = False
+
+    def _clear_gflat(self):
+        """Zero-fill of the accumulation buffer for the NEXT backward, on a side stream ordered after this step's hand-over: 607 MB of
+        writes (0.1 ms) leave the backward's critical path and overlap the next forward, which never touches the buffer."""
+        if self._dev is None or self._dev.type != "cuda":
+            self.gflat.zero_()
+            self._gflat_clean = True
+            return
+        if getattr(self, "_zero_stream", None) is None:
+            self._zero_stream = torch.cuda.Stream(device=self._dev)
+        zs = self._zero_stream
+        zs.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(zs):
+            self.gflat.zero_()
+            self._gflat_ev = torch.cuda.Event()
+            self._gflat_ev.record(zs)
+        self._gflat_clean = True
 
     def overflow_steps(self):
         """Number of steps whose gradient was non-finite so far (synchronises; for logging)."""
@@ -600,6 +656,7 @@ class RefTREngine:
         main.wait_stream(br)
         main.wait_stream(cs)
         self._finish_guard(flat)
+        self._clear_gflat()
         st["nb"] += 1
         self.launches += st["bl"]
         self.host_ms = {"clone": 0.0, "allreduce": 0.0}
@@ -1277,7 +1334,8 @@ class RefTREngine:
         rows, rt = B * S, B * T
         nl = len(self.dec)
         rh = nl * rt
-        self.gflat.zero_()
+        # (the 607 MB accumulation buffer is NOT zero-filled here, on the backward's critical path: run_backward clears it on a side
+        # stream right after the hand-over of the previous step, where it overlaps the next forward -- see _clear_gflat)
         # ---- box head (backbone.py:35-38) ---------------------------------------------------------------------------------
         bl = m.bbox_embed.layers
         gl = ws.get("bboxb.gl", [rh, 64], torch.float32, zero=True)

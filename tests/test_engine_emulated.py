@@ -348,3 +348,27 @@ def test_split_backward_plan_partitions_the_flat_gradient(name):
             assert part.startswith("bb:"), n
         else:
             assert part == "heads", (n, part)
+
+
+def test_loss_scale_backs_off_after_overflow_and_grows_when_clean(emulated):
+    """Lazy dynamic loss scaling (engine._maybe_adjust_scale): the overflow counter is read every SCALE_CHECK_EVERY backward passes;
+    new overflows shrink the scale (so training recovers without user action), a long clean stretch grows it back."""
+    case = CASES["cfg1_box"]
+    cand = build_candidate(case)
+    s = synthetic_samples(**case["inputs"])
+    eng = cand.engine()
+    eng.SCALE_CHECK_EVERY, eng.SCALE_GROWTH_INTERVAL = 2, 4
+    eng.grad_scale = 2.0 ** 100        # every step overflows until the scale has come down far enough
+    scales = []
+    for _ in range(12):
+        cand.zero_grad(set_to_none=True)
+        _loss(cand(s), case).backward()
+        scales.append(eng.grad_scale)
+    assert scales[-1] < scales[0] and eng.overflow_steps() >= 2
+    eng.grad_scale, n0 = 1024.0, eng.overflow_steps()
+    eng._scale_seen = n0
+    for _ in range(6):
+        cand.zero_grad(set_to_none=True)
+        _loss(cand(s), case).backward()
+    assert eng.overflow_steps() == n0 and eng.grad_scale == 2048.0
+    assert torch.isfinite(cand.bbox_embed.layers[0].weight.grad).all()
