@@ -124,7 +124,8 @@ def build_ours(device, workload="cfg2"):
     from reftr_b200 import build_reftr
     from reftr_b200.args import CONFIG_FLAGS, parse
     from reftr_b200.synthetic import synthetic_weights
-    args = parse(CONFIG_FLAGS[WORKLOADS[workload][0]] + ["--device", str(device)])
+    extra = os.environ.get("REFTR_B200_BENCH_FLAGS", "").split()  # diagnostics only (e.g. --freeze_bert): not the metric's configuration
+    args = parse(CONFIG_FLAGS[WORKLOADS[workload][0]] + ["--device", str(device)] + extra)
     torch.manual_seed(0)
     model, criterion, _ = build_reftr(args)
     synthetic_weights(model, seed=0)
@@ -432,6 +433,10 @@ def main():
         crit = None
     else:
         model, crit, _ = build_ours(device, a.workload)
+        for pref in os.environ.get("REFTR_B200_BENCH_FREEZE", "").split():  # diagnostics only: what a branch's backward costs
+            for n_, p_ in model.named_parameters():
+                if n_.startswith(pref):
+                    p_.requires_grad_(False)
         model.train() if os.environ.get("REFTR_B200_BENCH_EVAL") != "1" else model.eval()  # train mode: every dropout of the reference active
     net = model
     if a.diag == "replicas":
@@ -609,6 +614,9 @@ def main():
                     "loss_read": "every step's loss is copied to pinned host memory and read one step later (REFTR_B200_E2E_LAG=0: blocking read every step)" if lag_read else "blocking .item() every step"},
                windows_ms_per_step=[round(w / a.steps, 4) for w in win],
                gpu_launches=launches, clocks=clocks, host=host_ms)
+    if os.environ.get("REFTR_B200_BENCH_FLAGS") or os.environ.get("REFTR_B200_BENCH_FREEZE"):
+        out["config"]["diagnostic_flags"] = (os.environ.get("REFTR_B200_BENCH_FLAGS", "") + " frozen: " + os.environ.get("REFTR_B200_BENCH_FREEZE", "")
+                                             + " (NOT the metric's configuration)")
     if a.impl == "stock-gpu":
         out["impl"] = "stock-gpu"
         out["dtype"] = "f32 (cuDNN TF32 conv, fp32 matmul: PyTorch defaults)"
@@ -651,6 +659,10 @@ def main():
             g_fl += fl_g
             top.append((ms_g, len(members), sig, fl_g))
         top.sort(reverse=True)
+        if os.environ.get("REFTR_B200_BENCH_GROUPS"):  # diagnostics: every launch group, not only the six largest
+            with open(os.environ["REFTR_B200_BENCH_GROUPS"], "w") as fh:
+                for m_, n_, sg, f_ in top:
+                    fh.write(f"{m_ * 1e3:9.1f} us  x{n_:3d}  {m_ * 1e3 / n_:7.1f} us each  {f_ / (m_ * 1e-3) / 1e12:7.1f} TFLOP/s  {sg}\n")
         ach = g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
         out["roofline"] = {"bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                            "frac": ach / pk["bf16_tflops_sustained"], "traffic": None,

@@ -207,7 +207,12 @@ class RefTREngine:
         self.step_id = 0
         self.use_graphs = os.environ.get("REFTR_B200_GRAPHS", "1") != "0"
         self.use_side = os.environ.get("REFTR_B200_SIDE_STREAM", "1") != "0"
-        self._side, self._side_used = None, False
+        # one side stream per CATEGORY of off-critical-path work ("t": transformer / heads, "bert", "bb": conv backbone): within a
+        # category the launches form one chain in issue order, categories are independent of each other (they touch disjoint
+        # parameters).  With ONE chain for everything the conv backbone's weight gradients queued behind all of BERT's -- whose chain
+        # is issued first -- and ran as a 1.7 ms tail after the input-gradient chain instead of next to it.
+        self._sides, self._side_cat = {}, "t"
+        self._side_cats = os.environ.get("REFTR_B200_SIDE_CATEGORIES", "1") != "0"
         self._side2, self._side2_used = None, False
         self._tracked = [t for t in list(model.parameters()) + list(model.buffers())]
         self._rg_sig = tuple(p.requires_grad for p in model.parameters())
@@ -688,13 +693,27 @@ class RefTREngine:
         import contextlib
         if not self.use_side or self._dev is None or self._dev.type != "cuda":
             return contextlib.nullcontext()
-        if self._side is None:
-            self._side = torch.cuda.Stream(device=self._dev)
+        ent = self._sides.get(self._side_cat if self._side_cats else "t")
+        if ent is None:
+            ent = self._sides[self._side_cat if self._side_cats else "t"] = [torch.cuda.Stream(device=self._dev), False]
         ev = torch.cuda.Event()
         ev.record()  # on the main (current) stream: everything launched so far is visible to the side stream
-        self._side.wait_event(ev)
-        self._side_used = True
-        return torch.cuda.stream(self._side)
+        ent[0].wait_event(ev)
+        ent[1] = True
+        return torch.cuda.stream(ent[0])
+
+    def _side_category(self, cat):
+        """Context manager: off-critical-path launches issued inside go to the side stream of category ``cat``."""
+        import contextlib
+
+        @contextlib.contextmanager
+        def scope():
+            prev, self._side_cat = self._side_cat, cat
+            try:
+                yield
+            finally:
+                self._side_cat = prev
+        return scope()
 
     def _branch(self):
         """A second side stream for a whole independent CHAIN (BERT forward next to the conv backbone, BERT backward next to the
@@ -716,9 +735,13 @@ class RefTREngine:
             self._side2_used = False
 
     def _join_side(self):
-        if self._side_used:
-            torch.cuda.current_stream().wait_stream(self._side)
-            self._side_used = False
+        if not self._sides:
+            return
+        cur = torch.cuda.current_stream()
+        for ent in self._sides.values():
+            if ent[1]:
+                cur.wait_stream(ent[0])
+                ent[1] = False
 
     def colsum(self, x, out, rows=None, N=None):
         """Bias gradient: out[N] += column sums of x (off the critical path)."""
@@ -1392,15 +1415,16 @@ class RefTREngine:
         if part is not None and part.startswith("bb:"):
             layer = int(part[3:])
             layers = sorted({b.layer for b in self.blocks if b.trainable}, reverse=True)
-            if not layers or layer == layers[0]:
-                self._bb_gy = self._iproj_bwd(g, g_src, g_fpn)
-            if layers and self._bb_gy is not None:
-                self._bb_gy = self._backbone_bwd(self._bb_gy, g_fpn, only_layer=layer)
+            with self._side_category("bb"):
+                if not layers or layer == layers[0]:
+                    self._bb_gy = self._iproj_bwd(g, g_src, g_fpn)
+                if layers and self._bb_gy is not None:
+                    self._bb_gy = self._backbone_bwd(self._bb_gy, g_fpn, only_layer=layer)
             self._join_side()
             return None
         if native_bert and part in (None, "bert"):  # BERT's backward chain runs next to the backbone backward (independent of it)
             import contextlib
-            with (self._branch() if part is None else contextlib.nullcontext()):
+            with (self._branch() if part is None else contextlib.nullcontext()), self._side_category("bert"):
                 if has_phrases:
                     self.bert.backward("p", None, d_pooled)
                     self.bert.backward("s", d_sent, None)
@@ -1409,9 +1433,10 @@ class RefTREngine:
         if part == "bert":
             self._join_side()
             return None
-        g5y = self._iproj_bwd(g, g_src, g_fpn)
-        if g5y is not None:
-            self._backbone_bwd(g5y, g_fpn)
+        with self._side_category("bb"):
+            g5y = self._iproj_bwd(g, g_src, g_fpn)
+            if g5y is not None:
+                self._backbone_bwd(g5y, g_fpn)
         self._join_branch()
         self._join_side()
         return d_sent.view(B, L, -1), d_pooled
