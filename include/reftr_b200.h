@@ -100,6 +100,10 @@ typedef struct {
   float* bias_grad;
   const float* row_scale;
   float out_scale;
+  /* 0 = all SMs.  > 0: the persistent grid (and the tile-shape / split choice) uses at most this many SMs -- for launches that are
+   * OFF the critical path and run next to other kernels (the language backbone's chain beside the conv backbone): what they cost
+   * the step is the SM time they hold, not their latency. */
+  int sm_limit;
 } rb_gemm_args;
 
 int rb_gemm(const rb_gemm_args* args, void* stream);

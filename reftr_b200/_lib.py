@@ -47,6 +47,7 @@ class GemmArgs(C.Structure):
         ("bias_grad", C.c_void_p),
         ("row_scale", C.c_void_p),
         ("out_scale", C.c_float),
+        ("sm_limit", C.c_int),
     ]
 
 

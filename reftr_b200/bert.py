@@ -50,9 +50,20 @@ class BertEngine:
         self.pool = PackedLinear(bert.pooler.dense.weight, bert.pooler.dense.bias)
         self.packs.append(self.pool)
         self.saved = {}
+        # BERT's chains run BESIDE the conv backbone (engine._branch): what they cost the step is the SM time their launches hold, not
+        # their latency -- a 144-CTA launch that lives 8 us for 1 us of tensor-core work (M = 320 rows) blocks the whole chip.  The
+        # backward's GEMMs are therefore launched narrow (rb_gemm_args.sm_limit): input gradients on <= 72 SMs, weight gradients on <= 36 (measured: tools/gpu_bertsm.sh).
+        import os
+        self.lim_fwd = int(os.environ.get("REFTR_B200_BERT_SMS_FWD", "0"))
+        self.lim_bwd = int(os.environ.get("REFTR_B200_BERT_SMS_BWD", "72"))
+        self.lim_wgrad = int(os.environ.get("REFTR_B200_BERT_SMS_WGRAD", "36"))
 
     # ------------------------------------------------------------------------------------------------------------
     def forward(self, tag, ids, mask_u8, Bn, L):
+        with ops.sm_limit_scope(self.lim_fwd):
+            return self._forward(tag, ids, mask_u8, Bn, L)
+
+    def _forward(self, tag, ids, mask_u8, Bn, L):
         """ids int64 [Bn, L], mask_u8 [Bn, L] (1 = padding key).  Returns (seq fp32 [Bn*L, D], seq bf16, pooled fp32 [Bn, D])."""
         eng, ws, bert = self.eng, self.eng.ws, self.bert
         D, H, FF = self.D, self.H, self.FF
@@ -105,12 +116,17 @@ class BertEngine:
 
     # ------------------------------------------------------------------------------------------------------------
     def backward(self, tag, d_seq, d_pooled):
+        with ops.sm_limit_scope(self.lim_bwd):
+            return self._backward(tag, d_seq, d_pooled)
+
+    def _backward(self, tag, d_seq, d_pooled):
         """d_seq fp32 [Bn*L, D] or None, d_pooled fp32 [Bn, D] or None; parameter gradients are accumulated into the engine's
         flat gradient buffer (the sentence and the phrase invocation share the weights)."""
         if not self.trainable:
             return
         eng, ws, bert = self.eng, self.eng.ws, self.bert
         G = eng.G
+        wl = self.lim_wgrad if self.lim_wgrad > 0 else None
         D, H, FF = self.D, self.H, self.FF
         ids, mask_u8, Bn, L, e32, me, re_, per_layer, cls_b, pooled = self.saved[tag]
         rows = Bn * L
@@ -125,7 +141,7 @@ class BertEngine:
             dpre = ws.get(f"bertb.{tag}.dpre", [Bn, D], f32)
             dpreb = ws.get(f"bertb.{tag}.dpreb", [Bn, D])
             ops.tanh_bwd(d_pooled.reshape(Bn, D), pooled, dx=dpre, dxb=dpreb)
-            eng.wgrad_linear(dpreb, cls_b, G(bert.pooler.dense.weight), D, D, Bn, bias=G(bert.pooler.dense.bias))
+            eng.wgrad_linear(dpreb, cls_b, G(bert.pooler.dense.weight), D, D, Bn, bias=G(bert.pooler.dense.bias), sm_limit=wl)
             dcls = ws.get(f"bertb.{tag}.dcls", [Bn, D], f32)
             ops.gemm(dpreb, self.pool.wt, Bn, D, D, out32=dcls)
             ops.rows_scatter_add(dcls, g, Bn, D, map_dst=(1, L, 0, 0))
@@ -140,17 +156,17 @@ class BertEngine:
             k = f"bert.{tag}.{li}"
             dr1, dr2 = eng.drop(k + ".drop1", self.p_hidden), eng.drop(k + ".drop2", self.p_hidden)
             ops.ln_wide_bwd(g, y2, ln2.weight, m2, r2, rows, dx32=dy2, dxb=dy2b, dgamma=G(ln2.weight), dbeta=G(ln2.bias), dxb_drop=dr2)
-            eng.wgrad_linear(dy2b, h, G(lay.output.dense.weight), D, FF, rows, bias=G(lay.output.dense.bias))
+            eng.wgrad_linear(dy2b, h, G(lay.output.dense.weight), D, FF, rows, bias=G(lay.output.dense.bias), sm_limit=wl)
             dh = ws.get(f"bertb.{tag}.{li}.dh", [rows, FF])
             ops.gemm(dy2b, l.o2.wt, rows, FF, D, out=dh)
             dhp = ws.get(f"bertb.{tag}.{li}.dhp", [rows, FF])
             ops.gelu_bwd(dh, hpre, dhp)
-            eng.wgrad_linear(dhp, x1b, G(lay.intermediate.dense.weight), FF, D, rows, bias=G(lay.intermediate.dense.bias))
+            eng.wgrad_linear(dhp, x1b, G(lay.intermediate.dense.weight), FF, D, rows, bias=G(lay.intermediate.dense.bias), sm_limit=wl)
             g1 = ws.get(f"bertb.{tag}.{li}.g1", [rows, D], f32)
             ops.gemm(dhp, l.i.wt, rows, D, FF, res32=dy2, out32=g1)
             dy1, dy1b = ws.get(f"bertb.{tag}.{li}.dy1", [rows, D], f32), ws.get(f"bertb.{tag}.{li}.dy1b", [rows, D])
             ops.ln_wide_bwd(g1, y1, ln1.weight, m1, r1, rows, dx32=dy1, dxb=dy1b, dgamma=G(ln1.weight), dbeta=G(ln1.bias), dxb_drop=dr1)
-            eng.wgrad_linear(dy1b, ctx, G(a.output.dense.weight), D, D, rows, bias=G(a.output.dense.bias))
+            eng.wgrad_linear(dy1b, ctx, G(a.output.dense.weight), D, D, rows, bias=G(a.output.dense.bias), sm_limit=wl)
             dctx = ws.get(f"bertb.{tag}.{li}.dctx", [rows, D])
             ops.gemm(dy1b, l.o.wt, rows, D, D, out=dctx)
             dqkv = ws.get(f"bertb.{tag}.{li}.dqkv", [rows, 3 * D])
@@ -158,7 +174,7 @@ class BertEngine:
                                drop=eng.drop(k + ".attn", self.p_attn))
             for j, lin in enumerate((a.self.query, a.self.key, a.self.value)):
                 sl = dqkv[:, j * D:(j + 1) * D]
-                eng.wgrad_linear(sl, xb, G(lin.weight), D, D, rows, bias=G(lin.bias))
+                eng.wgrad_linear(sl, xb, G(lin.weight), D, D, rows, bias=G(lin.bias), sm_limit=wl)
             g_in = gbuf[1] if g is gbuf[0] else gbuf[0]
             ops.gemm(dqkv, l.qkv.wt, rows, D, 3 * D, res32=dy1, out32=g_in)
             g = g_in

@@ -728,9 +728,11 @@ extern "C" int rb_gemm(const rb_gemm_args* a, void* stream) {
     if (a->mode == 1) cl_mode = a->taps >= 9 ? 1 : 0;
     else cl_mode = (a->taps == 1 && kb >= 16 && a->mask_src && !a->res && !a->res32 && !a->out32) ? 1 : 0;
   }
+  // SMs this launch may use: all of them, or rb_gemm_args.sm_limit for launches that run beside other kernels
+  const int nsm = (a->sm_limit > 0 && a->sm_limit < sm_count()) ? (a->sm_limit < 2 ? 2 : a->sm_limit) : sm_count();
   if (a->mode == 1 && a->atomic && a->splits <= 0) {  // splits <= 0: chosen here, together with the tile shape
     int bn_t = 0, sp_t = 1, cl_t = 1;
-    pick_tn(a->M, a->N, a->taps, (a->K + BK - 1) / BK, sm_count(), a->bias_grad != nullptr, a->block_n == 32 ? 64 : a->block_n, cl_mode, &bn_t, &sp_t, &cl_t);
+    pick_tn(a->M, a->N, a->taps, (a->K + BK - 1) / BK, nsm, a->bias_grad != nullptr, a->block_n == 32 ? 64 : a->block_n, cl_mode, &bn_t, &sp_t, &cl_t);
     kp.splits = sp_t;
     auto_bn = bn_t;
     auto_cl = cl_t;
@@ -761,7 +763,6 @@ extern "C" int rb_gemm(const rb_gemm_args* a, void* stream) {
     if ((static_cast<long long>(a->M) + a->out_row_off) * kp.drop_wpr >= (1LL << 32)) return rb_fail("rb_gemm: dropout site too large for a 32-bit counter");
   }
   if (gemm_skinny_eligible(a) && !(getenv("RB_GEMM_NO_SKINNY"))) return gemm_skinny_launch(a, kp.drop, static_cast<int>(kp.drop_wpr), st);
-  const int nsm = sm_count();
   long long tiles_m = (a->M + BM - 1) / BM;
   const long long k_iters = a->mode == 0 ? static_cast<long long>(a->taps) * kp.kblocks : (kp.kblocks + kp.splits - 1) / kp.splits;
   int bn = a->block_n ? a->block_n : (auto_bn ? auto_bn : pick_bn(a->N, tiles_m * (a->mode == 1 ? a->taps * kp.splits : 1), k_iters, nsm));

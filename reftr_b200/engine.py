@@ -213,7 +213,10 @@ class RefTREngine:
         # is issued first -- and ran as a 1.7 ms tail after the input-gradient chain instead of next to it.
         self._sides, self._side_cat = {}, "t"
         self._side_cats = os.environ.get("REFTR_B200_SIDE_CATEGORIES", "1") != "0"
+        self._side_sms_t = int(os.environ.get("REFTR_B200_SIDE_SMS_T", "32"))  # SM limit of the transformer's weight-gradient launches
         self._side2, self._side2_used = None, False
+        self._side2u, self._side2u_used = None, False
+        self._prio_branch = os.environ.get("REFTR_B200_BRANCH_PRIORITY", "1") != "0"
         self._tracked = [t for t in list(model.parameters()) + list(model.buffers())]
         self._rg_sig = tuple(p.requires_grad for p in model.parameters())
         self._synced = False
@@ -695,7 +698,8 @@ class RefTREngine:
             return contextlib.nullcontext()
         ent = self._sides.get(self._side_cat if self._side_cats else "t")
         if ent is None:
-            ent = self._sides[self._side_cat if self._side_cats else "t"] = [torch.cuda.Stream(device=self._dev), False]
+            hi = self._side_cats and self._prio_branch and self._side_cat == "bert"
+            ent = self._sides[self._side_cat if self._side_cats else "t"] = [torch.cuda.Stream(device=self._dev, priority=-1 if hi else 0), False]
         ev = torch.cuda.Event()
         ev.record()  # on the main (current) stream: everything launched so far is visible to the side stream
         ent[0].wait_event(ev)
@@ -715,12 +719,23 @@ class RefTREngine:
                 self._side_cat = prev
         return scope()
 
-    def _branch(self):
+    def _branch(self, urgent=False):
         """A second side stream for a whole independent CHAIN (BERT forward next to the conv backbone, BERT backward next to the
-        backbone backward); ``_join_branch`` must be called on the main stream before the chain's results are consumed."""
+        backbone backward); ``_join_branch`` must be called on the main stream before the chain's results are consumed.
+        ``urgent``: a high-priority stream (the priority is kept by graph capture as a kernel-node attribute) -- for a chain of
+        many short, narrow launches next to wide persistent kernels: without it every one of its launches waits for a whole wide
+        kernel to drain (BERT's backward stretched from 1.2 ms to 3.9 ms and ended after the conv backbone's)."""
         import contextlib
         if not self.use_side or self._dev is None or self._dev.type != "cuda":
             return contextlib.nullcontext()
+        if urgent and self._prio_branch:
+            if self._side2u is None:
+                self._side2u = torch.cuda.Stream(device=self._dev, priority=-1)
+            ev = torch.cuda.Event()
+            ev.record()
+            self._side2u.wait_event(ev)
+            self._side2u_used = True
+            return torch.cuda.stream(self._side2u)
         if self._side2 is None:
             self._side2 = torch.cuda.Stream(device=self._dev)
         ev = torch.cuda.Event()
@@ -733,6 +748,9 @@ class RefTREngine:
         if self._side2_used:
             torch.cuda.current_stream().wait_stream(self._side2)
             self._side2_used = False
+        if self._side2u_used:
+            torch.cuda.current_stream().wait_stream(self._side2u)
+            self._side2u_used = False
 
     def _join_side(self):
         if not self._sides:
@@ -748,12 +766,14 @@ class RefTREngine:
         with self._off():
             ops.colsum(x, out, rows=rows, N=N)
 
-    def wgrad_linear(self, dY, X, gview, M, N, K, bias=None):
+    def wgrad_linear(self, dY, X, gview, M, N, K, bias=None, sm_limit=None):
         """gview[M, N] += dY[:K, :M]^T X[:K, :N]   (TN GEMM, split-K, fp32 atomics; off the critical path).
         ``bias`` [M]: the layer's bias gradient, bias[m] += sum_r dY[r, m], produced by the SAME launch (an extra N=16 MMA against
         ones in the tiles of the first column block) instead of a separate column-sum pass over dY."""
+        if sm_limit is None and self._side_cat == "t" and self._side_sms_t > 0:
+            sm_limit = self._side_sms_t
         with self._off():
-            ops.gemm(dY, X, M, N, K, mode=1, out32=gview, atomic=True, splits=0, bias_grad=bias)  # splits 0: picked by rb_gemm
+            ops.gemm(dY, X, M, N, K, mode=1, out32=gview, atomic=True, splits=0, bias_grad=bias, sm_limit=sm_limit)  # splits 0: picked by rb_gemm
 
     def wgrad_conv(self, pc, dY, X, K, key=None, b_offsets=None, bias=None):
         """Folded-layout weight gradient of a convolution; b_offsets = row offset of X per tap (None: 1x1, no shift);
@@ -1424,7 +1444,7 @@ class RefTREngine:
             return None
         if native_bert and part in (None, "bert"):  # BERT's backward chain runs next to the backbone backward (independent of it)
             import contextlib
-            with (self._branch() if part is None else contextlib.nullcontext()), self._side_category("bert"):
+            with (self._branch(urgent=True) if part is None else contextlib.nullcontext()), self._side_category("bert"):
                 if has_phrases:
                     self.bert.backward("p", None, d_pooled)
                     self.bert.backward("s", d_sent, None)

@@ -8,6 +8,7 @@ from . import _lib
 from ._lib import Dropout, GemmArgs, Geom
 
 
+SM_LIMIT = 0  # default rb_gemm_args.sm_limit of gemm(); set for a region by sm_limit_scope()
 PROFILE = None  # bench.py sets this to a list: every rb_gemm launch descriptor is then recorded -> (args, flops, signature)
 
 
@@ -71,14 +72,33 @@ def make_geom(mode=0, Wp=0, HpWp=0, H=0, W=0, Rs=0):
     return Geom(mode, Wp, HpWp, H, W, Rs)
 
 
+class sm_limit_scope:
+    """``with sm_limit_scope(n):`` GEMMs launched inside use at most n SMs (rb_gemm_args.sm_limit); n <= 0 leaves it unchanged."""
+
+    def __init__(self, n):
+        self.n = int(n)
+
+    def __enter__(self):
+        global SM_LIMIT
+        self.prev = SM_LIMIT
+        if self.n > 0:
+            SM_LIMIT = self.n
+
+    def __exit__(self, *exc):
+        global SM_LIMIT
+        SM_LIMIT = self.prev
+        return False
+
+
 def _check_2d(t, dtype, name):
     assert t.is_cuda and t.dtype == dtype and t.dim() == 2 and t.stride(1) == 1, (name, t.dtype, t.shape, t.stride())
 
 
 def gemm(A, B, M, N, K, *, mode=0, taps=((0, 0),), bias=None, res=None, res32=None, mask_src=None, relu=False,
          out=None, out32=None, atomic=False, splits=1, geom=None, out_row_off=0, out32_z_stride=0, block_n=0, drop=None, drop_gshift=0,
-         mask_scale=1.0, bias_grad=None, row_scale=None, out_scale=1.0):
-    """See rb_gemm in include/reftr_b200.h.  ``taps`` is a sequence of (a_rowoff, b_koff) pairs."""
+         mask_scale=1.0, bias_grad=None, row_scale=None, out_scale=1.0, sm_limit=None):
+    """See rb_gemm in include/reftr_b200.h.  ``taps`` is a sequence of (a_rowoff, b_koff) pairs.  ``sm_limit`` None: the value of the
+    enclosing ``sm_limit_scope`` (0 = all SMs)."""
     _check_2d(A, t16(), "A")
     _check_2d(B, t16(), "B")
     a = GemmArgs()
@@ -126,6 +146,7 @@ def gemm(A, B, M, N, K, *, mode=0, taps=((0, 0),), bias=None, res=None, res32=No
         assert row_scale.dtype == torch.float32 and row_scale.is_contiguous() and row_scale.numel() >= M
         a.row_scale = row_scale.data_ptr()
     a.out_scale = out_scale
+    a.sm_limit = SM_LIMIT if sm_limit is None else sm_limit
     if PROFILE is not None:  # bench.py: keep the launch descriptor so the launch can be re-issued and timed in isolation
         PROFILE.append((a, 2.0 * M * N * K * len(taps), (mode, M, N, K, len(taps), bool(atomic), res is not None, res32 is not None,
                                                        mask_src is not None, out32 is not None)))

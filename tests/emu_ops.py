@@ -76,9 +76,20 @@ def _cols(Bm, n, k0, K):
     return out
 
 
+class sm_limit_scope:
+    def __init__(self, n):
+        self.n = n
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
 def gemm(A, B, M, N, K, *, mode=0, taps=((0, 0),), bias=None, res=None, res32=None, mask_src=None, relu=False, out=None, out32=None,
          atomic=False, splits=1, geom=None, out_row_off=0, out32_z_stride=0, block_n=0, drop=None, drop_gshift=0, mask_scale=1.0,
-         bias_grad=None, row_scale=None, out_scale=1.0):
+         bias_grad=None, row_scale=None, out_scale=1.0, sm_limit=None):
     _LAUNCHES[0] += 1
     assert A.dtype == _lp() and B.dtype == _lp() and A.stride(1) == 1 and B.stride(1) == 1
     assert A.stride(0) % 8 == 0 and B.stride(0) % 8 == 0, "TMA pitch"
