@@ -49,7 +49,9 @@ def sigmoid_focal_loss(inputs, targets, num_boxes, alpha=0.25, gamma=2):  # mode
 
 class _FusedBoxLoss(torch.autograd.Function):
     """L1 + GIoU for every decoder layer in ONE kernel (rb_box_loss); the kernel also emits d(loss)/d(boxes), so the backward is
-    two broadcast multiplies."""
+    two broadcast multiplies.  Returns the 2 x n_layers losses as SEPARATE 0-dim outputs (views of one buffer): the training loop
+    weights and sums them one by one (engine_vg.py:42-43), and as ``L[i, j]`` selections of one output every term's backward was
+    two SelectBackward nodes = zeros + copy + accumulate, ~60 eager launches (0.25 ms of an idle GPU) before the backward graph."""
 
     @staticmethod
     def forward(ctx, boxes_all, tgt, valid, inv_norm, inv_norm_dev):
@@ -59,12 +61,17 @@ class _FusedBoxLoss(torch.autograd.Function):
         dl1, dgiou = torch.empty_like(boxes_all), torch.empty_like(boxes_all)
         ops.box_loss(boxes_all, tgt, valid, inv_norm, inv_norm_dev, losses, dl1, dgiou)
         ctx.save_for_backward(dl1, dgiou)
-        return losses
+        ctx.set_materialize_grads(False)
+        return tuple(losses.view(-1).unbind(0))  # (l1_0, giou_0, l1_1, giou_1, ...)
 
     @staticmethod
-    def backward(ctx, g):
+    def backward(ctx, *gs):
         dl1, dgiou = ctx.saved_tensors
         nl = dl1.shape[0]
+        if any(g is None for g in gs):
+            zero = torch.zeros((), dtype=torch.float32, device=dl1.device)
+            gs = [zero if g is None else g for g in gs]
+        g = torch.stack([x.reshape(()) for x in gs]).view(nl, 2)
         return torch.addcmul(dl1 * g[:, 0].view(nl, 1, 1), dgiou, g[:, 1].view(nl, 1, 1)), None, None, None, None
 
 
@@ -115,10 +122,10 @@ class CriterionVGMultiPhrase(nn.Module):
         else:
             inv, inv_dev = 1.0 / (num_boxes * k), None
         L = _FusedBoxLoss.apply(allb.reshape(nl, b * n_ph * k, 4).contiguous(), tgt, valid, inv, inv_dev)
-        losses = {"loss_bbox": L[nl - 1, 0], "loss_giou": L[nl - 1, 1]}
+        losses = {"loss_bbox": L[2 * (nl - 1)], "loss_giou": L[2 * (nl - 1) + 1]}
         for i in range(nl - 1):
-            losses[f"loss_bbox_{i}"] = L[i, 0]
-            losses[f"loss_giou_{i}"] = L[i, 1]
+            losses[f"loss_bbox_{i}"] = L[2 * i]
+            losses[f"loss_giou_{i}"] = L[2 * i + 1]
         return losses
 
     def loss_boxes(self, outputs, targets, num_boxes):  # criterion.py:113-153

@@ -1302,7 +1302,7 @@ class RefTREngine:
             raise ValueError(f"sentence length {L} exceeds max_lang_seq {vt.max_lang_seq} (reftr.py:81)")
         # ---- language backbone first, on a branch stream: it is independent of the conv backbone and latency-bound ---------
         if lang[0] == "ids":  # BERT on our kernels (reftr_transformer.py:200, :215-217)
-            with self._branch():
+            with self._branch(urgent=os.environ.get("REFTR_B200_BRANCH_PRIORITY_FWD", "1") == "1"):
                 _, sfb, pooled = self.bert.forward("s", lang[1], lang[2], B, L)
                 if len(lang) > 3:
                     _, _, pooled = self.bert.forward("p", lang[3], lang[4], B * n_ph, lang[3].shape[1])
