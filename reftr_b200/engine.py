@@ -623,7 +623,9 @@ class RefTREngine:
         per step at 8 GPUs.)  The all-reduces are issued in the same fixed order on every rank."""
         main = torch.cuda.current_stream()
         if self._split_stream is None:
-            self._split_stream = torch.cuda.Stream(device=self._dev)
+            # BERT's part runs on its own HIGH-PRIORITY stream (captured there, so its kernel nodes carry the priority): a chain of
+            # short, narrow launches that must finish early -- its 440 MB slice is the largest all-reduce of the step
+            self._split_stream = torch.cuda.Stream(device=self._dev, priority=-1 if self._prio_branch else 0)
             self._comm_stream = torch.cuda.Stream(device=self._dev)
         br, cs = self._split_stream, self._comm_stream
         if st.get("bwd3") is None:
@@ -631,8 +633,14 @@ class RefTREngine:
             graphs = {}
             for part, _ in plan:
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    self.backward(gl, gm, ga, part=part)
+                if part == "bert":
+                    br.wait_stream(main)
+                    with torch.cuda.graph(g, stream=br), self._side_category("bert"):
+                        self.backward(gl, gm, ga, part=part)
+                    main.wait_stream(br)
+                else:
+                    with torch.cuda.graph(g):
+                        self.backward(gl, gm, ga, part=part)
                 graphs[part] = g
             st["bwd3"] = (plan, graphs)
         plan, graphs = st["bwd3"]
@@ -649,14 +657,29 @@ class RefTREngine:
                     self._handover(lo, hi, flat)   # fresh storage + undo the loss scale + overflow sentinel (as in run_backward)
                     self._allreduce_(flat[lo:hi])
 
-        bert_ev = None
+        # Launch order: heads, then BERT (on its stream: it only needs the heads part) next to layer4 / layer3 / layer2 on the main
+        # stream.  Exchange order (the same on every rank): heads, layer4, BERT, layer3, layer2 -- BERT's exchange is issued after
+        # layer4's so that the short layer4 slice does not queue behind it on the communication stream.
+        early_bert = os.environ.get("REFTR_B200_SPLIT_BERT_EARLY", "1") != "0"
         for part, slices in plan:
-            if part == "bert":
-                ev = torch.cuda.Event()
-                ev.record(main)   # the heads part (which produced BERT's incoming gradient) precedes this point on the main stream
-                br.wait_event(ev)
-                with torch.cuda.stream(br):
+            if part == "heads" or not early_bert:
+                if part == "bert":
+                    ev = torch.cuda.Event()
+                    ev.record(main)
+                    br.wait_event(ev)
+                    with torch.cuda.stream(br):
+                        graphs[part].replay()
+                    exchange(br, slices)
+                else:
                     graphs[part].replay()
+                    exchange(main, slices)
+                if part == "heads" and early_bert and "bert" in graphs:
+                    ev = torch.cuda.Event()
+                    ev.record(main)   # the heads part produced BERT's incoming gradient
+                    br.wait_event(ev)
+                    with torch.cuda.stream(br):
+                        graphs["bert"].replay()
+            elif part == "bert":
                 exchange(br, slices)
             else:
                 graphs[part].replay()
