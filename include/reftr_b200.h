@@ -117,6 +117,12 @@ int rb_stem_im2col(const float* img, void* out, int B, int H, int W, int H1, int
 /* the whole stem in one kernel: 7x7/2 pad-3 conv 3->64 (+ folded FrozenBN bias + ReLU), im2col built in shared memory;
  * img fp32 NCHW, wf = rb_pack_conv output bf16 [64, ldk] (column (r*7+s)*3+c), out bf16 NHWC [B*H1*W1, 64] */
 int rb_stem_conv(const float* img, const void* wf, int ldk, const float* bias, void* out, int B, int H, int W, int H1, int W1, void* stream);
+/* conv1 + bn1 + relu + maxpool (torchvision ResNet stem as reached from backbone.py:99-102) in one pass: img fp32 NCHW [B,3,H,W] ->
+ * out 16-bit padded NHWC [B, H2+2, W2+2, 64] with a zero border (the layout rb_maxpool_3x3s2 writes); the 64-channel stride-2 map
+ * is never written.  wpk: the folded weights as [7 tap rows][4 K chunks][64][8] 16-bit, K index = 4 * s + c (s: tap column, c:
+ * channel; s = 7 and c = 3 are zero); hwc4: scratch of B*H*(W+2)*8 bytes (the batch as 16-bit HWC4 pixels, one zero pixel left and right of every row).  W must be even. */
+int rb_stem_pool(const float* img, const void* wpk, const float* bias, void* hwc4, void* out, int B, int H, int W, int H1, int W1, int H2, int W2,
+                 void* stream);
 /* in bf16 NHWC [B,H1,W1,C] -> out padded NHWC [B,H2+2,W2+2,C]; 3x3 stride 2 pad 1 max-pool */
 int rb_maxpool_3x3s2(const void* in, void* out, int B, int H1, int W1, int C, int H2, int W2, void* stream);
 /* padded NHWC [B,H+2,W+2,C] <-> 4 parity planes [4,B,Ho+2,Wo+2,C] (see header comment); merge = backward of split,

@@ -62,6 +62,22 @@ int make_tmap_2d_f32(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t
   return make_tmap_2d_impl(out, ptr, inner, rows, pitch_bytes, box_inner, box_rows, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4);
 }
 
+int make_tmap_3d_px8(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t rows, uint64_t imgs, uint64_t pitch_row_bytes,
+                     uint64_t pitch_img_bytes, uint32_t box_inner) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return rb_fail("cuTensorMapEncodeTiled not available (no CUDA driver?)");
+  cuuint64_t dims[3] = {inner, rows, imgs};
+  cuuint64_t strides[2] = {pitch_row_bytes, pitch_img_bytes};
+  cuuint32_t box[3] = {box_inner, 1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return rb_fail("cuTensorMapEncodeTiled (3D px8) failed (%d): inner=%llu rows=%llu imgs=%llu box=%u ptr=%p", static_cast<int>(r),
+                   static_cast<unsigned long long>(inner), static_cast<unsigned long long>(rows), static_cast<unsigned long long>(imgs), box_inner, ptr);
+  return 0;
+}
+
 int sm_count() {
   static int n = 0;
   if (!n) {

@@ -16,6 +16,10 @@ int make_tmap_2d(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t row
 // same for an fp32 tensor (box_inner * 4 bytes <= 128; swizzle chosen by the box row bytes: 128 -> 128B, 64 -> 64B, else 32B)
 int make_tmap_2d_f32(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t rows, uint64_t pitch_bytes, uint32_t box_inner,
                      uint32_t box_rows);
+// 3D tensor [imgs, rows, inner] of 8-byte elements (one 4-channel 16-bit pixel each), no swizzle; box = [1, 1, box_inner];
+// out-of-bounds elements (including negative coordinates) read as zero
+int make_tmap_3d_px8(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t rows, uint64_t imgs, uint64_t pitch_row_bytes,
+                     uint64_t pitch_img_bytes, uint32_t box_inner);
 int sm_count();
 // host rb_dropout (nullable) -> kernel parameter; off when NULL / seed == NULL / p <= 0
 inline DropK make_dropk(const rb_dropout* d) {

@@ -22,7 +22,7 @@ import os
 import torch
 
 from . import ops
-from .pack import PackedConv, PackedLinear, PackedStack
+from .pack import PackedStem, PackedConv, PackedLinear, PackedStack
 
 NH = 8      # heads
 DH = 32     # head dim
@@ -94,7 +94,8 @@ class RefTREngine:
         body = model.img_backbone[0].body
         self.return_interm = model.img_backbone[0].return_interm_layers
         # ---- packed weights -------------------------------------------------------------------------------------
-        self.stem = PackedConv(body.conv1, body.bn1, need_dgrad=False, ldk=160)
+        self.stem = PackedStem(body.conv1, body.bn1, need_dgrad=False, ldk=160)
+        self._stem_fused = os.environ.get("REFTR_B200_STEM_FUSED", "1") != "0"
         self.blocks = []
         first_trainable = True
         for li in range(1, 5):
@@ -908,11 +909,16 @@ class RefTREngine:
         B, _, H, W = img.shape
         H1, W1 = (H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1
         H2, W2 = (H1 + 2 - 3) // 2 + 1, (W1 + 2 - 3) // 2 + 1
-        c1 = ws.get("stem.out", [B * H1 * W1, 64])
-        ops.stem_conv(img, self.stem.wf, self.stem.bias, c1, B, H, W, H1, W1)  # conv1 + bn1 + relu, im2col in shared memory
         g = Grid(B, H2, W2)
         x = ws.get("stem.pool", [g.R, 64])
-        ops.maxpool_3x3s2(c1, x, B, H1, W1, 64, H2, W2)
+        if self._stem_fused and W % 2 == 0 and body_is_7x7(self.stem):
+            # conv1 + bn1 + relu + maxpool in one pass (the stride-2 map never reaches HBM); the batch is first rewritten as 16-bit HWC4
+            hwc4 = ws.get("stem.hwc4", [B * H * (W + 2), 4])
+            ops.stem_pool(img, self.stem.wrow, self.stem.bias, hwc4, x, B, H, W, H1, W1, H2, W2)
+        else:
+            c1 = ws.get("stem.out", [B * H1 * W1, 64])
+            ops.stem_conv(img, self.stem.wf, self.stem.bias, c1, B, H, W, H1, W1)  # conv1 + bn1 + relu, im2col in shared memory
+            ops.maxpool_3x3s2(c1, x, B, H1, W1, 64, H2, W2)
         feats = {}
         for b in self.blocks:
             x, g = self._block_fwd(b, x, g)
@@ -1500,6 +1506,10 @@ class RefTREngine:
         g5y = ws.get("iproj.gc5", [g5.R, 2048])
         ops.gemm(dproj, self.iproj.wd, g5.R, 2048, D, res=g_fpn.get(4), mask_src=c5, out=g5y)
         return g5y
+
+
+def body_is_7x7(stem):
+    return stem.kh == 7 and stem.kw == 7 and stem.Cin == 3 and stem.Cout == 64
 
 
 class HotPathFunction(torch.autograd.Function):

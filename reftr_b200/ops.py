@@ -178,6 +178,10 @@ def stem_conv(img, wf, bias, out, B, H, W, H1, W1):
     _lib.call("rb_stem_conv", _p(img), _p(wf), wf.stride(0), _p(bias), _p(out), B, H, W, H1, W1, _s())
 
 
+def stem_pool(img, wpk, bias, hwc4, out, B, H, W, H1, W1, H2, W2):
+    _lib.call("rb_stem_pool", _p(img), _p(wpk), _p(bias), _p(hwc4), _p(out), B, H, W, H1, W1, H2, W2, _s())
+
+
 def maxpool_3x3s2(x, out, B, H1, W1, C, H2, W2):
     _lib.call("rb_maxpool_3x3s2", _p(x), _p(out), B, H1, W1, C, H2, W2, _s())
 

@@ -49,6 +49,27 @@ class PackedConv:
         self._key = key
 
 
+class PackedStem(PackedConv):
+    """The 7x7 stem convolution: ``wf`` as for every convolution plus ``wrow`` [7 tap rows][4 K chunks][64][8], the layout
+    rb_stem_pool reads (K index 4 * s + c over 8 pixels x 4 channels of a 16-bit HWC4 image row; pixel 7 / channel 3 are zero)."""
+
+    wrow = None
+
+    def refresh(self):
+        key = self._key
+        super().refresh()
+        if self._key == key and self.wrow is not None:
+            return
+        dev = self.wf.device
+        k = torch.arange(32, device=dev)
+        s_, c_ = k // 4, k % 4
+        valid = (s_ < 7) & (c_ < 3)
+        r = torch.arange(7, device=dev).view(7, 1)
+        col = ((r * 7 + s_.clamp(max=6)) * 3 + c_.clamp(max=2)).reshape(-1)         # [7 * 32] columns of wf, order (r, s, c)
+        w = self.wf[:, col].view(self.Cout, 7, 32) * valid.view(1, 1, 32).to(self.wf.dtype)
+        self.wrow = w.permute(1, 2, 0).reshape(7, 4, 8, self.Cout).permute(0, 1, 3, 2).contiguous()
+
+
 class PackedLinear:
     """weight fp32 [N,K] -> wb bf16 [Npad,K], wt bf16 [K,Npad]; bias fp32 [Npad].  ``pad_to`` zero-pads the output dim
     (used for the 4-wide box head so every pitch is a multiple of 16 bytes)."""

@@ -159,6 +159,18 @@ def stem_conv(img, wf, bias, out, B, H, W, H1, W1):
     out.copy_(y.permute(0, 2, 3, 1).reshape(B * H1 * W1, 64).to(_lp()))
 
 
+def stem_pool(img, wpk, bias, hwc4, out, B, H, W, H1, W1, H2, W2):
+    _LAUNCHES[0] += 2
+    # wpk [7 (r), 4 (j), 64 (n), 8 (e)], K index 8 j + e = 4 s + c  ->  conv weight [64, 3, 7, 7]
+    w = wpk.float().permute(2, 0, 1, 3).reshape(64, 7, 8, 4)[:, :, :7, :3].permute(0, 3, 1, 2)
+    x = img if EXACT[0] else img.to(_BF).float()
+    y = F.relu(F.conv2d(x, w, bias, stride=2, padding=3)).to(_lp()).float()
+    p = F.max_pool2d(y, 3, 2, 1)
+    o = out.view(B, H2 + 2, W2 + 2, 64)
+    o.zero_()
+    o[:, 1:-1, 1:-1] = p.permute(0, 2, 3, 1).to(_lp())
+
+
 def maxpool_3x3s2(x, out, B, H1, W1, C, H2, W2):
     _LAUNCHES[0] += 1
     p = F.max_pool2d(x.view(B, H1, W1, C).permute(0, 3, 1, 2).float(), 3, 2, 1)

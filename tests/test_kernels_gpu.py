@@ -283,3 +283,42 @@ def test_stem_conv_fused(B, H, W):
     ops.stem_conv(img, wf, bias, out, B, H, W, H1, W1)
     ref = F.relu(F.conv2d(img.to(T16).float(), w.to(T16).float(), bias, stride=2, padding=3)).permute(0, 2, 3, 1).reshape(B * H1 * W1, 64)
     assert _rel(out, ref) < 1e-2
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 64, 96), (1, 224, 224), (2, 50, 70), (1, 640, 640), (3, 130, 514), (16, 96, 128)])
+def test_stem_pool_fused(B, H, W):
+    """conv1 + bn1 + relu + maxpool in one pass (rb_stem_pool: TMA-staged HWC4 rows read through overlapping UMMA descriptors, pool in
+    shared memory) against PyTorch; padded NHWC output with an exact zero border."""
+    from reftr_b200 import ops
+    from reftr_b200.pack import PackedStem
+    H1, W1 = (H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1
+    H2, W2 = (H1 + 2 - 3) // 2 + 1, (W1 + 2 - 3) // 2 + 1
+    torch.manual_seed(B * 1000 + H + W)
+    img = torch.randn(B, 3, H, W, device=dev)
+    conv = torch.nn.Conv2d(3, 64, 7, stride=2, padding=3, bias=False).to(dev)
+    with torch.no_grad():
+        conv.weight.mul_(3.0)
+    st = PackedStem(conv, None, need_dgrad=False, ldk=160)
+    st.refresh()
+    assert st.wrow.shape == (7, 4, 64, 8)
+    hwc4 = torch.full((B * H * (W + 2), 4), 3.0, device=dev, dtype=T16)
+    out = torch.full((B * (H2 + 2) * (W2 + 2), 64), 7.0, device=dev, dtype=T16)
+    ops.stem_pool(img, st.wrow, st.bias, hwc4, out, B, H, W, H1, W1, H2, W2)
+    torch.cuda.synchronize()
+    hv = hwc4.view(B, H, W + 2, 4)
+    assert torch.equal(hv[:, :, 1:-1, :3], img.permute(0, 2, 3, 1).to(T16))
+    assert hv[..., 3].abs().max().item() == 0 and hv[:, :, 0].abs().max().item() == 0 and hv[:, :, -1].abs().max().item() == 0
+    w16 = st.wf[:, :147].float().reshape(64, 7, 7, 3).permute(0, 3, 1, 2)
+    y = F.relu(F.conv2d(img.to(T16).float(), w16, st.bias, stride=2, padding=3))
+    ref = F.max_pool2d(y, 3, 2, 1).permute(0, 2, 3, 1)
+    o = out.view(B, H2 + 2, W2 + 2, 64).float()
+    assert o[:, 0].abs().max().item() == 0 and o[:, -1].abs().max().item() == 0
+    assert o[:, :, 0].abs().max().item() == 0 and o[:, :, -1].abs().max().item() == 0
+    assert _rel(o[:, 1:-1, 1:-1], ref) < 2e-3
+    assert (o[:, 1:-1, 1:-1] - ref).abs().max().item() < 2e-2 * max(1.0, ref.abs().max().item())
+    # and against the two-kernel path it replaces
+    c1 = torch.empty(B * H1 * W1, 64, device=dev, dtype=T16)
+    x2 = torch.empty_like(out)
+    ops.stem_conv(img, st.wf, st.bias, c1, B, H, W, H1, W1)
+    ops.maxpool_3x3s2(c1, x2, B, H1, W1, 64, H2, W2)
+    assert _rel(out, x2) < 2e-3
