@@ -115,11 +115,14 @@ class BertEngine:
         return x32, xb, pooled
 
     # ------------------------------------------------------------------------------------------------------------
-    def backward(self, tag, d_seq, d_pooled):
+    def backward(self, tag, d_seq, d_pooled, layers=None):
+        """``layers`` = (hi, lo): process encoder layers hi-1 .. lo only (the split backward under data parallelism runs BERT's backward
+        as two graphs so that the upper layers' gradient slice is exchanged while the lower layers still compute); the pooler part
+        belongs to the call with hi == n_layers, the embeddings to the call with lo == 0.  None = everything."""
         with ops.sm_limit_scope(self.lim_bwd):
-            return self._backward(tag, d_seq, d_pooled)
+            return self._backward(tag, d_seq, d_pooled, layers)
 
-    def _backward(self, tag, d_seq, d_pooled):
+    def _backward(self, tag, d_seq, d_pooled, layers=None):
         """d_seq fp32 [Bn*L, D] or None, d_pooled fp32 [Bn, D] or None; parameter gradients are accumulated into the engine's
         flat gradient buffer (the sentence and the phrase invocation share the weights)."""
         if not self.trainable:
@@ -132,12 +135,15 @@ class BertEngine:
         rows = Bn * L
         f32 = torch.float32
         gbuf = [ws.get(f"bertb.{tag}.gA", [rows, D], f32), ws.get(f"bertb.{tag}.gB", [rows, D], f32)]
-        g = gbuf[0]
-        if d_seq is None:
-            g.zero_()
-        else:
-            g.copy_(d_seq.reshape(rows, D))
-        if d_pooled is not None:
+        nL = len(self.layers)
+        hi, lo = layers if layers is not None else (nL, 0)
+        g = gbuf[0] if hi == nL else gbuf[(nL - hi) & 1]   # the buffers alternate per layer: after nL - hi layers the gradient sits here
+        if hi == nL:
+            if d_seq is None:
+                g.zero_()
+            else:
+                g.copy_(d_seq.reshape(rows, D))
+        if hi == nL and d_pooled is not None:
             dpre = ws.get(f"bertb.{tag}.dpre", [Bn, D], f32)
             dpreb = ws.get(f"bertb.{tag}.dpreb", [Bn, D])
             ops.tanh_bwd(d_pooled.reshape(Bn, D), pooled, dx=dpre, dxb=dpreb)
@@ -146,7 +152,7 @@ class BertEngine:
             ops.gemm(dpreb, self.pool.wt, Bn, D, D, out32=dcls)
             ops.rows_scatter_add(dcls, g, Bn, D, map_dst=(1, L, 0, 0))
         scale = 64 ** -0.5
-        for li in reversed(range(len(self.layers))):
+        for li in reversed(range(lo, hi)):
             l = self.layers[li]
             lay = l.mod
             a = lay.attention
@@ -178,6 +184,8 @@ class BertEngine:
             g_in = gbuf[1] if g is gbuf[0] else gbuf[0]
             ops.gemm(dqkv, l.qkv.wt, rows, D, 3 * D, res32=dy1, out32=g_in)
             g = g_in
+        if lo != 0:
+            return
         emb = bert.embeddings
         de = ws.get(f"bertb.{tag}.de", [rows, D], f32)
         ops.ln_wide_bwd(g, e32, emb.LayerNorm.weight, me, re_, rows, dx32=de, dgamma=G(emb.LayerNorm.weight), dbeta=G(emb.LayerNorm.bias),

@@ -593,6 +593,22 @@ class RefTREngine:
                         runs.append((lo, hi))
             return runs
         b0, b1 = self._bert_slice
+        bert_parts = [("bert", [(b0, b1)] if b1 > b0 else [])]
+        nL = len(self.bert.layers) if self.bert is not None else 0
+        if b1 > b0 and nL >= 2 and os.environ.get("REFTR_B200_SPLIT_BERT_HALVES", "1") != "0":
+            # two graphs: upper half of the encoder layers (+ pooler), lower half (+ embeddings); named_parameters() order is
+            # embeddings, layer 0 .. nL-1, pooler, so each half completes one or two contiguous runs of slots
+            half = nL // 2
+            def upper(n):
+                if not n.startswith("lang_backbone."):
+                    return False
+                if ".encoder.layer." in n:
+                    return int(n.split(".encoder.layer.")[1].split(".")[0]) >= half
+                return ".pooler." in n
+            up = spans(upper)
+            lw = spans(lambda n: n.startswith("lang_backbone.") and not upper(n))
+            if up and lw:
+                bert_parts = [(f"bert:{nL}:{half}", up), (f"bert:{half}:0", lw)]
         iproj = spans(lambda n: n.startswith("input_proj."))
         rest = spans(lambda n: not n.startswith(("img_backbone.", "lang_backbone.", "input_proj.")))
         plan = [("heads", rest)]
@@ -601,12 +617,12 @@ class RefTREngine:
         for li in layers:
             sl = spans(lambda n, li=li: n.startswith(f"img_backbone.0.body.layer{li}."))
             plan.append((f"bb:{li}", (iproj if first else []) + sl))
-            if first:
-                plan.append(("bert", [(b0, b1)] if b1 > b0 else []))
+            if bert_parts:  # exchange order: layer4, BERT's upper half, layer3, BERT's lower half, layer2 (roughly the order of completion)
+                plan.append(bert_parts.pop(0))
             first = False
         if not layers:  # frozen backbone: input_proj alone, then BERT
             plan.append(("bb:0", iproj))
-            plan.append(("bert", [(b0, b1)] if b1 > b0 else []))
+        plan.extend(bert_parts)
         covered = sorted(sl for _, sls in plan for sl in sls)
         pos = 0
         for lo, hi in covered:  # every slot is handed over exactly once
@@ -634,7 +650,7 @@ class RefTREngine:
             graphs = {}
             for part, _ in plan:
                 g = torch.cuda.CUDAGraph()
-                if part == "bert":
+                if part.startswith("bert"):
                     br.wait_stream(main)
                     with torch.cuda.graph(g, stream=br), self._side_category("bert"):
                         self.backward(gl, gm, ga, part=part)
@@ -649,42 +665,41 @@ class RefTREngine:
         flat.record_stream(br)
         flat.record_stream(cs)
 
-        def exchange(after_stream, slices):
-            ev = torch.cuda.Event()
-            ev.record(after_stream)
-            cs.wait_event(ev)
+        def exchange(event, slices):
+            cs.wait_event(event)
             with torch.cuda.stream(cs):
                 for lo, hi in slices:
                     self._handover(lo, hi, flat)   # fresh storage + undo the loss scale + overflow sentinel (as in run_backward)
                     self._allreduce_(flat[lo:hi])
 
-        # Launch order: heads, then BERT (on its stream: it only needs the heads part) next to layer4 / layer3 / layer2 on the main
-        # stream.  Exchange order (the same on every rank): heads, layer4, BERT, layer3, layer2 -- BERT's exchange is issued after
-        # layer4's so that the short layer4 slice does not queue behind it on the communication stream.
+        def done_event(stream):
+            ev = torch.cuda.Event()
+            ev.record(stream)
+            return ev
+
+        # Launch order: heads, then BERT's parts back to back on their own stream (they only need the heads part) next to layer4 /
+        # layer3 / layer2 on the main stream.  Exchange order (the same on every rank) = the plan's order: heads, layer4, BERT's upper
+        # half, layer3, BERT's lower half, layer2 -- roughly the order of completion, so no slice queues behind one that is not ready.
         early_bert = os.environ.get("REFTR_B200_SPLIT_BERT_EARLY", "1") != "0"
+        bert_done = {}
         for part, slices in plan:
-            if part == "heads" or not early_bert:
-                if part == "bert":
-                    ev = torch.cuda.Event()
-                    ev.record(main)
-                    br.wait_event(ev)
+            if part.startswith("bert"):
+                if part not in bert_done:  # (late mode: launched at its position in the plan)
+                    br.wait_event(done_event(main))
                     with torch.cuda.stream(br):
                         graphs[part].replay()
-                    exchange(br, slices)
-                else:
-                    graphs[part].replay()
-                    exchange(main, slices)
-                if part == "heads" and early_bert and "bert" in graphs:
-                    ev = torch.cuda.Event()
-                    ev.record(main)   # the heads part produced BERT's incoming gradient
-                    br.wait_event(ev)
-                    with torch.cuda.stream(br):
-                        graphs["bert"].replay()
-            elif part == "bert":
-                exchange(br, slices)
-            else:
-                graphs[part].replay()
-                exchange(main, slices)
+                    bert_done[part] = done_event(br)
+                exchange(bert_done[part], slices)
+                continue
+            graphs[part].replay()
+            exchange(done_event(main), slices)
+            if part == "heads" and early_bert:
+                br.wait_event(done_event(main))   # the heads part produced BERT's incoming gradient
+                with torch.cuda.stream(br):
+                    for bp, _ in plan:
+                        if bp.startswith("bert"):
+                            graphs[bp].replay()
+                            bert_done[bp] = done_event(br)
         main.wait_stream(br)
         main.wait_stream(cs)
         self._finish_guard(flat)
@@ -1471,15 +1486,19 @@ class RefTREngine:
                     self._bb_gy = self._backbone_bwd(self._bb_gy, g_fpn, only_layer=layer)
             self._join_side()
             return None
-        if native_bert and part in (None, "bert"):  # BERT's backward chain runs next to the backbone backward (independent of it)
+        is_bert = part is not None and part.startswith("bert")
+        if native_bert and (part is None or is_bert):  # BERT's backward chain runs next to the backbone backward (independent of it)
             import contextlib
+            layers = None
+            if is_bert and ":" in part:  # "bert:<hi>:<lo>": encoder layers hi-1 .. lo only (split backward)
+                layers = tuple(int(v) for v in part.split(":")[1:])
             with (self._branch(urgent=True) if part is None else contextlib.nullcontext()), self._side_category("bert"):
                 if has_phrases:
-                    self.bert.backward("p", None, d_pooled)
-                    self.bert.backward("s", d_sent, None)
+                    self.bert.backward("p", None, d_pooled, layers)
+                    self.bert.backward("s", d_sent, None, layers)
                 else:
-                    self.bert.backward("s", d_sent, d_pooled)
-        if part == "bert":
+                    self.bert.backward("s", d_sent, d_pooled, layers)
+        if is_bert:
             self._join_side()
             return None
         with self._side_category("bb"):

@@ -328,7 +328,7 @@ def test_split_backward_plan_partitions_the_flat_gradient(name):
         pytest.skip("no seg head")
     eng = build_candidate(case).engine()
     plan = eng._split_plan()
-    assert [p for p, _ in plan][0] == "heads" and "bert" in [p for p, _ in plan]
+    assert [p for p, _ in plan][0] == "heads" and sum(p.startswith("bert") for p, _ in plan) == 2
     slices = sorted(sl for _, sls in plan for sl in sls)
     assert slices[0][0] == 0 and slices[-1][1] == eng.n_grad
     assert all(a[1] == b[0] for a, b in zip(slices, slices[1:]))
@@ -341,7 +341,12 @@ def test_split_backward_plan_partitions_the_flat_gradient(name):
     assert len(owner) == len(eng.named)
     for n, part in owner.items():
         if n.startswith("lang_backbone."):
-            assert part == "bert", n
+            assert part.startswith("bert:"), n
+            hi, lo = (int(v) for v in part.split(":")[1:])
+            if ".encoder.layer." in n:
+                assert lo <= int(n.split(".encoder.layer.")[1].split(".")[0]) < hi, (n, part)
+            else:
+                assert (".pooler." in n) == (lo != 0), (n, part)
         elif n.startswith("img_backbone."):
             assert part == "bb:" + n.split("layer")[1][0], (n, part)
         elif n.startswith("input_proj."):
