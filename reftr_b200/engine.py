@@ -218,6 +218,8 @@ class RefTREngine:
         self._side2, self._side2_used = None, False
         self._side2u, self._side2u_used = None, False
         self._prio_branch = os.environ.get("REFTR_B200_BRANCH_PRIORITY", "1") != "0"
+        self._main_prio = int(os.environ.get("REFTR_B200_MAIN_PRIORITY", "-1"))
+        self._cap_stream = None
         self._tracked = [t for t in list(model.parameters()) + list(model.buffers())]
         self._rg_sig = tuple(p.requires_grad for p in model.parameters())
         self._synced = False
@@ -328,7 +330,7 @@ class RefTREngine:
         g = self._repack_graphs.get(ids)
         if g is None and self._repack_seen == ids and len(stale) > 8:
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, **self._capture_kw()):
                 for p in stale:
                     p.refresh()
             self._repack_graphs = {ids: g}
@@ -406,7 +408,7 @@ class RefTREngine:
             st["fwd"].replay()
         elif st["graphed"] and st["nf"] >= 1:
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, **self._capture_kw()):
                 st["outs"] = self.forward(*a)
             st["fwd"], st["saved"], st["dims"] = g, self.saved, self.dims
             g.replay()
@@ -446,7 +448,7 @@ class RefTREngine:
             st["bwd"].replay()
         elif st["graphed"] and st["fwd"] is not None and st["nb"] >= 1:
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, **self._capture_kw()):
                 st["bouts"] = self.backward(gl, gm, ga)
             st["bwd"] = g
             g.replay()
@@ -642,7 +644,7 @@ class RefTREngine:
         if self._split_stream is None:
             # BERT's part runs on its own HIGH-PRIORITY stream (captured there, so its kernel nodes carry the priority): a chain of
             # short, narrow launches that must finish early -- its 440 MB slice is the largest all-reduce of the step
-            self._split_stream = torch.cuda.Stream(device=self._dev, priority=-1 if self._prio_branch else 0)
+            self._split_stream = torch.cuda.Stream(device=self._dev, priority=self._main_prio - 1 if self._prio_branch else 0)
             self._comm_stream = torch.cuda.Stream(device=self._dev)
         br, cs = self._split_stream, self._comm_stream
         if st.get("bwd3") is None:
@@ -656,7 +658,7 @@ class RefTREngine:
                         self.backward(gl, gm, ga, part=part)
                     main.wait_stream(br)
                 else:
-                    with torch.cuda.graph(g):
+                    with torch.cuda.graph(g, **self._capture_kw()):
                         self.backward(gl, gm, ga, part=part)
                 graphs[part] = g
             st["bwd3"] = (plan, graphs)
@@ -738,12 +740,21 @@ class RefTREngine:
         ent = self._sides.get(self._side_cat if self._side_cats else "t")
         if ent is None:
             hi = self._side_cats and self._prio_branch and self._side_cat == "bert"
-            ent = self._sides[self._side_cat if self._side_cats else "t"] = [torch.cuda.Stream(device=self._dev, priority=-1 if hi else 0), False]
+            ent = self._sides[self._side_cat if self._side_cats else "t"] = [torch.cuda.Stream(device=self._dev, priority=self._main_prio - 1 if hi else 0), False]
         ev = torch.cuda.Event()
         ev.record()  # on the main (current) stream: everything launched so far is visible to the side stream
         ent[0].wait_event(ev)
         ent[1] = True
         return torch.cuda.stream(ent[0])
+
+    def _capture_kw(self):
+        """Graph-capture stream: REFTR_B200_MAIN_PRIORITY < 0 captures the main chain on a stream of that priority (kernel nodes keep
+        it), so critical-chain kernels are placed before pending side-stream CTAs; BERT's urgent branch then sits one level above."""
+        if self._main_prio >= 0 or self._dev is None or self._dev.type != "cuda":
+            return {}
+        if self._cap_stream is None:
+            self._cap_stream = torch.cuda.Stream(device=self._dev, priority=self._main_prio)
+        return {"stream": self._cap_stream}
 
     def _side_category(self, cat):
         """Context manager: off-critical-path launches issued inside go to the side stream of category ``cat``."""
@@ -769,7 +780,7 @@ class RefTREngine:
             return contextlib.nullcontext()
         if urgent and self._prio_branch:
             if self._side2u is None:
-                self._side2u = torch.cuda.Stream(device=self._dev, priority=-1)
+                self._side2u = torch.cuda.Stream(device=self._dev, priority=self._main_prio - 1)
             ev = torch.cuda.Event()
             ev.record()
             self._side2u.wait_event(ev)
