@@ -220,6 +220,7 @@ class RefTREngine:
         self._prio_branch = os.environ.get("REFTR_B200_BRANCH_PRIORITY", "1") != "0"
         self._main_prio = int(os.environ.get("REFTR_B200_MAIN_PRIORITY", "-1"))
         self._cap_stream = None
+        self._forks = os.environ.get("REFTR_B200_FORKS", "1") != "0" and self._side_cats
         self._tracked = [t for t in list(model.parameters()) + list(model.buffers())]
         self._rg_sig = tuple(p.requires_grad for p in model.parameters())
         self._synced = False
@@ -740,12 +741,26 @@ class RefTREngine:
         ent = self._sides.get(self._side_cat if self._side_cats else "t")
         if ent is None:
             hi = self._side_cats and self._prio_branch and self._side_cat == "bert"
-            ent = self._sides[self._side_cat if self._side_cats else "t"] = [torch.cuda.Stream(device=self._dev, priority=self._main_prio - 1 if hi else 0), False]
+            prio = self._main_prio - 1 if hi else (self._main_prio if self._side_cat == "fk" else 0)
+            ent = self._sides[self._side_cat if self._side_cats else "t"] = [torch.cuda.Stream(device=self._dev, priority=prio), False]
         ev = torch.cuda.Event()
         ev.record()  # on the main (current) stream: everything launched so far is visible to the side stream
         ent[0].wait_event(ev)
         ent[1] = True
         return torch.cuda.stream(ent[0])
+
+    def _fork(self):
+        """Context manager: launches inside go to the FORK stream (main-chain priority) -- for an independent piece of the critical
+        chain itself; forks from the current point of the main stream, ``_join_side()`` joins it back."""
+        import contextlib
+        if not self._forks:
+            return contextlib.nullcontext()
+
+        @contextlib.contextmanager
+        def scope():
+            with self._side_category("fk"), self._off():
+                yield
+        return scope()
 
     def _capture_kw(self):
         """Graph-capture stream: REFTR_B200_MAIN_PRIORITY < 0 captures the main chain on a stream of that priority (kernel nodes keep
@@ -1020,8 +1035,10 @@ class RefTREngine:
         k = f"enc{l}"
         lay = e.mod
         qkv = ws.get(k + ".qkv", [rows, 3 * D])
+        with self._fork():  # the value projection (of x) beside the query / key projection (of x + pos)
+            ops.gemm(xb, e.inp.wb[2 * D:], rows, D, D, bias=e.inp.bias[2 * D:], out=qkv[:, 2 * D:])
         ops.gemm(xpb, e.inp.wb[:2 * D], rows, 2 * D, D, bias=e.inp.bias[:2 * D], out=qkv[:, :2 * D])
-        ops.gemm(xb, e.inp.wb[2 * D:], rows, D, D, bias=e.inp.bias[2 * D:], out=qkv[:, 2 * D:])
+        self._join_side()
         o = ws.get(k + ".o", [rows, D])
         lse = ws.get(k + ".lse", [B, NH, S], torch.float32)
         ops.attn_fwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], kpm, o, lse, B, NH, S, S, DH ** -0.5, drop=self.drop(k + ".attn"))
@@ -1186,15 +1203,23 @@ class RefTREngine:
     # ------------------------------------------------------------------------------------------------------------
     # decoder (transformer.py:114-143, :231-252)
     # ------------------------------------------------------------------------------------------------------------
+    def _dec_kv_fwd(self, memb, mempb, rows):
+        """The cross-attention key / value projections of ALL decoder layers (two N = 6 x 256 GEMMs over the memory); they only need
+        the encoder's output, so they run on the fork stream beside the query encoder's chain of small launches."""
+        nl = len(self.dec)
+        kall = self.ws.get("dec.kall", [rows, nl * D])
+        vall = self.ws.get("dec.vall", [rows, nl * D])
+        ops.gemm(mempb, self.kstack.wb, rows, nl * D, D, bias=self.kstack.bias, out=kall)
+        ops.gemm(memb, self.vstack.wb, rows, nl * D, D, bias=self.vstack.bias, out=vall)
+
     def _dec_fwd(self, tgt32, tgtb, qpos32, tqb, memb, mempb, kpm, qmask, B, S, T):
         ws = self.ws
         rows, rt = B * S, B * T
         nl = len(self.dec)
         vt = self.model.vl_transformer
-        kall = ws.get("dec.kall", [rows, nl * D])
+        kall = ws.get("dec.kall", [rows, nl * D])   # written by _dec_kv_fwd on the fork stream
         vall = ws.get("dec.vall", [rows, nl * D])
-        ops.gemm(mempb, self.kstack.wb, rows, nl * D, D, bias=self.kstack.bias, out=kall)
-        ops.gemm(memb, self.vstack.wb, rows, nl * D, D, bias=self.vstack.bias, out=vall)
+        self._join_side()
         hs32 = ws.get("dec.hs32", [nl * rt, D], torch.float32)
         hsb = ws.get("dec.hsb", [nl * rt, D])
         mh, rh = ws.get("dec.mh", [nl * rt], torch.float32), ws.get("dec.rh", [nl * rt], torch.float32)
@@ -1400,6 +1425,8 @@ class RefTREngine:
             x32, xb, xpb = self._enc_fwd(l, e, x32, xb, xpb, kpm, pos32, B, S)
         mem32, memb, mempb = x32, xb, xpb
         # ---- query encoder + decoder + box head -------------------------------------------------------------------------
+        with self._fork():
+            self._dec_kv_fwd(memb, mempb, B * S)
         tgt32, tgtb, qpos32, tqb = self._qenc_fwd(mem32, ph32, mctx, B, S, L, n_ph, n_q)
         hs32, hsb = self._dec_fwd(tgt32, tgtb, qpos32, tqb, memb, mempb, kpm, qmask, B, S, T)
         nl = len(self.dec)
