@@ -140,6 +140,10 @@ int rb_pack_conv(const float* w, int Cout, int Cin, int kh, int kw, const float*
                  float eps, const float* conv_bias, void* fwd, int ldk, void* dgr, float* scale_out, float* bias_out, void* stream);
 /* linear weight fp32 [N,K] (dense) -> bf16 [N,K] (wb, pitch ldwb, nullable) and bf16 [K,N] (wt, pitch ldwt, nullable) */
 int rb_pack_linear(const float* w, int N, int K, void* wb, long long ldwb, void* wt, long long ldwt, void* stream);
+/* w fp32 [N,K] -> w2 16-bit [N, 2K] (pitch ld): columns [0,K) the weight rounded to 16 bits, [K,2K) the rounding residual.  An rb_gemm
+ * with taps {(0,0),(0,K)} over it multiplies by the fp32 weight to ~2^-22 (forward of the latency-bound transformer / BERT layers,
+ * where 16-bit weight rounding dominated the box error: DESIGN.md section 2). */
+int rb_pack_linear_hilo(const float* w, int N, int K, void* w2, long long ld, void* stream);
 /* folded-layout weight gradient fp32 [Cout,taps,Cin] -> parameter layout fp32 [Cout,Cin,kh,kw], times scale[co] (nullable) */
 int rb_unpack_conv_grad(const float* dwf, const float* scale, float* grad, int Cout, int Cin, int taps, void* stream);
 int rb_cast_bf16(const float* in, void* out, long long n, void* stream);

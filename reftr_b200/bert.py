@@ -10,7 +10,7 @@ Residual stream and LayerNorm statistics are fp32; GEMM operands bf16 (as in the
 import torch
 
 from . import ops
-from .pack import PackedLinear, PackedStack
+from .pack import PackedLinear, PackedStack, lin_taps
 
 
 class _L:
@@ -39,11 +39,13 @@ class BertEngine:
             a = lay.attention
             l = _L()
             l.mod = lay
+            from .engine import HILO
+            hl = "bert" in HILO  # forward GEMMs multiply by (hi | residual) weight pairs, see engine.py ("bert_qkv" .. : one layer type)
             l.qkv = PackedStack([a.self.query.weight, a.self.key.weight, a.self.value.weight],
-                                [a.self.query.bias, a.self.key.bias, a.self.value.bias], 0, self.D)
-            l.o = PackedLinear(a.output.dense.weight, a.output.dense.bias)
-            l.i = PackedLinear(lay.intermediate.dense.weight, lay.intermediate.dense.bias)
-            l.o2 = PackedLinear(lay.output.dense.weight, lay.output.dense.bias)
+                                [a.self.query.bias, a.self.key.bias, a.self.value.bias], 0, self.D, hilo=hl or "bert_qkv" in HILO)
+            l.o = PackedLinear(a.output.dense.weight, a.output.dense.bias, hilo=hl or "bert_o" in HILO)
+            l.i = PackedLinear(lay.intermediate.dense.weight, lay.intermediate.dense.bias, hilo=hl or "bert_ffn1" in HILO)
+            l.o2 = PackedLinear(lay.output.dense.weight, lay.output.dense.bias, hilo=hl or "bert_ffn2" in HILO)
             self.layers.append(l)
             self.packs += [l.qkv, l.o, l.i, l.o2]
         self.p_hidden, self.p_attn = float(cfg.hidden_dropout_prob), float(cfg.attention_probs_dropout_prob)
@@ -85,21 +87,25 @@ class BertEngine:
             k = f"bert.{tag}.{li}"
             lay = l.mod
             qkv = ws.get(k + ".qkv", [rows, 3 * D])
-            ops.gemm(xb, l.qkv.wb, rows, 3 * D, D, bias=l.qkv.bias, out=qkv)
+            wq, tq = lin_taps(l.qkv)
+            ops.gemm(xb, wq, rows, 3 * D, D, taps=tq, bias=l.qkv.bias, out=qkv)
             ctx = ws.get(k + ".ctx", [rows, D])
             P = ws.get(k + ".P", [Bn, H, L, L], f32)
             ops.attn_small_fwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], mask_u8, ctx, P, Bn, H, L, scale, drop=eng.drop(k + ".attn", self.p_attn))
             y1 = ws.get(k + ".y1", [rows, D], f32)
-            ops.gemm(ctx, l.o.wb, rows, D, D, bias=l.o.bias, res32=x32, out32=y1, drop=eng.drop(k + ".drop1", self.p_hidden))
+            wo, to = lin_taps(l.o)
+            ops.gemm(ctx, wo, rows, D, D, taps=to, bias=l.o.bias, res32=x32, out32=y1, drop=eng.drop(k + ".drop1", self.p_hidden))
             x1, x1b = ws.get(k + ".x1", [rows, D], f32), ws.get(k + ".x1b", [rows, D])
             m1, r1 = ws.get(k + ".m1", [rows], f32), ws.get(k + ".r1", [rows], f32)
             ln1 = lay.attention.output.LayerNorm
             ops.ln_wide_fwd(y1, ln1.weight, ln1.bias, rows, y32=x1, yb=x1b, mean=m1, rstd=r1, eps=self.eps)
             hpre, h = ws.get(k + ".hpre", [rows, FF]), ws.get(k + ".h", [rows, FF])
-            ops.gemm(x1b, l.i.wb, rows, FF, D, bias=l.i.bias, out=hpre)
+            wi, ti = lin_taps(l.i)
+            ops.gemm(x1b, wi, rows, FF, D, taps=ti, bias=l.i.bias, out=hpre)
             ops.gelu_fwd(hpre, h)
             y2 = ws.get(k + ".y2", [rows, D], f32)
-            ops.gemm(h, l.o2.wb, rows, D, FF, bias=l.o2.bias, res32=x1, out32=y2, drop=eng.drop(k + ".drop2", self.p_hidden))
+            wo2, to2 = lin_taps(l.o2)
+            ops.gemm(h, wo2, rows, D, FF, taps=to2, bias=l.o2.bias, res32=x1, out32=y2, drop=eng.drop(k + ".drop2", self.p_hidden))
             xo, xob = ws.get(k + ".xo", [rows, D], f32), ws.get(k + ".xob", [rows, D])
             m2, r2 = ws.get(k + ".m2", [rows], f32), ws.get(k + ".r2", [rows], f32)
             ln2 = lay.output.LayerNorm

@@ -174,6 +174,18 @@ __global__ void pack_linear_kernel(const float* __restrict__ w, int N, int K, rb
   }
 }
 
+// Linear weight fp32 [N,K] -> w2 [N, 2K] 16-bit: columns [0,K) = the weight rounded to 16 bits, columns [K,2K) = the rounding residual
+// (w - hi) rounded to 16 bits.  A GEMM over both halves (two taps reading the same A) multiplies by the weight to ~2^-22.
+__global__ void pack_linear_hilo_kernel(const float* __restrict__ w, int N, int K, rb_t* __restrict__ w2, long long ld) {
+  const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= static_cast<long long>(N) * K) return;
+  const int n = static_cast<int>(i / K), k = static_cast<int>(i - static_cast<long long>(n) * K);
+  const float v = w[i];
+  const rb_t hi = f2t(v);
+  w2[n * ld + k] = hi;
+  w2[n * ld + K + k] = f2t(v - t2f(hi));
+}
+
 // dWfold fp32 [Cout, taps, Cin] -> grad fp32 [Cout, Cin, kh, kw] * scale[co]
 __global__ void unpack_conv_grad_kernel(const float* __restrict__ dwf, const float* __restrict__ scale, float* __restrict__ grad, int Cout,
                                         int Cin, int taps) {
@@ -330,6 +342,13 @@ extern "C" int rb_pack_conv(const float* w, int Cout, int Cin, int kh, int kw, c
 extern "C" int rb_pack_linear(const float* w, int N, int K, void* wb, long long ldwb, void* wt, long long ldwt, void* stream) {
   dim3 grid((K + 31) / 32, (N + 31) / 32);
   pack_linear_kernel<<<grid, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(w, N, K, static_cast<rb_t*>(wb), ldwb, static_cast<rb_t*>(wt), ldwt);
+  RB_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int rb_pack_linear_hilo(const float* w, int N, int K, void* w2, long long ld, void* stream) {
+  if (!w || !w2 || N <= 0 || K <= 0 || ld < 2LL * K) return rb_fail("rb_pack_linear_hilo: bad arguments");
+  pack_linear_hilo_kernel<<<blocks_for(static_cast<long long>(N) * K, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(w, N, K, static_cast<rb_t*>(w2), ld);
   RB_CHECK_LAUNCH();
   return 0;
 }

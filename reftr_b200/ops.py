@@ -215,6 +215,12 @@ def pack_linear(w, wb, wt):
     _lib.call("rb_pack_linear", _p(w), N, K, _p(wb), wb.stride(0) if wb is not None else 0, _p(wt), wt.stride(0) if wt is not None else 0, _s())
 
 
+def pack_linear_hilo(w, w2):
+    N, K = w.shape
+    assert w.is_contiguous() and w2.shape[1] == 2 * K
+    _lib.call("rb_pack_linear_hilo", _p(w), N, K, _p(w2), w2.stride(0), _s())
+
+
 def unpack_conv_grad(dwf, scale, grad, Cout, Cin, taps):
     _lib.call("rb_unpack_conv_grad", _p(dwf), _p(scale), _p(grad), Cout, Cin, taps, _s())
 

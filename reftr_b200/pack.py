@@ -74,12 +74,15 @@ class PackedLinear:
     """weight fp32 [N,K] -> wb bf16 [Npad,K], wt bf16 [K,Npad]; bias fp32 [Npad].  ``pad_to`` zero-pads the output dim
     (used for the 4-wide box head so every pitch is a multiple of 16 bytes)."""
 
-    def __init__(self, weight, bias=None, pad_to=None):
+    def __init__(self, weight, bias=None, pad_to=None, hilo=False):
+        """``hilo``: also keep ``wb2`` [Npad, 2K] = (weight rounded to 16 bits | rounding residual) for a two-tap forward GEMM that
+        multiplies by the weight to ~2^-22 (``lin_taps``)."""
         self.weight, self.bias_p = weight, bias
         self.N, self.K = weight.shape
         self.Np = max(self.N, pad_to or 0)
         self._key = None
-        self.wb = self.wt = self.bias = None
+        self.hilo = hilo
+        self.wb = self.wt = self.bias = self.wb2 = None
 
     def current_key(self):
         return _ver(self.weight, self.bias_p)
@@ -95,6 +98,10 @@ class PackedLinear:
             if self.Np != self.N:
                 self.bias = torch.zeros(self.Np, dtype=torch.float32, device=dev)
         ops.pack_linear(self.weight.detach(), self.wb, self.wt)
+        if self.hilo:
+            if self.wb2 is None or self.wb2.device != dev:
+                self.wb2 = torch.zeros(self.Np, 2 * self.K, dtype=ops.t16(), device=dev)
+            ops.pack_linear_hilo(self.weight.detach(), self.wb2)
         if self.bias_p is not None:
             if self.Np != self.N:
                 self.bias[:self.N].copy_(self.bias_p.detach())
@@ -103,16 +110,27 @@ class PackedLinear:
         self._key = key
 
 
+def lin_taps(pack, rows=None):
+    """(B operand, taps) of the FORWARD GEMM of a packed linear layer: the plain 16-bit weight with one tap, or -- for ``hilo`` packs
+    -- the (hi | residual) pair with two taps that read the same A rows.  ``rows``: slice of the output features."""
+    w = pack.wb2 if getattr(pack, "wb2", None) is not None else pack.wb
+    if rows is not None:
+        w = w[rows]
+    taps = ((0, 0), (0, pack.K)) if getattr(pack, "wb2", None) is not None else ((0, 0),)
+    return w, taps
+
+
 class PackedStack:
     """Row-blocks of several weights packed side by side: wb [n*Nblk, K] and wt [K, n*Nblk] (decoder cross-attention K / V
     projections of all layers, so the memory is projected by ONE GEMM)."""
 
-    def __init__(self, weights, biases, row0, nrows):
+    def __init__(self, weights, biases, row0, nrows, hilo=False):
         self.weights, self.biases, self.row0, self.nrows = weights, biases, row0, nrows
         self.K = weights[0].shape[1]
         self.n = len(weights)
         self._key = None
-        self.wb = self.wt = self.bias = None
+        self.hilo = hilo
+        self.wb = self.wt = self.bias = self.wb2 = None
 
     def current_key(self):
         return _ver(*self.weights, *self.biases)
@@ -127,8 +145,12 @@ class PackedStack:
             self.wb = torch.empty(N, self.K, dtype=ops.t16(), device=dev)
             self.wt = torch.empty(self.K, N, dtype=ops.t16(), device=dev)
             self.bias = torch.empty(N, dtype=torch.float32, device=dev)
+        if self.hilo and (self.wb2 is None or self.wb2.device != dev):
+            self.wb2 = torch.empty(N, 2 * self.K, dtype=ops.t16(), device=dev)
         for i, (w, b) in enumerate(zip(self.weights, self.biases)):
             sl = slice(i * self.nrows, (i + 1) * self.nrows)
             ops.pack_linear(w.detach()[self.row0:self.row0 + self.nrows], self.wb[sl], self.wt[:, sl])
+            if self.hilo:
+                ops.pack_linear_hilo(w.detach()[self.row0:self.row0 + self.nrows], self.wb2[sl])
             self.bias[sl].copy_(b.detach()[self.row0:self.row0 + self.nrows])
         self._key = key

@@ -21,6 +21,12 @@ def _lp():
     return torch.float32 if EXACT[0] else _BF
 
 
+def _r(v, dest):
+    """v in the precision of the buffer it is stored to: the 16-bit type, or fp32 when the test / tools/err_attrib.py allocated that
+    buffer in fp32 (no rounding then)."""
+    return v.to(torch.float32 if dest.dtype == torch.float32 else _lp())
+
+
 def t16():
     return _lp()
 
@@ -91,7 +97,7 @@ def gemm(A, B, M, N, K, *, mode=0, taps=((0, 0),), bias=None, res=None, res32=No
          atomic=False, splits=1, geom=None, out_row_off=0, out32_z_stride=0, block_n=0, drop=None, drop_gshift=0, mask_scale=1.0,
          bias_grad=None, row_scale=None, out_scale=1.0, sm_limit=None):
     _LAUNCHES[0] += 1
-    assert A.dtype == _lp() and B.dtype == _lp() and A.stride(1) == 1 and B.stride(1) == 1
+    assert A.dtype in (_lp(), torch.float32) and B.dtype in (_lp(), torch.float32) and A.stride(1) == 1 and B.stride(1) == 1  # (fp32: tools/err_attrib.py)
     assert A.stride(0) % 8 == 0 and B.stride(0) % 8 == 0, "TMA pitch"
     assert 1 <= len(taps) <= 16
     m = torch.arange(M)
@@ -122,7 +128,7 @@ def gemm(A, B, M, N, K, *, mode=0, taps=((0, 0),), bias=None, res=None, res32=No
             v = torch.where(mask_src[rows, :N].float() > 0, v * mask_scale, torch.zeros(()))
         v = torch.where(_interior(geom, rows)[:, None], v, torch.zeros(()))
         if out is not None:
-            out[rows, :N] = v.to(_lp())
+            out[rows, :N] = _r(v, out)
         if out32 is not None:
             out32[rows, :N] = v
     else:
@@ -148,7 +154,7 @@ def stem_im2col(img, out, B, H, W, H1, W1):
     cols = F.unfold(img, 7, padding=3, stride=2)  # [B, 3*49, H1*W1], row index c*49 + r*7 + s
     cols = cols.view(B, 3, 49, H1 * W1).permute(0, 3, 2, 1).reshape(B * H1 * W1, 147)  # (r*7+s)*3 + c
     out.zero_()
-    out[:, :147] = cols.to(_lp())
+    out[:, :147] = _r(cols, out)
 
 
 def stem_conv(img, wf, bias, out, B, H, W, H1, W1):
@@ -156,7 +162,7 @@ def stem_conv(img, wf, bias, out, B, H, W, H1, W1):
     w = wf[:, :147].float().reshape(64, 7, 7, 3).permute(0, 3, 1, 2)
     x = img if EXACT[0] else img.to(_BF).float()
     y = F.relu(F.conv2d(x, w, bias, stride=2, padding=3))
-    out.copy_(y.permute(0, 2, 3, 1).reshape(B * H1 * W1, 64).to(_lp()))
+    out.copy_(_r(y.permute(0, 2, 3, 1).reshape(B * H1 * W1, 64), out))
 
 
 def stem_pool(img, wpk, bias, hwc4, out, B, H, W, H1, W1, H2, W2):
@@ -168,7 +174,7 @@ def stem_pool(img, wpk, bias, hwc4, out, B, H, W, H1, W1, H2, W2):
     p = F.max_pool2d(y, 3, 2, 1)
     o = out.view(B, H2 + 2, W2 + 2, 64)
     o.zero_()
-    o[:, 1:-1, 1:-1] = p.permute(0, 2, 3, 1).to(_lp())
+    o[:, 1:-1, 1:-1] = _r(p.permute(0, 2, 3, 1), o)
 
 
 def maxpool_3x3s2(x, out, B, H1, W1, C, H2, W2):
@@ -176,7 +182,7 @@ def maxpool_3x3s2(x, out, B, H1, W1, C, H2, W2):
     p = F.max_pool2d(x.view(B, H1, W1, C).permute(0, 3, 1, 2).float(), 3, 2, 1)
     o = out.view(B, H2 + 2, W2 + 2, C)
     o.zero_()
-    o[:, 1:-1, 1:-1] = p.permute(0, 2, 3, 1).to(_lp())
+    o[:, 1:-1, 1:-1] = _r(p.permute(0, 2, 3, 1), o)
 
 
 def parity_split(x, xs, B, H, W, C, Ho, Wo):
@@ -219,7 +225,7 @@ def parity_merge(dxs, add, mask_src, dx, B, H, W, C, Ho, Wo):
         o = torch.where(mask_src.view(B, H + 2, W + 2, C).float() > 0, o, torch.zeros(()))
     res = torch.zeros(B, H + 2, W + 2, C)
     res[:, 1:-1, 1:-1] = o[:, 1:-1, 1:-1]
-    dx.view(B, H + 2, W + 2, C).copy_(res.to(_lp()))
+    dx.view(B, H + 2, W + 2, C).copy_(_r(res, dx))
 
 
 def pack_conv(w, bn, conv_bias, fwd, ldk, dgr, scale_out, bias_out, eps=1e-5):
@@ -238,18 +244,26 @@ def pack_conv(w, bn, conv_bias, fwd, ldk, dgr, scale_out, bias_out, eps=1e-5):
         bias_out.copy_(bi)
     wf = (w * sc.view(-1, 1, 1, 1)).permute(0, 2, 3, 1).reshape(Cout, kh * kw * Cin)
     fwd.zero_()
-    fwd[:, :kh * kw * Cin] = wf.to(_lp())
+    fwd[:, :kh * kw * Cin] = _r(wf, fwd)
     if dgr is not None:
-        dgr.copy_((w * sc.view(-1, 1, 1, 1)).flip(2, 3).permute(1, 2, 3, 0).reshape(Cin, kh * kw * Cout).to(_lp()))
+        dgr.copy_(_r((w * sc.view(-1, 1, 1, 1)).flip(2, 3).permute(1, 2, 3, 0).reshape(Cin, kh * kw * Cout), dgr))
 
 
 def pack_linear(w, wb, wt):
     _LAUNCHES[0] += 1
     N, K = w.shape
     if wb is not None:
-        wb[:N, :K] = w.to(_lp())
+        wb[:N, :K] = _r(w, wb)
     if wt is not None:
-        wt[:K, :N] = w.t().to(_lp())
+        wt[:K, :N] = _r(w.t(), wt)
+
+
+def pack_linear_hilo(w, w2):
+    _LAUNCHES[0] += 1
+    N, K = w.shape
+    hi = _r(w, w2)
+    w2[:N, :K] = hi
+    w2[:N, K:2 * K] = _r(w - hi.float(), w2)
 
 
 def unpack_conv_grad(dwf, scale, grad, Cout, Cin, taps):
@@ -265,7 +279,7 @@ def cast_bf16(x, out=None):
     assert x.dtype == torch.float32 and x.is_contiguous()
     if out is None:
         out = torch.empty(x.shape, dtype=_lp())
-    out.view(-1).copy_(x.reshape(-1).to(_lp()))
+    out.view(-1).copy_(_r(x.reshape(-1), out))
     return out
 
 
@@ -282,7 +296,7 @@ def add(a, b, y=None, yb=None):
     if y is not None:
         y.copy_(v)
     if yb is not None:
-        yb.copy_(v.to(_lp()))
+        yb.copy_(_r(v, yb))
 
 
 def _map3(rowmap, r):
@@ -311,9 +325,9 @@ def layernorm_fwd(x, gamma, beta, rows, *, y32=None, yb=None, pos32=None, ypb=No
     if y32 is not None:
         y32[o] = y
     if yb is not None:
-        yb[o] = y.to(_lp())
+        yb[o] = _r(y, yb)
     if ypb is not None:
-        ypb[o] = (y + pos32[o]).to(_lp())
+        ypb[o] = _r((y + pos32[o]), ypb)
 
 
 def layernorm_bwd(dy, x, gamma, mean, rstd, rows, *, dy2=None, y_relu=None, relu_scale=1.0, dx32=None, dxb=None, dgamma=None, dbeta=None,
@@ -337,7 +351,7 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, rows, *, dy2=None, y_relu=None, relu
     if dxb is not None:
         if dxb_drop is not None:
             dx = dx * dxb_drop.mask(rows, dx.shape[1])
-        dxb[:rows] = dx.to(_lp())
+        dxb[:rows] = _r(dx, dxb)
 
 
 def groupnorm_tokens_fwd(x, gamma, beta, B, h, w, S, L, y32, yb, pos32, ypb, mean, rstd, eps=1e-5):
@@ -350,9 +364,9 @@ def groupnorm_tokens_fwd(x, gamma, beta, B, h, w, S, L, y32, yb, pos32, ypb, mea
     rstd.view(B, 32).copy_(rs.view(B, 32))
     y = ((xi - mu) * rs).reshape(B, h * w, 256) * gamma.detach() + beta.detach()
     y32.view(B, S, 256)[:, L:] = y
-    yb.view(B, S, 256)[:, L:] = y.to(_lp())
+    yb.view(B, S, 256)[:, L:] = _r(y, yb)
     if ypb is not None:
-        ypb.view(B, S, 256)[:, L:] = (y + pos32.view(B, S, 256)[:, L:]).to(_lp())
+        ypb.view(B, S, 256)[:, L:] = _r((y + pos32.view(B, S, 256)[:, L:]), ypb)
 
 
 def groupnorm_tokens_bwd(dy, dy2, x, gamma, mean, rstd, B, h, w, S, L, dx, dgamma, dbeta):
@@ -370,7 +384,7 @@ def groupnorm_tokens_bwd(dy, dy2, x, gamma, mean, rstd, B, h, w, S, L, dx, dgamm
     s1 = g.sum((1, 3), keepdim=True) / n
     s2 = (g * xh).sum((1, 3), keepdim=True) / n
     o = rstd.view(B, 1, 32, 1) * (g - s1 - xh * s2)
-    dx.view(B, h + 2, w + 2, 256)[:, 1:-1, 1:-1] = o.reshape(B, h, w, 256).to(_lp())
+    dx.view(B, h + 2, w + 2, 256)[:, 1:-1, 1:-1] = _r(o.reshape(B, h, w, 256), dx)
 
 
 def build_pos_mask(img_mask, B, H, W, h, w, sent_mask, L, lang_pos, token_type, level_embed, pos32, kpm):
@@ -433,7 +447,7 @@ def attn_fwd(Q, K, V, kpm, O, LSE, B, H, Tq, Sk, scale, drop=None):
     s, v = _attn(Q, K, V, kpm, B, H, Tq, Sk, scale)
     LSE.view(B, H, Tq).copy_(torch.logsumexp(s, -1))
     o = (_pdrop(s.softmax(-1), drop, B, H, Tq, Sk) @ v).transpose(1, 2).reshape(B * Tq, H * 32)
-    O[:, :H * 32] = o.to(_lp())
+    O[:, :H * 32] = _r(o, O)
 
 
 def attn_bwd(Q, K, V, kpm, O, dO, LSE, dQ, dK, dV, Dbuf, B, H, Tq, Sk, scale, drop=None):
@@ -445,9 +459,9 @@ def attn_bwd(Q, K, V, kpm, O, dO, LSE, dQ, dK, dV, Dbuf, B, H, Tq, Sk, scale, dr
         s, vh = _attn(q, k, v, kpm, B, H, Tq, Sk, scale)
         o = (_pdrop(s.softmax(-1), drop, B, H, Tq, Sk) @ vh).transpose(1, 2).reshape(B * Tq, H * 32)
         o.backward(dO[:, :H * 32].float())
-    dQ[:, :H * 32] = q.grad.to(_lp())
-    dK[:, :H * 32] = k.grad.to(_lp())
-    dV[:, :H * 32] = v.grad.to(_lp())
+    dQ[:, :H * 32] = _r(q.grad, dQ)
+    dK[:, :H * 32] = _r(k.grad, dK)
+    dV[:, :H * 32] = _r(v.grad, dV)
 
 
 def qenc_pool_fwd(k, q, v, mask, B, L, n_ph, att, c):
@@ -488,7 +502,7 @@ def rows_add(a, b, rows, D, *, y32=None, yb=None, map_a=None, map_b=None, map_y=
     if y32 is not None:
         y32[o, :D] = v
     if yb is not None:
-        yb[o, :D] = v.to(_lp())
+        yb[o, :D] = _r(v, yb)
 
 
 def rows_scatter_add(src, dst, rows, D, *, map_src=None, map_dst=None):
@@ -507,7 +521,7 @@ def require_device(t):
 def tokens_to_grid(tok, B, S, L, h, w, C, grid, col0):
     _LAUNCHES[0] += 1
     g = grid.view(B, h + 2, w + 2, -1)
-    g[:, 1:-1, 1:-1, col0:col0 + C] = tok.view(B, S, C)[:, L:].reshape(B, h, w, C).to(_lp())
+    g[:, 1:-1, 1:-1, col0:col0 + C] = _r(tok.view(B, S, C)[:, L:].reshape(B, h, w, C), g)
 
 
 def grid_to_tokens(grid, col0, B, S, L, h, w, C, dtok):
@@ -525,7 +539,7 @@ def attn_map_fwd(q, k, kpm, B, S, L, hw, w, scale, att, grid, col0):
     a = torch.softmax(lg.reshape(B, -1), -1).view(B, 8, hw)
     att.copy_(a)
     h = hw // w
-    grid.view(B, h + 2, w + 2, -1)[:, 1:-1, 1:-1, col0:col0 + 8] = a.permute(0, 2, 1).reshape(B, h, w, 8).to(_lp())
+    grid.view(B, h + 2, w + 2, -1)[:, 1:-1, 1:-1, col0:col0 + 8] = _r(a.permute(0, 2, 1).reshape(B, h, w, 8), grid)
 
 
 def attn_map_bwd(datt_ext, dgrid, col0, att, q, k, B, S, L, hw, w, scale, dq, dk):
@@ -555,7 +569,7 @@ def groupnorm_nhwc_fwd(x, gamma, beta, B, H, W, C, G, y, mean, rstd, relu=True, 
         o = o.clamp_min(0)
     yv = y.view(B, H + 2, W + 2, C)
     yv.zero_()
-    yv[:, 1:-1, 1:-1] = o.to(_lp())
+    yv[:, 1:-1, 1:-1] = _r(o, yv)
 
 
 def groupnorm_nhwc_bwd(dy, y, x, gamma, mean, rstd, B, H, W, C, G, dx, dgamma, dbeta, relu=True):
@@ -576,7 +590,7 @@ def groupnorm_nhwc_bwd(dy, y, x, gamma, mean, rstd, B, H, W, C, G, dx, dgamma, d
     o = rstd.view(B, 1, G, 1) * (g - s1 - xh * s2)
     dv = dx.view(B, H + 2, W + 2, C)
     dv.zero_()
-    dv[:, 1:-1, 1:-1] = o.reshape(B, H, W, C).to(_lp())
+    dv[:, 1:-1, 1:-1] = _r(o.reshape(B, H, W, C), dv)
 
 
 def upsample_add(lo, cur, y, B, h, w, H, W, C):
@@ -585,7 +599,7 @@ def upsample_add(lo, cur, y, B, h, w, H, W, C):
     up = F.interpolate(l, size=(H, W), mode="nearest").permute(0, 2, 3, 1)
     yv = y.view(B, H + 2, W + 2, C)
     yv.zero_()
-    yv[:, 1:-1, 1:-1] = (up + cur.view(B, H + 2, W + 2, C)[:, 1:-1, 1:-1].float()).to(_lp())
+    yv[:, 1:-1, 1:-1] = _r((up + cur.view(B, H + 2, W + 2, C)[:, 1:-1, 1:-1].float()), yv)
 
 
 def upsample_bwd(dy, dlo, B, h, w, H, W, C):
@@ -596,7 +610,7 @@ def upsample_bwd(dy, dlo, B, h, w, H, W, C):
     up.backward(dy.view(B, H + 2, W + 2, C)[:, 1:-1, 1:-1].permute(0, 3, 1, 2).float())
     dv = dlo.view(B, h + 2, w + 2, C)
     dv.zero_()
-    dv[:, 1:-1, 1:-1] = l.grad.permute(0, 2, 3, 1).to(_lp())
+    dv[:, 1:-1, 1:-1] = _r(l.grad.permute(0, 2, 3, 1), dv)
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -636,7 +650,7 @@ def ln_wide_fwd(x, gamma, beta, rows, *, y32=None, yb=None, mean=None, rstd=None
     if y32 is not None:
         y32[:rows] = y
     if yb is not None:
-        yb[:rows] = y.to(_lp())
+        yb[:rows] = _r(y, yb)
 
 
 def ln_wide_bwd(dy, x, gamma, mean, rstd, rows, *, dy2=None, dx32=None, dxb=None, dgamma=None, dbeta=None, dy_drop=None, dxb_drop=None):
@@ -658,19 +672,19 @@ def ln_wide_bwd(dy, x, gamma, mean, rstd, rows, *, dy2=None, dx32=None, dxb=None
     if dxb is not None:
         if dxb_drop is not None:
             dx = dx * dxb_drop.mask(rows, dx.shape[1])
-        dxb[:rows] = dx.to(_lp())
+        dxb[:rows] = _r(dx, dxb)
 
 
 def gelu_fwd(x, y):
     _LAUNCHES[0] += 1
-    y.copy_(F.gelu(x.float()).to(_lp()))
+    y.copy_(_r(F.gelu(x.float()), y))
 
 
 def gelu_bwd(dy, x, dx):
     _LAUNCHES[0] += 1
     xf = x.float()
     g = 0.5 * (1 + torch.erf(xf / math.sqrt(2))) + xf * torch.exp(-0.5 * xf * xf) / math.sqrt(2 * math.pi)
-    dx.copy_((dy.float() * g).to(_lp()))
+    dx.copy_(_r((dy.float() * g), dx))
 
 
 def tanh_fwd(x, y):
@@ -684,7 +698,7 @@ def tanh_bwd(dy, y, dx=None, dxb=None):
     if dx is not None:
         dx.copy_(v)
     if dxb is not None:
-        dxb.copy_(v.to(_lp()))
+        dxb.copy_(_r(v, dxb))
 
 
 def attn_small_fwd(Q, K, V, mask, O, P, B, H, S, scale, drop=None):
@@ -697,7 +711,7 @@ def attn_small_fwd(Q, K, V, mask, O, P, B, H, S, scale, drop=None):
         s = s.masked_fill(mask.view(B, 1, 1, S).bool(), float("-inf"))
     p = torch.softmax(s, -1)
     P.view(B, H, S, S).copy_(p)
-    O.copy_((_pdrop(p, drop, B, H, S, S) @ v).transpose(1, 2).reshape(B * S, H * 64).to(_lp()))
+    O.copy_(_r((_pdrop(p, drop, B, H, S, S) @ v).transpose(1, 2).reshape(B * S, H * 64), O))
 
 
 def attn_small_bwd(Q, K, V, dO, P, dQ, dK, dV, B, H, S, scale, drop=None):
@@ -713,7 +727,7 @@ def attn_small_bwd(Q, K, V, dO, P, dQ, dK, dV, B, H, S, scale, drop=None):
     dq = ds @ k
     dk = ds.transpose(-1, -2) @ q
     for dst, src in ((dQ, dq), (dK, dk), (dV, dv)):
-        dst.copy_(src.transpose(1, 2).reshape(B * S, H * 64).to(_lp()))
+        dst.copy_(_r(src.transpose(1, 2).reshape(B * S, H * 64), dst))
 
 
 # ---------------------------------------------------------------------------------------------------------------

@@ -54,3 +54,8 @@ lay_o = [a["pred_boxes"] for a in out_o["aux_outputs"]] + [out_o["pred_boxes"]]
 for l in range(6):
     print(f"boxes layer {l}: rel-L2 {rel(lay_c[l], lay_o[l]):.3e} max abs {(lay_c[l]-lay_o[l]).abs().max().item():.3e}")
 # how much of the decoder error is the decoder's own 16-bit arithmetic?  run the ORACLE's decoder on the CANDIDATE's memory
+# how much of the box error is the box head's own 16-bit arithmetic?  The ORACLE's fp32 head on the CANDIDATE's fp32 decoder outputs
+with torch.no_grad():
+    hb = oracle.bbox_embed(hs32.view(6, B, -1, 256)).sigmoid()
+for l in range(6):
+    print(f"boxes layer {l} with an fp32 head on the candidate's hs: rel-L2 {rel(hb[l].reshape(B, -1, 4), lay_o[l].reshape(B, -1, 4)):.3e}")
