@@ -96,7 +96,10 @@ def test_e2e_matches_oracle(name):
         assert len(errs) > 150
         # (query_encoder.linear1/2 feed the UN-scaled, near one-hot softmax of reftr_transformer.py:53: any operand rounding is
         # amplified there -- the oracle under bf16 autocast is 0.5 off itself on them -- so they get the loose bound)
-        lim = lambda n: 0.75 if "query_encoder.linear" in n else max(0.3, 3.0 * min(floor.get(n, 0.0), 0.6))
+        # Where the noise floor itself exceeds 1 (pad_box: the oracle under 16-bit autocast is 8.8 .. 9.7 off ITSELF on these three
+        # tensors) the fp32 gradient is not determined at 16-bit operand precision at all; only the order of magnitude is asserted.
+        lim = lambda n: ((1.5 if floor.get(n, 0.0) > 1.0 else 0.75) if "query_encoder.linear" in n
+                         else max(0.3, 3.0 * min(floor.get(n, 0.0), 0.6)))
         bad = {n: (e, floor.get(n)) for n, e in live.items() if e != e or e > lim(n)}
         assert not bad, bad
         med = sorted(live.values())[len(live) // 2]

@@ -33,10 +33,10 @@ FULL = {
     "cfg5": dict(backbone="resnet101", seg=False, inputs=dict(B=4, H=800, W=800, L=40)),
 }
 
-# rel-L2 bound per gradient tensor class = 3 x the largest value measured on B200 for that class (profiles/r02_full_size_parity.log)
-# measured maxima (round 2, first run at reduced batch): transformer/heads 3.2e-2 / 5.4e-2 / 4.7e-2, img_backbone 3.0e-2 / 4.1e-2 / 3.7e-2,
-# lang_backbone 2.8e-2 / 5.4e-2 / 2.5e-2 (cfg3 / cfg4 / cfg5)
-GRAD_BOUNDS = [("lang_backbone", 0.16), ("img_backbone", 0.12), ("query_encoder.linear", 0.75), ("mask_head", 0.16), ("bbox_attention", 0.16), ("", 0.16)]
+# rel-L2 bound per gradient tensor class = 3 x the largest value measured on B200 for that class (profiles/r02_full_size_parity.log,
+# final library of round 2: cfg2 / cfg3 / cfg4 / cfg5): transformer + heads 2.6e-2 / 1.0e-2 / 2.2e-2 / 1.5e-2, img_backbone 2.0e-2 /
+# 1.1e-2 / 2.2e-2 / 1.2e-2, lang_backbone 3.0e-2 / 1.6e-2 / 2.3e-2 / 1.7e-2
+GRAD_BOUNDS = [("lang_backbone", 0.09), ("img_backbone", 0.07), ("query_encoder.linear", 0.75), ("mask_head", 0.09), ("bbox_attention", 0.09), ("", 0.08)]
 
 
 def _bound(name):
