@@ -148,7 +148,8 @@ def gemm(A, B, M, N, K, *, mode=0, taps=((0, 0),), bias=None, res=None, res32=No
     a.out_scale = out_scale
     a.sm_limit = SM_LIMIT if sm_limit is None else sm_limit
     if PROFILE is not None:  # bench.py: keep the launch descriptor so the launch can be re-issued and timed in isolation
-        PROFILE.append((a, 2.0 * M * N * K * len(taps), (mode, M, N, K, len(taps), bool(atomic), res is not None, res32 is not None,
+        # algorithmic FLOPs: taps that read the SAME A rows are the (hi | residual) halves of one weight, counted once
+        PROFILE.append((a, 2.0 * M * N * K * (len({ro for ro, _ in taps}) if mode == 0 else len(taps)), (mode, M, N, K, len(taps), bool(atomic), res is not None, res32 is not None,
                                                        mask_src is not None, out32 is not None)))
     _lib.check(_lib.lib().rb_gemm(C.byref(a), _stream()), "rb_gemm")
     return out if out is not None else out32
