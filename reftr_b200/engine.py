@@ -224,7 +224,13 @@ class RefTREngine:
         self._side2, self._side2_used = None, False
         self._side2u, self._side2u_used = None, False
         self._prio_branch = os.environ.get("REFTR_B200_BRANCH_PRIORITY", "1") != "0"
+        # Priority of the stream the main chain is captured on (-1: above the side streams).  Under data parallelism it stays 0:
+        # ProcessGroupNCCL's kernels run on a normal-priority stream and must not queue behind this rank's own compute
+        # (measured at 2 GPUs: 10.89 ms with 0, 11.00 ms with -1; profiles/r02_branch_scheduling.log item 10)
         self._main_prio = int(os.environ.get("REFTR_B200_MAIN_PRIORITY", "-1"))
+        if self._main_prio < 0 and torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1 \
+                and os.environ.get("REFTR_B200_MAIN_PRIORITY_DDP", "0") == "0":
+            self._main_prio = 0
         self._cap_stream = None
         self._forks = os.environ.get("REFTR_B200_FORKS", "1") != "0" and self._side_cats
         self._tracked = [t for t in list(model.parameters()) + list(model.buffers())]
@@ -652,7 +658,7 @@ class RefTREngine:
             # BERT's part runs on its own HIGH-PRIORITY stream (captured there, so its kernel nodes carry the priority): a chain of
             # short, narrow launches that must finish early -- its 440 MB slice is the largest all-reduce of the step
             self._split_stream = torch.cuda.Stream(device=self._dev, priority=self._main_prio - 1 if self._prio_branch else 0)
-            self._comm_stream = torch.cuda.Stream(device=self._dev)
+            self._comm_stream = torch.cuda.Stream(device=self._dev, priority=self._main_prio - 2)  # hand-over copies before anything else
         br, cs = self._split_stream, self._comm_stream
         if st.get("bwd3") is None:
             plan = self._split_plan()
