@@ -185,3 +185,31 @@ def test_gemm_skinny_matches_torch_and_big_kernel(M, N, K):
             assert _rel(ob, ref) < 8e-3
             outs.append(o32)
         assert _rel(outs[0], outs[1]) < 1e-4  # the two kernels agree to fp32 summation order
+
+
+@pytest.mark.parametrize("M,N,K", [(6720, 256, 256), (6720, 256, 2048), (320, 768, 3072), (320, 2304, 768), (16, 256, 256)])
+def test_gemm_hilo_weight_pairs(M, N, K):
+    """(hi | residual) weight pairs (rb_pack_linear_hilo + a two-tap rb_gemm that reads the same A rows twice): the product with the
+    fp32 WEIGHT, i.e. what remains is the 16-bit rounding of the activations alone.  Checked against fp32 matmul of the 16-bit
+    activations with the fp32 weight -- to accumulation-order accuracy, ~50x tighter than the single-16-bit-weight product is."""
+    from reftr_b200 import ops
+    from reftr_b200.pack import PackedLinear, lin_taps
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    A = torch.randn(M, K, device="cuda", generator=g).to(T16)
+    w = torch.nn.Parameter(torch.randn(N, K, device="cuda", generator=g) / K ** 0.5)
+    bias = torch.nn.Parameter(torch.randn(N, device="cuda", generator=g))
+    pk = PackedLinear(w, bias, hilo=True)
+    pk.refresh()
+    assert pk.wb2.shape == (N, 2 * K)
+    assert torch.equal(pk.wb2[:, :K], pk.wb[:N])                                   # hi = the plain 16-bit weight
+    assert torch.equal(pk.wb2[:, K:], (w.detach() - pk.wb[:N].float()).to(T16))   # residual
+    B, taps = lin_taps(pk)
+    assert len(taps) == 2 and taps[1] == (0, K)
+    out32 = torch.empty(M, N, device="cuda")
+    ops.gemm(A, B, M, N, K, taps=taps, bias=pk.bias, out32=out32)
+    ref = A.float() @ w.detach().t() + bias.detach()
+    single = A.float() @ pk.wb[:N].float().t() + bias.detach()
+    e_pair = ((out32 - ref).norm() / ref.norm()).item()
+    e_single = ((single - ref).norm() / ref.norm()).item()
+    print(f"hi/lo M{M} N{N} K{K}: rel-L2 vs fp32 weights {e_pair:.2e} (one 16-bit weight: {e_single:.2e})")
+    assert e_pair < 2e-5 and e_pair < 0.1 * e_single
