@@ -40,8 +40,9 @@ def ncu_summary():
     """Profiler-derived figures (DRAM traffic of the GEMM family, tensor-pipe % of the encoder attention kernel) are NOT measured by
     this script (a number taken under a profiler is never a bench value, and ncu cannot run inside the timed process): they are
     read from profiles/ncu_summary.json, which tools/ncu_to_json.py writes from the committed ncu CSV captures.  The line carries
-    the file's SHA-256 and the library hash the capture was taken with, next to the hash of the library loaded now, so a stale
-    capture is visible instead of silently quoted."""
+    the file's SHA-256 and the hash of the kernel SOURCES the capture was taken with, next to the hash of the sources the loaded
+    library is built from, so a stale capture is visible instead of silently quoted (the binary's own hash is not reproducible from
+    build to build)."""
     import hashlib
     try:
         raw = open(NCU_SUMMARY, "rb").read()
@@ -52,8 +53,8 @@ def ncu_summary():
         return None
     try:
         from reftr_b200 import _lib
-        d["lib_sha256_now"] = hashlib.sha256(open(_lib.LIB_PATH, "rb").read()).hexdigest()[:16]
-        d["stale"] = d.get("lib_sha256") != d["lib_sha256_now"]
+        d["kernel_src_sha256_now"] = _lib.kernel_source_hash()
+        d["stale"] = d.get("kernel_src_sha256") != d["kernel_src_sha256_now"]
     except Exception:
         pass
     return d
@@ -680,8 +681,8 @@ def main():
                 out["roofline"]["traffic"] = gm["dram_bytes_per_launch"]
                 out["roofline"]["traffic_note"] = gm.get("note", "") + f" [{ns['file']} sha256 {ns['file_sha256']}, stale={ns.get('stale')}]"
             if ns.get("encoder_mha"):
-                out["encoder_mha"] = dict(ns["encoder_mha"], source=f"{ns['file']} sha256 {ns['file_sha256']}", lib_sha256_capture=ns.get("lib_sha256"),
-                                          lib_sha256_now=ns.get("lib_sha256_now"), stale=ns.get("stale"))
+                out["encoder_mha"] = dict(ns["encoder_mha"], source=f"{ns['file']} sha256 {ns['file_sha256']}", kernel_src_sha256_capture=ns.get("kernel_src_sha256"),
+                                          kernel_src_sha256_now=ns.get("kernel_src_sha256_now"), stale=ns.get("stale"))
         if world == 1 and a.workload == "cfg2" and os.environ.get("REFTR_B200_BENCH_STOCK", "1") == "1":
             out.update(stock_and_parity(model, s_dev, t_dev, device, value))
         if world == 1 and a.workload == "cfg2" and os.environ.get("REFTR_B200_BENCH_OPTIM", "1") == "1":

@@ -120,3 +120,19 @@ def check(rc, what):
     LAUNCHES += 1
     if rc != 0:
         raise RuntimeError(f"{what}: {lib().rb_last_error().decode()}")
+
+
+def kernel_source_hash():
+    """SHA-256 (first 16 hex digits) over the kernel sources the library is built from (csrc/*, include/reftr_b200.h).  The binary's
+    own hash is not reproducible (two builds of identical sources differ), so profile files record this one."""
+    import glob
+    import hashlib
+    root = os.path.dirname(os.path.abspath(__file__))
+    files = sorted(glob.glob(os.path.join(root, "csrc", "*.cu")) + glob.glob(os.path.join(root, "csrc", "*.cuh")) +
+                   glob.glob(os.path.join(root, "csrc", "*.h")) + glob.glob(os.path.join(root, "csrc", "*.sh")) +
+                   [os.path.join(os.path.dirname(root), "include", "reftr_b200.h")])
+    h = hashlib.sha256()
+    for f in files:
+        h.update(os.path.basename(f).encode())
+        h.update(open(f, "rb").read())
+    return h.hexdigest()[:16]

@@ -42,7 +42,10 @@ def main():
     ap.add_argument("--lib", default="reftr_b200/libreftr_b200.so")
     ap.add_argument("--out", default="profiles/ncu_summary.json")
     a = ap.parse_args()
-    res = {"lib_sha256": hashlib.sha256(open(a.lib, "rb").read()).hexdigest()[:16] if os.path.exists(a.lib) else None}
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from reftr_b200._lib import kernel_source_hash
+    res = {"kernel_src_sha256": kernel_source_hash()}  # the sources the profiled library was built from (run this right after the capture)
     if a.gemm:
         ks = load_long(a.gemm)
         n = len(ks)
