@@ -61,3 +61,29 @@ def test_no_cpu_fallback():
         if f.endswith(".py"):
             txt = open(os.path.join(pkg, f)).read()
             assert "emu_ops" not in txt and "import oracle" not in txt and "from oracle" not in txt, f
+
+
+def test_sm_limit_scope_nests_and_ignores_zero():
+    """ops.sm_limit_scope sets the default rb_gemm_args.sm_limit of a region (BERT's chains beside the conv backbone); 0 leaves the
+    enclosing value in place."""
+    from reftr_b200 import ops
+    assert ops.SM_LIMIT == 0
+    with ops.sm_limit_scope(36):
+        assert ops.SM_LIMIT == 36
+        with ops.sm_limit_scope(0):
+            assert ops.SM_LIMIT == 36
+        with ops.sm_limit_scope(12):
+            assert ops.SM_LIMIT == 12
+        assert ops.SM_LIMIT == 36
+    assert ops.SM_LIMIT == 0
+
+
+def test_kernel_source_hash_is_stable_and_tracks_the_sources():
+    from reftr_b200 import _lib
+    a, b = _lib.kernel_source_hash(), _lib.kernel_source_hash()
+    assert a == b and len(a) == 16
+    import json
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "ncu_summary.json")
+    if os.path.exists(path):  # the committed ncu summary must belong to the committed kernel sources
+        assert json.load(open(path)).get("kernel_src_sha256") == a

@@ -213,3 +213,31 @@ def test_gemm_hilo_weight_pairs(M, N, K):
     e_single = ((single - ref).norm() / ref.norm()).item()
     print(f"hi/lo M{M} N{N} K{K}: rel-L2 vs fp32 weights {e_pair:.2e} (one 16-bit weight: {e_single:.2e})")
     assert e_pair < 2e-5 and e_pair < 0.1 * e_single
+
+
+@pytest.mark.parametrize("limit", [2, 8, 36, 200])
+def test_gemm_sm_limit_gives_the_same_result(limit):
+    """rb_gemm_args.sm_limit only narrows the persistent grid (and the tile / split choice): NT output bit-identical for a fixed tile
+    width, TN weight gradient equal up to the order of the fp32 atomics."""
+    from reftr_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(limit)
+    M, N, K = 1500, 768, 512
+    A = torch.randn(M, K, device="cuda", generator=g).to(T16)
+    B = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).to(T16)
+    o0, o1 = torch.empty(M, N, device="cuda", dtype=T16), torch.empty(M, N, device="cuda", dtype=T16)
+    ops.gemm(A, B, M, N, K, out=o0, block_n=128)
+    ops.gemm(A, B, M, N, K, out=o1, block_n=128, sm_limit=limit)
+    assert torch.equal(o0, o1)
+    with ops.sm_limit_scope(limit):
+        o2 = torch.empty(M, N, device="cuda", dtype=T16)
+        ops.gemm(A, B, M, N, K, out=o2, block_n=128)
+    assert torch.equal(o0, o2)
+    R, Mo, No = 2000, 256, 384
+    dY = torch.randn(R, Mo, device="cuda", generator=g).to(T16)
+    X = torch.randn(R, No, device="cuda", generator=g).to(T16)
+    gw = torch.zeros(Mo, No, device="cuda")
+    gb = torch.zeros(Mo, device="cuda")
+    ops.gemm(dY, X, Mo, No, R, mode=1, out32=gw, atomic=True, splits=0, bias_grad=gb, sm_limit=limit)
+    ref = dY.float().t() @ X.float()
+    assert _rel(gw, ref) < 1e-4
+    assert _rel(gb, dY.float().sum(0)) < 1e-4
