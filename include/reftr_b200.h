@@ -311,6 +311,14 @@ int rb_adamw_flat(float* p, const float* g, float* m, float* v, long long n, con
 int rb_collate_u8(const void* packed, const long long* table, int B, int H, int W, float mean0, float mean1, float mean2, float std0, float std1,
                   float std2, float* out, void* mask, void* stream);
 
+/* Resize of one raw uint8 HWC image on the device, bit-exact with torchvision's F.resize on a PIL image (= Pillow's bilinear
+ * ImagingResample; datasets/transforms.py:81-111, RandomResize :196-204): horizontal then vertical pass over uint8 with 22-bit
+ * fixed-point coefficients.  bounds_* int32 [out, 2] = (first input index, count), kk_* int32 [out, ksize_*] -- computed on the host
+ * exactly as Pillow does (reftr_b200/data.py:pil_bilinear_coeffs); a pass whose size does not change is skipped (its tables may
+ * be NULL); tmp: [h, ow, 3] bytes, needed when both passes run. */
+int rb_resize_u8(const void* src, int h, int w, void* dst, int oh, int ow, const int* bounds_h, const int* kk_h, int ksize_h, const int* bounds_v,
+                 const int* kk_v, int ksize_v, void* tmp, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -122,17 +122,18 @@ def check(rc, what):
         raise RuntimeError(f"{what}: {lib().rb_last_error().decode()}")
 
 
+PROFILED_SOURCES = ("common.cuh", "host.h", "host.cu", "build.sh", "gemm.cu", "gemm_skinny.cu", "attention_tc.cu", "attention.cu", "stem_pool.cu")
+
+
 def kernel_source_hash():
-    """SHA-256 (first 16 hex digits) over the kernel sources the library is built from (csrc/*, include/reftr_b200.h).  The binary's
-    own hash is not reproducible (two builds of identical sources differ), so profile files record this one."""
-    import glob
+    """SHA-256 (first 16 hex digits) over the sources of the kernels whose ncu captures are committed (the GEMM family, the attention
+    kernels, the fused stem) and of the headers / build script they share.  The binary's own hash is not reproducible (two builds of
+    identical sources differ), so profile files record this one; sources of other kernels (input pipeline, optimizer ...) do not
+    invalidate those captures."""
     import hashlib
-    root = os.path.dirname(os.path.abspath(__file__))
-    files = sorted(glob.glob(os.path.join(root, "csrc", "*.cu")) + glob.glob(os.path.join(root, "csrc", "*.cuh")) +
-                   glob.glob(os.path.join(root, "csrc", "*.h")) + glob.glob(os.path.join(root, "csrc", "*.sh")) +
-                   [os.path.join(os.path.dirname(root), "include", "reftr_b200.h")])
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
     h = hashlib.sha256()
-    for f in files:
-        h.update(os.path.basename(f).encode())
-        h.update(open(f, "rb").read())
+    for f in PROFILED_SOURCES:
+        h.update(f.encode())
+        h.update(open(os.path.join(root, f), "rb").read())
     return h.hexdigest()[:16]

@@ -16,14 +16,76 @@ IMAGENET_MEAN = (0.485, 0.456, 0.406)
 IMAGENET_STD = (0.229, 0.224, 0.225)
 
 
+def resized_size(w, h, size, max_size=None):
+    """(oh, ow) of datasets/transforms.py:84-101 (``get_size_with_aspect_ratio``): the SHORTER side becomes ``size`` unless the longer
+    one would exceed ``max_size``; int() truncation and round() exactly as there."""
+    if max_size is not None:
+        mn, mx = float(min(w, h)), float(max(w, h))
+        if mx / mn * size > max_size:
+            size = int(round(max_size * mn / mx))
+    if (w <= h and w == size) or (h <= w and h == size):
+        return h, w
+    if w < h:
+        return int(size * h / w), size
+    return size, int(size * w / h)
+
+
+_PIL_PREC = 22  # Pillow: PRECISION_BITS = 32 - 8 - 2
+
+
+def pil_bilinear_coeffs(in_size, out_size):
+    """Pillow's ``precompute_coeffs`` + ``normalize_coeffs_8bpc`` (src/libImaging/Resample.c) for the bilinear filter (support 1) over
+    the whole axis: (bounds int32 [out, 2] = (first input index, count), kk int32 [out, ksize]).  The double arithmetic, the (int)
+    truncations and the +-0.5 roundings are Pillow's, so the two-pass uint8 resample built on them (``rb_resize_u8``) is bit-exact
+    with ``PIL.Image.resize(..., BILINEAR)``, i.e. with torchvision's ``F.resize`` of a PIL image (datasets/transforms.py:111)."""
+    import math
+    scale = filterscale = in_size / out_size
+    if filterscale < 1.0:
+        filterscale = 1.0
+    support = 1.0 * filterscale
+    ksize = int(math.ceil(support)) * 2 + 1
+    ss = 1.0 / filterscale
+    bounds = torch.zeros(out_size, 2, dtype=torch.int32)
+    kk = torch.zeros(out_size, ksize, dtype=torch.int32)
+    one = float(1 << _PIL_PREC)
+    for xx in range(out_size):
+        center = 0.0 + (xx + 0.5) * scale
+        xmin = int(center - support + 0.5)
+        if xmin < 0:
+            xmin = 0
+        xmax = int(center + support + 0.5)
+        if xmax > in_size:
+            xmax = in_size
+        xmax -= xmin
+        w, ww = [], 0.0
+        for x in range(xmax):
+            a = (x + xmin - center + 0.5) * ss
+            if a < 0.0:
+                a = -a
+            v = 1.0 - a if a < 1.0 else 0.0
+            w.append(v)
+            ww += v
+        for x in range(xmax):
+            v = w[x] / ww if ww != 0.0 else w[x]
+            kk[xx, x] = int(-0.5 + v * one) if v < 0 else int(0.5 + v * one)
+        bounds[xx, 0], bounds[xx, 1] = xmin, xmax
+    return bounds, kk
+
+
 class DeviceCollator:
     """Reusable pinned staging buffers + device buffers for one data loader (one instance per process)."""
 
     N_SLOTS = 2  # pinned staging slots: batch i+1 is packed on the host while the DMA of batch i may still be in flight
 
-    def __init__(self, device, mean=IMAGENET_MEAN, std=IMAGENET_STD):
+    def __init__(self, device, mean=IMAGENET_MEAN, std=IMAGENET_STD, resize=None):
+        """``resize`` = (size, max_size): the images are resized ON THE DEVICE after the H2D copy of their raw bytes, like
+        ``T.RandomResize([size], max_size=max_size)`` of the reference's datasets (refer_multiphrase.py:42, transforms.py:81-111;
+        Pillow's bilinear resample, bit-exact) -- the host ships the ORIGINAL pixels and never resizes.  ``resized_size`` gives the
+        output size of an image (the caller scales its boxes by the same ratios, transforms.py:116-122)."""
         self.device = torch.device(device)
         self.mean, self.std = tuple(mean), tuple(std)
+        self.resize = tuple(resize) if resize is not None else None
+        self._coef = {}  # (in, out) -> device (bounds, kk)
         self._slots = [dict(pinned=None, table=None, event=None) for _ in range(self.N_SLOTS)]
         self._next = 0
 
@@ -58,11 +120,16 @@ class DeviceCollator:
         ctx = torch.cuda.stream(stream) if stream is not None else _null()
         with ctx:
             dbuf = packed.buf.to(self.device, non_blocking=True)
-            dtab = packed.table.to(self.device, non_blocking=True)
-            out = torch.empty(B, 3, packed.H, packed.W, dtype=torch.float32, device=self.device)
-            mask = torch.empty(B, packed.H, packed.W, dtype=torch.bool, device=self.device)
+            H, W = packed.H, packed.W
+            if self.resize is not None:
+                dbuf, table, H, W = self._resize_packed(dbuf, packed.table)
+                dtab = table.to(self.device, non_blocking=True)
+            else:
+                dtab = packed.table.to(self.device, non_blocking=True)
+            out = torch.empty(B, 3, H, W, dtype=torch.float32, device=self.device)
+            mask = torch.empty(B, H, W, dtype=torch.bool, device=self.device)
             ops.require_device(out)
-            ops.collate_u8(dbuf, dtab, B, packed.H, packed.W, self.mean, self.std, out, mask)
+            ops.collate_u8(dbuf, dtab, B, H, W, self.mean, self.std, out, mask)
             ready = None
             if cuda:
                 ready = torch.cuda.Event()
@@ -73,6 +140,33 @@ class DeviceCollator:
         res = ImageList(out, mask)
         res.ready = ready
         return res
+
+    def _tables(self, n_in, n_out):
+        key = (int(n_in), int(n_out))
+        t = self._coef.get(key)
+        if t is None:
+            b, k = pil_bilinear_coeffs(*key)
+            t = self._coef[key] = (b.to(self.device), k.to(self.device))
+        return t
+
+    def _resize_packed(self, dbuf, table):
+        """dbuf: the raw images back to back on the device, table: their host (offset, h, w) rows.  Returns the resized images packed
+        the same way + their host table (pinned when CUDA is there) + the batch's padded size."""
+        size, max_size = self.resize
+        rows = [(int(o), int(h), int(w)) + resized_size(int(w), int(h), size, max_size) for o, h, w in table.tolist()]
+        total = sum(oh * ow * 3 for _, _, _, oh, ow in rows)
+        dst = torch.empty(total, dtype=torch.uint8, device=self.device)
+        tmp = torch.empty(max(h * ow * 3 for _, h, _, _, ow in rows), dtype=torch.uint8, device=self.device)
+        new = torch.empty(len(rows), 3, dtype=torch.int64)
+        if torch.cuda.is_available():
+            new = new.pin_memory()
+        off = 0
+        for b, (o, h, w, oh, ow) in enumerate(rows):
+            ops.resize_u8(dbuf[o:o + h * w * 3], h, w, dst[off:off + oh * ow * 3], oh, ow, self._tables(w, ow) if ow != w else None,
+                          self._tables(h, oh) if oh != h else None, tmp)
+            new[b, 0], new[b, 1], new[b, 2] = off, oh, ow
+            off += oh * ow * 3
+        return dst, new, max(r[3] for r in rows), max(r[4] for r in rows)
 
     def __call__(self, images, stream=None, consumer_stream=None):
         """images: list of uint8 tensors [h_i, w_i, 3] on the host.  Returns ImageList(tensors fp32 [B,3,H,W], mask bool [B,H,W])

@@ -439,3 +439,11 @@ def adamw_flat(p, g, m, v, seg_end, seg_group, lrs, wds, beta1, beta2, eps, step
 def collate_u8(packed, table, B, H, W, mean, std, out, mask):
     _lib.call("rb_collate_u8", _p(packed), _p(table), B, H, W, float(mean[0]), float(mean[1]), float(mean[2]), float(std[0]), float(std[1]),
               float(std[2]), _p(out), _p(mask), _s())
+
+
+def resize_u8(src, h, w, dst, oh, ow, tab_h, tab_v, tmp):
+    """tab_* = (bounds int32 [out, 2], kk int32 [out, ksize]) on the device, or None for a pass that does not change the size."""
+    bh, kh = tab_h if tab_h is not None else (None, None)
+    bv, kv = tab_v if tab_v is not None else (None, None)
+    _lib.call("rb_resize_u8", _p(src), h, w, _p(dst), oh, ow, _p(bh), _p(kh), kh.shape[1] if kh is not None else 0, _p(bv), _p(kv),
+              kv.shape[1] if kv is not None else 0, _p(tmp), _s())

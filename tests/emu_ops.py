@@ -768,3 +768,25 @@ def adamw_flat(p, g, m, v, seg_end, seg_group, lrs, wds, beta1, beta2, eps, step
         v[sl] = beta2 * v[sl] + (1 - beta2) * gg * gg
         p[sl] = p[sl] * (1 - lr * wd) - (lr / bc1) * m[sl] / (v[sl].sqrt() / math.sqrt(bc2) + eps)
         lo = end
+
+
+def resize_u8(src, h, w, dst, oh, ow, tab_h, tab_v, tmp):
+    """Pillow's two-pass bilinear resample on uint8 (restated with int64 torch arithmetic)."""
+    _LAUNCHES[0] += 2
+    cur = src.view(h, w, 3).to(torch.int64)
+    half = 1 << 21
+    if ow != w:
+        b, k = tab_h
+        out = torch.zeros(h, ow, 3, dtype=torch.int64)
+        for xx in range(ow):
+            x0, n = int(b[xx, 0]), int(b[xx, 1])
+            out[:, xx] = ((cur[:, x0:x0 + n] * k[xx, :n].to(torch.int64).view(1, n, 1)).sum(1) + half >> 22).clamp(0, 255)
+        cur = out
+    if oh != h:
+        b, k = tab_v
+        out = torch.zeros(oh, cur.shape[1], 3, dtype=torch.int64)
+        for yy in range(oh):
+            y0, n = int(b[yy, 0]), int(b[yy, 1])
+            out[yy] = ((cur[y0:y0 + n] * k[yy, :n].to(torch.int64).view(n, 1, 1)).sum(0) + half >> 22).clamp(0, 255)
+        cur = out
+    dst.view(oh, ow, 3).copy_(cur.to(torch.uint8))
