@@ -377,3 +377,34 @@ def test_loss_scale_backs_off_after_overflow_and_grows_when_clean(emulated):
         _loss(cand(s), case).backward()
     assert eng.overflow_steps() == n0 and eng.grad_scale == 2048.0
     assert torch.isfinite(cand.bbox_embed.layers[0].weight.grad).all()
+
+
+@pytest.mark.parametrize("cut", [1, 2])
+def test_bert_backward_by_layer_ranges_equals_the_whole(cut, emulated_exact):
+    """Under data parallelism BERT's backward runs as TWO graphs (upper / lower encoder layers, engine._split_plan): calling
+    ``bert.backward(layers=(hi, lo))`` range by range must leave exactly the gradients of one whole call -- the running gradient lives in
+    two alternating buffers, so an odd and an even cut are both checked (3-layer BERT)."""
+    case = dict(CASES["cfg1_box"], bert_layers=3)
+    torch.set_num_threads(os.cpu_count())
+    cand = build_candidate(case)
+    s = synthetic_samples(**case["inputs"])
+    _linear_loss(cand(s)).backward()          # runs the forward (saved activations) and allocates the flat gradient buffer
+    eng = cand.engine()
+    bert = eng.bert
+    assert bert is not None and len(bert.layers) == 3
+    B, L = case["inputs"]["B"], case["inputs"]["L"]
+    g = torch.Generator().manual_seed(7)
+    d_seq = torch.randn(B * L, bert.D, generator=g)
+    d_pooled = torch.randn(B, bert.D, generator=g)
+    b0, b1 = eng._bert_slice
+
+    def run(ranges):
+        eng.gflat.zero_()
+        for r in ranges:
+            bert.backward("s", d_seq, d_pooled, layers=r)
+        return eng.gflat[b0:b1].clone()
+
+    whole = run([None])
+    parts = run([(3, cut), (cut, 0)])
+    assert whole.abs().max().item() > 0
+    assert torch.equal(parts, whole) or (parts - whole).abs().max().item() <= 1e-6 * whole.abs().max().item()
